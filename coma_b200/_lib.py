@@ -1,0 +1,84 @@
+"""ctypes binding of libcoma_b200.so (the C ABI declared in include/coma_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or a kernel cannot run, the call raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcoma_b200.so")
+
+_c = ctypes
+_vp, _i64, _f32, _f64, _int = _c.c_void_p, _c.c_int64, _c.c_float, _c.c_double, _c.c_int
+_f32p = _c.POINTER(_c.c_float)
+
+# name -> argtypes, exactly the prototypes of include/coma_b200.h (device pointers travel as void*)
+SIGNATURES = {
+    "coma_nearest_vertex_f64": [_vp, _i64, _vp, _i64, _vp, _vp],
+    "coma_pair_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp],
+    "coma_orient_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _vp, _vp],
+    "coma_canonicalize_f32": [_vp, _i64, _vp, _i64, _f32p, _f32p, _f32, _vp, _vp],
+    "coma_occupancy_accumulate": [_vp, _i64, _i64, _vp, _i64, _f64, _vp, _vp],
+    "coma_normalize_contact_readout_f32": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
+    "coma_significant_pairs": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp],
+    "coma_masked_max_f32": [_vp, _i64, _i64, _vp, _int, _vp, _vp],
+    "coma_entropy_readout_f32": [_vp, _i64, _i64, _f32, _vp, _vp],
+    "coma_occupancy_readout_f32": [_vp, _i64, _i64, _vp, _i64, _vp, _vp],
+}
+
+_LIB = None
+
+
+class ComaB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the in-tree CUDA library; raise (never fall back) if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ComaB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m coma_b200.build` (nvcc, sm_100a). "
+                "coma_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.coma_b200_version.restype = _int
+        lib.coma_b200_last_error.restype = _c.c_char_p
+        lib.coma_b200_launch_count.restype = _i64
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = _int
+        _LIB = lib
+    return _LIB
+
+
+def launch_count():
+    return int(load().coma_b200_launch_count())
+
+
+def _ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ComaB200Error("coma_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise ComaB200Error("coma_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _host3(v):
+    return (ctypes.c_float * 3)(float(v[0]), float(v[1]), float(v[2]))
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise ComaB200Error(f"{name} failed (code {rc}): {lib.coma_b200_last_error().decode()}")

@@ -1,0 +1,189 @@
+"""ComA_Occupancy — drop-in mirror of the reference's `utils/coma_occupancy.py` (:160-343) on B200.
+
+Per-human-vertex voxel-hit counting relative to object vertex 0. Same constructor, methods, asserts and pickle layout;
+the dense [H, Sg^3] fp64 distance test of the reference is replaced by the K4 scatter kernel (bit-exact counts) and the
+read-out by the K5c kernels.  Multi-GPU: shard the HUMAN-VERTEX axis (`human_slice`), every rank sees all samples and
+owns H/world full grids; the only collective is a MAX all-reduce of the [Sg^3] field.
+"""
+import pickle
+
+import numpy as np
+import torch
+
+from . import ops
+from .misc import get_3d_indexgrid_ijk, to_np_torch_recursive
+from .staging import BatchStager
+
+_EXPORT_KEYS = (
+    "device", "human_res", "obj_res", "normal_res", "spatial_res", "spatial_grid", "spatial_indexgrid",
+    "spatial_grid_metadata", "N_x", "N_y", "N_z", "spatial_occupancy_grids", "cache_count", "used_count",
+    "principle_vec", "sub_principle_vec", "rel_dist_method", "rel_dist_thres", "normal_gaussian_sigma", "eps",
+    "debug_obj_vert", "debug_obj_normal",
+)
+
+_STAGING_BYTES = 64 << 20
+
+
+def load_voxelgrid(gridsize=3.0, resolution=24, center=[0, 0, 0]):
+    """utils/coma_occupancy.py:160-183, expression for expression: the middle term `voxel_size * indexgrid.astype(f32)`
+    is an fp32 product that numpy then promotes to fp64 — the bit-exact hit counts depend on it."""
+    length_x = length_y = length_z = gridsize
+    N_x = N_y = N_z = resolution
+    voxel_size = gridsize / resolution
+    center = np.array(center)
+    start_point = center - np.array([length_x / 2, length_y / 2, length_z / 2])
+    indexgrid = get_3d_indexgrid_ijk(N_x, N_y, N_z)
+    canon_grid = start_point.reshape(3, 1, 1, 1) + voxel_size * indexgrid.astype(np.float32) + voxel_size / 2
+    grid_metadata = dict(length_x=length_x, length_y=length_y, length_z=length_z, N_x=N_x, N_y=N_y, N_z=N_z,
+                         start_point=start_point, voxel_size=voxel_size)
+    return canon_grid, indexgrid, grid_metadata
+
+
+class ComA_Occupancy:
+    selected_obj_idxs = [0]
+
+    def __init__(self, scale_tolerance: float, human_res: int, obj_res: int, normal_res: int, spatial_res: int,
+                 proximity_settings=dict(), principle_vec=[0, 0, 1], sub_principle_vec=[0, 1, 0],
+                 rel_dist_method: str = "dist", normal_gaussian_sigma: float = 0.1, selected_obj_idx: int = None,
+                 eps: float = 1e-8, device: str = "cuda", human_slice=None):
+        self.device = device
+        self.human_res, self.obj_res = human_res, obj_res
+        self.normal_res, self.spatial_res = normal_res, spatial_res
+        assert normal_res == 0, "In this version, normal res is 0."
+
+        grid, self.spatial_indexgrid, self.spatial_grid_metadata = load_voxelgrid(gridsize=2.4, resolution=self.spatial_res, center=[0, 0, 0])
+        self.N_x, self.N_y, self.N_z = (self.spatial_grid_metadata[k] for k in ("N_x", "N_y", "N_z"))
+        # per-axis centres (the [3,S,S,S] grid is separable); fp64, exactly the reference's values
+        centers = np.stack([grid[0, :, 0, 0], grid[1, 0, :, 0], grid[2, 0, 0, :]])
+        self._centers = torch.from_numpy(np.ascontiguousarray(centers)).to(device)
+        self.spatial_grid = torch.from_numpy(grid).to(device)
+
+        # B200 extension: this rank may own only a slice [h0, h1) of the human vertices (H-sharded multi-GPU)
+        self._human_slice = (0, human_res) if human_slice is None else (int(human_slice[0]), int(human_slice[1]))
+        h_local = self._human_slice[1] - self._human_slice[0]
+        self.spatial_occupancy_grids = torch.zeros([h_local, self.N_x, self.N_y, self.N_z], dtype=torch.float32, device=device)
+
+        self.cache_count = 0
+        self.used_count = 0
+        self.cache = dict()
+        self.used = dict()
+
+        self.principle_vec = torch.tensor(principle_vec, dtype=torch.float32).to(device)
+        self.sub_principle_vec = torch.tensor(sub_principle_vec, dtype=torch.float32).to(device)
+
+        assert rel_dist_method in ["dist", "sdf"], f"rel_dist_method: '{rel_dist_method}' not allowed"
+        self.rel_dist_method = rel_dist_method
+        self.rel_dist_thres = self.spatial_grid_metadata["voxel_size"] * scale_tolerance
+        self.normal_gaussian_sigma = normal_gaussian_sigma
+        self.eps = eps
+        self.debug_obj_vert = None
+        self.debug_obj_normal = None
+
+    def register_sample_to_cache(self, **kwargs):
+        self.cache[f"{self.cache_count:05}"] = kwargs
+        self.cache_count = len(self.cache.keys())
+
+    def aggregate_all_samples(self):
+        keys = list(self.cache.keys())
+        self._aggregate_samples([self.cache[k] for k in keys])
+        for k in keys:
+            self.used[f"{self.used_count:05}"] = self.cache[k]
+            self.used_count = len(self.used.keys())
+        self.cache = {}
+        self.cache_count = 0
+
+    def aggregate_single_sample(self, **kwargs):
+        self._aggregate_samples([kwargs])
+
+    def _canonical_human_verts(self, sample):
+        """Host part of aggregate_single_sample_for_occupancy (:274-288): invariants + subtraction in the input dtype."""
+        human_verts, obj_verts, obj_normals = sample["human_verts"], sample["obj_verts"], sample["obj_normals"]
+        out = None
+        for obj_idx in self.selected_obj_idxs:
+            obj_vert, obj_normal = obj_verts[obj_idx], obj_normals[obj_idx]
+            if self.debug_obj_vert is None:
+                self.debug_obj_vert = obj_vert
+            else:
+                assert np.allclose(self.debug_obj_vert, obj_vert)
+            if self.debug_obj_normal is None:
+                self.debug_obj_normal = obj_normal
+            else:
+                assert np.allclose(self.debug_obj_normal, obj_normal)
+            out = human_verts - obj_vert[None]
+            assert out.shape[0] == self.human_res
+        h0, h1 = self._human_slice
+        return out[h0:h1]
+
+    def _aggregate_samples(self, samples):
+        if not samples:
+            return
+        if not self.spatial_occupancy_grids.is_cuda:
+            raise RuntimeError("ComA_Occupancy.aggregate: coma_b200 runs on CUDA (sm_100a) only — no CPU fallback")
+        assert len(self.selected_obj_idxs) == 1
+        h_local = self._human_slice[1] - self._human_slice[0]
+        chunk = max(32, min(8192, (_STAGING_BYTES // (h_local * 12)) // 32 * 32))
+        chunk = min(chunk, (len(samples) + 31) // 32 * 32)
+        stager = BatchStager(dict(hvc=h_local), chunk, self.spatial_occupancy_grids.device)
+        getters = dict(hvc=lambda i: self._canonical_human_verts(samples[i]))
+        for n, b in stager.batches(getters, len(samples)):
+            self.aggregate_batch_for_occupancy(b["hvc"])
+        self.last_h2d_bytes = stager.h2d_bytes
+
+    def aggregate_batch_for_occupancy(self, human_verts_canon):
+        """Device-resident batched form of :289-295: human_verts_canon [S,H_local,3] fp32 (already minus obj vertex 0)."""
+        ops.occupancy_accumulate(human_verts_canon, self._centers, self.rel_dist_thres, self.spatial_occupancy_grids)
+
+    def normalize_prob_grid_for_spatials(self):
+        """:297-300 (in place; NaN rows where a vertex never hit, as in the reference)."""
+        ops.occupancy_readout(self.spatial_occupancy_grids, None)
+
+    def normalize_prob_grid_for_spatials_v2(self):
+        self.spatial_occupancy_grids = self.spatial_occupancy_grids / self.used_count
+
+    def return_aggregated_spatial_grids(self, human_indices=None, group=None):
+        """:305-312 -> torch tensor [N,N,N] on the device. With an H-sharded instance the per-rank fields are combined
+        by one MAX all-reduce (NaN-propagating, like torch.max over the full vertex axis)."""
+        sel = None
+        if human_indices is not None:
+            h0, h1 = self._human_slice
+            idx = np.asarray(list(human_indices), dtype=np.int64)
+            idx = np.where(idx < 0, idx + self.human_res, idx)
+            idx = idx[(idx >= h0) & (idx < h1)] - h0
+            sel = torch.tensor(idx, dtype=torch.int64, device=self.spatial_occupancy_grids.device)
+        field = ops.occupancy_readout(self.spatial_occupancy_grids, sel)
+        return _all_reduce_max_nan(field, group)
+
+    def export(self, save_pth=None):
+        to_export = {}
+        for k in _EXPORT_KEYS:
+            v = getattr(self, k)
+            if isinstance(v, torch.Tensor):
+                v = v.detach().clone()
+            elif isinstance(v, np.ndarray):
+                v = v.copy()
+            elif isinstance(v, dict):
+                v = {kk: (vv.copy() if isinstance(vv, np.ndarray) else vv) for kk, vv in v.items()}
+            to_export[k] = v
+        to_export = to_np_torch_recursive(to_export, use_torch=False, device="cpu")
+        if save_pth is None:
+            return to_export
+        with open(save_pth, "wb") as handle:
+            pickle.dump(to_export, handle, protocol=pickle.HIGHEST_PROTOCOL)
+
+    def load(self, load_pth):
+        with open(load_pth, "rb") as handle:
+            loadables = pickle.load(handle)
+        loadables = to_np_torch_recursive(loadables, use_torch=True, device=self.device)
+        for k, v in loadables.items():
+            setattr(self, k, v)
+
+
+def _all_reduce_max_nan(field, group=None):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return field
+    # NCCL/gloo MAX does not define NaN ordering: carry NaN as +inf through the collective
+    nan = torch.isnan(field)
+    carried = torch.where(nan, torch.full_like(field, float("inf")), field)
+    dist.all_reduce(carried, op=dist.ReduceOp.MAX, group=group)
+    return torch.where(torch.isinf(carried) & (carried > 0), torch.full_like(carried, float("nan")), carried)

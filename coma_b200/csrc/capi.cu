@@ -1,0 +1,24 @@
+// Library-level entry points: version, thread-local error string, launch counter.
+#include <atomic>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace coma {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace coma
+
+extern "C" {
+int coma_b200_version(void) { return 100; }
+const char *coma_b200_last_error(void) { return coma::g_err; }
+int64_t coma_b200_launch_count(void) { return coma::g_launches.load(std::memory_order_relaxed); }
+}

@@ -1,0 +1,57 @@
+// Shared helpers for the coma_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/coma_b200.h"
+
+namespace coma {
+
+constexpr int kNumSM = 148;  // B200
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+inline int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    count_launch();
+    return 0;
+}
+
+#define COMA_REQUIRE(cond, msg)                          \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            coma::set_error("%s: %s", __func__, msg);    \
+            return COMA_E_BADARG;                        \
+        }                                                \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max_nan(float v) {
+    // max that propagates NaN like torch.max
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (u != u || v != v) ? __int_as_float(0x7fc00000) : fmaxf(u, v);
+    }
+    return v;
+}
+
+// Streaming (read-once / write-once) global accesses: keep them out of L1.
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+}  // namespace coma

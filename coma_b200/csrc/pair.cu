@@ -1,0 +1,98 @@
+// K2 — pair distance -> contact count + proximity expectation (reference: utils/coma.py:284-291, :116-119).
+//
+// Layout: one CTA owns a 16(h) x 128(o) tile of the [H,O] accumulators, each thread 8 pairs (8 h-rows x 1 o-column)
+// held in registers across ALL samples of the call; vertices of the current sample chunk are staged in shared memory
+// (object vertices as SoA so the per-lane reads are conflict-free, human vertices as float4 so one broadcast LDS.128
+// serves the warp).  The accumulators are read-modify-written once per launch, coalesced along o.
+//   bytes per launch  = 12*S*(H+O) (vertices) + 2 accumulators * (4 R + 4 W) * H*O  = 16 B / vertex-pair at S = 1
+//   => HBM-bound at S = 1 (the reference's per-sample streaming form), ALU/SFU-bound once S >~ 8.
+// Bit-exactness of `count`: every product/sum is an explicitly rounded __fmul_rn/__fadd_rn in the reference's order
+// ((x+y)+z), the root is __fsqrt_rn and the comparison is done in fp32 against fp32(thres), exactly like torch.
+#include "common.cuh"
+
+namespace coma {
+
+constexpr int K2_TO = 128;  // object columns per CTA (= blockDim.x)
+constexpr int K2_TY = 2;    // blockDim.y
+constexpr int K2_RH = 8;    // human rows per thread
+constexpr int K2_TH = K2_TY * K2_RH;
+constexpr int K2_CS = 16;   // samples staged per chunk
+
+__global__ void __launch_bounds__(K2_TO *K2_TY)
+    pair_accumulate_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float thres,
+                           float grid_size, float *__restrict__ count, float *__restrict__ nom) {
+    __shared__ float4 sh[K2_CS][K2_TH];
+    __shared__ float so[K2_CS][3][K2_TO];
+
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * K2_TO + tx;
+    const int o0 = blockIdx.x * K2_TO, h0 = blockIdx.y * K2_TH;
+    const int o = o0 + tx;
+
+    float cnt[K2_RH], acc[K2_RH];
+#pragma unroll
+    for (int r = 0; r < K2_RH; ++r) cnt[r] = acc[r] = 0.0f;
+
+    for (int s0 = 0; s0 < S; s0 += K2_CS) {
+        const int ns = min(K2_CS, S - s0);
+        // stage human rows: ns x 16 vertices
+        for (int i = tid; i < ns * K2_TH; i += K2_TO * K2_TY) {
+            int cs = i / K2_TH, r = i % K2_TH, h = h0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (h < H) {
+                const float *p = hv + ((size_t)(s0 + cs) * H + h) * 3;
+                v.x = p[0]; v.y = p[1]; v.z = p[2];
+            }
+            sh[cs][r] = v;
+        }
+        // stage object columns: ns x 128 vertices, coalesced over the 384 contiguous floats of a sample's tile
+        for (int i = tid; i < ns * K2_TO * 3; i += K2_TO * K2_TY) {
+            int cs = i / (K2_TO * 3), e = i % (K2_TO * 3);
+            int oo = e / 3, k = e % 3;
+            float v = 0.f;
+            if (o0 + oo < O) v = ov[((size_t)(s0 + cs) * O + o0) * 3 + e];
+            so[cs][k][oo] = v;
+        }
+        __syncthreads();
+        for (int cs = 0; cs < ns; ++cs) {
+            const float ox = so[cs][0][tx], oy = so[cs][1][tx], oz = so[cs][2][tx];
+#pragma unroll
+            for (int r = 0; r < K2_RH; ++r) {
+                const float4 hvv = sh[cs][ty * K2_RH + r];
+                const float dx = __fsub_rn(hvv.x, ox), dy = __fsub_rn(hvv.y, oy), dz = __fsub_rn(hvv.z, oz);
+                const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                const float d = __fsqrt_rn(sq);
+                cnt[r] += (d < thres) ? 1.0f : 0.0f;
+                acc[r] += expf(__fdiv_rn(-d, grid_size));
+            }
+        }
+        __syncthreads();
+    }
+    if (o < O) {
+#pragma unroll
+        for (int r = 0; r < K2_RH; ++r) {
+            const int h = h0 + ty * K2_RH + r;
+            if (h < H) {
+                const size_t q = (size_t)h * O + o;
+                count[q] += cnt[r];
+                nom[q] += acc[r];
+            }
+        }
+    }
+}
+
+}  // namespace coma
+
+extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_t S, int64_t H, int64_t O, float thres,
+                                        float grid_size, float *count, float *nom, coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(hv && ov && count && nom, "null pointer");
+    COMA_REQUIRE(S >= 0 && H > 0 && O > 0, "bad sizes");
+    COMA_REQUIRE(H * O < (int64_t)1 << 40 && S < (int64_t)1 << 30, "sizes out of range");
+    if (S == 0) return 0;
+    dim3 block(K2_TO, K2_TY);
+    dim3 grid((unsigned)((O + K2_TO - 1) / K2_TO), (unsigned)((H + K2_TH - 1) / K2_TH));
+    COMA_REQUIRE(grid.y <= 65535u, "H too large for one launch (max 1048560)");
+    pair_accumulate_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(hv, ov, (int)S, (int)H, (int)O, thres, grid_size,
+                                                                     count, nom);
+    return check_launch("pair_accumulate_kernel");
+}

@@ -1,0 +1,235 @@
+// K5 — read-out reductions (reference: utils/coma.py:328-476, utils/coma_occupancy.py:297-312).
+// All of them are single streaming passes over the accumulators (HBM-bound): one warp per (h,o) row of the [H*O, N]
+// grids with coalesced 128-byte row segments and shuffle reductions, persistent grid of kNumSM * 8 CTAs.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace coma {
+
+constexpr int K5_WARPS = 8;
+
+// K5a: P[q,:] /= (sum P[q,:] + eps) in place; cmap[q] = (sum_n P[q,n] w[n]) * nom[q]/denom[q]
+__global__ void __launch_bounds__(K5_WARPS * 32)
+    normalize_contact_kernel(float *__restrict__ P, long long HO, int N, float eps, const float *__restrict__ w,
+                             const float *__restrict__ nom, const float *__restrict__ denom, float *__restrict__ cmap) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * K5_WARPS + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * K5_WARPS;
+    for (long long q = warp0; q < HO; q += nwarps) {
+        float *row = P + (size_t)q * N;
+        float s = 0.f;
+        for (int n = lane; n < N; n += 32) s += row[n];
+        s = warp_sum(s);
+        const float d = __fadd_rn(s, eps);
+        float acc = 0.f;
+        for (int n = lane; n < N; n += 32) {
+            const float v = __fdiv_rn(row[n], d);
+            row[n] = v;
+            if (cmap) acc = fmaf(v, w[n], acc);
+        }
+        if (cmap) {
+            acc = warp_sum(acc);
+            if (lane == 0) cmap[q] = acc * __fdiv_rn(nom[q], denom[q]);
+        }
+    }
+}
+
+// K5b: entropy read-out of a normalised grid
+__global__ void __launch_bounds__(K5_WARPS * 32)
+    entropy_kernel(const float *__restrict__ P, long long HO, int N, float n_bin, float log_n_bin, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * K5_WARPS + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * K5_WARPS;
+    for (long long q = warp0; q < HO; q += nwarps) {
+        const float *row = P + (size_t)q * N;
+        float acc = 0.f;
+        for (int n = lane; n < N; n += 32) {
+            const float qv = __fdiv_rn(rintf(__fmul_rn(row[n], n_bin)), n_bin);  // torch.round = half-to-even
+            acc += (qv == 0.0f) ? 0.0f : qv * logf(qv);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[q] = __fadd_rn(__fdiv_rn(acc, log_n_bin), 1.0f);
+    }
+}
+
+__global__ void significant_pairs_kernel(const float *__restrict__ count, int H, int O, float num, uint8_t *__restrict__ sig,
+                                         uint8_t *__restrict__ any_o, uint8_t *__restrict__ any_h) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)H * O) return;
+    const bool s = count[q] >= num;
+    if (sig) sig[q] = s ? 1 : 0;
+    if (s) {  // benign races: every writer stores the same value
+        if (any_o) any_o[q / O] = 1;
+        if (any_h) any_h[q % O] = 1;
+    }
+}
+
+// axis = 1: out[h] = max over masked o (one warp per row)
+__global__ void __launch_bounds__(256)
+    masked_rowmax_kernel(const float *__restrict__ cmap, int H, int O, const uint8_t *__restrict__ mask, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (h >= H) return;
+    float m = -INFINITY;
+    bool nan = false, any = false;
+    for (int o = lane; o < O; o += 32) {
+        if (mask[o]) {
+            const float v = cmap[(size_t)h * O + o];
+            any = true;
+            nan |= (v != v);
+            m = fmaxf(m, v);
+        }
+    }
+    any = __any_sync(0xffffffffu, any);
+    nan = __any_sync(0xffffffffu, nan);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if (lane == 0) out[h] = !any ? 0.0f : (nan ? __int_as_float(0x7fc00000) : m);
+}
+
+// axis = 0: out[o] = max over masked h (one thread per column, coalesced across o)
+__global__ void __launch_bounds__(256)
+    masked_colmax_kernel(const float *__restrict__ cmap, int H, int O, const uint8_t *__restrict__ mask, float *__restrict__ out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= O) return;
+    float m = -INFINITY;
+    bool nan = false, any = false;
+    for (int h = 0; h < H; ++h) {
+        if (mask[h]) {
+            const float v = cmap[(size_t)h * O + o];
+            any = true;
+            nan |= (v != v);
+            m = fmaxf(m, v);
+        }
+    }
+    out[o] = !any ? 0.0f : (nan ? __int_as_float(0x7fc00000) : m);
+}
+
+// K5c pass 1: per-vertex sums of the occupancy grid (one CTA per vertex)
+__global__ void __launch_bounds__(256) occupancy_rowsum_kernel(const float *__restrict__ grids, long long V, float *__restrict__ sums) {
+    const float *row = grids + (size_t)blockIdx.x * V;
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < V; i += blockDim.x) s += row[i];
+    s = warp_sum(s);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        sums[blockIdx.x] = t;
+    }
+}
+
+// K5c pass 2: normalise in place and take the NaN-propagating max over the selected vertices
+__global__ void __launch_bounds__(256)
+    occupancy_norm_max_kernel(float *__restrict__ grids, int H, long long V, const float *__restrict__ sums,
+                              const uint8_t *__restrict__ sel, float *__restrict__ field) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float m = -INFINITY;
+    bool nan = false, any = false;
+    for (int h = 0; h < H; ++h) {
+        const size_t i = (size_t)h * V + v;
+        const float x = __fdiv_rn(grids[i], sums[h]);
+        grids[i] = x;
+        if (!sel || sel[h]) {
+            any = true;
+            nan |= (x != x);
+            m = fmaxf(m, x);
+        }
+    }
+    field[v] = !any ? 0.0f : (nan ? __int_as_float(0x7fc00000) : m);
+}
+
+__global__ void mark_selected_kernel(const long long *__restrict__ idx, long long n, int H, uint8_t *__restrict__ sel) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        long long h = idx[i];
+        if (h < 0) h += H;  // python-style negative index
+        if (h >= 0 && h < H) sel[h] = 1;
+    }
+}
+
+}  // namespace coma
+
+extern "C" int coma_normalize_contact_readout_f32(float *P, int64_t HO, int64_t N, float eps, const float *w, const float *nom,
+                                                  const float *denom, float *cmap, coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(P, "null pointer");
+    COMA_REQUIRE(!cmap || (w && nom && denom), "w/nom/denom are required when cmap is requested");
+    COMA_REQUIRE(HO > 0 && N > 0 && N < (int64_t)1 << 30, "bad sizes");
+    const long long blocks = (HO + K5_WARPS - 1) / K5_WARPS;
+    const unsigned grid = (unsigned)(blocks < kNumSM * 8 ? blocks : kNumSM * 8);
+    normalize_contact_kernel<<<grid, K5_WARPS * 32, 0, (cudaStream_t)stream>>>(P, HO, (int)N, eps, w, nom, denom, cmap);
+    return check_launch("normalize_contact_kernel");
+}
+
+extern "C" int coma_entropy_readout_f32(const float *P, int64_t HO, int64_t N, float n_bin, float *out, coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(P && out, "null pointer");
+    COMA_REQUIRE(HO > 0 && N > 0 && N < (int64_t)1 << 30 && n_bin > 1.0f, "bad sizes");
+    const long long blocks = (HO + K5_WARPS - 1) / K5_WARPS;
+    const unsigned grid = (unsigned)(blocks < kNumSM * 8 ? blocks : kNumSM * 8);
+    entropy_kernel<<<grid, K5_WARPS * 32, 0, (cudaStream_t)stream>>>(P, HO, (int)N, n_bin, (float)log((double)n_bin), out);
+    return check_launch("entropy_kernel");
+}
+
+extern "C" int coma_significant_pairs(const float *count, int64_t H, int64_t O, float num, uint8_t *sig, uint8_t *any_o,
+                                      uint8_t *any_h, coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(count, "null pointer");
+    COMA_REQUIRE(H > 0 && O > 0 && H < (int64_t)1 << 31 && O < (int64_t)1 << 31 && H * O < (int64_t)1 << 38, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (any_o) cudaMemsetAsync(any_o, 0, (size_t)H, st);
+    if (any_h) cudaMemsetAsync(any_h, 0, (size_t)O, st);
+    significant_pairs_kernel<<<(unsigned)((H * O + 255) / 256), 256, 0, st>>>(count, (int)H, (int)O, num, sig, any_o, any_h);
+    return check_launch("significant_pairs_kernel");
+}
+
+extern "C" int coma_masked_max_f32(const float *cmap, int64_t H, int64_t O, const uint8_t *mask, int axis, float *out,
+                                   coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(cmap && mask && out, "null pointer");
+    COMA_REQUIRE(H > 0 && O > 0 && H < (int64_t)1 << 31 && O < (int64_t)1 << 31, "bad sizes");
+    COMA_REQUIRE(axis == 0 || axis == 1, "axis must be 0 or 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (axis == 1) {
+        masked_rowmax_kernel<<<(unsigned)((H + 7) / 8), 256, 0, st>>>(cmap, (int)H, (int)O, mask, out);
+        return check_launch("masked_rowmax_kernel");
+    }
+    masked_colmax_kernel<<<(unsigned)((O + 255) / 256), 256, 0, st>>>(cmap, (int)H, (int)O, mask, out);
+    return check_launch("masked_colmax_kernel");
+}
+
+extern "C" int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, const int64_t *sel_idx, int64_t nsel, float *field,
+                                          coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(grids && field, "null pointer");
+    COMA_REQUIRE(H > 0 && V > 0 && H < (int64_t)1 << 24, "bad sizes");
+    COMA_REQUIRE(!sel_idx || nsel >= 0, "bad selection");
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch: H row sums (+ H selection flags) — stream-ordered allocation, freed on the same stream
+    float *sums = nullptr;
+    uint8_t *sel = nullptr;
+    cudaError_t e = cudaMallocAsync(&sums, sizeof(float) * H + (size_t)H, st);
+    if (e != cudaSuccess) {
+        set_error("coma_occupancy_readout_f32: scratch allocation failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    occupancy_rowsum_kernel<<<(unsigned)H, 256, 0, st>>>(grids, V, sums);
+    int rc = check_launch("occupancy_rowsum_kernel");
+    if (!rc && sel_idx) {
+        sel = reinterpret_cast<uint8_t *>(sums + H);
+        cudaMemsetAsync(sel, 0, (size_t)H, st);
+        if (nsel > 0) {
+            mark_selected_kernel<<<(unsigned)((nsel + 255) / 256), 256, 0, st>>>((const long long *)sel_idx, nsel, (int)H, sel);
+            rc = check_launch("mark_selected_kernel");
+        }
+    }
+    if (!rc) {
+        occupancy_norm_max_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
+        rc = check_launch("occupancy_norm_max_kernel");
+    }
+    cudaFreeAsync(sums, st);
+    return rc;
+}

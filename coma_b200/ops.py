@@ -1,0 +1,120 @@
+"""Typed torch-level wrappers over the C ABI (include/coma_b200.h). Tensors must live on a CUDA device;
+torch is only the owner of device memory and streams here."""
+import torch
+
+from . import _lib
+from ._lib import _host3, _ptr, _stream, call
+
+
+def _chk(t, dtype, name):
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def nearest_vertex(pts, verts):
+    """utils/coma.py:88-91. pts [N,3] f64, verts [V,3] f64 (cuda) -> int64 [N]."""
+    pts, verts = _chk(pts, torch.float64, "pts").contiguous(), _chk(verts, torch.float64, "verts").contiguous()
+    out = torch.empty(pts.shape[0], dtype=torch.int64, device=pts.device)
+    with torch.cuda.device(pts.device):
+        call("coma_nearest_vertex_f64", _ptr(pts), pts.shape[0], _ptr(verts), verts.shape[0], _ptr(out), _stream())
+    return out
+
+
+def pair_accumulate(hv, ov, thres, grid_size, count, nom):
+    """utils/coma.py:284-291 over S samples. hv [S,H,3], ov [S,O,3] f32; count, nom [H,O] f32 updated in place."""
+    S, H, _ = hv.shape
+    O = ov.shape[1]
+    assert ov.shape[0] == S and count.shape == (H, O) and nom.shape == (H, O)
+    for t, n in ((hv, "hv"), (ov, "ov"), (count, "count"), (nom, "nom")):
+        _chk(t, torch.float32, n)
+    with torch.cuda.device(hv.device):
+        call("coma_pair_accumulate_f32", _ptr(hv), _ptr(ov), S, H, O, float(thres), float(grid_size), _ptr(count), _ptr(nom),
+             _stream())
+
+
+def orient_accumulate(hn, on, grid, sigma, eps, p, sub_p, PH, PO):
+    """utils/coma.py:295-323 over S samples. hn [S,H,3], on [S,O,3] f32; grid [N,3] f64; PH, PO [H,O,N] f32 in place."""
+    S, H, _ = hn.shape
+    O, N = on.shape[1], grid.shape[0]
+    assert on.shape[0] == S and PH.shape == (H, O, N) and PO.shape == (H, O, N)
+    for t, n in ((hn, "hn"), (on, "on"), (PH, "PH"), (PO, "PO")):
+        _chk(t, torch.float32, n)
+    _chk(grid, torch.float64, "grid")
+    with torch.cuda.device(hn.device):
+        call("coma_orient_accumulate_f32", _ptr(hn), _ptr(on), S, H, O, _ptr(grid), N, float(sigma), float(eps), _host3(p),
+             _host3(sub_p), _ptr(PH), _ptr(PO), _stream())
+
+
+def canonicalize(a, b, p, sub_p, eps):
+    """utils/coma.py:123-172 -> [A,B,3] f32."""
+    a, b = _chk(a, torch.float32, "a").contiguous(), _chk(b, torch.float32, "b").contiguous()
+    out = torch.empty((a.shape[0], b.shape[0], 3), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        call("coma_canonicalize_f32", _ptr(a), a.shape[0], _ptr(b), b.shape[0], _host3(p), _host3(sub_p), float(eps), _ptr(out),
+             _stream())
+    return out
+
+
+def occupancy_accumulate(hvc, centers, thr, grids):
+    """utils/coma_occupancy.py:289-295 over S samples. hvc [S,H,3] f32; centers [3,Sg] f64; grids [H,Sg,Sg,Sg] f32."""
+    S, H, _ = hvc.shape
+    Sg = centers.shape[1]
+    assert grids.shape == (H, Sg, Sg, Sg)
+    _chk(hvc, torch.float32, "hvc"), _chk(centers, torch.float64, "centers"), _chk(grids, torch.float32, "grids")
+    with torch.cuda.device(hvc.device):
+        call("coma_occupancy_accumulate", _ptr(hvc), S, H, _ptr(centers), Sg, float(thr), _ptr(grids), _stream())
+
+
+def normalize_contact_readout(P, eps, w=None, nom=None, denom=None):
+    """utils/coma.py:328-330 (in place) fused with :342-356. P [H,O,N] f32 -> contact map [H,O] (or None if w is None)."""
+    H, O, N = P.shape
+    _chk(P, torch.float32, "P")
+    cmap = torch.empty((H, O), dtype=torch.float32, device=P.device) if w is not None else None
+    with torch.cuda.device(P.device):
+        call("coma_normalize_contact_readout_f32", _ptr(P), H * O, N, float(eps), _ptr(w), _ptr(nom), _ptr(denom), _ptr(cmap),
+             _stream())
+    return cmap
+
+
+def significant_pairs(count, num):
+    """utils/coma.py:376-377,:407,:421 -> (sig [H,O] bool, any_o [H] bool, any_h [O] bool)."""
+    H, O = count.shape
+    _chk(count, torch.float32, "count")
+    sig = torch.empty((H, O), dtype=torch.uint8, device=count.device)
+    any_o = torch.empty(H, dtype=torch.uint8, device=count.device)
+    any_h = torch.empty(O, dtype=torch.uint8, device=count.device)
+    with torch.cuda.device(count.device):
+        call("coma_significant_pairs", _ptr(count), H, O, float(num), _ptr(sig), _ptr(any_o), _ptr(any_h), _stream())
+    return sig.view(torch.bool), any_o.view(torch.bool), any_h.view(torch.bool)
+
+
+def masked_max(cmap, mask, axis):
+    """utils/coma.py:412-413 (axis=1, mask over O) / :426-427 (axis=0, mask over H); zeros if the mask is empty."""
+    H, O = cmap.shape
+    _chk(cmap, torch.float32, "cmap")
+    mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    out = torch.empty(H if axis == 1 else O, dtype=torch.float32, device=cmap.device)
+    with torch.cuda.device(cmap.device):
+        call("coma_masked_max_f32", _ptr(cmap.contiguous()), H, O, _ptr(mask.contiguous()), int(axis), _ptr(out), _stream())
+    return out
+
+
+def entropy_readout(P, n_bin):
+    """utils/coma.py:455-463 on a normalised grid. P [H,O,N] f32 -> [H,O] f32."""
+    H, O, N = P.shape
+    out = torch.empty((H, O), dtype=torch.float32, device=P.device)
+    with torch.cuda.device(P.device):
+        call("coma_entropy_readout_f32", _ptr(P), H * O, N, float(n_bin), _ptr(out), _stream())
+    return out
+
+
+def occupancy_readout(grids, sel_idx=None):
+    """utils/coma_occupancy.py:297-312: normalises `grids` [H,...] in place, returns the max field over `sel_idx`."""
+    H = grids.shape[0]
+    V = grids[0].numel()
+    field = torch.empty(grids.shape[1:], dtype=torch.float32, device=grids.device)
+    nsel = 0 if sel_idx is None else sel_idx.numel()
+    with torch.cuda.device(grids.device):
+        call("coma_occupancy_readout_f32", _ptr(grids), H, V, _ptr(sel_idx), nsel, _ptr(field), _stream())
+    return field

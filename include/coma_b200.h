@@ -1,0 +1,109 @@
+/*
+ * coma_b200.h — C ABI of libcoma_b200.so (hand-written sm_100a CUDA kernels for snuvclab/coma's hot paths).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`; buffers are caller-owned, row-major,
+ *     contiguous; nothing is allocated, retained or freed by the library.
+ *   - `stream` is a cudaStream_t (as void*); every call only enqueues work on it and returns.
+ *   - return value: 0 on success, otherwise a cudaError_t value (launch/config failure) or a negative COMA_E_* code;
+ *     coma_b200_last_error() gives a thread-local human-readable message.
+ *   - accumulating entry points ADD into their output buffers (they mirror the reference's in-place `+=`), so
+ *     repeated calls over successive sample batches are equivalent to one call over the concatenation.
+ *
+ * Each entry point names the reference code (snuvclab/coma @ c89e2d1, paths relative to its root) it replaces.
+ */
+#ifndef COMA_B200_H
+#define COMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COMA_E_BADARG (-1)   /* null pointer / non-positive size / unsupported parameter */
+#define COMA_E_NODEVICE (-2) /* no sm_100 device / driver */
+
+typedef void *coma_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define COMA_API __attribute__((visibility("default")))
+#else
+#define COMA_API
+#endif
+
+COMA_API int coma_b200_version(void);
+COMA_API const char *coma_b200_last_error(void);
+/* Number of kernel launches enqueued by this library in the calling process (bench.py's `gpu_launches`). */
+COMA_API int64_t coma_b200_launch_count(void);
+
+/* ---- K1: nearest mesh vertex of each sampled point --------------------------------------------------------------
+ * Replaces utils/coma.py:88-91 (dup. utils/coma_occupancy.py:70-74): idx[n] = argmin_v ((p0-v0)^2+(p1-v1)^2)+(p2-v2)^2
+ * evaluated in fp64 with separately rounded products/sums; first minimum wins (np.argmin). Bit-exact.
+ * pts [N,3] f64, verts [V,3] f64 -> out_idx [N] i64. */
+COMA_API int coma_nearest_vertex_f64(const double *pts, int64_t N, const double *verts, int64_t V, int64_t *out_idx,
+                            coma_stream_t stream);
+
+/* ---- K2: pair distance -> contact count + proximity expectation -------------------------------------------------
+ * Replaces ComA.aggregate_single_sample_for_contact, utils/coma.py:284-291 (+ negative_exp :116-119), for S samples:
+ *   d = sqrt(((hx-ox)^2+(hy-oy)^2)+(hz-oz)^2) (fp32, separately rounded);  count[h,o] += (d < thres);
+ *   nom[h,o] += exp(-d / grid_size).          (`denom` is the scalar number of samples: the caller keeps it.)
+ * hv [S,H,3] f32, ov [S,O,3] f32; count, nom [H,O] f32 (accumulated in place). count is bit-exact. */
+COMA_API int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_t S, int64_t H, int64_t O, float thres,
+                             float grid_size, float *count, float *nom, coma_stream_t stream);
+
+/* ---- K3: relative-orientation soft histograms --------------------------------------------------------------------
+ * Replaces canonicalize_a_wrt_b_to_p (utils/coma.py:123-172, both calls :295-309) + geodesic_gaussian_scores
+ * (:102-112) + the two in-place adds (:312-323), for S samples:
+ *   PH[h,o,n] += exp(-acos(clip(G[n] . canon(hn[h] | on[o])))^2 / sigma^2), PO likewise with canon(on[o] | hn[h]).
+ * hn [S,H,3], on [S,O,3] f32 (un-normalised is fine); grid [N,3] f64 (ComA.canon_normal_grid);
+ * p_host, sub_p_host: 3 floats each on the HOST (principle / sub-principle vectors); PH, PO [H,O,N] f32. */
+COMA_API int coma_orient_accumulate_f32(const float *hn, const float *on, int64_t S, int64_t H, int64_t O, const double *grid,
+                               int64_t N, double sigma, double eps, const float *p_host, const float *sub_p_host,
+                               float *PH, float *PO, coma_stream_t stream);
+
+/* Canonicalised normals only (utils/coma.py:123-172): out[i,j,:] = canon(a[i] | b[j]); a [A,3], b [B,3] f32. */
+COMA_API int coma_canonicalize_f32(const float *a, int64_t A, const float *b, int64_t B, const float *p_host,
+                          const float *sub_p_host, float eps, float *out, coma_stream_t stream);
+
+/* ---- K4: per-vertex occupancy voxel counts ----------------------------------------------------------------------
+ * Replaces ComA_Occupancy.aggregate_single_sample_for_occupancy, utils/coma_occupancy.py:289-295, for S samples:
+ *   grids[h,i,j,k] += ( sqrt(((cx[i]-v0)^2+(cy[j]-v1)^2)+(cz[k]-v2)^2) < thr )  in fp64, v = (double)hvc[s,h,:].
+ * hvc [S,H,3] f32 = fp32(human_verts - obj_verts[0]) (the host-side subtraction of :287-288);
+ * centers [3,Sg] f64 per-axis voxel centres (load_voxelgrid :160-171); thr = voxel_size*scale_tolerance;
+ * grids [H,Sg,Sg,Sg] f32 accumulated in place. Bit-exact (integer counts). */
+COMA_API int coma_occupancy_accumulate(const float *hvc, int64_t S, int64_t H, const double *centers, int64_t Sg, double thr,
+                              float *grids, coma_stream_t stream);
+
+/* ---- K5: read-outs ---------------------------------------------------------------------------------------------------
+ * K5a  normalize_prob_grid_for_normals (utils/coma.py:328-330) fused with compute_contact_map (:342-356):
+ *      P[q,:] /= (sum_n P[q,:] + eps)  IN PLACE, then cmap[q] = (sum_n P[q,n]*w[n]) * nom[q]/denom[q].
+ *      P [HO,N] f32, w [N] f32 ((1 - p.G[n])/2), nom/denom [HO] f32, cmap [HO] f32 (may be NULL: normalise only). */
+COMA_API int coma_normalize_contact_readout_f32(float *P, int64_t HO, int64_t N, float eps, const float *w, const float *nom,
+                                       const float *denom, float *cmap, coma_stream_t stream);
+
+/* K5a' significant_contact_pairs (:369-382) + the two `any` reductions (:407,:421):
+ *      sig[h,o] = count[h,o] >= num; any_o[h] = OR_o sig[h,o]; any_h[o] = OR_h sig[h,o]. u8 outputs. */
+COMA_API int coma_significant_pairs(const float *count, int64_t H, int64_t O, float num, uint8_t *sig, uint8_t *any_o,
+                           uint8_t *any_h, coma_stream_t stream);
+
+/* K5a'' aggregate_contact_for_significant_pairs (:398-427): masked max of cmap [H,O].
+ *      axis=1: out[h] = max_{o: mask[o]} cmap[h,o] (mask [O]);  axis=0: out[o] = max_{h: mask[h]} cmap[h,o] (mask [H]).
+ *      If no mask bit is set the output is all zeros (the reference's fallback). NaN propagates like torch.max. */
+COMA_API int coma_masked_max_f32(const float *cmap, int64_t H, int64_t O, const uint8_t *mask, int axis, float *out,
+                        coma_stream_t stream);
+
+/* K5b  compute_nonphysical_response_sphere (:455-463) on an already-normalised grid:
+ *      q = rint(P*n_bin)/n_bin; out[q] = 1 + sum_n (q==0 ? 0 : q*log q) / log(n_bin). P [HO,N] f32 -> out [HO] f32. */
+COMA_API int coma_entropy_readout_f32(const float *P, int64_t HO, int64_t N, float n_bin, float *out, coma_stream_t stream);
+
+/* K5c  normalize_prob_grid_for_spatials + max over vertices (utils/coma_occupancy.py:297-312):
+ *      grids[h,:] /= sum(grids[h,:]) IN PLACE (NaN where a vertex never hit, as in the reference), then
+ *      field[v] = max_{h in sel} grids[h,v] (NaN-propagating). sel_idx [nsel] i64 vertex indices, or NULL for all H. */
+COMA_API int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, const int64_t *sel_idx, int64_t nsel, float *field,
+                               coma_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMA_B200_H */

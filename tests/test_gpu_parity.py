@@ -1,0 +1,338 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`). Every call goes through the C ABI (libcoma_b200.so) and is
+checked against (a) the reference-generated golden vectors and (b) the CPU oracle on seeded inputs.
+
+Bars: bit-exact for nearest-vertex indices, contact counts, occupancy hit counts, significant-vertex index lists;
+rtol 1e-4 (the north-star tolerance) for fp32 quantities, with the absolute floors written next to each check.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + ".npz")))
+
+
+def _t(a, dev, dt=torch.float32):
+    return torch.tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+
+
+def _grid_close(mine, ref, rtol=RTOL):
+    """Orientation grids: pure relative tolerance down to 1e-30; below that an absolute floor of 1e-7 x the pair's
+    largest bin (such entries are < 1e-23 of the pair's mass and vanish in every read-out)."""
+    floor = 1e-30 + 1e-7 * 0  # noqa
+    pair_max = ref.max(axis=-1, keepdims=True)
+    err = np.abs(mine.astype(np.float64) - ref.astype(np.float64))
+    tol = rtol * np.abs(ref).astype(np.float64) + 1e-30 + 1e-23 * pair_max
+    bad = err > tol
+    assert not bad.any(), f"{bad.sum()} / {bad.size} entries off; worst rel {np.max(err / (np.abs(ref) + 1e-30)):.3e}"
+
+
+# --------------------------------------------------------------------------------------------- K1
+def test_nearest_vertex_golden(dev, golden_dir):
+    from coma_b200 import ops
+    g = _load(golden_dir, "nearest_small")
+    idx = ops.nearest_vertex(_t(g["pts"], dev, torch.float64), _t(g["verts"], dev, torch.float64)).cpu().numpy()
+    np.testing.assert_array_equal(idx, g["idx"])
+
+
+def test_nearest_vertex_oracle_large(dev):
+    from coma_b200 import ops
+    from oracle import oracle
+    rng = np.random.default_rng(0)
+    verts = rng.standard_normal((10475, 3))
+    verts[5000] = verts[17]
+    pts = np.concatenate([verts[rng.integers(0, 10475, 1500)] + rng.standard_normal((1500, 3)) * 1e-3, verts[[17, 5000]]])
+    idx = ops.nearest_vertex(_t(pts, dev, torch.float64), _t(verts, dev, torch.float64)).cpu().numpy()
+    np.testing.assert_array_equal(idx, oracle.nearest_vertex(pts, verts))
+    assert idx[-1] == 17 and idx[-2] == 17
+
+
+# --------------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("name", ["contact_small", "contact_sigma02"])
+def test_pair_accumulate_golden(dev, golden_dir, name):
+    from coma_b200 import ops
+    g = _load(golden_dir, name)
+    size, thres = g["params"][:2]
+    S, H, _ = g["hv"].shape
+    O = g["ov"].shape[1]
+    count = torch.zeros((H, O), device=dev)
+    nom = torch.zeros((H, O), device=dev)
+    ops.pair_accumulate(_t(g["hv"], dev), _t(g["ov"], dev), thres, size, count, nom)
+    np.testing.assert_array_equal(count.cpu().numpy(), g["count"])
+    np.testing.assert_allclose(nom.cpu().numpy(), g["nom"], rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("H,O,S,thres", [(300, 200, 37, 0.05), (1000, 180, 8, 0.03), (17, 129, 33, 0.24), (5, 3, 1, 0.1)])
+def test_pair_accumulate_oracle(dev, H, O, S, thres):
+    from coma_b200 import ops, synth
+    from oracle import oracle
+    samples = synth.make_samples(S, H, O, seed=H + O) + synth.make_adversarial_samples(H, O, thres, seed=S)
+    hv = np.stack([s["human_verts"] for s in samples])
+    ov = np.stack([s["obj_verts"] for s in samples])
+    rc, rn = oracle.pair_accumulate(hv, ov, thres, 0.07)
+    count = torch.zeros((H, O), device=dev)
+    nom = torch.zeros((H, O), device=dev)
+    # two calls over split batches == one call over the concatenation (accumulating ABI)
+    k = len(samples) // 2
+    ops.pair_accumulate(_t(hv[:k], dev), _t(ov[:k], dev), thres, 0.07, count, nom)
+    ops.pair_accumulate(_t(hv[k:], dev), _t(ov[k:], dev), thres, 0.07, count, nom)
+    np.testing.assert_array_equal(count.cpu().numpy(), rc)
+    np.testing.assert_allclose(nom.cpu().numpy(), rn, rtol=RTOL, atol=0)
+    assert rc.sum() > 0
+
+
+def test_pair_threshold_boundary_ulps(dev):
+    """Distances planted exactly at / one ulp around fp32(thres): the verdict must be torch's `d < fp32(thres)`."""
+    from coma_b200 import ops
+    from oracle import oracle
+    t32 = np.float32(0.03)
+    ds = np.array([np.nextafter(t32, np.float32(0)), t32, np.nextafter(t32, np.float32(1))], dtype=np.float32)
+    hv = np.zeros((1, 3, 3), np.float32)
+    hv[0, :, 0] = ds                                   # |hv - 0| == ds exactly (single non-zero component)
+    ov = np.zeros((1, 1, 3), np.float32)
+    count = torch.zeros((3, 1), device=dev)
+    nom = torch.zeros((3, 1), device=dev)
+    ops.pair_accumulate(_t(hv, dev), _t(ov, dev), 0.03, 0.07, count, nom)
+    np.testing.assert_array_equal(count.cpu().numpy()[:, 0], [1.0, 0.0, 0.0])
+    np.testing.assert_array_equal(count.cpu().numpy(), oracle.pair_accumulate(hv, ov, 0.03, 0.07)[0])
+
+
+# --------------------------------------------------------------------------------------------- K3
+def test_canonicalize_bit_exact(dev):
+    from coma_b200 import ops, synth
+    from oracle import oracle
+    s = synth.make_adversarial_samples(64, 48, 0.03, seed=2)[0]
+    a, b = s["human_normals"].astype(np.float32), s["obj_normals"].astype(np.float32)
+    for eps in (1e-10, 1e-8):
+        mine = ops.canonicalize(_t(a, dev), _t(b, dev), [0, 0, 1], [0, 1, 0], eps).cpu().numpy()
+        np.testing.assert_array_equal(mine, oracle.canonicalize(a, b, eps=eps))
+    mine = ops.canonicalize(_t(b, dev), _t(a, dev), [0.3, -0.2, 0.9], [0.1, 1, 0.2], 1e-8).cpu().numpy()
+    ref = oracle.canonicalize(b, a, p=[0.3, -0.2, 0.9], sub_p=[0.1, 1, 0.2], eps=1e-8)
+    np.testing.assert_allclose(mine, ref, rtol=0, atol=2e-7)  # general p: einsum order is BLAS-defined in the reference
+
+
+@pytest.mark.parametrize("name", ["contact_small", "contact_sigma02"])
+def test_orient_accumulate_golden(dev, golden_dir, name):
+    from coma_b200 import ops
+    from oracle import oracle
+    g = _load(golden_dir, name)
+    sigma, eps = g["params"][2:4]
+    S, H, _ = g["hn"].shape
+    O, N = g["on"].shape[1], int(g["N"])
+    PH = torch.zeros((H, O, N), device=dev)
+    PO = torch.zeros((H, O, N), device=dev)
+    grid = _t(oracle.fibonacci_sphere(N), dev, torch.float64)
+    ops.orient_accumulate(_t(g["hn"], dev), _t(g["on"], dev), grid, sigma, eps, [0, 0, 1], [0, 1, 0], PH, PO)
+    _grid_close(PH.cpu().numpy(), g["PH"])
+    _grid_close(PO.cpu().numpy(), g["PO"])
+
+
+@pytest.mark.parametrize("H,O,N,S,sigma", [(40, 33, 250, 70, 0.25), (24, 20, 250, 33, 0.2), (16, 9, 64, 5, 0.1),
+                                           (9, 7, 300, 3, 1.0), (3, 2, 31, 1, 0.25)])
+def test_orient_accumulate_oracle(dev, H, O, N, S, sigma):
+    from coma_b200 import ops, synth
+    from oracle import oracle
+    samples = synth.make_samples(S, H, O, seed=N + S) + synth.make_adversarial_samples(H, O, 0.03, seed=S)
+    hn = np.stack([s["human_normals"] for s in samples])
+    on = np.stack([s["obj_normals"] for s in samples])
+    grid = oracle.fibonacci_sphere(N)
+    rPH, rPO = oracle.orient_accumulate(hn, on, grid, sigma, 1e-10)
+    PH = torch.zeros((H, O, N), device=dev)
+    PO = torch.zeros((H, O, N), device=dev)
+    k = len(samples) // 2
+    gt = _t(grid, dev, torch.float64)
+    ops.orient_accumulate(_t(hn[:k], dev), _t(on[:k], dev), gt, sigma, 1e-10, [0, 0, 1], [0, 1, 0], PH, PO)
+    ops.orient_accumulate(_t(hn[k:], dev), _t(on[k:], dev), gt, sigma, 1e-10, [0, 0, 1], [0, 1, 0], PH, PO)
+    _grid_close(PH.cpu().numpy(), rPH)
+    _grid_close(PO.cpu().numpy(), rPO)
+
+
+# --------------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("name", ["occupancy_small", "occupancy_s30"])
+def test_occupancy_golden(dev, golden_dir, name):
+    from coma_b200 import ops
+    from oracle import oracle
+    g = _load(golden_dir, name)
+    Sg = int(g["Sg"])
+    centers, voxel = oracle.voxel_centers(Sg)
+    hvc = (g["hv"] - g["ov"][:, 0:1, :]).astype(np.float32)
+    H = hvc.shape[1]
+    grids = torch.zeros((H, Sg, Sg, Sg), device=dev)
+    ops.occupancy_accumulate(_t(hvc, dev), _t(centers, dev, torch.float64), voxel * float(g["tol"]), grids)
+    np.testing.assert_array_equal(grids.cpu().numpy(), g["grids"])
+    field = ops.occupancy_readout(grids, None).cpu().numpy()
+    np.testing.assert_allclose(field, g["field"], rtol=1e-6, equal_nan=True)
+
+
+@pytest.mark.parametrize("H,Sg,S,tol", [(64, 30, 24, 3.0), (33, 40, 9, 3.0), (20, 64, 5, 2.5), (8, 7, 3, 1.2)])
+def test_occupancy_oracle(dev, H, Sg, S, tol):
+    """Sg <= 36 exercises the shared-memory path, larger grids the global-atomic path."""
+    from coma_b200 import ops, synth
+    from oracle import oracle
+    samples = synth.make_samples(S, H, 5, seed=Sg)
+    hv = np.stack([s["human_verts"] for s in samples])
+    ov = np.stack([s["obj_verts"] for s in samples])
+    hv[0, 0] = [5.0, 0.0, 0.0]        # far outside the 2.4 m cube: no hits, no out-of-bounds
+    hv[0, 1] = ov[0, 0] + [1.19, -1.19, 1.19]   # at the cube corner: clipped boxes
+    ref = oracle.occupancy_accumulate(hv, ov, Sg, tol)
+    centers, voxel = oracle.voxel_centers(Sg)
+    hvc = (hv - ov[:, 0:1, :]).astype(np.float32)
+    grids = torch.zeros((H, Sg, Sg, Sg), device=dev)
+    k = S // 2
+    ct = _t(centers, dev, torch.float64)
+    ops.occupancy_accumulate(_t(hvc[:k], dev), ct, voxel * tol, grids) if k else None
+    ops.occupancy_accumulate(_t(hvc[k:], dev), ct, voxel * tol, grids)
+    np.testing.assert_array_equal(grids.cpu().numpy(), ref)
+    assert ref.sum() > 0
+    ref_field, ref_norm = oracle.occupancy_field(ref)
+    sel = torch.tensor([1, 3, 5], device=dev)
+    f_sel = ops.occupancy_readout(grids.clone(), sel).cpu().numpy()
+    np.testing.assert_allclose(f_sel, np.where(np.isnan(ref_norm[[1, 3, 5]]).any(0), np.nan, ref_norm[[1, 3, 5]].max(0)),
+                               rtol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(ops.occupancy_readout(grids, None).cpu().numpy(), ref_field, rtol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(grids.cpu().numpy(), ref_norm, rtol=1e-6, equal_nan=True)   # normalised in place
+
+
+# --------------------------------------------------------------------------------------------- classes / read-outs
+@pytest.mark.parametrize("name", ["contact_small", "contact_sigma02"])
+def test_coma_class_matches_reference_golden(dev, golden_dir, name, tmp_path):
+    """The reference's call sequence of tests/golden/make_golden.py replayed through the drop-in class."""
+    from utils.coma import ComA, get_aggregated_contact
+    g = _load(golden_dir, name)
+    size, thres, sigma, eps, ratio = (float(v) for v in g["params"])
+    S, H, _ = g["hv"].shape
+    O, N = g["ov"].shape[1], int(g["N"])
+    coma = ComA(human_res=H, obj_res=O, normal_res=N, spatial_res=0,
+                proximity_settings=dict(spatial_grid_size=size, spatial_grid_thres=thres),
+                normal_gaussian_sigma=sigma, eps=eps, device="cuda")
+    for s in range(S):
+        coma.register_sample_to_cache(human_verts=g["hv"][s], human_normals=g["hn"][s], obj_verts=g["ov"][s], obj_normals=g["on"][s])
+    assert coma.cache_count == S
+    coma.aggregate_all_samples()
+    assert coma.used_count == int(g["used_count"]) and coma.cache_count == 0
+    pth = str(tmp_path / "coma.pickle")
+    coma.export(save_pth=pth)
+    exp = coma.export()
+    np.testing.assert_array_equal(exp["significant_contact_count"], g["count"])
+    np.testing.assert_array_equal(exp["contact_dist_expectation_grid_denom"], g["denom"])
+    np.testing.assert_array_equal(exp["canon_normal_grid"], g["canon_normal_grid"])
+    np.testing.assert_allclose(exp["contact_dist_expectation_grid_nom"], g["nom"], rtol=RTOL)
+    _grid_close(exp["prob_grid_canon_human_wrt_obj"], g["PH"])
+    _grid_close(exp["prob_grid_canon_obj_wrt_human"], g["PO"])
+
+    agg_h, idx_o = get_aggregated_contact(coma, "human", ratio)
+    agg_o, idx_h = get_aggregated_contact(coma, "obj", ratio)
+    cm = coma.compute_contact_map("both", as_numpy=True)
+    ent = coma.compute_nonphysical_response_sphere(n_bin=1e6, nonphysical_type="both", as_numpy=True)
+    np.testing.assert_array_equal(idx_o, g["sig_obj_idx"])
+    np.testing.assert_array_equal(idx_h, g["sig_human_idx"])
+    np.testing.assert_array_equal(coma.significant_contact_pairs(ratio), g["sig_pairs"])
+    assert agg_h.dtype == np.float32 and idx_o.dtype == np.int64
+    np.testing.assert_allclose(agg_h, g["agg_human"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(agg_o, g["agg_obj"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(cm["human"], g["contact_map_human"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(cm["obj"], g["contact_map_obj"], rtol=RTOL, atol=1e-12)
+    # entropy: round(P*1e6) may flip for a P one ulp away from a half-integer; each flip moves the score by ~1e-6
+    np.testing.assert_allclose(ent["human"], g["entropy_human"], rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(ent["obj"], g["entropy_obj"], rtol=RTOL, atol=2e-5)
+
+    # checkpoint round trip (the ComA pickle IS the checkpoint, `--skip_done`)
+    again = ComA(human_res=H, obj_res=O, normal_res=N, spatial_res=0,
+                 proximity_settings=dict(spatial_grid_size=size, spatial_grid_thres=thres),
+                 normal_gaussian_sigma=sigma, eps=eps, device="cuda")
+    again.load(pth)
+    assert again.used_count == S and again.canon_normal_grid.dtype == torch.float32
+    np.testing.assert_array_equal(again.significant_contact_count.cpu().numpy(), g["count"])
+    agg_h2, _ = get_aggregated_contact(again, "human", ratio)
+    np.testing.assert_allclose(agg_h2, g["agg_human"], rtol=RTOL, atol=1e-12)
+
+
+def test_occupancy_class_matches_reference_golden(dev, golden_dir, tmp_path):
+    from utils.coma_occupancy import ComA_Occupancy
+    g = _load(golden_dir, "occupancy_small")
+    S, H, _ = g["hv"].shape
+    Sg = int(g["Sg"])
+    occ = ComA_Occupancy(scale_tolerance=float(g["tol"]), human_res=H, obj_res=g["ov"].shape[1], normal_res=0, spatial_res=Sg, device="cuda")
+    for s in range(S):
+        occ.register_sample_to_cache(human_verts=g["hv"][s], human_normals=g["hn"][s], obj_verts=g["ov"][s], obj_normals=g["on"][s])
+    occ.aggregate_all_samples()
+    exp = occ.export()
+    np.testing.assert_array_equal(exp["spatial_occupancy_grids"], g["grids"])
+    np.testing.assert_array_equal(exp["spatial_grid"], g["spatial_grid"])
+    assert exp["rel_dist_thres"] == float(g["rel_dist_thres"]) and exp["used_count"] == S
+    field = occ.return_aggregated_spatial_grids(human_indices=None).cpu().numpy()
+    np.testing.assert_allclose(field, g["field"], rtol=1e-6, equal_nan=True)
+    # the object must not move between samples (reference asserts, utils/coma_occupancy.py:277-284)
+    occ.register_sample_to_cache(human_verts=g["hv"][0], human_normals=g["hn"][0], obj_verts=g["ov"][0] + 1.0, obj_normals=g["on"][0])
+    with pytest.raises(AssertionError):
+        occ.aggregate_all_samples()
+
+
+def test_error_behaviour(dev):
+    from utils.coma import ComA
+    with pytest.raises(NotImplementedError):
+        ComA(4, 4, 8, spatial_res=3, device="cuda")
+    c = ComA(4, 3, 8, 0, proximity_settings=dict(spatial_grid_size=.07, spatial_grid_thres=.03), device="cuda")
+    with pytest.raises(AssertionError):
+        c.aggregate_single_sample(human_verts=np.zeros((5, 3)), human_normals=np.zeros((4, 3)), obj_verts=np.zeros((3, 3)), obj_normals=np.zeros((3, 3)))
+    with pytest.raises(AssertionError):
+        c.compute_contact_map("nope")
+    # no significant vertex at all -> zero maps (reference fallback, utils/coma.py:408-409)
+    c.aggregate_single_sample(human_verts=np.ones((4, 3)) * 9, human_normals=np.ones((4, 3)), obj_verts=np.zeros((3, 3)), obj_normals=np.ones((3, 3)))
+    c.used_count = 1
+    from utils.coma import get_aggregated_contact
+    agg, idx = get_aggregated_contact(c, "human", 0.5)
+    assert agg.shape == (4,) and not agg.any() and idx.size == 0
+
+
+# --------------------------------------------------------------------------------------------- size-independent properties
+def test_full_size_properties(dev):
+    """BASELINE cfg-4 vertex counts (H=10475, O=1500): properties that need no oracle run."""
+    from coma_b200 import ops, synth
+    H, O, S = 10475, 1500, 8
+    hv, hn, ov, on = (torch.from_numpy(a).to(dev) for a in synth.make_sample_arrays(S, H, O, seed=1))
+    c1, n1 = torch.zeros((H, O), device=dev), torch.zeros((H, O), device=dev)
+    ops.pair_accumulate(hv, ov, 0.05, 0.15, c1, n1)
+    # (1) integer histogram is invariant to the sample order; (2) additive over batches
+    perm = torch.randperm(S, device=dev)
+    c2, n2 = torch.zeros_like(c1), torch.zeros_like(n1)
+    ops.pair_accumulate(hv[perm].contiguous(), ov[perm].contiguous(), 0.05, 0.15, c2, n2)
+    assert torch.equal(c1, c2)
+    torch.testing.assert_close(n1, n2, rtol=1e-5, atol=0)
+    # (3) against a direct torch evaluation of the same formula on a slice of rows (fp32 eager, same op order)
+    rows = slice(5000, 5064)
+    d = torch.sqrt(torch.sum(torch.square(hv[:, rows, None, :] - ov[:, None, :, :]), dim=-1))
+    assert torch.equal(c1[rows], (d < 0.05).sum(0).float())
+    torch.testing.assert_close(n1[rows], torch.exp(-d / 0.15).sum(0), rtol=1e-4, atol=0)
+    assert 0 < c1.sum().item() < 0.05 * H * O * S
+
+
+def test_orient_property_mass_and_symmetry(dev):
+    """Each sample adds a fixed, pair-independent amount of mass up to the bin-grid's quadrature error, and swapping the
+    roles of human and object swaps the two grids."""
+    from coma_b200 import ops, synth
+    from oracle import oracle
+    H, O, N, S = 96, 80, 250, 16
+    hv, hn, ov, on = (torch.from_numpy(a).to(dev) for a in synth.make_sample_arrays(S, H, O, seed=9))
+    grid = _t(oracle.fibonacci_sphere(N), dev, torch.float64)
+    PH, PO = torch.zeros((H, O, N), device=dev), torch.zeros((H, O, N), device=dev)
+    ops.orient_accumulate(hn, on, grid, 0.25, 1e-10, [0, 0, 1], [0, 1, 0], PH, PO)
+    QH, QO = torch.zeros((O, H, N), device=dev), torch.zeros((O, H, N), device=dev)
+    ops.orient_accumulate(on, hn, grid, 0.25, 1e-10, [0, 0, 1], [0, 1, 0], QH, QO)
+    assert torch.equal(PH, QO.permute(1, 0, 2)) and torch.equal(PO, QH.permute(1, 0, 2))
+    mass = PH.sum(-1) / S
+    assert (mass.max() - mass.min()) / mass.mean() < 0.05
