@@ -12,6 +12,7 @@
 // {x : sqrt_rn(x) < thr} == {x : x < T}, so the verdict equals the reference's sqrt-then-compare exactly, without
 // paying for an fp64 square root per candidate.  Counts are integers in fp32 (exact below 2^24 samples).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -117,7 +118,9 @@ extern "C" int coma_occupancy_accumulate(const float *hvc, int64_t S, int64_t H,
     const size_t V = (size_t)Sg * Sg * Sg;
     const size_t smem_small = 3 * sizeof(double) * Sg + sizeof(float) * V;
     cudaStream_t st = (cudaStream_t)stream;
-    if (smem_small <= 200 * 1024) {
+    const char *force = getenv("COMA_B200_OCC_PATH");  // experiments only: "smem" | "global"
+    const bool use_smem = smem_small <= 200 * 1024 && !(force && force[0] == 'g');
+    if (use_smem) {
         static bool attr_set[16] = {false};
         int dev = 0;
         cudaGetDevice(&dev);

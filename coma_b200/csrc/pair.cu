@@ -3,7 +3,7 @@
 // Layout: one CTA owns a 16(h) x 128(o) tile of the [H,O] accumulators, each thread 8 pairs (8 h-rows x 1 o-column)
 // held in registers across ALL samples of the call; vertices of the current sample chunk are staged in shared memory
 // (object vertices as SoA so the per-lane reads are conflict-free, human vertices as float4 so one broadcast LDS.128
-// serves the warp).  The accumulators are read-modify-written once per launch, coalesced along o.
+// serves the warp).  The accumulators are read once at kernel start and written once at the end, coalesced along o.
 //   bytes per launch  = 12*S*(H+O) (vertices) + 2 accumulators * (4 R + 4 W) * H*O  = 16 B / vertex-pair at S = 1
 //   => HBM-bound at S = 1 (the reference's per-sample streaming form), ALU/SFU-bound once S >~ 8.
 // Bit-exactness of `count`: every product/sum is an explicitly rounded __fmul_rn/__fadd_rn in the reference's order
@@ -18,7 +18,7 @@ constexpr int K2_RH = 8;    // human rows per thread
 constexpr int K2_TH = K2_TY * K2_RH;
 constexpr int K2_CS = 16;   // samples staged per chunk
 
-__global__ void __launch_bounds__(K2_TO *K2_TY)
+__global__ void __launch_bounds__(K2_TO *K2_TY, 4)
     pair_accumulate_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float thres,
                            float grid_size, float *__restrict__ count, float *__restrict__ nom) {
     __shared__ float4 sh[K2_CS][K2_TH];
@@ -28,9 +28,17 @@ __global__ void __launch_bounds__(K2_TO *K2_TY)
     const int o0 = blockIdx.x * K2_TO, h0 = blockIdx.y * K2_TH;
     const int o = o0 + tx;
 
+    // The running accumulators are fetched FIRST (their HBM latency hides behind the vertex staging and the first
+    // distances) and every sample is then added on top in sample order, exactly like the reference's in-place `+=`.
     float cnt[K2_RH], acc[K2_RH];
 #pragma unroll
-    for (int r = 0; r < K2_RH; ++r) cnt[r] = acc[r] = 0.0f;
+    for (int r = 0; r < K2_RH; ++r) {
+        const int h = h0 + ty * K2_RH + r;
+        const bool ok = (h < H) && (o < O);
+        const size_t q = (size_t)h * O + o;
+        cnt[r] = ok ? __ldcs(count + q) : 0.0f;
+        acc[r] = ok ? __ldcs(nom + q) : 0.0f;
+    }
 
     for (int s0 = 0; s0 < S; s0 += K2_CS) {
         const int ns = min(K2_CS, S - s0);
@@ -73,8 +81,8 @@ __global__ void __launch_bounds__(K2_TO *K2_TY)
             const int h = h0 + ty * K2_RH + r;
             if (h < H) {
                 const size_t q = (size_t)h * O + o;
-                count[q] += cnt[r];
-                nom[q] += acc[r];
+                __stcs(count + q, cnt[r]);
+                __stcs(nom + q, acc[r]);
             }
         }
     }

@@ -120,25 +120,26 @@ __global__ void __launch_bounds__(256) occupancy_rowsum_kernel(const float *__re
     }
 }
 
-// K5c pass 2: normalise in place and take the NaN-propagating max over the selected vertices
+// K5c pass 2: normalise in place and take the NaN-propagating max over the selected vertices.
+// grid = (ceil(V/256), HSPLIT): each CTA covers a slab of vertices so that small grids (Sg = 30 -> 27 000 voxels) still
+// fill the machine; slabs are merged with an integer atomicMax on the float bits — the normalised values are >= 0, for
+// which the int order equals the float order and the canonical NaN (0/0 of a vertex that never hit) compares highest,
+// i.e. exactly torch.max's NaN propagation. `field` must be zero-filled before the launch.
 __global__ void __launch_bounds__(256)
     occupancy_norm_max_kernel(float *__restrict__ grids, int H, long long V, const float *__restrict__ sums,
                               const uint8_t *__restrict__ sel, float *__restrict__ field) {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
-    float m = -INFINITY;
-    bool nan = false, any = false;
-    for (int h = 0; h < H; ++h) {
+    const int per = (H + gridDim.y - 1) / gridDim.y;
+    const int h_lo = blockIdx.y * per, h_hi = min(H, h_lo + per);
+    int m = 0;
+    for (int h = h_lo; h < h_hi; ++h) {
         const size_t i = (size_t)h * V + v;
         const float x = __fdiv_rn(grids[i], sums[h]);
         grids[i] = x;
-        if (!sel || sel[h]) {
-            any = true;
-            nan |= (x != x);
-            m = fmaxf(m, x);
-        }
+        if (!sel || sel[h]) m = max(m, __float_as_int(x) & 0x7fffffff);
     }
-    field[v] = !any ? 0.0f : (nan ? __int_as_float(0x7fc00000) : m);
+    if (m != 0) atomicMax(reinterpret_cast<int *>(field) + v, m);
 }
 
 __global__ void mark_selected_kernel(const long long *__restrict__ idx, long long n, int H, uint8_t *__restrict__ sel) {
@@ -227,7 +228,11 @@ extern "C" int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, co
         }
     }
     if (!rc) {
-        occupancy_norm_max_kernel<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
+        const long long vb = (V + 255) / 256;
+        long long hsplit = (4LL * kNumSM + vb - 1) / vb;
+        hsplit = hsplit < 1 ? 1 : (hsplit > H ? H : (hsplit > 65535 ? 65535 : hsplit));
+        cudaMemsetAsync(field, 0, sizeof(float) * (size_t)V, st);
+        occupancy_norm_max_kernel<<<dim3((unsigned)vb, (unsigned)hsplit), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
         rc = check_launch("occupancy_norm_max_kernel");
     }
     cudaFreeAsync(sums, st);

@@ -1,0 +1,152 @@
+"""Host-side logic that needs no GPU: drop-in import paths, pickle layout, cache bookkeeping, voxel-grid tables,
+fp32 boundary semantics, sharding rules, and the loud failure when the CUDA path is unavailable."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+
+def _coma(H=6, O=4, N=16):
+    from utils.coma import ComA
+    return ComA(human_res=H, obj_res=O, normal_res=N, spatial_res=0,
+                proximity_settings=dict(spatial_grid_size=0.07, spatial_grid_thres=0.03),
+                normal_gaussian_sigma=0.25, eps=1e-10, device="cpu")
+
+
+def test_dropin_import_paths():
+    import utils.coma as uc
+    import utils.coma_occupancy as uo
+    import utils.misc as um
+    for name in ("ComA", "get_aggregated_contact", "negative_exp", "get_uniform_points_on_sphere"):
+        assert hasattr(uc, name)
+    assert hasattr(uo, "ComA_Occupancy") and hasattr(uo, "load_voxelgrid")
+    assert hasattr(um, "to_np_torch_recursive") and hasattr(um, "get_3d_indexgrid_ijk")
+
+
+def test_export_layout_matches_reference(golden_dir):
+    """Key list, dtypes and shapes of ComA.export (measured on the reference)."""
+    c = _coma()
+    e = c.export()
+    assert list(e.keys()) == [
+        "device", "human_res", "obj_res", "normal_res", "spatial_res", "canon_normal_grid",
+        "prob_grid_canon_human_wrt_obj", "prob_grid_canon_obj_wrt_human", "contact_dist_expectation_grid_nom",
+        "contact_dist_expectation_grid_denom", "significant_contact_count", "proximity_settings", "contact_dist_func",
+        "cross_contact_scores_nom", "cross_contact_scores_denom", "cache_count", "used_count", "principle_vec",
+        "sub_principle_vec", "rel_dist_method", "normal_gaussian_sigma", "eps"]
+    assert e["canon_normal_grid"].dtype == np.float32 and e["canon_normal_grid"].shape == (16, 3)
+    assert e["prob_grid_canon_human_wrt_obj"].shape == (6, 4, 16)
+    for k in ("contact_dist_expectation_grid_nom", "contact_dist_expectation_grid_denom", "significant_contact_count",
+              "cross_contact_scores_nom", "cross_contact_scores_denom"):
+        assert e[k].dtype == np.float32 and e[k].shape == (6, 4)
+    assert e["principle_vec"].tolist() == [0, 0, 1] and e["sub_principle_vec"].tolist() == [0, 1, 0]
+    # the reference's grid, bit for bit
+    g = np.load(f"{golden_dir}/contact_small.npz")
+    from utils.coma import ComA
+    big = ComA(2, 2, int(g["N"]), 0, proximity_settings=dict(spatial_grid_size=1, spatial_grid_thres=1), device="cpu")
+    assert big.canon_normal_grid.dtype == torch.float64
+    np.testing.assert_array_equal(big.export()["canon_normal_grid"], g["canon_normal_grid"])
+
+
+def test_pickle_roundtrip_and_negative_exp_path(tmp_path):
+    c = _coma()
+    c.used_count = 7
+    c.significant_contact_count += 3
+    p = tmp_path / "c.pickle"
+    c.export(save_pth=str(p))
+    raw = pickle.load(open(p, "rb"))
+    fn = raw["contact_dist_func"]
+    assert fn.func.__module__ == "utils.coma" and fn.func.__name__ == "negative_exp"   # reference pickles load here and vice versa
+    assert fn.keywords == dict(spatial_grid_size=0.07, spatial_grid_thres=0.03)
+    x = torch.tensor([0.0, 0.07])
+    torch.testing.assert_close(fn(x), torch.exp(-x / 0.07))
+    d = _coma()
+    d.load(str(p))
+    assert d.used_count == 7 and d.significant_contact_count.dtype == torch.float32
+    assert d.canon_normal_grid.dtype == torch.float32          # reference behaviour after a load() round trip
+    assert torch.equal(d.significant_contact_count, torch.full((6, 4), 3.0))
+
+
+def test_cache_bookkeeping_and_borrowed_arrays():
+    c = _coma()
+    arrs = dict(human_verts=np.zeros((6, 3)), human_normals=np.ones((6, 3)), obj_verts=np.zeros((4, 3)), obj_normals=np.ones((4, 3)))
+    c.register_sample_to_cache(**arrs)
+    c.register_sample_to_cache(**arrs)
+    assert c.cache_count == 2 and list(c.cache) == ["00000", "00001"]
+    assert c.cache["00000"]["human_verts"] is arrs["human_verts"]     # borrowed, not copied
+
+
+def test_no_cpu_fallback():
+    c = _coma()
+    c.register_sample_to_cache(human_verts=np.zeros((6, 3)), human_normals=np.ones((6, 3)), obj_verts=np.zeros((4, 3)), obj_normals=np.ones((4, 3)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.aggregate_all_samples()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.compute_contact_map("human")
+    from utils.coma_occupancy import ComA_Occupancy
+    o = ComA_Occupancy(3.0, 6, 4, 0, 5, device="cpu")
+    o.register_sample_to_cache(human_verts=np.zeros((6, 3)), human_normals=np.ones((6, 3)), obj_verts=np.zeros((4, 3)), obj_normals=np.ones((4, 3)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        o.aggregate_all_samples()
+
+
+def test_input_asserts_and_not_implemented():
+    from utils.coma import ComA
+    from utils.coma_occupancy import ComA_Occupancy
+    c = _coma()
+    with pytest.raises(AssertionError):
+        c.assert_inputs(human_verts=np.zeros((5, 3)))
+    with pytest.raises(AssertionError):
+        c.assert_inputs(obj_normals=np.zeros((4, 2)))
+    with pytest.raises(AssertionError):
+        c.assert_inputs(contact_map_type="x")
+    with pytest.raises(NotImplementedError):
+        ComA(2, 2, 4, spatial_res=2, device="cpu")
+    with pytest.raises(AssertionError):
+        ComA(2, 2, 4, 0, rel_dist_method="nope", device="cpu")
+    with pytest.raises(AssertionError):
+        ComA_Occupancy(3.0, 2, 2, normal_res=4, spatial_res=4, device="cpu")
+
+
+def test_occupancy_grid_tables_and_export(golden_dir):
+    from utils.coma_occupancy import ComA_Occupancy, load_voxelgrid
+    g = np.load(f"{golden_dir}/occupancy_small.npz")
+    Sg = int(g["Sg"])
+    o = ComA_Occupancy(float(g["tol"]), 5, 3, 0, Sg, device="cpu")
+    e = o.export()
+    np.testing.assert_array_equal(e["spatial_grid"], g["spatial_grid"])
+    assert e["spatial_grid"].dtype == np.float32 and e["spatial_indexgrid"].dtype == np.int64
+    assert e["spatial_indexgrid"].shape == (3, Sg, Sg, Sg) and e["spatial_indexgrid"][:, 1, 2, 3].tolist() == [1, 2, 3]
+    assert e["rel_dist_thres"] == float(g["rel_dist_thres"])
+    md = e["spatial_grid_metadata"]
+    assert md["start_point"].dtype == np.float32 and md["voxel_size"] == float(g["voxel_size"]) and md["N_x"] == Sg
+    assert o._centers.dtype == torch.float64
+    grid, idx, meta = load_voxelgrid(2.4, 30)
+    # the fp32-rounded middle term of the reference's expression (utils/coma_occupancy.py:171)
+    exact = -1.2 + (2.4 / 30) * np.arange(30) + (2.4 / 30) / 2
+    assert np.abs(grid[0, :, 0, 0] - exact).max() > 0 and np.abs(grid[0, :, 0, 0] - exact).max() < 1e-6
+
+
+def test_to_np_torch_recursive_forces_fp32_int64():
+    from utils.misc import to_np_torch_recursive
+    d = dict(a=np.array([0.1], dtype=np.float64), b=[np.array([1], dtype=np.int32)], c=dict(t=torch.tensor([0.1], dtype=torch.float64)))
+    t = to_np_torch_recursive(d, use_torch=True, device="cpu")
+    assert t["a"].dtype == torch.float32 and t["b"][0].dtype == torch.int64 and t["c"]["t"].dtype == torch.float32
+    assert t["a"].item() == float(np.float32(0.1))
+    n = to_np_torch_recursive(t, use_torch=False, device="cpu")
+    assert n["a"].dtype == np.float32 and n["b"][0].dtype == np.int64
+
+
+def test_sharding_rules():
+    from coma_b200 import dist
+    assert sorted(sum((dist.sample_shard(37, r, 8) for r in range(8)), [])) == list(range(37))
+    sl = [dist.human_slice(10475, r, 8) for r in range(8)]
+    assert sl[0][0] == 0 and sl[-1][1] == 10475 and all(sl[i][1] == sl[i + 1][0] for i in range(7))
+    assert max(b - a for a, b in sl) - min(b - a for a, b in sl) <= 1
+    # the reference's rule: sub = n//N + 1 (src/generation/inpaint.py:272-278)
+    n, N = 100, 8
+    got = [dist.work_item_slice(n, i, N) for i in range(N)]
+    items = list(range(n))
+    sub = n // N + 1
+    assert [items[a:b] for a, b in got] == [items[i * sub:(i + 1) * sub] for i in range(N)]
+    assert sum(b - a for a, b in got) == n
