@@ -8,8 +8,11 @@
 // samples reading them back as warp-broadcast LDS.128/LDS.64 and evaluates its 2 x NB bins.
 //
 // Per bin evaluation:  c = G[n] . cn   (3 FP32 ops)  ->  score = 2^(-(acos(c) * sqrt(log2 e)/sigma)^2)
-// with a branch-free acos (one MUFU.SQRT, degree-4 minimax asin core, |err| <= 3e-7 rad) and one MUFU.EX2.
-// The kernel is instruction-issue / SFU bound (2 x N = 500 evaluations per pair-sample at N = 250), not HBM bound:
+// with a branch-free acos(|c|) = sqrt(1-|c|) * P6(|c|) (Abramowitz-Stegun 4.4.45 form, one MUFU.SQRT, |err| <= 4.3e-7
+// rad; fit: tools/fit_acos.py) and one MUFU.EX2.  Two bins are evaluated per instruction with Blackwell's packed
+// FP32x2 pipe (FFMA2 / FMUL2 / FADD2, sm_100+): the FMA-type work costs half the issue slots, which moves the kernel
+// from issue-bound to the SFU/FMA-pipe balance point (2 MUFU and ~15 FMA-pipe cycles per bin evaluation).
+// The kernel is SFU / FP32-pipe bound (2 x N = 500 evaluations per pair-sample at N = 250), not HBM bound:
 //   bytes per launch = 24*S*(H+O) (normals, L2-resident) + 2 grids * (4 R + 4 W) * H*O*N.
 //
 // Numerics.  The canonicalisation prologue uses explicitly rounded __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn in the
@@ -17,6 +20,8 @@
 // branch), so the canonical normals are bit-identical to torch's fp32 result.  The reference then promotes to fp64 for
 // dot/acos/exp and rounds each per-sample sum to fp32; here those run in fp32, which keeps every grid entry within
 // ~4e-5 relative of the reference for any sigma (tolerance 1e-4).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace coma {
@@ -156,6 +161,101 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
     }
 }
 
+
+// ---- packed FP32x2 variant (default) -----------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+
+// Two scores at once. sk2 = (sk, sk), hp2 = (hp_sk, hp_sk), nsk2 = (-sk, -sk).
+__device__ __forceinline__ float2 orient_score2(float2 c, float2 nsk2, float2 hp2) {
+    const float2 a = make_float2(fminf(fabsf(c.x), 1.0f), fminf(fabsf(c.y), 1.0f));
+    const float2 w = __ffma2_rn(a, f2(-1.0f), f2(1.0f));
+    const float2 s = make_float2(mufu_sqrt(w.x), mufu_sqrt(w.y));
+    float2 r = f2(2.251368249e-03f);
+    r = __ffma2_rn(r, a, f2(-1.101238653e-02f));
+    r = __ffma2_rn(r, a, f2(2.674933150e-02f));
+    r = __ffma2_rn(r, a, f2(-4.872440174e-02f));
+    r = __ffma2_rn(r, a, f2(8.873733133e-02f));
+    r = __ffma2_rn(r, a, f2(-2.145836949e-01f));
+    r = __ffma2_rn(r, a, f2(1.570796132e+00f));
+    const float2 ga = __fmul2_rn(s, r);                 // acos(|c|)
+    const float2 u = __ffma2_rn(ga, nsk2, hp2);         // sk*(pi/2 - acos|c|) >= 0
+    const float2 us = make_float2(copysignf(u.x, c.x), copysignf(u.y, c.y));
+    const float2 gs = __ffma2_rn(us, f2(-1.0f), hp2);   // sk*acos(c)
+    const float2 q = __fmul2_rn(gs, gs);
+    return make_float2(mufu_ex2(-q.x), mufu_ex2(-q.y));
+}
+
+constexpr int K3_NP = 4;  // bin PAIRS per lane -> 8 bins per lane, 256 bins per launch
+
+__global__ void __launch_bounds__(K3_WARPS * 32, 2)
+    orient_accumulate_kernel_x2(const float *__restrict__ hn, const float *__restrict__ on, int S, int H, int O,
+                                const double *__restrict__ grid, int N, int n_base, float sk, float hp_sk, float eps, Vec3 p,
+                                Vec3 sp, float *__restrict__ PH, float *__restrict__ PO) {
+    // per warp: 32 samples x {chx,chx,chy,chy | chz,chz,cox,cox | coy,coy,coz,coz}: broadcast LDS.128 yields (v,v) pairs
+    __shared__ __align__(16) float4 cnbuf[K3_WARPS][32][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long pair = (long long)blockIdx.x * K3_WARPS + warp;
+    if (pair >= (long long)H * O) return;
+    const int h = (int)(pair / O), o = (int)(pair % O);
+
+    // lane owns bins n = n_base + lane + 32*j, j < 8; packed as (j, j+4) so both halves are valid together more often
+    float2 gx[K3_NP], gy[K3_NP], gz[K3_NP], ah[K3_NP], ao[K3_NP];
+    float *ph = PH + (size_t)pair * N, *po = PO + (size_t)pair * N;
+#pragma unroll
+    for (int j = 0; j < K3_NP; ++j) {
+        const int n0 = n_base + lane + 32 * j, n1 = n0 + 32 * K3_NP;
+        const bool ok0 = n0 < N, ok1 = n1 < N;
+        gx[j] = make_float2(ok0 ? (float)grid[3 * n0 + 0] : 0.f, ok1 ? (float)grid[3 * n1 + 0] : 0.f);
+        gy[j] = make_float2(ok0 ? (float)grid[3 * n0 + 1] : 0.f, ok1 ? (float)grid[3 * n1 + 1] : 0.f);
+        gz[j] = make_float2(ok0 ? (float)grid[3 * n0 + 2] : 0.f, ok1 ? (float)grid[3 * n1 + 2] : 0.f);
+        ah[j] = make_float2(ok0 ? ph[n0] : 0.f, ok1 ? ph[n1] : 0.f);
+        ao[j] = make_float2(ok0 ? po[n0] : 0.f, ok1 ? po[n1] : 0.f);
+    }
+    const float2 nsk2 = f2(-sk), hp2 = f2(hp_sk);
+
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int ns = min(32, S - s0);
+        if (lane < ns) {
+            const float *ph3 = hn + ((size_t)(s0 + lane) * H + h) * 3;
+            const float *po3 = on + ((size_t)(s0 + lane) * O + o) * 3;
+            const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps);
+            const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps);
+            const Vec3 ch = canonicalize_ref(a, b, p, sp, eps);  // human normal w.r.t. object normal (:295-301)
+            const Vec3 co = canonicalize_ref(b, a, p, sp, eps);  // object normal w.r.t. human normal (:302-309)
+            cnbuf[warp][lane][0] = make_float4(ch.x, ch.x, ch.y, ch.y);
+            cnbuf[warp][lane][1] = make_float4(ch.z, ch.z, co.x, co.x);
+            cnbuf[warp][lane][2] = make_float4(co.y, co.y, co.z, co.z);
+        }
+        __syncwarp();
+#pragma unroll 2
+        for (int i = 0; i < ns; ++i) {
+            const float4 v0 = cnbuf[warp][i][0], v1 = cnbuf[warp][i][1], v2 = cnbuf[warp][i][2];
+            const float2 hx = make_float2(v0.x, v0.y), hy = make_float2(v0.z, v0.w), hz = make_float2(v1.x, v1.y);
+            const float2 ox = make_float2(v1.z, v1.w), oy = make_float2(v2.x, v2.y), oz = make_float2(v2.z, v2.w);
+#pragma unroll
+            for (int j = 0; j < K3_NP; ++j) {
+                const float2 ch_c = __ffma2_rn(gx[j], hx, __ffma2_rn(gy[j], hy, __fmul2_rn(gz[j], hz)));
+                const float2 co_c = __ffma2_rn(gx[j], ox, __ffma2_rn(gy[j], oy, __fmul2_rn(gz[j], oz)));
+                ah[j] = __fadd2_rn(ah[j], orient_score2(ch_c, nsk2, hp2));
+                ao[j] = __fadd2_rn(ao[j], orient_score2(co_c, nsk2, hp2));
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < K3_NP; ++j) {
+        const int n0 = n_base + lane + 32 * j, n1 = n0 + 32 * K3_NP;
+        if (n0 < N) {
+            ph[n0] = ah[j].x;
+            po[n0] = ao[j].x;
+        }
+        if (n1 < N) {
+            ph[n1] = ah[j].y;
+            po[n1] = ao[j].y;
+        }
+    }
+}
+
 __global__ void canonicalize_kernel(const float *__restrict__ a, int A, const float *__restrict__ b, int B, Vec3 p, Vec3 sp,
                                     float eps, float *__restrict__ out) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,6 +295,8 @@ extern "C" int coma_orient_accumulate_f32(const float *hn, const float *on, int6
     const Vec3 p = normalize_host(p_host, epsf), sp = normalize_host(sub_p_host, epsf);
     const double sk = sqrt(1.4426950408889634) / sigma;
     const float skf = (float)sk, hp = (float)(sk * 1.5707963267948966);
+    const char *variant = getenv("COMA_B200_K3");  // experiments only: "v1" selects the scalar-FP32 kernel
+    const bool use_x2 = !(variant && variant[0] == 'v' && variant[1] == '1');
     const long long pairs = (long long)H * O;
     const unsigned blocks = (unsigned)((pairs + K3_WARPS - 1) / K3_WARPS);
     for (int64_t n_base = 0; n_base < N; n_base += 256) {
@@ -203,7 +305,10 @@ extern "C" int coma_orient_accumulate_f32(const float *hn, const float *on, int6
 #define LAUNCH(NBV)                                                                                                   \
     orient_accumulate_kernel<NBV><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N,     \
                                                                      (int)n_base, skf, hp, epsf, p, sp, PH, PO)
-        if (nb <= 1) LAUNCH(1);
+        if (use_x2) {
+            orient_accumulate_kernel_x2<<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, (int)n_base,
+                                                                          skf, hp, epsf, p, sp, PH, PO);
+        } else if (nb <= 1) LAUNCH(1);
         else if (nb <= 2) LAUNCH(2);
         else if (nb <= 4) LAUNCH(4);
         else LAUNCH(8);

@@ -6,8 +6,13 @@
 // serves the warp).  The accumulators are read once at kernel start and written once at the end, coalesced along o.
 //   bytes per launch  = 12*S*(H+O) (vertices) + 2 accumulators * (4 R + 4 W) * H*O  = 16 B / vertex-pair at S = 1
 //   => HBM-bound at S = 1 (the reference's per-sample streaming form), ALU/SFU-bound once S >~ 8.
-// Bit-exactness of `count`: every product/sum is an explicitly rounded __fmul_rn/__fadd_rn in the reference's order
-// ((x+y)+z), the root is __fsqrt_rn and the comparison is done in fp32 against fp32(thres), exactly like torch.
+// Bit-exactness of `count`: the squared distance is built from explicitly rounded __fsub_rn/__fmul_rn/__fadd_rn in the
+// reference's order ((x+y)+z). torch then takes the correctly rounded fp32 sqrt and compares with fp32(thres); because
+// IEEE sqrt is monotone, {x : sqrt_rn(x) < thres} == {x : x < T} with T the smallest float whose rounded root is >=
+// thres (found on the host), so the verdict `sq < T` is identical and the hot loop needs no IEEE square root.
+// The proximity term exp(-d/size) only has to hold 1e-4: d = sq*rsqrt(sq) (MUFU) and exp via one MUFU.EX2.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace coma {
@@ -19,8 +24,8 @@ constexpr int K2_TH = K2_TY * K2_RH;
 constexpr int K2_CS = 16;   // samples staged per chunk
 
 __global__ void __launch_bounds__(K2_TO *K2_TY, 4)
-    pair_accumulate_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float thres,
-                           float grid_size, float *__restrict__ count, float *__restrict__ nom) {
+    pair_accumulate_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float sq_thres,
+                           float neg_log2e_over_size, float *__restrict__ count, float *__restrict__ nom) {
     __shared__ float4 sh[K2_CS][K2_TH];
     __shared__ float so[K2_CS][3][K2_TO];
 
@@ -68,9 +73,11 @@ __global__ void __launch_bounds__(K2_TO *K2_TY, 4)
                 const float4 hvv = sh[cs][ty * K2_RH + r];
                 const float dx = __fsub_rn(hvv.x, ox), dy = __fsub_rn(hvv.y, oy), dz = __fsub_rn(hvv.z, oz);
                 const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                const float d = __fsqrt_rn(sq);
-                cnt[r] += (d < thres) ? 1.0f : 0.0f;
-                acc[r] += expf(__fdiv_rn(-d, grid_size));
+                cnt[r] += (sq < sq_thres) ? 1.0f : 0.0f;
+                float d, e;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(sq));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d * neg_log2e_over_size));
+                acc[r] += e;
             }
         }
         __syncthreads();
@@ -88,6 +95,17 @@ __global__ void __launch_bounds__(K2_TO *K2_TY, 4)
     }
 }
 
+// Smallest float T with sqrtf_rn(T) >= thres, so that  sqrtf_rn(x) < thres  <=>  x < T  for every x >= 0.
+static float squared_threshold_f32(float thres) {
+    if (!(thres > 0.0f)) return 0.0f;  // d < thres never holds for thres <= 0 or NaN (d >= 0)
+    if (isinf(thres)) return INFINITY;
+    volatile float t = thres * thres;
+    if (isinf(t)) t = 3.402823466e+38f;
+    while (t > 0.0f && sqrtf(t) >= thres) t = nextafterf(t, 0.0f);
+    while (sqrtf(t) < thres) t = nextafterf(t, INFINITY);
+    return t;
+}
+
 }  // namespace coma
 
 extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_t S, int64_t H, int64_t O, float thres,
@@ -100,7 +118,9 @@ extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_
     dim3 block(K2_TO, K2_TY);
     dim3 grid((unsigned)((O + K2_TO - 1) / K2_TO), (unsigned)((H + K2_TH - 1) / K2_TH));
     COMA_REQUIRE(grid.y <= 65535u, "H too large for one launch (max 1048560)");
-    pair_accumulate_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(hv, ov, (int)S, (int)H, (int)O, thres, grid_size,
-                                                                     count, nom);
+    COMA_REQUIRE(grid_size > 0.0f, "spatial_grid_size must be positive");
+    const float nl2e = (float)(-1.4426950408889634 / (double)grid_size);
+    pair_accumulate_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(hv, ov, (int)S, (int)H, (int)O,
+                                                                     squared_threshold_f32(thres), nl2e, count, nom);
     return check_launch("pair_accumulate_kernel");
 }

@@ -39,11 +39,14 @@ def main():
         out[f"k2_S{S}"] = dict(ms=ms, pairs_per_s=S * H * O / ms * 1e3, gbs_16B=16 * H * O / ms / 1e6)
     grid = torch.tensor(np.stack(__import__("coma_b200.misc", fromlist=["x"]).get_uniform_points_on_sphere(N), -1), device=dev)
     PH, PO = torch.zeros((H, O, N), device=dev), torch.zeros((H, O, N), device=dev)
-    for S in (1, 32, 64):
-        hv, hn, ov, on = (torch.from_numpy(a).to(dev) for a in synth.make_sample_arrays(S, H, O, seed=1))
-        ms = timeit(lambda: ops.orient_accumulate(hn, on, grid, 0.25, 1e-10, [0, 0, 1], [0, 1, 0], PH, PO), iters=3, warm=1)
-        out[f"k3_S{S}"] = dict(ms=ms, pair_samples_per_s=S * H * O / ms * 1e3, bin_evals_per_s=2 * N * S * H * O / ms * 1e3,
-                               gbs_rmw=16 * H * O * N / ms / 1e6)
+    for variant in ("v1", "x2"):
+        os.environ["COMA_B200_K3"] = variant
+        for S in (1, 64):
+            hv, hn, ov, on = (torch.from_numpy(a).to(dev) for a in synth.make_sample_arrays(S, H, O, seed=1))
+            ms = timeit(lambda: ops.orient_accumulate(hn, on, grid, 0.25, 1e-10, [0, 0, 1], [0, 1, 0], PH, PO), iters=3, warm=1)
+            out[f"k3_{variant}_S{S}"] = dict(ms=ms, pair_samples_per_s=S * H * O / ms * 1e3, bin_evals_per_s=2 * N * S * H * O / ms * 1e3,
+                                             gbs_rmw=16 * H * O * N / ms / 1e6)
+    os.environ["COMA_B200_K3"] = "x2"
     del PH, PO
     for Sg, S in ((30, 256), (128, 64)):
         Hh = 10475 if Sg == 30 else 2048
@@ -53,9 +56,13 @@ def main():
         g, _, meta = load_voxelgrid(2.4, Sg)
         centers = torch.from_numpy(np.ascontiguousarray(np.stack([g[0, :, 0, 0], g[1, 0, :, 0], g[2, 0, 0, :]]))).to(dev)
         grids = torch.zeros((Hh, Sg, Sg, Sg), device=dev)
-        ms = timeit(lambda: ops.occupancy_accumulate(hvc, centers, meta["voxel_size"] * 3.0, grids), iters=3, warm=1)
-        hits = grids.sum().item() / 4
-        out[f"k4_Sg{Sg}"] = dict(ms=ms, vertex_samples_per_s=S * Hh / ms * 1e3, hits_per_vs=hits / (S * Hh))
+        for path in (("smem", "global") if Sg == 30 else ("global",)):
+            os.environ["COMA_B200_OCC_PATH"] = path
+            grids.zero_()
+            ms = timeit(lambda: ops.occupancy_accumulate(hvc, centers, meta["voxel_size"] * 3.0, grids), iters=3, warm=1)
+            hits = grids.sum().item() / 4
+            out[f"k4_Sg{Sg}_{path}"] = dict(ms=ms, vertex_samples_per_s=S * Hh / ms * 1e3, hits_per_vs=hits / (S * Hh))
+        os.environ.pop("COMA_B200_OCC_PATH")
         ms = timeit(lambda: ops.occupancy_readout(grids, None), iters=2, warm=1)
         out[f"k5c_Sg{Sg}"] = dict(ms=ms, gbs=3 * 4 * Hh * Sg**3 / ms / 1e6)
         del grids
