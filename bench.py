@@ -36,7 +36,8 @@ H, O, N = 10475, 1500, 250
 S_PER_RANK = 256
 PRESET = dict(spatial_grid_size=0.15, spatial_grid_thres=0.05, normal_gaussian_sigma=0.25, eps=1e-10,
               significant_contact_ratio=0.1)  # constants/coma/qual.py "qual:backpack_object_contact"
-K3_INSTR_PER_EVAL = 21.5   # SASS instructions per bin evaluation in the K3 inner loop (cuobjdump)
+K3_MUFU_PER_EVAL = 2.0     # MUFU.SQRT + MUFU.EX2 per bin evaluation in the K3 inner loop (cuobjdump)
+MUFU_CLK_PER_WARP_INSTR = 8.05  # measured on B200 with tools/ubench_pipes.cu (4 lanes/clk per SM sub-partition)
 
 
 class ClockSampler:
@@ -277,16 +278,16 @@ def main():
                     "ms_per_step": e2e_t.item(), "api": "ComA.register_sample_to_cache/aggregate_all_samples/get_aggregated_contact"},
             "gpu_launches": int(launches),
             "clocks": ck,
-            "roofline": {"bound": "hbm", "kernel": "orient_accumulate_kernel<8> (K3)", "achieved": k3_bytes / (k3_ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "orient_accumulate_kernel_x2 (K3)", "achieved": k3_bytes / (k3_ms * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "ms": k3_ms,
-                         "note": "K3 is FP32-issue/SFU bound once samples are fused (500 bin evaluations per pair-sample): "
-                                 "see roofline_issue; the HBM fraction is reported because the schema asks for it"},
-            "roofline_issue": {"bound": "fp32-issue", "kernel": "orient_accumulate_kernel<8> (K3)", "achieved": evals_per_s * K3_INSTR_PER_EVAL / 32 / 1e9,
-                               "peak": 148 * 4 * sm_hz / 1e9, "unit": "Gwarp-instr/s",
-                               "frac": evals_per_s * K3_INSTR_PER_EVAL / 32 / (148 * 4 * sm_hz),
-                               "bin_evals_per_s": evals_per_s, "instr_per_eval": K3_INSTR_PER_EVAL,
-                               "peak_source": "148 SMs x 4 schedulers x 1 warp-instr/clk x median SM clock under load"},
+                         "note": "K3 is SFU (MUFU) / FP32-pipe bound once samples are fused (500 bin evaluations per pair-sample, "
+                                 "2 MUFU each): see roofline_sfu; the HBM fraction is reported because the schema asks for it"},
+            "roofline_sfu": {"bound": "sfu", "kernel": "orient_accumulate_kernel_x2 (K3)", "achieved": evals_per_s * K3_MUFU_PER_EVAL / 1e9,
+                             "peak": 148 * 4 * 32 * sm_hz / MUFU_CLK_PER_WARP_INSTR / 1e9, "unit": "G MUFU lane-ops/s",
+                             "frac": evals_per_s * K3_MUFU_PER_EVAL / (148 * 4 * 32 * sm_hz / MUFU_CLK_PER_WARP_INSTR),
+                             "bin_evals_per_s": evals_per_s, "mufu_per_eval": K3_MUFU_PER_EVAL,
+                             "peak_source": "148 SMs x 4 sub-partitions x 32 lanes / 8.05 clk per MUFU warp-instr (tools/ubench_pipes.cu) x median SM clock under load"},
             "roofline_k2_stream": {"bound": "hbm", "kernel": "pair_accumulate_kernel (K2, S=1)", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9,
                                    "peak": peak, "unit": "GB/s", "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak, "traffic": None,
                                    "ms": k2_ms, "peak_source": peak_src},

@@ -185,9 +185,9 @@ __device__ __forceinline__ float2 orient_score2(float2 c, float2 nsk2, float2 hp
     return make_float2(mufu_ex2(-q.x), mufu_ex2(-q.y));
 }
 
-constexpr int K3_NP = 4;  // bin PAIRS per lane -> 8 bins per lane, 256 bins per launch
-
-__global__ void __launch_bounds__(K3_WARPS * 32, 2)
+// K3_NP = bin PAIRS per lane -> 2*NP bins per lane, 64*NP bins per launch
+template <int K3_NP, int MINB>
+__global__ void __launch_bounds__(K3_WARPS * 32, MINB)
     orient_accumulate_kernel_x2(const float *__restrict__ hn, const float *__restrict__ on, int S, int H, int O,
                                 const double *__restrict__ grid, int N, int n_base, float sk, float hp_sk, float eps, Vec3 p,
                                 Vec3 sp, float *__restrict__ PH, float *__restrict__ PO) {
@@ -297,17 +297,24 @@ extern "C" int coma_orient_accumulate_f32(const float *hn, const float *on, int6
     const float skf = (float)sk, hp = (float)(sk * 1.5707963267948966);
     const char *variant = getenv("COMA_B200_K3");  // experiments only: "v1" selects the scalar-FP32 kernel
     const bool use_x2 = !(variant && variant[0] == 'v' && variant[1] == '1');
+    // x3 (default: 8 bins/lane, 80 regs, 3 CTAs/SM) | x2 (128 regs, 2 CTAs/SM) | x4 (4 bins/lane, 4 CTAs/SM, two passes)
+    const int x2_kind = (variant && variant[0] == 'x') ? atoi(variant + 1) : 3;
     const long long pairs = (long long)H * O;
     const unsigned blocks = (unsigned)((pairs + K3_WARPS - 1) / K3_WARPS);
-    for (int64_t n_base = 0; n_base < N; n_base += 256) {
+    const int64_t bins_per_launch = (use_x2 && x2_kind == 4) ? 128 : 256;
+    for (int64_t n_base = 0; n_base < N; n_base += bins_per_launch) {
         const int64_t rem = N - n_base;
         const int nb = (int)((rem > 256 ? 256 : rem) + 31) / 32;
 #define LAUNCH(NBV)                                                                                                   \
     orient_accumulate_kernel<NBV><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N,     \
                                                                      (int)n_base, skf, hp, epsf, p, sp, PH, PO)
+#define LAUNCH_X2(NP, MINB)                                                                                          \
+    orient_accumulate_kernel_x2<NP, MINB><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, \
+                                                                            (int)n_base, skf, hp, epsf, p, sp, PH, PO)
         if (use_x2) {
-            orient_accumulate_kernel_x2<<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, (int)n_base,
-                                                                          skf, hp, epsf, p, sp, PH, PO);
+            if (x2_kind == 3) LAUNCH_X2(4, 3);
+            else if (x2_kind == 4) LAUNCH_X2(2, 4);
+            else LAUNCH_X2(4, 2);
         } else if (nb <= 1) LAUNCH(1);
         else if (nb <= 2) LAUNCH(2);
         else if (nb <= 4) LAUNCH(4);
