@@ -95,6 +95,93 @@ __global__ void __launch_bounds__(K2_TO *K2_TY, 4)
     }
 }
 
+// ---- 16-byte variant: each thread owns 4 consecutive object columns x 4 human rows (needs O % 4 == 0 and 16-byte aligned
+// accumulators). Same arithmetic; the accumulator traffic moves as LDG.128 / STG.128 with streaming cache hints, which
+// is what lets the S = 1 form run close to the HBM copy rate.
+constexpr int K2V_TX = 128;            // threads along o, 4 columns each -> 512 columns per CTA
+constexpr int K2V_TY = 2;
+constexpr int K2V_RH = 4;              // human rows per thread
+constexpr int K2V_TH = K2V_TY * K2V_RH;
+constexpr int K2V_TO = K2V_TX * 4;
+constexpr int K2V_CS = 4;              // samples staged per chunk
+
+__device__ __forceinline__ void pair_update(float hx, float hy, float hz, float ox, float oy, float oz, float sq_thres,
+                                            float nl2e, float &cnt, float &acc) {
+    const float dx = __fsub_rn(hx, ox), dy = __fsub_rn(hy, oy), dz = __fsub_rn(hz, oz);
+    const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    cnt += (sq < sq_thres) ? 1.0f : 0.0f;
+    float d, e;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(sq));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d * nl2e));
+    acc += e;
+}
+
+__global__ void __launch_bounds__(K2V_TX *K2V_TY, 4)
+    pair_accumulate_vec4_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float sq_thres,
+                                float nl2e, float *__restrict__ count, float *__restrict__ nom) {
+    __shared__ float4 sh[K2V_CS][K2V_TH];
+    __shared__ __align__(16) float so[K2V_CS][3][K2V_TO];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * K2V_TX + tx;
+    const int o0 = blockIdx.x * K2V_TO, h0 = blockIdx.y * K2V_TH;
+    const int o = o0 + 4 * tx;
+    const bool col_ok = o < O;  // O % 4 == 0: a float4 is either fully inside or fully outside
+
+    float4 cnt[K2V_RH], acc[K2V_RH];
+#pragma unroll
+    for (int r = 0; r < K2V_RH; ++r) {
+        const int h = h0 + ty * K2V_RH + r;
+        const bool ok = col_ok && h < H;
+        const size_t q = (size_t)h * O + o;
+        cnt[r] = ok ? __ldcs(reinterpret_cast<const float4 *>(count + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[r] = ok ? __ldcs(reinterpret_cast<const float4 *>(nom + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int s0 = 0; s0 < S; s0 += K2V_CS) {
+        const int ns = min(K2V_CS, S - s0);
+        for (int i = tid; i < ns * K2V_TH; i += K2V_TX * K2V_TY) {
+            const int cs = i / K2V_TH, r = i % K2V_TH, h = h0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (h < H) {
+                const float *p = hv + ((size_t)(s0 + cs) * H + h) * 3;
+                v.x = p[0]; v.y = p[1]; v.z = p[2];
+            }
+            sh[cs][r] = v;
+        }
+        for (int i = tid; i < ns * K2V_TO * 3; i += K2V_TX * K2V_TY) {
+            const int cs = i / (K2V_TO * 3), e = i % (K2V_TO * 3);
+            const int oo = e / 3, k = e % 3;
+            float v = 0.f;
+            if (o0 + oo < O) v = ov[((size_t)(s0 + cs) * O + o0) * 3 + e];
+            so[cs][k][oo] = v;
+        }
+        __syncthreads();
+        for (int cs = 0; cs < ns; ++cs) {
+            const float4 ox = *reinterpret_cast<const float4 *>(&so[cs][0][4 * tx]);
+            const float4 oy = *reinterpret_cast<const float4 *>(&so[cs][1][4 * tx]);
+            const float4 oz = *reinterpret_cast<const float4 *>(&so[cs][2][4 * tx]);
+#pragma unroll
+            for (int r = 0; r < K2V_RH; ++r) {
+                const float4 hvv = sh[cs][ty * K2V_RH + r];
+                pair_update(hvv.x, hvv.y, hvv.z, ox.x, oy.x, oz.x, sq_thres, nl2e, cnt[r].x, acc[r].x);
+                pair_update(hvv.x, hvv.y, hvv.z, ox.y, oy.y, oz.y, sq_thres, nl2e, cnt[r].y, acc[r].y);
+                pair_update(hvv.x, hvv.y, hvv.z, ox.z, oy.z, oz.z, sq_thres, nl2e, cnt[r].z, acc[r].z);
+                pair_update(hvv.x, hvv.y, hvv.z, ox.w, oy.w, oz.w, sq_thres, nl2e, cnt[r].w, acc[r].w);
+            }
+        }
+        __syncthreads();
+    }
+    if (col_ok) {
+#pragma unroll
+        for (int r = 0; r < K2V_RH; ++r) {
+            const int h = h0 + ty * K2V_RH + r;
+            if (h < H) {
+                const size_t q = (size_t)h * O + o;
+                __stcs(reinterpret_cast<float4 *>(count + q), cnt[r]);
+                __stcs(reinterpret_cast<float4 *>(nom + q), acc[r]);
+            }
+        }
+    }
+}
+
 // Smallest float T with sqrtf_rn(T) >= thres, so that  sqrtf_rn(x) < thres  <=>  x < T  for every x >= 0.
 static float squared_threshold_f32(float thres) {
     if (!(thres > 0.0f)) return 0.0f;  // d < thres never holds for thres <= 0 or NaN (d >= 0)
@@ -120,7 +207,16 @@ extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_
     COMA_REQUIRE(grid.y <= 65535u, "H too large for one launch (max 1048560)");
     COMA_REQUIRE(grid_size > 0.0f, "spatial_grid_size must be positive");
     const float nl2e = (float)(-1.4426950408889634 / (double)grid_size);
-    pair_accumulate_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(hv, ov, (int)S, (int)H, (int)O,
-                                                                     squared_threshold_f32(thres), nl2e, count, nom);
+    const float sq_thres = squared_threshold_f32(thres);
+    const bool vec4 = (O % 4 == 0) && (((uintptr_t)count | (uintptr_t)nom) % 16 == 0);
+    if (vec4) {
+        dim3 vblock(K2V_TX, K2V_TY);
+        dim3 vgrid((unsigned)((O + K2V_TO - 1) / K2V_TO), (unsigned)((H + K2V_TH - 1) / K2V_TH));
+        COMA_REQUIRE(vgrid.y <= 65535u, "H too large for one launch (max 524280)");
+        pair_accumulate_vec4_kernel<<<vgrid, vblock, 0, (cudaStream_t)stream>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e,
+                                                                                count, nom);
+        return check_launch("pair_accumulate_vec4_kernel");
+    }
+    pair_accumulate_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
     return check_launch("pair_accumulate_kernel");
 }

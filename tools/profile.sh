@@ -1,6 +1,6 @@
 #!/bin/bash
 # Runs on the GPU box (under gpurun): launch list of the bench command + one full ncu capture of K3 and of K2 (S=1).
-# Outputs land in gpurun_out/ ; summaries are copied to profiles/ by tools/summarize_profiles.py in the dev container.
+# Outputs land in gpurun_out/ ; tools/summarize_profiles.py turns them into the committed summaries under profiles/.
 set -x
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
