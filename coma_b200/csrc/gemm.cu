@@ -1,0 +1,306 @@
+// G1 — fp16 GEMM on 5th-gen tensor cores for the inpainting UNet / VAE (HP-A):  D[M,N] = A[M,K] · W[N,K]^T (+ epilogue)
+//
+// Every dense contraction of the SD-1.5 inpainting UNet and the VAE — 1x1 convs, linear layers, the im2col form of the
+// 3x3 convs, attention projections — is this shape with A = activations (row-major [M,K], K contiguous = NHWC) and
+// W = weights ([N,K], K contiguous). Reference call sites: utils/adaptive_mask_inpainting.py:1001-1007 (UNet),
+// :680,:1086,:1112 (VAE) — the arithmetic itself lives in diffusers' UNet2DConditionModel / AutoencoderKL [ext].
+//
+// Blackwell structure (one CTA per 128 x BN output tile, 6 warps, warp-specialised):
+//   warp 0    : TMA producer — cp.async.bulk.tensor.2d of the A (128 x 64) and W (BN x 64) K-slabs into a 4-stage
+//               128B-swizzled shared-memory ring, completion on `full` mbarriers
+//   warp 1    : MMA issuer — one elected thread issues 4 x tcgen05.mma.kind::f16 (M128 x BN x K16) per slab from shared-memory
+//               descriptors, fp32 accumulator in TMEM; tcgen05.commit releases the slab (`empty`) and finally signals
+//               `tmem_full`
+//   warps 2-5 : epilogue — tcgen05.ld (32 lanes x 32 columns per warp-instruction) TMEM -> registers, + bias, + residual,
+//               optional SiLU, store fp16 and/or fp32
+// Operands are fp16, accumulation fp32 (the reference runs the models in fp16, src/generation/inpaint.py:64).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace coma {
+
+constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4;
+constexpr int G_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+                 : "memory");
+}
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4, LBO = 1 (ignored for
+// swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout SWIZZLE_128B (2).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// act: 0 = identity, 1 = SiLU
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS, 1)
+    gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                       const float *__restrict__ bias, const __half *__restrict__ residual, int act, __half *__restrict__ out16,
+                       float *__restrict__ out32, int ldo) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = G_BM * G_BK * 2, B_BYTES = BN * G_BK * 2;
+    uint8_t *sA = smem, *sB = smem + G_STAGES * A_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + G_STAGES * B_BYTES);
+    uint64_t *empty = full + G_STAGES;
+    uint64_t *tmem_full = empty + G_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * BN;
+    const int num_k = (K + G_BK - 1) / G_BK;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;  // power of two >= 32
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int i = 0; i < G_STAGES; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % G_STAGES;
+                const uint32_t ph = (kb / G_STAGES) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                mbar_expect_tx(full + s, A_BYTES + B_BYTES);
+                tma_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0);
+                tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N>>3, M>>4
+            constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % G_STAGES;
+                const uint32_t ph = (kb / G_STAGES) & 1;
+                mbar_wait(full + s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = umma_desc_sw128(smem_u32(sA + s * A_BYTES));
+                const uint64_t db = umma_desc_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < G_BK / 16; ++k)  // advance 32 B (16 fp16) inside the 128 B swizzle atom: +2 in 16-B units
+                    umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(empty + s);  // frees the slab once the MMAs that read it have retired
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (row < M) {
+                const int nb = n0 + c0;
+                const size_t off = (size_t)row * ldo + nb;
+                if (nb + 32 <= N && (ldo % 8) == 0) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + nb + j) : 0.0f);
+                    if (residual) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 r = *reinterpret_cast<const uint4 *>(residual + off + j);
+                            const __half2 *h = reinterpret_cast<const __half2 *>(&r);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 x = __half22float2(h[t]);
+                                f[j + 2 * t] += x.x;
+                                f[j + 2 * t + 1] += x.y;
+                            }
+                        }
+                    }
+                    if (act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+                    }
+                    if (out16) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 w;
+                            __half2 *h = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                            *reinterpret_cast<uint4 *>(out16 + off + j) = w;
+                        }
+                    }
+                    if (out32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(out32 + off + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) {
+                        if (nb + j < N) {
+                            float x = __uint_as_float(v[j]) + (bias ? bias[nb + j] : 0.0f);
+                            if (residual) x += __half2float(residual[off + j]);
+                            if (act == 1) x = x / (1.0f + __expf(-x));
+                            if (out16) out16[off + j] = __float2half_rn(x);
+                            if (out32) out32[off + j] = x;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp16 tensor map over a row-major [rows, cols] matrix with row stride `ld` elements; box = box_rows x 64 columns.
+static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return COMA_E_NODEVICE;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld);
+        return COMA_E_BADARG;
+    }
+    return 0;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const float *bias, const __half *residual,
+                       int act, __half *out16, float *out32, int ldo, cudaStream_t st) {
+    constexpr size_t smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 256 + 1024;
+    static bool attr[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !attr[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr[dev] = true;
+    }
+    dim3 grid((N + BN - 1) / BN, (M + G_BM - 1) / G_BM);
+    gemm_f16_tn_kernel<BN><<<grid, G_THREADS, smem, st>>>(ta, tb, M, N, K, bias, residual, act, out16, out32, ldo);
+    return check_launch("gemm_f16_tn_kernel");
+}
+
+}  // namespace coma
+
+extern "C" int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                                const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
+                                coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(A && W && (out_f16 || out_f32), "null pointer");
+    COMA_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "bad sizes");
+    COMA_REQUIRE(lda >= K && ldw >= K && ldo >= N, "leading dimensions smaller than the row length");
+    COMA_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "lda / ldw must be multiples of 8 elements (16-byte TMA strides)");
+    COMA_REQUIRE(((uintptr_t)A | (uintptr_t)W) % 16 == 0, "A and W must be 16-byte aligned");
+    COMA_REQUIRE(act == 0 || act == 1, "act must be 0 (identity) or 1 (SiLU)");
+    COMA_REQUIRE(!out_f16 || (uintptr_t)out_f16 % 16 == 0, "out_f16 must be 16-byte aligned");
+    COMA_REQUIRE(!out_f32 || (uintptr_t)out_f32 % 16 == 0, "out_f32 must be 16-byte aligned");
+    COMA_REQUIRE(!residual || (uintptr_t)residual % 16 == 0, "residual must be 16-byte aligned");
+    const int bn = (N <= 64) ? 64 : 128;
+    CUtensorMap ta, tb;
+    if (int e = make_map(&ta, A, M, K, lda, G_BM)) return e;
+    if (int e = make_map(&tb, W, N, K, ldw, bn)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 64)
+        return launch_gemm<64>(ta, tb, (int)M, (int)N, (int)K, bias, (const __half *)residual, act, (__half *)out_f16, out_f32, (int)ldo, st);
+    return launch_gemm<128>(ta, tb, (int)M, (int)N, (int)K, bias, (const __half *)residual, act, (__half *)out_f16, out_f32, (int)ldo, st);
+}

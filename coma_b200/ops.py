@@ -118,3 +118,25 @@ def occupancy_readout(grids, sel_idx=None):
     with torch.cuda.device(grids.device):
         call("coma_occupancy_readout_f32", _ptr(grids), H, V, _ptr(sel_idx), nsel, _ptr(field), _stream())
     return field
+
+
+def gemm_f16(a, w, bias=None, residual=None, act=0, out_dtype=torch.float16, out=None):
+    """G1: out = act(a @ w.T + bias + residual) on the tcgen05 tensor cores. a [M,K] f16, w [N,K] f16 (K contiguous),
+    bias [N] f32, residual [M,N] f16; out f16 or f32 [M,N]."""
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.float16, torch.float32)
+    if residual is not None:
+        assert residual.dtype == torch.float16 and residual.shape == (M, N) and residual.stride(1) == 1 and residual.stride(0) == out.stride(0)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    o16 = out.data_ptr() if out.dtype == torch.float16 else None
+    o32 = out.data_ptr() if out.dtype == torch.float32 else None
+    with torch.cuda.device(a.device):
+        call("coma_gemm_f16_tn", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, _ptr(bias),
+             None if residual is None else residual.data_ptr(), int(act), o16, o32, out.stride(0), _stream())
+    return out

@@ -103,6 +103,20 @@ COMA_API int coma_entropy_readout_f32(const float *P, int64_t HO, int64_t N, flo
 COMA_API int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, const int64_t *sel_idx, int64_t nsel, float *field,
                                coma_stream_t stream);
 
+/* ==== HP-A: adaptive-mask inpainting loop (utils/adaptive_mask_inpainting.py:984-1157) ================================= */
+
+/* ---- G1: fp16 tensor-core GEMM with fused epilogue (tcgen05 / TMEM / TMA) ------------------------------------------------
+ * out[m,n] = act( sum_k A[m,k]*W[n,k] + bias[n] + residual[m,n] ),  fp16 operands, fp32 accumulation.
+ * The dense contractions of the UNet / VAE the pipeline calls at utils/adaptive_mask_inpainting.py:1001-1007 (unet),
+ * :680 (vae.encode), :1086,:1112 (vae.decode): linear layers, 1x1 convs, attention projections and the im2col form of
+ * the 3x3 convs (diffusers UNet2DConditionModel / AutoencoderKL, not vendored in the reference).
+ * A [M,K] fp16 row stride lda; W [N,K] fp16 row stride ldw (lda, ldw multiples of 8); bias [N] f32 or NULL;
+ * residual [M,N] fp16 with row stride ldo or NULL; act: 0 identity, 1 SiLU; out_f16 / out_f32 [M,N] row stride ldo
+ * (either may be NULL, not both). */
+COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                              const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
+                              coma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
