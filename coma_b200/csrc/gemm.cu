@@ -44,11 +44,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
-                 : "memory");
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z, int w) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w)
+        : "memory");
 }
 // K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4, LBO = 1 (ignored for
 // swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout SWIZZLE_128B (2).
@@ -85,12 +86,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// act: 0 = identity, 1 = SiLU
+struct GemmEpilogue {
+    const float *bias;       // [N] or null
+    const float *bias_rows;  // [ceil(M/rows_per_bias), N] or null (e.g. the per-sample time-embedding term of a ResnetBlock)
+    int rows_per_bias;
+    const __half *residual;  // same layout as the output, or null
+    __half *out16;
+    float *out32;
+    int ldo;
+    long long o_s1, o_s2;    // output element strides of the two batch dims
+    float alpha;             // scales the accumulator (attention: 1/sqrt(d))
+    int act;                 // 0 = identity, 1 = SiLU
+    int nb1;                 // extent of batch dim 1 (blockIdx.z = b2 * nb1 + b1)
+};
+
 template <int BN>
 __global__ void __launch_bounds__(G_THREADS, 1)
     gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                       const float *__restrict__ bias, const __half *__restrict__ residual, int act, __half *__restrict__ out16,
-                       float *__restrict__ out32, int ldo) {
+                       const GemmEpilogue ep) {
+    const float *__restrict__ bias = ep.bias;
+    const int act = ep.act, ldo = ep.ldo;
+    const int b1 = blockIdx.z % ep.nb1, b2 = blockIdx.z / ep.nb1;
+    const size_t obase = (size_t)b1 * ep.o_s1 + (size_t)b2 * ep.o_s2;
+    const __half *__restrict__ residual = ep.residual ? ep.residual + obase : nullptr;
+    __half *__restrict__ out16 = ep.out16 ? ep.out16 + obase : nullptr;
+    float *__restrict__ out32 = ep.out32 ? ep.out32 + obase : nullptr;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = G_BM * G_BK * 2, B_BYTES = BN * G_BK * 2;
@@ -132,8 +152,8 @@ __global__ void __launch_bounds__(G_THREADS, 1)
                 const uint32_t ph = (kb / G_STAGES) & 1;
                 mbar_wait(empty + s, ph ^ 1);
                 mbar_expect_tx(full + s, A_BYTES + B_BYTES);
-                tma_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0);
-                tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0);
+                tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
+                tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0, b1, b2);
             }
         }
     } else if (warp == 1) {
@@ -166,10 +186,14 @@ __global__ void __launch_bounds__(G_THREADS, 1)
             if (row < M) {
                 const int nb = n0 + c0;
                 const size_t off = (size_t)row * ldo + nb;
-                if (nb + 32 <= N && (ldo % 8) == 0) {
+                const float *brow = ep.bias_rows ? ep.bias_rows + (size_t)(row / ep.rows_per_bias) * N : nullptr;
+                if (nb + 32 <= N && (ldo % 8) == 0 && (obase % 8) == 0) {
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + nb + j) : 0.0f);
+                    for (int j = 0; j < 32; ++j) {
+                        f[j] = __uint_as_float(v[j]) * ep.alpha + (bias ? __ldg(bias + nb + j) : 0.0f);
+                        if (brow) f[j] += __ldg(brow + nb + j);
+                    }
                     if (residual) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -205,7 +229,8 @@ __global__ void __launch_bounds__(G_THREADS, 1)
                 } else {
                     for (int j = 0; j < 32; ++j) {
                         if (nb + j < N) {
-                            float x = __uint_as_float(v[j]) + (bias ? bias[nb + j] : 0.0f);
+                            float x = __uint_as_float(v[j]) * ep.alpha + (bias ? bias[nb + j] : 0.0f);
+                            if (brow) x += brow[nb + j];
                             if (residual) x += __half2float(residual[off + j]);
                             if (act == 1) x = x / (1.0f + __expf(-x));
                             if (out16) out16[off + j] = __float2half_rn(x);
@@ -238,18 +263,21 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp16 tensor map over a row-major [rows, cols] matrix with row stride `ld` elements; box = box_rows x 64 columns.
-static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 4-D fp16 tensor map {cols, rows, nb1, nb2} over row-major [rows, cols] matrices with row stride `ld` and batch strides
+// s1, s2 (elements); box = 64 columns x box_rows rows x 1 x 1.
+static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int64_t nb1, int64_t s1,
+                    int64_t nb2, int64_t s2) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
         return COMA_E_NODEVICE;
     }
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nb1, (cuuint64_t)nb2};
+    // a batch dim of extent 1 may carry any (valid) stride
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(nb1 > 1 ? s1 : ld) * 2, (cuuint64_t)(nb2 > 1 ? s2 : ld) * 2};
+    cuuint32_t box[4] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -261,8 +289,8 @@ static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols,
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const float *bias, const __half *residual,
-                       int act, __half *out16, float *out32, int ldo, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const GemmEpilogue &ep, int nbatch,
+                       cudaStream_t st) {
     constexpr size_t smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 256 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
@@ -275,32 +303,56 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, int M, int 
         }
         attr[dev] = true;
     }
-    dim3 grid((N + BN - 1) / BN, (M + G_BM - 1) / G_BM);
-    gemm_f16_tn_kernel<BN><<<grid, G_THREADS, smem, st>>>(ta, tb, M, N, K, bias, residual, act, out16, out32, ldo);
+    dim3 grid((N + BN - 1) / BN, (M + G_BM - 1) / G_BM, nbatch);
+    gemm_f16_tn_kernel<BN><<<grid, G_THREADS, smem, st>>>(ta, tb, M, N, K, ep);
     return check_launch("gemm_f16_tn_kernel");
 }
 
 }  // namespace coma
 
+extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(g && g->A && g->W && (g->out_f16 || g->out_f32), "null pointer");
+    const int64_t M = g->M, N = g->N, K = g->K, nb1 = g->nb1 > 0 ? g->nb1 : 1, nb2 = g->nb2 > 0 ? g->nb2 : 1;
+    COMA_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "bad sizes");
+    COMA_REQUIRE(nb1 * nb2 <= 65535, "too many batches for one launch");
+    COMA_REQUIRE(g->lda >= K && g->ldw >= K && g->ldo >= N, "leading dimensions smaller than the row length");
+    COMA_REQUIRE(g->lda % 8 == 0 && g->ldw % 8 == 0, "lda / ldw must be multiples of 8 elements (16-byte TMA strides)");
+    COMA_REQUIRE((nb1 == 1 || (g->a_s1 % 8 == 0 && g->w_s1 % 8 == 0)) && (nb2 == 1 || (g->a_s2 % 8 == 0 && g->w_s2 % 8 == 0)),
+                 "batch strides of A / W must be multiples of 8 elements");
+    COMA_REQUIRE(((uintptr_t)g->A | (uintptr_t)g->W) % 16 == 0, "A and W must be 16-byte aligned");
+    COMA_REQUIRE(g->act == 0 || g->act == 1, "act must be 0 (identity) or 1 (SiLU)");
+    COMA_REQUIRE(!g->out_f16 || (uintptr_t)g->out_f16 % 16 == 0, "out_f16 must be 16-byte aligned");
+    COMA_REQUIRE(!g->out_f32 || (uintptr_t)g->out_f32 % 16 == 0, "out_f32 must be 16-byte aligned");
+    COMA_REQUIRE(!g->residual || (uintptr_t)g->residual % 16 == 0, "residual must be 16-byte aligned");
+    COMA_REQUIRE(!g->bias_rows || g->rows_per_bias > 0, "rows_per_bias must be positive");
+    const int bn = (N <= 64) ? 64 : 128;
+    CUtensorMap ta, tb;
+    if (int e = make_map(&ta, g->A, M, K, g->lda, G_BM, nb1, g->a_s1, nb2, g->a_s2)) return e;
+    if (int e = make_map(&tb, g->W, N, K, g->ldw, bn, nb1, g->w_s1, nb2, g->w_s2)) return e;
+    GemmEpilogue ep;
+    ep.bias = g->bias;
+    ep.bias_rows = g->bias_rows;
+    ep.rows_per_bias = (int)(g->rows_per_bias > 0 ? g->rows_per_bias : 1);
+    ep.residual = (const __half *)g->residual;
+    ep.out16 = (__half *)g->out_f16;
+    ep.out32 = g->out_f32;
+    ep.ldo = (int)g->ldo;
+    ep.o_s1 = g->o_s1;
+    ep.o_s2 = g->o_s2;
+    ep.alpha = g->alpha;
+    ep.act = g->act;
+    ep.nb1 = (int)nb1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 64) return launch_gemm<64>(ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st);
+    return launch_gemm<128>(ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st);
+}
+
 extern "C" int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                                 const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
                                 coma_stream_t stream) {
-    using namespace coma;
-    COMA_REQUIRE(A && W && (out_f16 || out_f32), "null pointer");
-    COMA_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "bad sizes");
-    COMA_REQUIRE(lda >= K && ldw >= K && ldo >= N, "leading dimensions smaller than the row length");
-    COMA_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "lda / ldw must be multiples of 8 elements (16-byte TMA strides)");
-    COMA_REQUIRE(((uintptr_t)A | (uintptr_t)W) % 16 == 0, "A and W must be 16-byte aligned");
-    COMA_REQUIRE(act == 0 || act == 1, "act must be 0 (identity) or 1 (SiLU)");
-    COMA_REQUIRE(!out_f16 || (uintptr_t)out_f16 % 16 == 0, "out_f16 must be 16-byte aligned");
-    COMA_REQUIRE(!out_f32 || (uintptr_t)out_f32 % 16 == 0, "out_f32 must be 16-byte aligned");
-    COMA_REQUIRE(!residual || (uintptr_t)residual % 16 == 0, "residual must be 16-byte aligned");
-    const int bn = (N <= 64) ? 64 : 128;
-    CUtensorMap ta, tb;
-    if (int e = make_map(&ta, A, M, K, lda, G_BM)) return e;
-    if (int e = make_map(&tb, W, N, K, ldw, bn)) return e;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64)
-        return launch_gemm<64>(ta, tb, (int)M, (int)N, (int)K, bias, (const __half *)residual, act, (__half *)out_f16, out_f32, (int)ldo, st);
-    return launch_gemm<128>(ta, tb, (int)M, (int)N, (int)K, bias, (const __half *)residual, act, (__half *)out_f16, out_f32, (int)ldo, st);
+    coma_gemm_args g = {};
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.nb1 = 1; g.nb2 = 1;
+    g.bias = bias; g.residual = residual; g.act = act; g.out_f16 = out_f16; g.out_f32 = out_f32; g.ldo = ldo; g.alpha = 1.0f;
+    return coma_gemm_f16_ex(&g, stream);
 }

@@ -1,0 +1,399 @@
+// HP-A support kernels around the tensor-core GEMM: everything in the UNet / VAE that is not a contraction.
+// Activations are NHWC fp16 ([B, H*W, C] matrices, the GEMM's A operand layout); statistics and epilogues are fp32.
+// Reference call sites: utils/adaptive_mask_inpainting.py:1001-1007 (unet), :680/:1086/:1112 (vae) — the layer
+// definitions themselves are diffusers' (UNet2DConditionModel / AutoencoderKL 0.20.2, not vendored).
+//   groupnorm_partial/finalize  GroupNorm(32) statistics (fp32 partial sums per channel, fp64 combination)
+//   groupnorm_apply             y = act(gn(x))                        (Transformer2D / VAE attention inputs, conv_norm_out)
+//   im2col3x3                   [B,H,W,C] -> [B*Ho*Wo, 9C] with the GroupNorm affine + SiLU applied on the fly, stride 1/2,
+//                               nearest x2 upsampling and the VAE encoder's asymmetric (0,1,0,1) padding folded in
+//   layernorm                   per-token LayerNorm
+//   softmax_rows                in-place row softmax of fp16 attention scores (fp32 math), padding columns zeroed
+//   geglu                       hidden * gelu(gate)  (exact erf GELU)
+//   transpose_heads             V [B,L,heads*d] -> V^T [B,heads,d,Lpad]   (K-major B operand for P·V)
+//   timestep_embedding          sinusoidal embedding (flip_sin_to_cos, shift 0)
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace coma {
+
+// ---------------------------------------------------------------------------------------------- GroupNorm statistics
+// grid (chunks, B), block 256. Thread t owns channels t, t+256, ...; sums over the chunk's pixels are coalesced.
+__global__ void __launch_bounds__(256)
+    groupnorm_partial_kernel(const __half *__restrict__ x, int HW, int C, long long ldx, int G, int rows_per_chunk,
+                             double *__restrict__ acc /* [B,G,2] */) {
+    extern __shared__ float sm[];  // [2][C]
+    const int b = blockIdx.y, p0 = blockIdx.x * rows_per_chunk, p1 = min(HW, p0 + rows_per_chunk);
+    const __half *xb = x + (size_t)b * HW * ldx;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int p = p0; p < p1; ++p) {
+            const float v = __half2float(xb[(size_t)p * ldx + c]);
+            s += v;
+            q = fmaf(v, v, q);
+        }
+        sm[c] = s;
+        sm[C + c] = q;
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            s += (double)sm[c];
+            q += (double)sm[C + c];
+        }
+        atomicAdd(acc + ((size_t)b * G + g) * 2 + 0, s);
+        atomicAdd(acc + ((size_t)b * G + g) * 2 + 1, q);
+    }
+}
+
+// mean/rstd per (b,g) and the per-(b,c) affine  y = x*scale + shift  (scale = rstd*gamma, shift = beta - mean*rstd*gamma)
+__global__ void groupnorm_finalize_kernel(const double *__restrict__ acc, int B, int C, int G, long long count, float eps,
+                                          const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ mean,
+                                          float *__restrict__ rstd, float *__restrict__ scale, float *__restrict__ shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i % C, g = c / (C / G);
+    const double s = acc[((size_t)b * G + g) * 2], q = acc[((size_t)b * G + g) * 2 + 1];
+    const double m = s / (double)count;
+    double var = q / (double)count - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    const double r = 1.0 / sqrt(var + (double)eps);
+    if (c % (C / G) == 0) {
+        if (mean) mean[b * G + g] = (float)m;
+        if (rstd) rstd[b * G + g] = (float)r;
+    }
+    const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+    scale[i] = (float)(r * ga);
+    shift[i] = (float)(be - m * r * ga);
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+// y[b,p,c] = act(x*scale[b,c] + shift[b,c]); 8 channels (16 B) per thread. act: 0 none, 1 SiLU
+__global__ void __launch_bounds__(256)
+    affine_act_kernel(const __half *__restrict__ x, long long rows, int HW, int C, long long ldx, const float *__restrict__ scale,
+                      const float *__restrict__ shift, int act, __half *__restrict__ y, long long ldy) {
+    const int c8n = C / 8;
+    const long long total = rows * c8n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c8n;
+        const int c = (int)(i % c8n) * 8;
+        const int b = (int)(r / HW);
+        const uint4 raw = *reinterpret_cast<const uint4 *>(x + r * ldx + c);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+        uint4 o;
+        __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float2 v = __half22float2(h[t]);
+            const int cc = b * C + c + 2 * t;
+            v.x = fmaf(v.x, scale[cc], shift[cc]);
+            v.y = fmaf(v.y, scale[cc + 1], shift[cc + 1]);
+            if (act == 1) {
+                v.x = silu_f(v.x);
+                v.y = silu_f(v.y);
+            }
+            oh[t] = __floats2half2_rn(v.x, v.y);
+        }
+        *reinterpret_cast<uint4 *>(y + r * ldy + c) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- im2col 3x3
+// out[(b,oy,ox), tap*C + c] = act(x[b, iy, ix, c]*scale + shift), 0 outside the (upsampled) image.
+// iy = oy*stride + ky - pad, ix likewise; with `up` the source pixel is (iy>>1, ix>>1) of the stored tensor.
+template <bool VEC8>
+__global__ void __launch_bounds__(256)
+    im2col3x3_kernel(const __half *__restrict__ x, int B, int H, int W, int C, long long ldx, int Ho, int Wo, int stride, int pad,
+                     int up, const float *__restrict__ scale, const float *__restrict__ shift, int act, __half *__restrict__ out,
+                     long long ldo) {
+    const int Hin = up ? 2 * H : H, Win = up ? 2 * W : W;  // logical input extent
+    const int cv = VEC8 ? C / 8 : C;
+    const long long total = (long long)B * Ho * Wo * 9 * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv) * (VEC8 ? 8 : 1);
+        long long r = i / cv;
+        const int tap = (int)(r % 9);
+        r /= 9;
+        const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho), b = (int)(r / ((long long)Wo * Ho));
+        const int iy = oy * stride + tap / 3 - pad, ix = ox * stride + tap % 3 - pad;
+        const bool in = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+        __half *dst = out + r * ldo + (long long)tap * C + c;
+        if (VEC8) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (in) {
+                const int sy = up ? iy >> 1 : iy, sx = up ? ix >> 1 : ix;
+                o = *reinterpret_cast<const uint4 *>(x + ((size_t)(b * H + sy) * W + sx) * ldx + c);
+                if (scale) {
+                    __half2 *h = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float2 v = __half22float2(h[t]);
+                        const int cc = b * C + c + 2 * t;
+                        v.x = fmaf(v.x, scale[cc], shift[cc]);
+                        v.y = fmaf(v.y, scale[cc + 1], shift[cc + 1]);
+                        if (act == 1) {
+                            v.x = silu_f(v.x);
+                            v.y = silu_f(v.y);
+                        }
+                        h[t] = __floats2half2_rn(v.x, v.y);
+                    }
+                }
+            }
+            *reinterpret_cast<uint4 *>(dst) = o;
+        } else {
+            float v = 0.f;
+            if (in) {
+                const int sy = up ? iy >> 1 : iy, sx = up ? ix >> 1 : ix;
+                v = __half2float(x[((size_t)(b * H + sy) * W + sx) * ldx + c]);
+                if (scale) {
+                    v = fmaf(v, scale[b * C + c], shift[b * C + c]);
+                    if (act == 1) v = silu_f(v);
+                }
+            }
+            *dst = __float2half_rn(v);
+        }
+    }
+}
+
+// zero the K-padding columns [K, ldo) of an im2col matrix (only when 9C is not a multiple of 8)
+__global__ void zero_cols_kernel(__half *__restrict__ out, long long rows, int K, long long ldo) {
+    const int padc = (int)(ldo - K);
+    const long long total = rows * padc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[(i / padc) * ldo + K + (i % padc)] = __float2half_rn(0.f);
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm (warp per row)
+__global__ void __launch_bounds__(256)
+    layernorm_kernel(const __half *__restrict__ x, long long M, int C, long long ldx, const float *__restrict__ gamma,
+                     const float *__restrict__ beta, float eps, __half *__restrict__ y, long long ldy) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const __half *xr = x + row * ldx;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __half2float(xr[c]);
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float d = __half2float(xr[c]) - mean;
+        q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    __half *yr = y + row * ldy;
+    for (int c = lane; c < C; c += 32) yr[c] = __float2half_rn((__half2float(xr[c]) - mean) * rstd * gamma[c] + beta[c]);
+}
+
+// ---------------------------------------------------------------------------------------------- row softmax (in place)
+// one warp per row for L <= 1024 columns held in registers? General: block (256 threads) per row, three passes.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__half *__restrict__ s, int L, long long ld) {
+    __half *row = s + (long long)blockIdx.x * ld;
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) m = fmaxf(m, __half2float(row[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = red[0];
+        for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w]);
+        bc = t;
+    }
+    __syncthreads();
+    m = bc;
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) sum += __expf(__half2float(row[c]) - m);
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        bc = 1.0f / t;
+    }
+    __syncthreads();
+    const float inv = bc;
+    for (int c = threadIdx.x; c < (int)ld; c += blockDim.x)
+        row[c] = __float2half_rn(c < L ? __expf(__half2float(row[c]) - m) * inv : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------- GEGLU
+__global__ void __launch_bounds__(256)
+    geglu_kernel(const __half *__restrict__ h, long long M, int C, long long ldh, __half *__restrict__ y, long long ldy) {
+    const int c2n = C / 2;
+    const long long total = M * c2n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c2n;
+        const int c = (int)(i % c2n) * 2;
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(h + r * ldh + c));
+        const float2 g = __half22float2(*reinterpret_cast<const __half2 *>(h + r * ldh + C + c));
+        const float gx = 0.5f * g.x * (1.0f + erff(g.x * 0.70710678118654752f));
+        const float gy = 0.5f * g.y * (1.0f + erff(g.y * 0.70710678118654752f));
+        *reinterpret_cast<__half2 *>(y + r * ldy + c) = __floats2half2_rn(a.x * gx, a.y * gy);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- V -> V^T per head
+// v [B, L, heads*d] (row stride ldv) -> vt [B, heads, d, Lpad], zero padded. 32x32 smem tiles.
+__global__ void __launch_bounds__(256)
+    transpose_heads_kernel(const __half *__restrict__ v, int L, int heads, int d, long long ldv, __half *__restrict__ vt, int Lpad) {
+    __shared__ __half tile[32][33];
+    const int bh = blockIdx.z, b = bh / heads, hd = bh % heads;
+    const int l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int l = l0 + j, dd = d0 + tx;
+        tile[j][tx] = (l < L && dd < d) ? v[((size_t)b * L + l) * ldv + hd * d + dd] : __float2half_rn(0.f);
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int dd = d0 + j, l = l0 + tx;
+        if (dd < d && l < Lpad) vt[(((size_t)b * heads + hd) * d + dd) * Lpad + l] = tile[tx][j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- timestep embedding
+// diffusers get_timestep_embedding(t, dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i) | sin(t f_i)]
+__global__ void timestep_embedding_kernel(const float *__restrict__ t, int B, int dim, __half *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim / 2;
+    if (i >= B * half) return;
+    const int b = i / half, k = i % half;
+    const float f = expf(-logf(10000.0f) * (float)k / (float)half);
+    const float a = t[b] * f;
+    out[b * dim + k] = __float2half_rn(cosf(a));
+    out[b * dim + half + k] = __float2half_rn(sinf(a));
+}
+
+// elementwise SiLU on fp16 (time-embedding MLP input of every ResnetBlock)
+__global__ void silu_kernel(const __half *__restrict__ x, long long n, __half *__restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __float2half_rn(silu_f(__half2float(x[i])));
+}
+
+static inline unsigned blocks_for(long long total, int threads = 256) {
+    long long b = (total + threads - 1) / threads;
+    const long long cap = (long long)kNumSM * 16;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace coma
+
+using namespace coma;
+
+extern "C" int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, int G, float eps,
+                                         const float *gamma, const float *beta, double *workspace, float *mean, float *rstd,
+                                         float *scale, float *shift, coma_stream_t stream) {
+    COMA_REQUIRE(x && workspace && scale && shift, "null pointer");
+    COMA_REQUIRE(B > 0 && HW > 0 && C > 0 && G > 0 && C % G == 0 && ldx >= C, "bad sizes");
+    COMA_REQUIRE(C <= 8192 && B <= 65535, "C or B too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * B * G, st);
+    // enough chunks to fill the machine, each at least 16 pixel rows
+    long long chunks = (4LL * kNumSM + B - 1) / B;
+    long long rows = (HW + chunks - 1) / chunks;
+    rows = rows < 16 ? 16 : rows;
+    chunks = (HW + rows - 1) / rows;
+    groupnorm_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, sizeof(float) * 2 * C, st>>>(
+        (const __half *)x, (int)HW, (int)C, ldx, G, (int)rows, workspace);
+    if (int e = check_launch("groupnorm_partial_kernel")) return e;
+    groupnorm_finalize_kernel<<<(unsigned)((B * C + 255) / 256), 256, 0, st>>>(workspace, (int)B, (int)C, G, HW * (C / G), eps, gamma,
+                                                                              beta, mean, rstd, scale, shift);
+    return check_launch("groupnorm_finalize_kernel");
+}
+
+extern "C" int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, const float *scale,
+                                   const float *shift, int act, void *y, int64_t ldy, coma_stream_t stream) {
+    COMA_REQUIRE(x && y && scale && shift, "null pointer");
+    COMA_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "C, ldx, ldy must be multiples of 8");
+    COMA_REQUIRE(((uintptr_t)x | (uintptr_t)y) % 16 == 0, "x / y must be 16-byte aligned");
+    affine_act_kernel<<<blocks_for(B * HW * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)x, B * HW, (int)HW, (int)C, ldx,
+                                                                                    scale, shift, act, (__half *)y, ldy);
+    return check_launch("affine_act_kernel");
+}
+
+extern "C" int coma_im2col3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, int stride, int pad,
+                                  int upsample, const float *scale, const float *shift, int act, void *out, int64_t ldo,
+                                  coma_stream_t stream) {
+    COMA_REQUIRE(x && out, "null pointer");
+    COMA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && ldx >= C, "bad sizes");
+    COMA_REQUIRE((stride == 1 || stride == 2) && (pad == 0 || pad == 1) && (upsample == 0 || upsample == 1), "bad conv geometry");
+    COMA_REQUIRE(ldo >= 9 * C && ldo % 8 == 0, "ldo must be >= 9*C and a multiple of 8");
+    COMA_REQUIRE(!scale == !shift, "scale and shift come together");
+    const int64_t Hin = upsample ? 2 * H : H, Win = upsample ? 2 * W : W;
+    // stride 1: same size; stride 2 with pad 1 (UNet Downsample2D): floor((H+2-3)/2)+1; stride 2, pad 0 after the VAE
+    // encoder's (0,1,0,1) padding: floor((H+1-3)/2)+1
+    const int64_t Ho = stride == 1 ? Hin : (pad ? (Hin + 2 - 3) / 2 + 1 : (Hin + 1 - 3) / 2 + 1);
+    const int64_t Wo = stride == 1 ? Win : (pad ? (Win + 2 - 3) / 2 + 1 : (Win + 1 - 3) / 2 + 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && (((uintptr_t)x | (uintptr_t)out) % 16 == 0);
+    const long long rows = B * Ho * Wo;
+    if (vec)
+        im2col3x3_kernel<true><<<blocks_for(rows * 9 * (C / 8)), 256, 0, st>>>((const __half *)x, (int)B, (int)H, (int)W, (int)C, ldx,
+                                                                            (int)Ho, (int)Wo, stride, pad, upsample, scale, shift, act,
+                                                                            (__half *)out, ldo);
+    else
+        im2col3x3_kernel<false><<<blocks_for(rows * 9 * C), 256, 0, st>>>((const __half *)x, (int)B, (int)H, (int)W, (int)C, ldx, (int)Ho,
+                                                                       (int)Wo, stride, pad, upsample, scale, shift, act,
+                                                                       (__half *)out, ldo);
+    if (int e = check_launch("im2col3x3_kernel")) return e;
+    if (ldo > 9 * C) {
+        zero_cols_kernel<<<blocks_for(rows * (ldo - 9 * C)), 256, 0, st>>>((__half *)out, rows, (int)(9 * C), ldo);
+        return check_launch("zero_cols_kernel");
+    }
+    return 0;
+}
+
+extern "C" int coma_layernorm_f16(const void *x, int64_t M, int64_t C, int64_t ldx, const float *gamma, const float *beta, float eps,
+                                  void *y, int64_t ldy, coma_stream_t stream) {
+    COMA_REQUIRE(x && y && gamma && beta, "null pointer");
+    COMA_REQUIRE(M > 0 && C > 0 && ldx >= C && ldy >= C, "bad sizes");
+    layernorm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const __half *)x, M, (int)C, ldx, gamma, beta, eps,
+                                                                              (__half *)y, ldy);
+    return check_launch("layernorm_kernel");
+}
+
+extern "C" int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, coma_stream_t stream) {
+    COMA_REQUIRE(s, "null pointer");
+    COMA_REQUIRE(R > 0 && L > 0 && ld >= L && R < (1LL << 31), "bad sizes");
+    softmax_rows_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>((__half *)s, (int)L, ld);
+    return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int coma_geglu_f16(const void *h, int64_t M, int64_t C, int64_t ldh, void *y, int64_t ldy, coma_stream_t stream) {
+    COMA_REQUIRE(h && y, "null pointer");
+    COMA_REQUIRE(M > 0 && C > 0 && C % 2 == 0 && ldh >= 2 * C && ldy >= C && ldh % 2 == 0 && ldy % 2 == 0, "bad sizes");
+    geglu_kernel<<<blocks_for(M * (C / 2)), 256, 0, (cudaStream_t)stream>>>((const __half *)h, M, (int)C, ldh, (__half *)y, ldy);
+    return check_launch("geglu_kernel");
+}
+
+extern "C" int coma_transpose_heads_f16(const void *v, int64_t B, int64_t L, int64_t heads, int64_t d, int64_t ldv, void *vt,
+                                        int64_t Lpad, coma_stream_t stream) {
+    COMA_REQUIRE(v && vt, "null pointer");
+    COMA_REQUIRE(B > 0 && L > 0 && heads > 0 && d > 0 && Lpad >= L && ldv >= heads * d && B * heads <= 65535, "bad sizes");
+    dim3 grid((unsigned)((Lpad + 31) / 32), (unsigned)((d + 31) / 32), (unsigned)(B * heads));
+    transpose_heads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half *)v, (int)L, (int)heads, (int)d, ldv, (__half *)vt,
+                                                                 (int)Lpad);
+    return check_launch("transpose_heads_kernel");
+}
+
+extern "C" int coma_timestep_embedding_f16(const float *t, int64_t B, int64_t dim, void *out, coma_stream_t stream) {
+    COMA_REQUIRE(t && out, "null pointer");
+    COMA_REQUIRE(B > 0 && dim > 0 && dim % 2 == 0, "bad sizes");
+    timestep_embedding_kernel<<<(unsigned)((B * dim / 2 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(t, (int)B, (int)dim, (__half *)out);
+    return check_launch("timestep_embedding_kernel");
+}
+
+extern "C" int coma_silu_f16(const void *x, int64_t n, void *y, coma_stream_t stream) {
+    COMA_REQUIRE(x && y && n > 0, "bad arguments");
+    silu_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>((const __half *)x, n, (__half *)y);
+    return check_launch("silu_kernel");
+}

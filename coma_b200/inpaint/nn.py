@@ -1,0 +1,198 @@
+"""Layer-level building blocks of the inpainting UNet / VAE on the B200 kernels (include/coma_b200.h, G1 + U*).
+
+Activations are NHWC fp16: an `Act` wraps a 2-D tensor [B*H*W, C] (row stride may exceed C) plus its (B, H, W).
+torch is used for allocation and views only; every arithmetic op is a coma_b200 kernel.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from .. import _lib
+from .._lib import GemmArgs, _ptr, _stream, call
+
+F16, F32 = torch.float16, torch.float32
+
+
+def rup(x, m=8):
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class Act:
+    t: torch.Tensor  # [B*H*W, C] fp16, stride(1) == 1
+    B: int
+    H: int
+    W: int
+
+    @property
+    def C(self):
+        return self.t.shape[1]
+
+    @property
+    def ld(self):
+        return self.t.stride(0)
+
+    @property
+    def M(self):
+        return self.t.shape[0]
+
+
+def new_act(B, H, W, C, device, dtype=F16):
+    """Fresh activation; channel counts that are not multiples of 8 get zero-padded rows (TMA needs 16-byte row strides)."""
+    ld = rup(C)
+    buf = torch.zeros((B * H * W, ld), dtype=dtype, device=device) if ld != C else torch.empty((B * H * W, C), dtype=dtype, device=device)
+    return Act(buf[:, :C], B, H, W)
+
+
+def gemm(a, w, bias=None, residual=None, act=0, out=None, out_dtype=F16, bias_rows=None, rows_per_bias=0, alpha=1.0, K=None):
+    """out[M,N] = act(alpha * a @ w[:, :K].T + bias + bias_rows[m // rows_per_bias] + residual). a [M,K] f16, w [N,>=K] f16."""
+    M = a.shape[0]
+    K = a.shape[1] if K is None else K
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    g = GemmArgs()
+    g.A, g.lda, g.W, g.ldw = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
+    g.M, g.N, g.K, g.nb1, g.nb2 = M, N, K, 1, 1
+    g.out_f16 = out.data_ptr() if out.dtype == F16 else None
+    g.out_f32 = out.data_ptr() if out.dtype == F32 else None
+    g.ldo = out.stride(0)
+    if residual is not None:
+        assert residual.dtype == F16 and residual.stride(0) == out.stride(0) and residual.shape == out.shape
+        g.residual = residual.data_ptr()
+    g.bias = _ptr(bias)
+    if bias_rows is not None:
+        assert bias_rows.dtype == F32 and bias_rows.stride(0) == N and rows_per_bias > 0
+        g.bias_rows, g.rows_per_bias = bias_rows.data_ptr(), rows_per_bias
+    g.alpha, g.act = alpha, act
+    with torch.cuda.device(a.device):
+        call("coma_gemm_f16_ex", ctypes.addressof(g), _stream())
+    return out
+
+
+def gemm_batched(A, lda, a_s1, a_s2, W, ldw, w_s1, w_s2, out, ldo, o_s1, o_s2, M, N, K, nb1, nb2, alpha=1.0):
+    g = GemmArgs()
+    g.A, g.lda, g.a_s1, g.a_s2 = A.data_ptr(), lda, a_s1, a_s2
+    g.W, g.ldw, g.w_s1, g.w_s2 = W.data_ptr(), ldw, w_s1, w_s2
+    g.out_f16 = out.data_ptr() if out.dtype == F16 else None
+    g.out_f32 = out.data_ptr() if out.dtype == F32 else None
+    g.ldo, g.o_s1, g.o_s2 = ldo, o_s1, o_s2
+    g.M, g.N, g.K, g.nb1, g.nb2, g.alpha, g.act = M, N, K, nb1, nb2, alpha, 0
+    with torch.cuda.device(A.device):
+        call("coma_gemm_f16_ex", ctypes.addressof(g), _stream())
+    return out
+
+
+def gn_affine(x: Act, gamma, beta, groups, eps):
+    """GroupNorm statistics folded with the affine: gn(x) = x*scale[b,c] + shift[b,c] (fp32 [B,C] each)."""
+    dev = x.t.device
+    ws = torch.empty(2 * x.B * groups, dtype=torch.float64, device=dev)
+    scale = torch.empty((x.B, x.C), dtype=F32, device=dev)
+    shift = torch.empty((x.B, x.C), dtype=F32, device=dev)
+    with torch.cuda.device(dev):
+        call("coma_groupnorm_affine_f16", x.t.data_ptr(), x.B, x.H * x.W, x.C, x.ld, groups, float(eps), _ptr(gamma), _ptr(beta),
+             ws.data_ptr(), None, None, scale.data_ptr(), shift.data_ptr(), _stream())
+    return scale, shift
+
+
+def affine_act(x: Act, scale, shift, act=0):
+    y = new_act(x.B, x.H, x.W, x.C, x.t.device)
+    with torch.cuda.device(x.t.device):
+        call("coma_affine_act_f16", x.t.data_ptr(), x.B, x.H * x.W, x.C, x.ld, scale.data_ptr(), shift.data_ptr(), act,
+             y.t.data_ptr(), y.ld, _stream())
+    return y
+
+
+def conv_out_hw(H, W, stride, pad, up):
+    Hin, Win = (2 * H, 2 * W) if up else (H, W)
+    if stride == 1:
+        return Hin, Win
+    return ((Hin + 2 - 3) // 2 + 1, (Win + 2 - 3) // 2 + 1) if pad else ((Hin + 1 - 3) // 2 + 1, (Win + 1 - 3) // 2 + 1)
+
+
+def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual=None, bias_rows=None, out_dtype=F16):
+    """3x3 convolution = im2col (GroupNorm affine + SiLU applied while gathering) + tensor-core GEMM.
+    w: [Cout, ld >= 9*Cin] f16 with K order (ky, kx, cin)."""
+    Ho, Wo = conv_out_hw(x.H, x.W, stride, pad, up)
+    K = 9 * x.C
+    cols = torch.empty((x.B * Ho * Wo, rup(K)), dtype=F16, device=x.t.device)
+    scale, shift = gn if gn is not None else (None, None)
+    with torch.cuda.device(x.t.device):
+        call("coma_im2col3x3_f16", x.t.data_ptr(), x.B, x.H, x.W, x.C, x.ld, stride, pad, int(up), _ptr(scale), _ptr(shift),
+             act if gn is not None else 0, cols.data_ptr(), cols.stride(0), _stream())
+    N = w.shape[0]
+    out = new_act(x.B, Ho, Wo, N, x.t.device, out_dtype)
+    gemm(cols, w, bias, None if residual is None else residual, 0, out.t, bias_rows=bias_rows, rows_per_bias=Ho * Wo, K=rup(K))
+    return out
+
+
+def layernorm(x2d, gamma, beta, eps=1e-5):
+    y = torch.empty((x2d.shape[0], x2d.shape[1]), dtype=F16, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        call("coma_layernorm_f16", x2d.data_ptr(), x2d.shape[0], x2d.shape[1], x2d.stride(0), gamma.data_ptr(), beta.data_ptr(),
+             float(eps), y.data_ptr(), y.stride(0), _stream())
+    return y
+
+
+def geglu(h):
+    C = h.shape[1] // 2
+    y = torch.empty((h.shape[0], C), dtype=F16, device=h.device)
+    with torch.cuda.device(h.device):
+        call("coma_geglu_f16", h.data_ptr(), h.shape[0], C, h.stride(0), y.data_ptr(), y.stride(0), _stream())
+    return y
+
+
+def silu(x):
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        call("coma_silu_f16", x.data_ptr(), x.numel(), y.data_ptr(), _stream())
+    return y
+
+
+def timestep_embedding(t, dim):
+    out = torch.empty((t.shape[0], dim), dtype=F16, device=t.device)
+    with torch.cuda.device(t.device):
+        call("coma_timestep_embedding_f16", t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream())
+    return out
+
+
+def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual):
+    """softmax(Q K^T / sqrt(d)) V followed by the output projection (+bias +residual). xq [B*S, C], xkv [B*L, Ckv] f16.
+    Scores and probabilities are materialised in fp16 ([B,heads,S,Lp]); the products run as batched tensor-core GEMMs."""
+    dev = xq.device
+    C = wq.shape[0]
+    d = C // heads
+    q, k, v = gemm(xq, wq), gemm(xkv, wk), gemm(xkv, wv)
+    Lp = rup(L)
+    scores = torch.empty((B, heads, S, Lp), dtype=F16, device=dev)
+    gemm_batched(q, C, d, S * C, k, C, d, L * C, scores, Lp, S * Lp, heads * S * Lp, S, L, d, heads, B, alpha=d ** -0.5)
+    vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)
+    with torch.cuda.device(dev):
+        call("coma_softmax_rows_f16", scores.data_ptr(), B * heads * S, L, Lp, _stream())
+        call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
+    o = torch.empty((B * S, C), dtype=F16, device=dev)
+    gemm_batched(scores, Lp, S * Lp, heads * S * Lp, vt, Lp, d * Lp, heads * d * Lp, o, C, d, S * C, S, d, Lp, heads, B)
+    return gemm(o, wo, bo, residual)
+
+
+# ------------------------------------------------------------------------------------------------ weight preparation
+def prep_conv3x3(w, device):
+    """[Cout, Cin, 3, 3] -> [Cout, rup(9*Cin)] f16 with K order (ky, kx, cin), zero padded."""
+    cout, cin = w.shape[:2]
+    k = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    out = torch.zeros((cout, rup(9 * cin)), dtype=F16, device=device)
+    out[:, : 9 * cin] = k.to(device=device, dtype=F16)
+    return out
+
+
+def prep_linear(w, device):
+    """[N, K] (or 1x1 conv [N, K, 1, 1]) -> [N, rup(K)] f16."""
+    w = w.reshape(w.shape[0], -1)
+    out = torch.zeros((w.shape[0], rup(w.shape[1])), dtype=F16, device=device)
+    out[:, : w.shape[1]] = w.to(device=device, dtype=F16)
+    return out
+
+
+def prep_vec(v, device):
+    return v.to(device=device, dtype=F32).contiguous()

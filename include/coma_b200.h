@@ -113,9 +113,57 @@ COMA_API int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, cons
  * A [M,K] fp16 row stride lda; W [N,K] fp16 row stride ldw (lda, ldw multiples of 8); bias [N] f32 or NULL;
  * residual [M,N] fp16 with row stride ldo or NULL; act: 0 identity, 1 SiLU; out_f16 / out_f32 [M,N] row stride ldo
  * (either may be NULL, not both). */
+/* General form: two batch dimensions (nb1 fastest) with independent element strides for A, W and the output, an
+ * accumulator scale `alpha` (applied before the bias terms) and a second, per-row-group bias
+ * `bias_rows[(m / rows_per_bias), n]` (the time-embedding term of a ResnetBlock). Batched attention products
+ * (Q K^T per head, P V per head) are expressed with the strides; `residual` shares the output's layout. */
+typedef struct coma_gemm_args {
+    const void *A; int64_t lda, a_s1, a_s2;
+    const void *W; int64_t ldw, w_s1, w_s2;
+    void *out_f16; float *out_f32; int64_t ldo, o_s1, o_s2;
+    const void *residual;
+    const float *bias;
+    const float *bias_rows; int64_t rows_per_bias;
+    int64_t M, N, K, nb1, nb2;
+    float alpha;
+    int act;
+} coma_gemm_args;
+COMA_API int coma_gemm_f16_ex(const coma_gemm_args *args, coma_stream_t stream);
+
 COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
                               coma_stream_t stream);
+
+/* ---- U*: the non-contraction layers of the UNet / VAE, NHWC fp16 activations ([B, H*W, C], row stride ld*) -------------
+ * (diffusers UNet2DConditionModel / AutoencoderKL layers reached from utils/adaptive_mask_inpainting.py:1001, :680, :1086) */
+
+/* GroupNorm statistics + folded affine: scale[b,c] = rstd*gamma[c], shift[b,c] = beta[c] - mean*rstd*gamma[c] so that
+ * gn(x) = x*scale + shift. workspace: 2*B*G doubles. mean / rstd ([B,G] f32) may be NULL. */
+COMA_API int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, int G, float eps,
+                                       const float *gamma, const float *beta, double *workspace, float *mean, float *rstd,
+                                       float *scale, float *shift, coma_stream_t stream);
+/* y = act(x*scale[b,c] + shift[b,c]); act 0 none / 1 SiLU. C, ldx, ldy multiples of 8. */
+COMA_API int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, const float *scale,
+                                 const float *shift, int act, void *y, int64_t ldy, coma_stream_t stream);
+/* im2col for 3x3 convolutions: out[(b,oy,ox), (ky*3+kx)*C + c] = act(x[b,iy,ix,c]*scale+shift) (0 outside the image),
+ * iy = oy*stride + ky - pad. stride 1|2; pad 1 (symmetric) | 0 (VAE encoder's bottom/right-only padding);
+ * upsample 1 folds a nearest x2 upsampling of x in front of the convolution. scale/shift NULL = raw x.
+ * out [B*Ho*Wo, ldo] f16, ldo >= 9C and a multiple of 8 (extra columns are zeroed). */
+COMA_API int coma_im2col3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, int stride, int pad,
+                                int upsample, const float *scale, const float *shift, int act, void *out, int64_t ldo,
+                                coma_stream_t stream);
+COMA_API int coma_layernorm_f16(const void *x, int64_t M, int64_t C, int64_t ldx, const float *gamma, const float *beta, float eps,
+                                void *y, int64_t ldy, coma_stream_t stream);
+/* In-place softmax over the first L columns of each of R rows (row stride ld); columns [L, ld) are set to 0. */
+COMA_API int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, coma_stream_t stream);
+/* GEGLU: y[m,c] = h[m,c] * gelu(h[m,C+c]) (exact erf GELU), h [M,2C] -> y [M,C]. */
+COMA_API int coma_geglu_f16(const void *h, int64_t M, int64_t C, int64_t ldh, void *y, int64_t ldy, coma_stream_t stream);
+/* v [B,L,heads*d] (row stride ldv) -> vt [B,heads,d,Lpad] zero padded: the K-major operand of P.V. */
+COMA_API int coma_transpose_heads_f16(const void *v, int64_t B, int64_t L, int64_t heads, int64_t d, int64_t ldv, void *vt,
+                                      int64_t Lpad, coma_stream_t stream);
+/* Sinusoidal timestep embedding [cos | sin] (flip_sin_to_cos, freq shift 0): t [B] f32 -> out [B,dim] f16. */
+COMA_API int coma_timestep_embedding_f16(const float *t, int64_t B, int64_t dim, void *out, coma_stream_t stream);
+COMA_API int coma_silu_f16(const void *x, int64_t n, void *y, coma_stream_t stream);
 
 #ifdef __cplusplus
 }

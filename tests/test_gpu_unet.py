@@ -1,0 +1,152 @@
+"""HP-A layer / block / model parity on the GPU against the torch restatement (oracle/sd_oracle.py, parity UNPINNED to
+diffusers — see its header). Both sides use the same fp16-rounded weights and inputs.
+
+Tolerances: single kernels with fp32 outputs hold 1e-4 of the output scale (accumulation order only). Blocks and whole
+models store fp16 between layers; the oracle rounds at the same places (`emulate_fp16=True`), and what remains are
+occasional one-ulp flips of those fp16 roundings (2^-11 relative each), so the bound there is 4e-3 of the output scale.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _nhwc(x):  # [B,C,H,W] fp32 -> Act
+    from coma_b200.inpaint import nn
+    B, C, H, W = x.shape
+    a = nn.new_act(B, H, W, C, x.device)
+    a.t.copy_(x.permute(0, 2, 3, 1).reshape(B * H * W, C).half())
+    return a
+
+
+def _nchw(t2d, B, H, W):
+    return t2d.float().reshape(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+def _close(mine, ref, tol):
+    err = (mine - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * scale, f"max err {err:.3e} vs scale {scale:.3e} ({err / scale:.2e} > {tol})"
+
+
+@pytest.mark.parametrize("C,Cout,H,stride,pad,up", [(64, 96, 16, 1, 1, False), (320, 320, 32, 1, 1, False), (64, 64, 16, 2, 1, False),
+                                                    (32, 32, 15, 2, 0, False), (64, 48, 8, 1, 1, True), (9, 32, 16, 1, 1, False),
+                                                    (4, 64, 8, 1, 1, False)])
+def test_conv3x3_with_groupnorm_prologue(dev, C, Cout, H, stride, pad, up):
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(C + H)
+    B = 2
+    x = torch.randn((B, C, H, H), device=dev, generator=g).half().float()
+    w = (torch.randn((Cout, C, 3, 3), device=dev, generator=g) * (9 * C) ** -0.5).half().float()
+    b = torch.randn(Cout, device=dev, generator=g)
+    use_gn = C % 8 == 0
+    xa = _nhwc(x)
+    gn = None
+    if use_gn:
+        gamma, beta = 1 + 0.1 * torch.randn(C, device=dev, generator=g), 0.1 * torch.randn(C, device=dev, generator=g)
+        gn = nn.gn_affine(xa, gamma, beta, 8, 1e-5)
+        xin = F.silu(F.group_norm(x, 8, gamma, beta, 1e-5)).half().float()   # operand is stored in fp16 by im2col
+    else:
+        xin = x
+    if up:
+        xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
+    if stride == 2 and pad == 0:
+        xin = F.pad(xin, (0, 1, 0, 1))
+    ref = F.conv2d(xin, w, b, stride=stride, padding=pad)
+    out = nn.conv3x3(xa, nn.prep_conv3x3(w, dev), b, stride=stride, pad=pad, up=up, gn=gn, act=1, out_dtype=torch.float32)
+    assert (out.H, out.W) == tuple(ref.shape[-2:])
+    # 1e-4 when the operand is exact; with the GN prologue a handful of fp16 roundings of the operand may flip (see header)
+    _close(_nchw(out.t, B, out.H, out.W), ref, 2e-3 if use_gn else 1e-4)
+
+
+def test_groupnorm_layernorm_geglu_softmax(dev):
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = (torch.randn((2, 64, 12, 12), device=dev, generator=g) * 2 + 0.5).half().float()
+    gamma, beta = torch.randn(64, device=dev, generator=g), torch.randn(64, device=dev, generator=g)
+    xa = _nhwc(x)
+    s, sh = nn.gn_affine(xa, gamma, beta, 8, 1e-6)
+    y = nn.affine_act(xa, s, sh, 0)
+    torch.testing.assert_close(_nchw(y.t, 2, 12, 12), F.group_norm(x, 8, gamma, beta, 1e-6), rtol=2e-3, atol=2e-3)
+    h = torch.randn((300, 320), device=dev, generator=g).half()
+    torch.testing.assert_close(nn.layernorm(h, gamma.repeat(5), beta.repeat(5)).float(),
+                               F.layer_norm(h.float(), (320,), gamma.repeat(5), beta.repeat(5), 1e-5), rtol=2e-3, atol=2e-3)
+    hh = torch.randn((100, 2 * 256), device=dev, generator=g).half()
+    a, gg = hh.float().chunk(2, dim=-1)
+    torch.testing.assert_close(nn.geglu(hh).float(), a * F.gelu(gg), rtol=2e-3, atol=2e-3)
+    sc = torch.randn((40, 80), device=dev, generator=g).half() * 3
+    ref = torch.softmax(sc[:, :77].float(), -1)
+    nn.call("coma_softmax_rows_f16", sc.data_ptr(), 40, 77, 80, nn._stream())
+    torch.testing.assert_close(sc[:, :77].float(), ref, rtol=2e-3, atol=1e-5)
+    assert (sc[:, 77:] == 0).all()
+    t = torch.tensor([981.0, 1.0, 500.0], device=dev)
+    from oracle import sd_oracle as so
+    torch.testing.assert_close(nn.timestep_embedding(t, 320).float(), so.timestep_embedding(t, 320), rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("S,L,C,heads", [(64, 64, 64, 2), (256, 77, 320, 8), (1024, 1024, 640, 8)])
+def test_attention(dev, S, L, C, heads):
+    from coma_b200.inpaint import nn
+    from oracle import sd_oracle as so
+    g = torch.Generator(device=dev).manual_seed(S)
+    B = 2
+    Ckv = C if L == S else 96
+    xq = torch.randn((B, S, C), device=dev, generator=g).half()
+    xkv = xq if L == S else torch.randn((B, L, Ckv), device=dev, generator=g).half()
+    sd = {}
+    for n, (o, i) in dict(to_q=(C, C), to_k=(C, Ckv), to_v=(C, Ckv)).items():
+        sd[f"a.{n}.weight"] = (torch.randn((o, i), device=dev, generator=g) * i ** -0.5).half().float()
+    sd["a.to_out.0.weight"] = (torch.randn((C, C), device=dev, generator=g) * C ** -0.5).half().float()
+    sd["a.to_out.0.bias"] = torch.randn(C, device=dev, generator=g)
+    ref = so.attention(xq.float(), xkv.float(), sd, "a", heads, so._R(True)) + xq.float()
+    w = {k: nn.prep_linear(v, dev) for k, v in sd.items() if k.endswith("weight")}
+    out = nn.attention(xq.reshape(B * S, C), xkv.reshape(B * L, Ckv), B, S, L, w["a.to_q.weight"], w["a.to_k.weight"],
+                       w["a.to_v.weight"], w["a.to_out.0.weight"], sd["a.to_out.0.bias"], heads, xq.reshape(B * S, C))
+    _close(out.float().reshape(B, S, C), ref, 4e-3)
+
+
+def test_unet_tiny_full_forward(dev):
+    from coma_b200.inpaint.nn import Act
+    from coma_b200.inpaint.unet import UNet
+    from oracle import sd_oracle as so
+    cfg = so.tiny_unet_cfg()
+    sd = so.round_weights_fp16(so.make_unet_state_dict(0, cfg))
+    B, hw = 2, 32
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((B, 9, hw, hw), generator=g).half().float()
+    ctx = torch.randn((B, 77, cfg["cross_attention_dim"]), generator=g).half().float()
+    t = torch.tensor([981.0, 441.0])
+    ref, rtaps = so.unet_forward({k: v.to(dev) for k, v in sd.items()}, x.to(dev), t.to(dev), ctx.to(dev), cfg, emulate_fp16=True, return_taps=True)
+    net = UNet(sd, cfg, dev)
+    taps = {}
+    out = net.forward(_nhwc(x.to(dev)), t.to(dev), ctx.to(dev).reshape(B * 77, -1).half().contiguous(), 77, taps)
+    for k in ("down", "mid", "up"):
+        _close(_nchw(taps[k].t, B, taps[k].H, taps[k].W), rtaps[k], 1e-2)
+    _close(_nchw(out, B, hw, hw), ref, 1e-2)
+
+
+def test_vae_tiny_decode_encode(dev):
+    from coma_b200.inpaint.vae import VAE
+    from oracle import sd_oracle as so
+    cfg = so.tiny_vae_cfg()
+    sd = so.round_weights_fp16(so.make_vae_state_dict(1, cfg))
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn((2, 4, 16, 16), generator=g).half().float().to(dev)
+    vae = VAE(sd, cfg, dev)
+    img = vae.decode(_nhwc(z))
+    ref = so.vae_decode(sdd, z, cfg, emulate_fp16=True)
+    _close(_nchw(img.t, 2, 128, 128), ref, 1e-2)
+    x = torch.tanh(torch.randn((2, 3, 64, 64), generator=g)).half().float().to(dev)
+    mean, logvar = vae.encode_moments(_nhwc(x))
+    rm, rl = so.vae_encode_moments(sdd, x, cfg, emulate_fp16=True)
+    _close(_nchw(mean, 2, 8, 8), rm, 1e-2)
+    _close(_nchw(logvar, 2, 8, 8), rl, 1e-2)
