@@ -35,6 +35,11 @@ SIGNATURES = {
     "coma_transpose_heads_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp],
     "coma_timestep_embedding_f16": [_vp, _i64, _i64, _vp, _vp],
     "coma_silu_f16": [_vp, _i64, _vp, _vp],
+    "coma_cfg_ddim_step_f32": [_vp, _i64, _i64, _i64, _f32, _vp, _f64, _f64, _vp, _vp, _vp],
+    "coma_assemble_unet_input_f16": [_vp, _vp, _vp, _i64, _vp, _i64, _vp],
+    "coma_adaptive_mask_u8": [_vp, _vp, _i64, _i64, _i64, _int, _f32, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "coma_image_to_u8": [_vp, _i64, _i64, _vp, _vp],
+    "coma_sample_latents_f32": [_vp, _vp, _vp, _i64, _f32, _vp, _vp],
 }
 
 

@@ -165,6 +165,31 @@ COMA_API int coma_transpose_heads_f16(const void *v, int64_t B, int64_t L, int64
 COMA_API int coma_timestep_embedding_f16(const float *t, int64_t B, int64_t dim, void *out, coma_stream_t stream);
 COMA_API int coma_silu_f16(const void *x, int64_t n, void *y, coma_stream_t stream);
 
+/* ---- L*: the denoising-loop glue of AdaptiveMaskInpaintPipeline.__call__ ---------------------------------------------- */
+
+/* Classifier-free guidance + DDIMScheduler.step (eta 0, epsilon prediction, no clipping):
+ * utils/adaptive_mask_inpainting.py:1009-1017. eps [2*half_rows, ld] f32 (uncond rows first, then text rows), C latent
+ * channels; x, x_prev, x0 [half_rows, C] f32; alpha_t / alpha_prev = alphas_cumprod at t and t - 1000/steps. */
+COMA_API int coma_cfg_ddim_step_f32(const float *eps, int64_t half_rows, int64_t ld, int64_t C, float guidance, const float *x,
+                                    double alpha_t, double alpha_prev, float *x_prev, float *x0, coma_stream_t stream);
+/* :990-996 — 9-channel UNet input (latents | mask | masked-image latents), duplicated for CFG: out [2*rows, ldo] f16. */
+COMA_API int coma_assemble_unet_input_f16(const float *latents, const float *mask64, const float *masked_latents, int64_t rows,
+                                          void *out, int64_t ldo, coma_stream_t stream);
+/* adapt_mask (:1123-1141) + prepare_mask_and_masked_image tensor branch (:166-206, :239) + nearest /8 (:690), B images:
+ *   area[b] = sum(seg[b]);  use_default = force_default || area[b] < area_thres  (area_thres = 512*512*human_detection_thres)
+ *   mask = use_default ? (default >= 128) : (dilate(seg, 3x3 ones, iterations) != 0 && default != 0)
+ *   masked_image = image * (1 - mask) (f16, row stride ldm);  mask_small[b, i, j] = mask[b, 8i, 8j]
+ * seg [B,H,W] u8, default_mask [H,W] u8 (0..255), image [B,H,W,3] f32; scratch 2*B*H*W bytes; area_ws B uint64. Bit-exact. */
+COMA_API int coma_adaptive_mask_u8(const uint8_t *seg, const uint8_t *default_mask, int64_t B, int64_t H, int64_t W, int dilate_iters,
+                                   float area_thres, int force_default, const float *image, uint8_t *scratch, uint8_t *mask_out,
+                                   void *masked_image, int64_t ldm, float *mask_small, int *used_default,
+                                   unsigned long long *area_ws, coma_stream_t stream);
+/* decode_to_npuint8_image (:1111-1115): (x/2+0.5).clamp(0,1)*255 truncated; img [rows, ld>=3] f32 -> out [rows,3] u8. */
+COMA_API int coma_image_to_u8(const float *img, int64_t rows, int64_t ld, uint8_t *out, coma_stream_t stream);
+/* DiagonalGaussianDistribution.sample * scaling_factor (:675-684): out = (mean + exp(0.5*logvar)*noise) * scaling. */
+COMA_API int coma_sample_latents_f32(const float *mean, const float *logvar, const float *noise, int64_t n, float scaling,
+                                     float *out, coma_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
