@@ -100,10 +100,20 @@ struct GemmEpilogue {
     int nb1;                 // extent of batch dim 1 (blockIdx.z = b2 * nb1 + b1)
 };
 
-template <int BN>
+// Implicit-GEMM 3x3 convolution (stride 1, pad 1) on an NHWC tensor: the A operand of K-slab (tap, channel block) is the
+// 128-pixel output tile shifted by (ky-1, kx-1), fetched by ONE 4-D TMA load whose out-of-image coordinates are
+// zero-filled by the hardware (= the convolution's zero padding). No im2col matrix is ever materialised.
+struct ConvGeom {
+    int H, W, B;         // image extent
+    int TW, TH, TB;      // tile = TB images x TH rows x TW columns = 128 output pixels
+    int tiles_x, tiles_y;
+    int cblocks;         // input channels / 64
+};
+
+template <int BN, bool CONV>
 __global__ void __launch_bounds__(G_THREADS, 1)
     gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                       const GemmEpilogue ep) {
+                       const GemmEpilogue ep, const ConvGeom cg) {
     const float *__restrict__ bias = ep.bias;
     const int act = ep.act, ldo = ep.ldo;
     const int b1 = blockIdx.z % ep.nb1, b2 = blockIdx.z / ep.nb1;
@@ -123,6 +133,18 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * BN;
     const int num_k = (K + G_BK - 1) / G_BK;
+    int cx0 = 0, cy0 = 0, cb0 = 0;  // CONV: origin of this CTA's pixel tile
+    if (CONV) {
+        if (cg.TB > 1) {
+            cb0 = blockIdx.y * cg.TB;
+        } else {
+            const int per_img = cg.tiles_x * cg.tiles_y;
+            cb0 = blockIdx.y / per_img;
+            const int rem = blockIdx.y % per_img;
+            cy0 = (rem / cg.tiles_x) * cg.TH;
+            cx0 = (rem % cg.tiles_x) * cg.TW;
+        }
+    }
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;  // power of two >= 32
 
     if (warp == 0 && lane == 0) {
@@ -152,7 +174,12 @@ __global__ void __launch_bounds__(G_THREADS, 1)
                 const uint32_t ph = (kb / G_STAGES) & 1;
                 mbar_wait(empty + s, ph ^ 1);
                 mbar_expect_tx(full + s, A_BYTES + B_BYTES);
-                tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
+                if (CONV) {
+                    const int tap = kb / cg.cblocks, cb = kb % cg.cblocks;
+                    tma_load_4d(sA + s * A_BYTES, &tmA, full + s, cb * G_BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb0);
+                } else {
+                    tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
+                }
                 tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0, b1, b2);
             }
         }
@@ -178,7 +205,12 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;
+        int row = m0 + q * 32 + lane;
+        if (CONV) {  // TMEM lane -> pixel of the tile (x fastest, then y, then image)
+            const int r = q * 32 + lane;
+            const int tx = r % cg.TW, ty = (r / cg.TW) % cg.TH, tb = r / (cg.TW * cg.TH);
+            row = (cb0 + tb < cg.B) ? ((cb0 + tb) * cg.H + cy0 + ty) * cg.W + cx0 + tx : M;
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -288,23 +320,23 @@ static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols,
     return 0;
 }
 
-template <int BN>
+template <int BN, bool CONV>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const GemmEpilogue &ep, int nbatch,
-                       cudaStream_t st) {
+                       cudaStream_t st, const ConvGeom &cg = ConvGeom{}, int m_tiles = 0) {
     constexpr size_t smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 256 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
             return (int)e;
         }
         attr[dev] = true;
     }
-    dim3 grid((N + BN - 1) / BN, (M + G_BM - 1) / G_BM, nbatch);
-    gemm_f16_tn_kernel<BN><<<grid, G_THREADS, smem, st>>>(ta, tb, M, N, K, ep);
+    dim3 grid((N + BN - 1) / BN, CONV ? m_tiles : (M + G_BM - 1) / G_BM, nbatch);
+    gemm_f16_tn_kernel<BN, CONV><<<grid, G_THREADS, smem, st>>>(ta, tb, M, N, K, ep, cg);
     return check_launch("gemm_f16_tn_kernel");
 }
 
@@ -344,8 +376,64 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     ep.act = g->act;
     ep.nb1 = (int)nb1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64) return launch_gemm<64>(ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st);
-    return launch_gemm<128>(ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st);
+    if (bn == 64) return launch_gemm<64, false>(ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st);
+    return launch_gemm<128, false>(ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st);
+}
+
+namespace coma {
+// NHWC tensor map {C, W, H, B} with box {64, TW, TH, TB}
+static int make_conv_map(CUtensorMap *m, const void *ptr, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, int TW, int TH,
+                         int TB) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return COMA_E_NODEVICE;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)(W * ldx) * 2, (cuuint64_t)(H * W * ldx) * 2};
+    cuuint32_t box[4] = {(cuuint32_t)G_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (conv) failed with CUresult %d", (int)r);
+        return COMA_E_BADARG;
+    }
+    return 0;
+}
+}  // namespace coma
+
+extern "C" int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const void *Wt, int64_t ldw,
+                                int64_t N, const float *bias, const float *bias_rows, const void *residual, int act, void *out_f16,
+                                float *out_f32, int64_t ldo, coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(x && Wt && (out_f16 || out_f32), "null pointer");
+    COMA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && N > 0, "bad sizes");
+    COMA_REQUIRE(C % 64 == 0 && ldx % 8 == 0 && ldx >= C, "implicit-GEMM conv needs C % 64 == 0 (use im2col otherwise)");
+    COMA_REQUIRE(ldw >= 9 * C && ldw % 8 == 0 && ldo >= N, "bad leading dimensions");
+    COMA_REQUIRE(((uintptr_t)x | (uintptr_t)Wt) % 16 == 0, "x and W must be 16-byte aligned");
+    COMA_REQUIRE(act == 0 || act == 1, "act must be 0 or 1");
+    // tile geometry: 128 output pixels = TB images x TH rows x TW columns
+    int TW = (int)(W < 128 ? W : 128), TH = (int)(128 / TW < H ? 128 / TW : H), TB = 128 / (TW * TH);
+    COMA_REQUIRE(TW * TH * TB == 128 && W % TW == 0 && H % TH == 0, "image extent does not tile into 128-pixel blocks (use im2col)");
+    ConvGeom cg;
+    cg.H = (int)H; cg.W = (int)W; cg.B = (int)B; cg.TW = TW; cg.TH = TH; cg.TB = TB;
+    cg.tiles_x = (int)(W / TW); cg.tiles_y = (int)(H / TH); cg.cblocks = (int)(C / 64);
+    const int64_t m_tiles = TB > 1 ? (B + TB - 1) / TB : B * cg.tiles_x * cg.tiles_y;
+    COMA_REQUIRE(m_tiles <= 65535, "too many output tiles for one launch");
+    const int64_t M = B * H * W, K = 9 * C;
+    const int bn = (N <= 64) ? 64 : 128;
+    CUtensorMap ta, tb;
+    if (int e = make_conv_map(&ta, x, B, H, W, C, ldx, TW, TH, TB)) return e;
+    if (int e = make_map(&tb, Wt, N, K, ldw, bn, 1, 0, 1, 0)) return e;
+    GemmEpilogue ep;
+    ep.bias = bias; ep.bias_rows = bias_rows; ep.rows_per_bias = (int)(H * W); ep.residual = (const __half *)residual;
+    ep.out16 = (__half *)out_f16; ep.out32 = out_f32; ep.ldo = (int)ldo; ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = act;
+    ep.nb1 = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 64) return launch_gemm<64, true>(ta, tb, (int)M, (int)N, (int)K, ep, 1, st, cg, (int)m_tiles);
+    return launch_gemm<128, true>(ta, tb, (int)M, (int)N, (int)K, ep, 1, st, cg, (int)m_tiles);
 }
 
 extern "C" int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,

@@ -102,6 +102,37 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// nearest x2 upsampling fused with the affine + activation: y[b, Y, X, c] = act(x[b, Y/2, X/2, c]*scale + shift)
+__global__ void __launch_bounds__(256)
+    upsample2x_affine_act_kernel(const __half *__restrict__ x, int B, int H, int W, int C, long long ldx,
+                                 const float *__restrict__ scale, const float *__restrict__ shift, int act, __half *__restrict__ y,
+                                 long long ldy) {
+    const int c8n = C / 8;
+    const long long total = (long long)B * 4 * H * W * c8n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c8n) * 8;
+        long long r = i / c8n;
+        const int X = (int)(r % (2 * W)), Y = (int)((r / (2 * W)) % (2 * H)), b = (int)(r / ((long long)4 * H * W));
+        uint4 o = *reinterpret_cast<const uint4 *>(x + ((size_t)(b * H + (Y >> 1)) * W + (X >> 1)) * ldx + c);
+        if (scale) {
+            __half2 *h = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float2 v = __half22float2(h[t]);
+                const int cc = b * C + c + 2 * t;
+                v.x = fmaf(v.x, scale[cc], shift[cc]);
+                v.y = fmaf(v.y, scale[cc + 1], shift[cc + 1]);
+                if (act == 1) {
+                    v.x = silu_f(v.x);
+                    v.y = silu_f(v.y);
+                }
+                h[t] = __floats2half2_rn(v.x, v.y);
+            }
+        }
+        *reinterpret_cast<uint4 *>(y + r * ldy + c) = o;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- im2col 3x3
 // out[(b,oy,ox), tap*C + c] = act(x[b, iy, ix, c]*scale + shift), 0 outside the (upsampled) image.
 // iy = oy*stride + ky - pad, ix likewise; with `up` the source pixel is (iy>>1, ix>>1) of the stored tensor.
@@ -189,7 +220,101 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------- row softmax (in place)
-// one warp per row for L <= 1024 columns held in registers? General: block (256 threads) per row, three passes.
+// Rows are read ONCE into registers, reduced with shuffles, and written once.
+//   L <= 1024 : one warp per row, up to 32 values per lane (cross-attention rows, L = 77, and the 16x16 / 32x32 levels)
+//   L <= 4096 and 16-byte aligned rows: one 256-thread CTA per row, 16 values per thread as two 16-byte loads
+//   otherwise : three-pass fallback
+__global__ void __launch_bounds__(256) softmax_rows_warp_kernel(__half *__restrict__ s, long long R, int L, long long ld) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= R) return;
+    __half *row = s + r * ld;
+    float v[32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int c = lane + 32 * j;
+        v[j] = (c < L) ? __half2float(row[c]) : -INFINITY;
+        m = fmaxf(m, v[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        v[j] = (lane + 32 * j < L) ? __expf(v[j] - m) : 0.f;
+        sum += v[j];
+    }
+    const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int c = lane + 32 * j;
+        if (c < ld && c < 1024) row[c] = __float2half_rn(v[j] * inv);  // columns [L, ld) receive 0
+    }
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_block_kernel(__half *__restrict__ s, int L, long long ld) {
+    __half *row = s + (long long)blockIdx.x * ld;
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float v[16];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = (threadIdx.x + 256 * j) * 8;
+        uint4 raw = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);  // -inf halves
+        if (c < L) raw = *reinterpret_cast<const uint4 *>(row + c);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(h[t]);
+            v[8 * j + 2 * t] = (c + 2 * t < L) ? f.x : -INFINITY;
+            v[8 * j + 2 * t + 1] = (c + 2 * t + 1 < L) ? f.y : -INFINITY;
+            m = fmaxf(m, fmaxf(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = red[0];
+        for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w]);
+        bc = t;
+    }
+    __syncthreads();
+    m = bc;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        v[j] = __expf(v[j] - m);  // exp(-inf) = 0 for the masked tail
+        sum += v[j];
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        bc = 1.0f / t;
+    }
+    __syncthreads();
+    const float inv = bc;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = (threadIdx.x + 256 * j) * 8;
+        if (c < ld) {
+            uint4 o;
+            __half2 *h = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[8 * j + 2 * t] * inv, v[8 * j + 2 * t + 1] * inv);
+            *reinterpret_cast<uint4 *>(row + c) = o;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__half *__restrict__ s, int L, long long ld) {
     __half *row = s + (long long)blockIdx.x * ld;
     __shared__ float red[8];
@@ -320,6 +445,17 @@ extern "C" int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t
     return check_launch("affine_act_kernel");
 }
 
+extern "C" int coma_upsample2x_affine_act_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx,
+                                              const float *scale, const float *shift, int act, void *y, int64_t ldy,
+                                              coma_stream_t stream) {
+    COMA_REQUIRE(x && y, "null pointer");
+    COMA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "C, ldx, ldy must be multiples of 8");
+    COMA_REQUIRE(((uintptr_t)x | (uintptr_t)y) % 16 == 0 && !scale == !shift, "bad arguments");
+    upsample2x_affine_act_kernel<<<blocks_for(B * 4 * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+        (const __half *)x, (int)B, (int)H, (int)W, (int)C, ldx, scale, shift, act, (__half *)y, ldy);
+    return check_launch("upsample2x_affine_act_kernel");
+}
+
 extern "C" int coma_im2col3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, int stride, int pad,
                                   int upsample, const float *scale, const float *shift, int act, void *out, int64_t ldo,
                                   coma_stream_t stream) {
@@ -364,7 +500,16 @@ extern "C" int coma_layernorm_f16(const void *x, int64_t M, int64_t C, int64_t l
 extern "C" int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, coma_stream_t stream) {
     COMA_REQUIRE(s, "null pointer");
     COMA_REQUIRE(R > 0 && L > 0 && ld >= L && R < (1LL << 31), "bad sizes");
-    softmax_rows_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>((__half *)s, (int)L, ld);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ld <= 1024) {
+        softmax_rows_warp_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>((__half *)s, R, (int)L, ld);
+        return check_launch("softmax_rows_warp_kernel");
+    }
+    if (ld <= 4096 && ld % 8 == 0 && (uintptr_t)s % 16 == 0) {
+        softmax_rows_block_kernel<<<(unsigned)R, 256, 0, st>>>((__half *)s, (int)L, ld);
+        return check_launch("softmax_rows_block_kernel");
+    }
+    softmax_rows_kernel<<<(unsigned)R, 256, 0, st>>>((__half *)s, (int)L, ld);
     return check_launch("softmax_rows_kernel");
 }
 

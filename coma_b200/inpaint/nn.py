@@ -111,10 +111,46 @@ def conv_out_hw(H, W, stride, pad, up):
     return ((Hin + 2 - 3) // 2 + 1, (Win + 2 - 3) // 2 + 1) if pad else ((Hin + 1 - 3) // 2 + 1, (Win + 1 - 3) // 2 + 1)
 
 
+def _tiles_128(H, W):
+    tw = min(W, 128)
+    th = min(128 // tw, H)
+    return tw * th * (128 // (tw * th)) == 128 and W % tw == 0 and H % th == 0
+
+
+def upsample2x_affine_act(x: Act, scale, shift, act):
+    y = new_act(x.B, 2 * x.H, 2 * x.W, x.C, x.t.device)
+    with torch.cuda.device(x.t.device):
+        call("coma_upsample2x_affine_act_f16", x.t.data_ptr(), x.B, x.H, x.W, x.C, x.ld, _ptr(scale), _ptr(shift), act,
+             y.t.data_ptr(), y.ld, _stream())
+    return y
+
+
+IMPLICIT_CONV = True
+
+
 def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual=None, bias_rows=None, out_dtype=F16):
-    """3x3 convolution = im2col (GroupNorm affine + SiLU applied while gathering) + tensor-core GEMM.
-    w: [Cout, ld >= 9*Cin] f16 with K order (ky, kx, cin)."""
+    """3x3 convolution on the tensor cores. w: [Cout, ld >= 9*Cin] f16 with K order (ky, kx, cin).
+    stride 1, Cin % 64 == 0: implicit GEMM (shifted TMA tiles, no im2col matrix) on the pre-activated tensor;
+    otherwise (stride 2, tiny Cin): im2col with the GroupNorm affine + SiLU applied while gathering, then GEMM."""
     Ho, Wo = conv_out_hw(x.H, x.W, stride, pad, up)
+    if IMPLICIT_CONV and stride == 1 and pad == 1 and x.C % 64 == 0 and _tiles_128(Ho, Wo):
+        scale, shift = gn if gn is not None else (None, None)
+        if up:
+            xa = upsample2x_affine_act(x, scale, shift, act if gn is not None else 0)
+        elif gn is not None:
+            xa = affine_act(x, scale, shift, act)
+        else:
+            xa = x
+        N = w.shape[0]
+        out = new_act(x.B, Ho, Wo, N, x.t.device, out_dtype)
+        if residual is not None:
+            assert residual.dtype == F16 and residual.stride(0) == out.t.stride(0)
+        with torch.cuda.device(x.t.device):
+            call("coma_conv3x3_f16", xa.t.data_ptr(), xa.B, xa.H, xa.W, xa.C, xa.ld, w.data_ptr(), w.stride(0), N, _ptr(bias),
+                 _ptr(bias_rows), None if residual is None else residual.data_ptr(), 0,
+                 out.t.data_ptr() if out_dtype == F16 else None, out.t.data_ptr() if out_dtype == F32 else None, out.t.stride(0),
+                 _stream())
+        return out
     K = 9 * x.C
     cols = torch.empty((x.B * Ho * Wo, rup(K)), dtype=F16, device=x.t.device)
     scale, shift = gn if gn is not None else (None, None)
@@ -196,3 +232,21 @@ def prep_linear(w, device):
 
 def prep_vec(v, device):
     return v.to(device=device, dtype=F32).contiguous()
+
+
+class Graphed:
+    """Captures `fn(*static_args)` into a CUDA graph (after an eager warm-up that also sizes the allocator pool and sets
+    kernel attributes) and replays it: the ~650 launches of a UNet forward then cost one host call instead of being bound by
+    per-launch host overhead. Inputs are updated IN PLACE in `static_args`; the output tensors are reused across replays."""
+
+    def __init__(self, fn, *static_args):
+        self.args = static_args
+        fn(*static_args)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(*static_args)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out

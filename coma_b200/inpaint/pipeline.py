@@ -89,8 +89,10 @@ class PipelineOutput:
 class AdaptiveMaskInpaintPipeline:
     vae_scale_factor = 8
 
-    def __init__(self, unet, vae, text_encoder=None, scheduler=None):
+    def __init__(self, unet, vae, text_encoder=None, scheduler=None, use_cuda_graphs=True):
         self.unet, self.vae, self.text_encoder = unet, vae, text_encoder
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs = {}
         self.scheduler = scheduler or DDIMSchedule()
         self.dev = unet.dev
         self.adaptive_mask_model = None
@@ -119,8 +121,34 @@ class AdaptiveMaskInpaintPipeline:
         outs = [torch.randn((1,) + shape, generator=g, device=self.dev, dtype=F16) for g in generators]
         return torch.cat(outs, 0).float().permute(0, 2, 3, 1).reshape(-1, shape[0]).contiguous()     # -> [B*h*w, C] fp32
 
+    def _graphed(self, key, fn, *static_args):
+        """Run fn(*static_args) through a cached CUDA graph (captured on first use for this key)."""
+        if not self.use_cuda_graphs:
+            return fn(*static_args)
+        if key not in self._graphs:
+            self._graphs[key] = nn.Graphed(fn, *static_args)
+        return self._graphs[key]()
+
+    def _static(self, key, make):
+        buf = self._graphs.get(("buf",) + key)
+        if buf is None:
+            buf = self._graphs[("buf",) + key] = make()
+        return buf
+
+    def _encode_moments(self, img_act: Act):
+        key = ("enc", img_act.B, img_act.H, img_act.W)
+        static = self._static(key, lambda: nn.new_act(img_act.B, img_act.H, img_act.W, 3, self.dev))
+        static.t.copy_(img_act.t)
+        return self._graphed(key, self.vae.encode_moments, static)
+
+    def _decode(self, z: Act):
+        key = ("dec", z.B, z.H, z.W)
+        static = self._static(key, lambda: nn.new_act(z.B, z.H, z.W, z.C, self.dev))
+        static.t.copy_(z.t)
+        return self._graphed(key, lambda a: self.vae.decode(a, out_dtype=F32), static)
+
     def _encode_sample(self, img_act: Act, generators):
-        mean, logvar = self.vae.encode_moments(img_act)
+        mean, logvar = self._encode_moments(img_act)
         h, w = img_act.H // 8, img_act.W // 8
         noise = self._randn((mean.shape[1], h, w), generators)
         out = torch.empty_like(mean)
@@ -147,7 +175,7 @@ class AdaptiveMaskInpaintPipeline:
         """decode_to_npuint8_image (:1111-1115) for the whole batch -> uint8 cuda tensor [B,8h,8w,3]."""
         z = nn.new_act(B, h, w, latents.shape[1], self.dev)
         z.t.copy_(latents / self.vae.cfg["scaling_factor"])
-        img = self.vae.decode(z, out_dtype=F32)
+        img = self._decode(z)
         out = torch.empty((B, img.H, img.W, 3), dtype=torch.uint8, device=self.dev)
         with torch.cuda.device(self.dev):
             call("coma_image_to_u8", img.t.data_ptr(), img.M, img.ld, out.data_ptr(), _stream())
@@ -209,15 +237,19 @@ class AdaptiveMaskInpaintPipeline:
         masked_latents = self._encode_sample(masked_img, gens)                  # :953 prepare_mask_latents
 
         rows = B * h * w
-        x_in = nn.new_act(2 * B, h, w, 9, dev)
+        ukey = ("unet", B, h, w, L)
+        x_in = self._static(ukey + ("x",), lambda: nn.new_act(2 * B, h, w, 9, dev))
+        tt = self._static(ukey + ("t",), lambda: torch.zeros((2 * B,), dtype=F32, device=dev))
+        ctx_static = self._static(ukey + ("ctx",), lambda: torch.empty_like(ctx))
+        ctx_static.copy_(ctx)
         trace = [] if return_trace else None
         settings = self.adaptive_mask_settings
         for i, t in enumerate(timesteps):
             with torch.cuda.device(dev):
                 call("coma_assemble_unet_input_f16", latents.data_ptr(), mask64.data_ptr(), masked_latents.data_ptr(), rows,
                      x_in.t.data_ptr(), x_in.ld, _stream())
-            tt = torch.full((2 * B,), float(t), dtype=F32, device=dev)
-            eps = self.unet.forward(x_in, tt, ctx, L)                            # fp32 [2*rows, 4 (ld 8)]
+            tt.fill_(float(t))
+            eps = self._graphed(ukey, lambda a, b, c: self.unet.forward(a, b, c, L), x_in, tt, ctx_static)  # fp32 [2*rows, 4 (ld 8)]
             a_t, a_prev = self.scheduler.alphas(t, ratio)
             new_latents, x0 = torch.empty_like(latents), torch.empty_like(latents)
             with torch.cuda.device(dev):
@@ -255,7 +287,7 @@ class AdaptiveMaskInpaintPipeline:
         """:1086-1097: final decode + VaeImageProcessor.postprocess (denormalise, clamp, round to uint8 like PIL does)."""
         z = nn.new_act(B, h, w, latents.shape[1], self.dev)
         z.t.copy_(latents / self.vae.cfg["scaling_factor"])
-        img = self.vae.decode(z, out_dtype=F32)
+        img = self._decode(z)
         x = (img.t[:, :3].reshape(B, img.H, img.W, 3) * 0.5 + 0.5).clamp(0, 1)
         if output_type == "pt":
             return x

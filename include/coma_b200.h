@@ -130,6 +130,14 @@ typedef struct coma_gemm_args {
 } coma_gemm_args;
 COMA_API int coma_gemm_f16_ex(const coma_gemm_args *args, coma_stream_t stream);
 
+/* 3x3 convolution, stride 1, zero padding 1, as an IMPLICIT GEMM: the A operand of every (tap, 64-channel) K-slab is a
+ * shifted 128-pixel tile fetched by one 4-D TMA load (out-of-image rows/columns are hardware zero-filled), so no im2col
+ * matrix exists. x [B,H,W,C] NHWC f16 (row stride ldx, C % 64 == 0, H and W must tile into 128-pixel blocks);
+ * W [N, ldw >= 9C] f16 with K order (ky, kx, c); epilogue as in coma_gemm_f16_ex with rows_per_bias = H*W. */
+COMA_API int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const void *Wt, int64_t ldw,
+                              int64_t N, const float *bias, const float *bias_rows, const void *residual, int act, void *out_f16,
+                              float *out_f32, int64_t ldo, coma_stream_t stream);
+
 COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
                               coma_stream_t stream);
@@ -145,6 +153,10 @@ COMA_API int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, int
 /* y = act(x*scale[b,c] + shift[b,c]); act 0 none / 1 SiLU. C, ldx, ldy multiples of 8. */
 COMA_API int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, const float *scale,
                                  const float *shift, int act, void *y, int64_t ldy, coma_stream_t stream);
+/* Nearest x2 upsampling fused with the affine + activation (input of the Upsample2D convolutions): y [B,2H,2W,C]. */
+COMA_API int coma_upsample2x_affine_act_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx,
+                                            const float *scale, const float *shift, int act, void *y, int64_t ldy,
+                                            coma_stream_t stream);
 /* im2col for 3x3 convolutions: out[(b,oy,ox), (ky*3+kx)*C + c] = act(x[b,iy,ix,c]*scale+shift) (0 outside the image),
  * iy = oy*stride + ky - pad. stride 1|2; pad 1 (symmetric) | 0 (VAE encoder's bottom/right-only padding);
  * upsample 1 folds a nearest x2 upsampling of x in front of the convolution. scale/shift NULL = raw x.

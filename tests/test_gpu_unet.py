@@ -37,13 +37,16 @@ def _close(mine, ref, tol):
     assert err <= tol * scale, f"max err {err:.3e} vs scale {scale:.3e} ({err / scale:.2e} > {tol})"
 
 
-@pytest.mark.parametrize("C,Cout,H,stride,pad,up", [(64, 96, 16, 1, 1, False), (320, 320, 32, 1, 1, False), (64, 64, 16, 2, 1, False),
-                                                    (32, 32, 15, 2, 0, False), (64, 48, 8, 1, 1, True), (9, 32, 16, 1, 1, False),
-                                                    (4, 64, 8, 1, 1, False)])
-def test_conv3x3_with_groupnorm_prologue(dev, C, Cout, H, stride, pad, up):
+@pytest.mark.parametrize("C,Cout,H,stride,pad,up,B", [
+    (64, 96, 16, 1, 1, False, 2), (320, 320, 32, 1, 1, False, 2), (64, 64, 16, 2, 1, False, 2), (32, 32, 15, 2, 0, False, 2),
+    (64, 48, 8, 1, 1, True, 2), (9, 32, 16, 1, 1, False, 2), (4, 64, 8, 1, 1, False, 2),
+    (128, 72, 8, 1, 1, False, 3),      # implicit conv, 8x8 images: two images per 128-pixel tile, odd batch
+    (64, 8, 128, 1, 1, False, 1),      # implicit conv, one 128-pixel row segment per tile, N < 64
+    (128, 128, 64, 1, 1, True, 1),     # upsample folded in front of an implicit conv (128x128 output)
+    (192, 64, 24, 1, 1, False, 2)])    # 24x24 does not tile into 128 pixels -> im2col fallback
+def test_conv3x3_with_groupnorm_prologue(dev, C, Cout, H, stride, pad, up, B):
     from coma_b200.inpaint import nn
     g = torch.Generator(device=dev).manual_seed(C + H)
-    B = 2
     x = torch.randn((B, C, H, H), device=dev, generator=g).half().float()
     w = (torch.randn((Cout, C, 3, 3), device=dev, generator=g) * (9 * C) ** -0.5).half().float()
     b = torch.randn(Cout, device=dev, generator=g)
