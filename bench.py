@@ -128,6 +128,68 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def hoi_leg(args, dev, rank, world, barrier):
+    """BASELINE.json configs[1]/[2]: adaptive-mask SD inpainting, 512x512, 50 DDIM steps (strength 0.98 -> 49 UNet x2
+    evaluations, CFG 11, 21 adapt calls), `--hoi-batch` work items per rank sharing (render, mask, prompt); one rank = one
+    viewpoint shard (no collective: outputs are images). Seeded random weights with the real architecture (no checkpoints
+    offline), synthetic render, rectangular default mask, deterministic stub segmenter. images/s = finished 512x512
+    outputs per second, whole job (all ranks), wall clock around the public pipeline call (host image in, host images out)."""
+    import torch
+    import torch.distributed as dist
+    from coma_b200 import _lib
+    from coma_b200.inpaint.pipeline import AdaptiveMaskInpaintPipeline, default_adaptive_mask_settings
+    from coma_b200.inpaint.segmenter import LuminanceSegmenter
+    from coma_b200.inpaint.unet import UNet
+    from coma_b200.inpaint.vae import VAE
+    from oracle import sd_oracle as so   # weight generator only (seeded random state dicts with diffusers key names)
+    B = args.hoi_batch
+    torch.cuda.empty_cache()
+    pipe = AdaptiveMaskInpaintPipeline(UNet(so.make_unet_state_dict(0), device=dev), VAE(so.make_vae_state_dict(1), device=dev))
+    pipe.register_adaptive_mask_model(LuminanceSegmenter(128))
+    pipe.register_adaptive_mask_settings(default_adaptive_mask_settings(50))
+    rng = np.random.default_rng(100 + rank)
+    image = rng.integers(0, 256, (512, 512, 3), dtype=np.uint8)
+    default = np.zeros((512, 512), np.uint8)
+    default[64:448, 128:384] = 255
+    pe = torch.randn((77, 768), generator=torch.Generator().manual_seed(1)) * 0.02
+    ne = torch.zeros((77, 768))
+
+    def run():
+        gens = [torch.Generator(device=dev).manual_seed(i) for i in range(B)]
+        return pipe(image=image, default_mask_image=default, prompt_embeds=pe, negative_prompt_embeds=ne, guidance_scale=11.0,
+                    strength=0.98, num_inference_steps=50, generator=gens, enforce_full_mask_ratio=0.0, human_detection_thres=0.015,
+                    batch_size=B, output_type="np")
+    run()                                   # warm-up: captures the CUDA graphs
+    times = []
+    l0 = _lib.launch_count()
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        out = run()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    launches = (_lib.launch_count() - l0) // 2
+    t = torch.tensor([min(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"metric": "HOI images/s (512x512, 50-step DDIM, adaptive mask)", "value": world * B / t.item(), "unit": "images/s",
+           "s_per_batch": t.item(), "batch_per_gpu": B, "n_gpus": world, "data": "synthetic render + random weights (SD-1.5 inpainting UNet, SD VAE architectures)",
+           "flop_per_image_T": 159.7, "tensor_tflops_achieved": world * B * 159.7 / t.item(),
+           "d2h_bytes": int(out.images.nbytes) if hasattr(out.images, "nbytes") else None,
+           "launches_outside_graphs_per_batch": int(launches)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle.inpaint_loop_oracle import time_reference_loop
+            s = time_reference_loop(dev)
+            res["reference_torch_eager_fp16"] = {"images_per_s": 1.0 / s, "s_per_image": s,
+                                                 "what": "reference-shaped loop (batch 1, decode every step, unfused attention, cv2 on host) in torch eager fp16 on the same GPU"}
+        except Exception as ex:  # the baseline is informative only
+            res["reference_torch_eager_fp16"] = {"error": repr(ex)[:200]}
+    del pipe
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -136,6 +198,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples-per-rank", type=int, default=S_PER_RANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hoi", action="store_true", help="skip the HOI images/s leg (adaptive-mask inpainting loop)")
+    ap.add_argument("--hoi-batch", type=int, default=4)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -261,6 +325,10 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * S * H * O / (e2e_t.item() * 1e-3)
 
+    hoi = None
+    if not args.no_hoi:
+        hoi = hoi_leg(args, dev, rank, world, barrier)
+
     if rank == 0:
         ck = clocks.summary()
         k3_bytes = 24.0 * S * (H + O) + 16.0 * H * O * N
@@ -292,6 +360,8 @@ def main():
                                    "peak": peak, "unit": "GB/s", "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak, "traffic": None,
                                    "ms": k2_ms, "peak_source": peak_src},
         }
+        if hoi is not None:
+            line["hoi"] = hoi
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate()
         print(json.dumps(line), flush=True)

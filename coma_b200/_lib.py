@@ -27,6 +27,7 @@ SIGNATURES = {
     "coma_gemm_f16_tn": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp, _i64, _vp],
     "coma_gemm_f16_ex": [_vp, _vp],
     "coma_conv3x3_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp, _vp, _i64, _vp],
+    "coma_attention_fwd_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
     "coma_groupnorm_affine_f16": [_vp, _i64, _i64, _i64, _i64, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "coma_affine_act_f16": [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _vp],
     "coma_upsample2x_affine_act_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _vp],

@@ -1,0 +1,404 @@
+// A1 — fused multi-head attention forward on tcgen05 (the UNet's self- and cross-attention, diffusers `Attention` called
+// from BasicTransformerBlock; reference call site utils/adaptive_mask_inpainting.py:1001-1007. The reference itself runs
+// the UNFUSED baddbmm + softmax + bmm of torch 1.13 and materialises [2B*8, 4096, 4096] scores).
+//
+//   O[b, s, h*d : (h+1)*d] = softmax(Q_h K_h^T / sqrt(d)) V_h        Q [B,S,heads*d], K [B,L,heads*d], V^T [B,heads,d,Lp]
+//
+// One CTA per (128-query tile, head, batch), 6 warps:
+//   warp 0    TMA producer: Q tile once; K tiles [128 keys x d] and V^T tiles [d x 128 keys] through a 2-stage ring
+//   warp 1    MMA issuer (one thread): S = Q K^T  (M128 x N128 x K16 steps) into TMEM, then O_j = P V (M128 x Nd x K16)
+//   warps 2-5 softmax: tcgen05.ld S (one query row per thread), online max / sum in base 2, P -> fp16 into shared memory
+//             in the 128B-swizzled K-major layout the MMA reads, then O = O*alpha + O_j with the running output in registers
+// Scores never leave the SM: HBM traffic is Q, K, V once per tile and O once.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace coma {
+
+// ---- small PTX helpers (same conventions as gemm.cu) ------------------------------------------------------------------
+namespace fa {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z, int w) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+          "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+          "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+}  // namespace fa
+
+constexpr int FA_BQ = 128, FA_BKV = 128, FA_THREADS = 192;
+
+// DKB = number of 64-wide K blocks of the head dimension (d <= 64*DKB); DN = head dim rounded up to a multiple of 16
+template <int DKB, int DN, int STAGES>
+__global__ void __launch_bounds__(FA_THREADS, 1)
+    attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
+                         long long ldo, long long o_bstride) {
+    using namespace fa;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int QK_BLOCK = FA_BQ * 64 * 2;     // one [128 x 64] fp16 K-block, 16 KB
+    constexpr int Q_BYTES = DKB * QK_BLOCK, K_BYTES = DKB * QK_BLOCK;
+    constexpr int VT_BLOCK = DN * 64 * 2;        // one [DN x 64 keys] block
+    constexpr int VT_BYTES = ((2 * VT_BLOCK + 1023) / 1024) * 1024;
+    constexpr int VT_BLOCK_AL = VT_BYTES / 2;    // keep every block 1024-byte aligned (DN*128 is a multiple of 1024 for DN%8==0)
+    constexpr int P_BYTES = 2 * QK_BLOCK;        // P [128 x 128] fp16 as two K-blocks
+    uint8_t *sQ = smem;
+    uint8_t *sK = sQ + Q_BYTES;
+    uint8_t *sVt = sK + STAGES * K_BYTES;
+    uint8_t *sP = sVt + STAGES * VT_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sP + P_BYTES);
+    uint64_t *q_full = bar, *k_full = bar + 1, *k_empty = k_full + STAGES, *v_full = k_empty + STAGES, *v_empty = v_full + STAGES;
+    uint64_t *s_full = v_empty + STAGES, *s_empty = s_full + 1, *p_full = s_empty + 1, *o_full = p_full + 1, *o_empty = o_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * FA_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int n_kv = (L + FA_BKV - 1) / FA_BKV;
+    constexpr uint32_t TMEM_COLS = (128 + DN <= 256) ? 256 : 512;  // S: 128 columns at 0, O_j: DN columns at 128 (power of two)
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVt) : "memory");
+        mbar_init(q_full, 1);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(k_full + i, 1);
+            mbar_init(k_empty + i, 1);
+            mbar_init(v_full + i, 1);
+            mbar_init(v_empty + i, 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 128);
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        mbar_init(o_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sQ + kb * QK_BLOCK, &tmQ, q_full, kb * 64, q0, h, b);
+            for (int j = 0; j < n_kv; ++j) {
+                const int s = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                mbar_wait(k_empty + s, ph ^ 1);
+                mbar_expect_tx(k_full + s, K_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sK + s * K_BYTES + kb * QK_BLOCK, &tmK, k_full + s, kb * 64, j * FA_BKV, h, b);
+                mbar_wait(v_empty + s, ph ^ 1);
+                mbar_expect_tx(v_full + s, 2 * VT_BLOCK);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_4d(sVt + s * VT_BYTES + kb * VT_BLOCK_AL, &tmVt, v_full + s, j * FA_BKV + kb * 64, 0, h, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(FA_BKV >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+            constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+            const int ksteps = (d + 15) / 16;  // columns d..63 of the Q / K blocks are TMA zero-filled
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < n_kv; ++j) {
+                const int s = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                // ---- S = Q K_j^T
+                mbar_wait(k_full + s, ph);
+                mbar_wait(s_empty, (j & 1) ^ 1);  // softmax warps have drained S_{j-1}
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t off = (uint32_t)(k / 4) * QK_BLOCK + (uint32_t)(k % 4) * 32;
+                    umma_f16(tmem_S, umma_desc_sw128(smem_u32(sQ) + off), umma_desc_sw128(smem_u32(sK + s * K_BYTES) + off), idesc_s, k != 0);
+                }
+                umma_commit(k_empty + s);
+                umma_commit(s_full);
+                // ---- O_j = P V_j  (fresh accumulator: the running output lives in the softmax warps' registers)
+                mbar_wait(v_full + s, ph);
+                mbar_wait(p_full, j & 1);         // P_j is in shared memory (and O_{j-1} has been read: same warps)
+                mbar_wait(o_empty, (j & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < FA_BKV / 16; ++k) {
+                    const uint32_t offp = (uint32_t)(k / 4) * QK_BLOCK + (uint32_t)(k % 4) * 32;
+                    const uint32_t offv = (uint32_t)(k / 4) * VT_BLOCK_AL + (uint32_t)(k % 4) * 32;
+                    umma_f16(tmem_O, umma_desc_sw128(smem_u32(sP) + offp), umma_desc_sw128(smem_u32(sVt + s * VT_BYTES) + offv), idesc_o,
+                             k != 0);
+                }
+                umma_commit(v_empty + s);
+                umma_commit(o_full);
+            }
+        }
+    } else {
+        // ---- softmax / accumulate: thread owns query row r of the tile
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float o_acc[DN];
+#pragma unroll
+        for (int c = 0; c < DN; ++c) o_acc[c] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        // P row r inside a [128 x 64] K-major 128B-swizzled block: atom (r/8)*1024 + (r%8)*128, 16-byte chunk index ^ (r%8)
+        uint8_t *p_row = sP + (r >> 3) * 1024 + (r & 7) * 128;
+        const int xr = r & 7;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, j & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int valid = min(FA_BKV, L - j * FA_BKV);  // keys beyond L are masked out
+            // pass 1 over S (TMEM reads are cheap; keeping all 128 scores live would spill next to the running output)
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                float sv[32];
+                tmem_ld32(tmem_S + lane_addr + c0, sv);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (c0 + c < valid) ? sv[c] : -INFINITY);
+            }
+            mx *= scale_log2;  // scale > 0: the max commutes with the scaling
+            const float m_new = fmaxf(m_run, mx);
+            const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+            float rs = 0.f;
+            // pass 2: probabilities -> fp16 -> shared memory. P_{j-1} has been consumed (o_full_{j-1} was waited on below).
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                float sv[32];
+                tmem_ld32(tmem_S + lane_addr + c0, sv);
+#pragma unroll
+                for (int c8 = 0; c8 < 32; c8 += 8) {
+                    uint4 w;
+                    __half2 *hp = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int c = c0 + c8 + 2 * t;
+                        const float p0 = (c < valid) ? ex2(fmaf(sv[c8 + 2 * t], scale_log2, -m_new)) : 0.f;
+                        const float p1 = (c + 1 < valid) ? ex2(fmaf(sv[c8 + 2 * t + 1], scale_log2, -m_new)) : 0.f;
+                        hp[t] = __floats2half2_rn(p0, p1);
+                        const float2 back = __half22float2(hp[t]);  // the row sum uses the fp16-rounded probabilities the MMA sees
+                        rs += back.x + back.y;
+                    }
+                    const int cc = c0 + c8, blk = cc >> 6, chunk = (cc & 63) >> 3;
+                    *reinterpret_cast<uint4 *>(p_row + blk * QK_BLOCK + ((chunk ^ xr) << 4)) = w;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(s_empty);  // S may be overwritten by the next QK^T
+            l_run = l_run * alpha + rs;
+            m_run = m_new;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(p_full);
+            // ---- O = O*alpha + O_j
+            mbar_wait(o_full, j & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < DN; c0 += 16) {
+                float t16[16];
+                tmem_ld16(tmem_O + lane_addr + c0, t16);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) o_acc[c0 + c] = fmaf(o_acc[c0 + c], alpha, t16[c]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(o_empty);
+        }
+        const int row = q0 + r;
+        if (row < S) {
+            const float inv = 1.0f / l_run;
+            __half *dst = out + (size_t)b * o_bstride + (size_t)row * ldo + (size_t)h * d;
+#pragma unroll
+            for (int c = 0; c < DN; c += 8) {  // static indices keep o_acc in registers; d % 8 == 0
+                if (c >= d) break;
+                uint4 w;
+                __half2 *hp = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) hp[t] = __floats2half2_rn(o_acc[c + 2 * t] * inv, o_acc[c + 2 * t + 1] * inv);
+                *reinterpret_cast<uint4 *>(dst + c) = w;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFnA)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map4(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3],
+                     const cuuint32_t box[4]) {
+    static EncodeTiledFnA fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFnA>(p);
+    }
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return COMA_E_NODEVICE;
+    }
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r);
+        return COMA_E_BADARG;
+    }
+    return 0;
+}
+
+template <int DKB, int DN, int STAGES>
+static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads, int S, int L, int d,
+                            float scale_log2, __half *out, long long ldo, long long o_bstride, cudaStream_t st) {
+    constexpr size_t smem = (size_t)DKB * 16384 * (1 + STAGES) + (size_t)STAGES * (((2 * DN * 128 + 1023) / 1024) * 1024) + 32768 + 256 + 1024;
+    static bool attr[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !attr[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<DKB, DN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr[dev] = true;
+    }
+    dim3 grid((S + FA_BQ - 1) / FA_BQ, heads, B);
+    attention_fwd_kernel<DKB, DN, STAGES><<<grid, FA_THREADS, smem, st>>>(tq, tk, tv, S, L, d, scale_log2, out, ldo, o_bstride);
+    return check_launch("attention_fwd_kernel");
+}
+
+}  // namespace coma
+
+extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                      int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, int64_t ldo,
+                                      coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(q && k && vt && out, "null pointer");
+    COMA_REQUIRE(B > 0 && heads > 0 && S > 0 && L > 0 && d > 0 && B <= 65535 && heads <= 65535, "bad sizes");
+    COMA_REQUIRE(d % 8 == 0 && d <= 192, "head dim must be a multiple of 8 and <= 192");
+    COMA_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && Lp % 8 == 0 && Lp >= L && ldo % 8 == 0, "strides must be multiples of 8 elements");
+    COMA_REQUIRE(ldq >= heads * d && ldk >= heads * d && ldo >= heads * d, "row strides smaller than heads*d");
+    COMA_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out) % 16 == 0, "pointers must be 16-byte aligned");
+    // DN = accumulator width of the kernel instantiation that will run; the V^T TMA box must have exactly DN rows
+    // (rows >= d are zero-filled) or the producer's expect_tx byte count never completes.
+    const int d16 = (int)((d + 15) / 16 * 16);
+    const int DN = d <= 64 ? (d16 == 48 ? 48 : (d16 <= 32 ? 32 : 64)) : (d <= 128 ? (d16 == 80 ? 80 : 128) : (d16 == 160 ? 160 : 192));
+    CUtensorMap tq, tk, tv;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)S, (cuuint64_t)heads, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)ldq * 2, (cuuint64_t)d * 2, (cuuint64_t)(S * ldq) * 2};
+        cuuint32_t box[4] = {64, 128, 1, 1};
+        if (int e = make_map4(&tq, q, dims, str, box)) return e;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)L, (cuuint64_t)heads, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)ldk * 2, (cuuint64_t)d * 2, (cuuint64_t)(L * ldk) * 2};
+        cuuint32_t box[4] = {64, 128, 1, 1};
+        if (int e = make_map4(&tk, k, dims, str, box)) return e;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Lp, (cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Lp * 2, (cuuint64_t)(d * Lp) * 2, (cuuint64_t)(heads * d * Lp) * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)DN, 1, 1};
+        if (int e = make_map4(&tv, vt, dims, str, box)) return e;
+    }
+    const float scale_log2 = scale * 1.4426950408889634f;
+    cudaStream_t st = (cudaStream_t)stream;
+    __half *o = (__half *)out;
+    const long long obs = (long long)S * ldo;
+    if (d <= 64) {
+        if (DN == 48) return launch_attention<1, 48, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        if (DN == 32) return launch_attention<1, 32, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        return launch_attention<1, 64, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+    }
+    if (d <= 128) {
+        if (DN == 80) return launch_attention<2, 80, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        return launch_attention<2, 128, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+    }
+    if (DN == 160) return launch_attention<3, 160, 1>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+    return launch_attention<3, 192, 1>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+}

@@ -193,6 +193,9 @@ def timestep_embedding(t, dim):
     return out
 
 
+FUSED_ATTENTION = True
+
+
 def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual):
     """softmax(Q K^T / sqrt(d)) V followed by the output projection (+bias +residual). xq [B*S, C], xkv [B*L, Ckv] f16.
     Scores and probabilities are materialised in fp16 ([B,heads,S,Lp]); the products run as batched tensor-core GEMMs."""
@@ -201,6 +204,14 @@ def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual):
     d = C // heads
     q, k, v = gemm(xq, wq), gemm(xkv, wk), gemm(xkv, wv)
     Lp = rup(L)
+    if FUSED_ATTENTION and d % 8 == 0 and d <= 192:
+        vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)
+        o = torch.empty((B * S, C), dtype=F16, device=dev)
+        with torch.cuda.device(dev):
+            call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
+            call("coma_attention_fwd_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, q.stride(0), k.stride(0), Lp,
+                 float(d ** -0.5), o.data_ptr(), o.stride(0), _stream())
+        return gemm(o, wo, bo, residual)
     scores = torch.empty((B, heads, S, Lp), dtype=F16, device=dev)
     gemm_batched(q, C, d, S * C, k, C, d, L * C, scores, Lp, S * Lp, heads * S * Lp, S, L, d, heads, B, alpha=d ** -0.5)
     vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)

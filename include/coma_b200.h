@@ -142,6 +142,15 @@ COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
                               coma_stream_t stream);
 
+/* ---- A1: fused multi-head attention forward (tcgen05: S = Q K^T and O = P V on the tensor cores, online softmax between
+ * them, scores never leave the SM). out[b,s,h*d:(h+1)*d] = softmax(Q_h K_h^T * scale) V_h.
+ * q [B,S,heads*d] (row stride ldq), k [B,L,heads*d] (ldk), vt = V^T [B,heads,d,Lp] (coma_transpose_heads_f16), all f16;
+ * d % 8 == 0, d <= 192; out [B,S,heads*d] f16 (row stride ldo). Replaces the baddbmm + softmax + bmm of the reference's
+ * attention (diffusers Attention under torch 1.13, reached from utils/adaptive_mask_inpainting.py:1001). */
+COMA_API int coma_attention_fwd_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                    int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, int64_t ldo,
+                                    coma_stream_t stream);
+
 /* ---- U*: the non-contraction layers of the UNet / VAE, NHWC fp16 activations ([B, H*W, C], row stride ld*) -------------
  * (diffusers UNet2DConditionModel / AutoencoderKL layers reached from utils/adaptive_mask_inpainting.py:1001, :680, :1086) */
 

@@ -180,11 +180,13 @@ def _gn(x, sd, name, groups, eps):
 
 
 def _conv(x, sd, name, stride=1, padding=1):
-    return F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], stride=stride, padding=padding)
+    w = sd[name + ".weight"]
+    return F.conv2d(x.to(w.dtype), w, sd[name + ".bias"], stride=stride, padding=padding)
 
 
 def _lin(x, sd, name):
-    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+    w = sd[name + ".weight"]
+    return F.linear(x.to(w.dtype), w, sd.get(name + ".bias"))
 
 
 def resnet_block(x, temb, sd, name, groups, eps, r):

@@ -95,9 +95,12 @@ def test_groupnorm_layernorm_geglu_softmax(dev):
     torch.testing.assert_close(nn.timestep_embedding(t, 320).float(), so.timestep_embedding(t, 320), rtol=0, atol=2e-3)
 
 
-@pytest.mark.parametrize("S,L,C,heads", [(64, 64, 64, 2), (256, 77, 320, 8), (1024, 1024, 640, 8)])
-def test_attention(dev, S, L, C, heads):
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("S,L,C,heads", [(64, 64, 64, 2), (256, 77, 320, 8), (1024, 1024, 640, 8), (4096, 4096, 320, 8),
+                                         (256, 256, 1280, 8), (64, 77, 1280, 8), (200, 300, 128, 2), (64, 64, 32, 2), (128, 200, 176, 1)])
+def test_attention(dev, S, L, C, heads, fused):
     from coma_b200.inpaint import nn
+    nn.FUSED_ATTENTION = fused
     from oracle import sd_oracle as so
     g = torch.Generator(device=dev).manual_seed(S)
     B = 2
@@ -113,6 +116,7 @@ def test_attention(dev, S, L, C, heads):
     w = {k: nn.prep_linear(v, dev) for k, v in sd.items() if k.endswith("weight")}
     out = nn.attention(xq.reshape(B * S, C), xkv.reshape(B * L, Ckv), B, S, L, w["a.to_q.weight"], w["a.to_k.weight"],
                        w["a.to_v.weight"], w["a.to_out.0.weight"], sd["a.to_out.0.bias"], heads, xq.reshape(B * S, C))
+    nn.FUSED_ATTENTION = True
     _close(out.float().reshape(B, S, C), ref, 4e-3)
 
 
