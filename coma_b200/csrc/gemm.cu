@@ -22,7 +22,7 @@
 
 namespace coma {
 
-constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4;
+constexpr int G_BM = 128, G_BK = 64, G_STAGES = 3;  // 3 x 32 KB per CTA -> two CTAs per SM: one CTA's epilogue overlaps the other's main loop
 constexpr int G_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,7 +111,7 @@ struct ConvGeom {
 };
 
 template <int BN, bool CONV>
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS, 2)
     gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                        const GemmEpilogue ep, const ConvGeom cg) {
     const float *__restrict__ bias = ep.bias;
