@@ -102,7 +102,7 @@ constexpr int FA_BQ = 128, FA_BKV = 128, FA_THREADS = 192;
 
 // DKB = number of 64-wide K blocks of the head dimension (d <= 64*DKB); DN = head dim rounded up to a multiple of 16
 template <int DKB, int DN, int STAGES>
-__global__ void __launch_bounds__(FA_THREADS, 1)
+__global__ void __launch_bounds__(FA_THREADS, (DKB == 1 ? 2 : 1))
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
                          long long ldo, long long o_bstride) {
@@ -216,30 +216,39 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         // ---- softmax / accumulate: thread owns query row r of the tile
         const int q = warp & 3, r = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float o_acc[DN];
+        float2 o_acc[DN / 2];  // running output, packed pairs (FP32x2 FMAs)
 #pragma unroll
-        for (int c = 0; c < DN; ++c) o_acc[c] = 0.f;
+        for (int c = 0; c < DN / 2; ++c) o_acc[c] = make_float2(0.f, 0.f);
         float m_run = -INFINITY, l_run = 0.f;
         // P row r inside a [128 x 64] K-major 128B-swizzled block: atom (r/8)*1024 + (r%8)*128, 16-byte chunk index ^ (r%8)
         uint8_t *p_row = sP + (r >> 3) * 1024 + (r & 7) * 128;
         const int xr = r & 7;
+        const float2 scale2 = make_float2(scale_log2, scale_log2);
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(s_full, j & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int valid = min(FA_BKV, L - j * FA_BKV);  // keys beyond L are masked out
-            // pass 1 over S (TMEM reads are cheap; keeping all 128 scores live would spill next to the running output)
+            const int valid = min(FA_BKV, L - j * FA_BKV);  // keys beyond L are masked out (last tile only)
+            const bool full_tile = valid == FA_BKV;          // warp-uniform
+            // pass 1 over S: row maximum (TMEM reads are cheap; keeping all 128 scores live next to the running output
+            // would cost the second resident CTA)
             float mx = -INFINITY;
 #pragma unroll
             for (int c0 = 0; c0 < 128; c0 += 32) {
                 float sv[32];
                 tmem_ld32(tmem_S + lane_addr + c0, sv);
+                if (full_tile) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (c0 + c < valid) ? sv[c] : -INFINITY);
+                    for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(sv[c], sv[c + 1]));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (c0 + c < valid) ? sv[c] : -INFINITY);
+                }
             }
             mx *= scale_log2;  // scale > 0: the max commutes with the scaling
             const float m_new = fmaxf(m_run, mx);
             const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-            float rs = 0.f;
+            const float2 negm2 = make_float2(-m_new, -m_new);
+            float2 rs2 = make_float2(0.f, 0.f);
             // pass 2: probabilities -> fp16 -> shared memory. P_{j-1} has been consumed (o_full_{j-1} was waited on below).
 #pragma unroll
             for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -252,11 +261,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         const int c = c0 + c8 + 2 * t;
-                        const float p0 = (c < valid) ? ex2(fmaf(sv[c8 + 2 * t], scale_log2, -m_new)) : 0.f;
-                        const float p1 = (c + 1 < valid) ? ex2(fmaf(sv[c8 + 2 * t + 1], scale_log2, -m_new)) : 0.f;
-                        hp[t] = __floats2half2_rn(p0, p1);
-                        const float2 back = __half22float2(hp[t]);  // the row sum uses the fp16-rounded probabilities the MMA sees
-                        rs += back.x + back.y;
+                        const float2 x = __ffma2_rn(make_float2(sv[c8 + 2 * t], sv[c8 + 2 * t + 1]), scale2, negm2);
+                        float2 pr = make_float2(ex2(x.x), ex2(x.y));
+                        if (!full_tile) {
+                            pr.x = (c < valid) ? pr.x : 0.f;
+                            pr.y = (c + 1 < valid) ? pr.y : 0.f;
+                        }
+                        hp[t] = __floats2half2_rn(pr.x, pr.y);
+                        rs2 = __fadd2_rn(rs2, pr);
                     }
                     const int cc = c0 + c8, blk = cc >> 6, chunk = (cc & 63) >> 3;
                     *reinterpret_cast<uint4 *>(p_row + blk * QK_BLOCK + ((chunk ^ xr) << 4)) = w;
@@ -264,19 +276,21 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(s_empty);  // S may be overwritten by the next QK^T
-            l_run = l_run * alpha + rs;
+            l_run = l_run * alpha + (rs2.x + rs2.y);
             m_run = m_new;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
             mbar_arrive(p_full);
             // ---- O = O*alpha + O_j
             mbar_wait(o_full, j & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float2 alpha2 = make_float2(alpha, alpha);
 #pragma unroll
             for (int c0 = 0; c0 < DN; c0 += 16) {
                 float t16[16];
                 tmem_ld16(tmem_O + lane_addr + c0, t16);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) o_acc[c0 + c] = fmaf(o_acc[c0 + c], alpha, t16[c]);
+                for (int c = 0; c < 16; c += 2)
+                    o_acc[(c0 + c) / 2] = __ffma2_rn(o_acc[(c0 + c) / 2], alpha2, make_float2(t16[c], t16[c + 1]));
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(o_empty);
@@ -291,7 +305,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
                 uint4 w;
                 __half2 *hp = reinterpret_cast<__half2 *>(&w);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) hp[t] = __floats2half2_rn(o_acc[c + 2 * t] * inv, o_acc[c + 2 * t + 1] * inv);
+                for (int t = 0; t < 4; ++t) hp[t] = __floats2half2_rn(o_acc[c / 2 + t].x * inv, o_acc[c / 2 + t].y * inv);
                 *reinterpret_cast<uint4 *>(dst + c) = w;
             }
         }

@@ -22,7 +22,7 @@
 
 namespace coma {
 
-constexpr int G_BM = 128, G_BK = 64, G_STAGES = 3;  // 3 x 32 KB per CTA -> two CTAs per SM: one CTA's epilogue overlaps the other's main loop
+constexpr int G_BM = 128, G_BK = 64;
 constexpr int G_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -32,6 +32,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -110,51 +113,44 @@ struct ConvGeom {
     int cblocks;         // input channels / 64
 };
 
-template <int BN, bool CONV>
-__global__ void __launch_bounds__(G_THREADS, 2)
+struct TileSched {
+    int n_tiles, m_tiles, total;  // total = n_tiles * m_tiles * batches; tile id = (z * m_tiles + mt) * n_tiles + nt
+};
+
+// Persistent, warp-specialised kernel: gridDim.x CTAs walk the tile list with stride gridDim.x. The fp32 accumulator is
+// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1; consecutive tile
+// ids share the A tile (N fastest), which keeps the activation slab L2-resident while its N-tiles are produced.
+// BN in {64, 128, 160, 256}: wider tiles raise the flop/byte of the operand stream (L2 -> SMEM is what bounds a 128x128
+// tile at ~0.75 PFLOP/s on this part: 32 KB per 2.1 MFLOP).
+template <int BN, bool CONV, int STAGES>
+__global__ void __launch_bounds__(G_THREADS, (BN <= 128 ? 2 : 1))
     gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                       const GemmEpilogue ep, const ConvGeom cg) {
-    const float *__restrict__ bias = ep.bias;
-    const int act = ep.act, ldo = ep.ldo;
-    const int b1 = blockIdx.z % ep.nb1, b2 = blockIdx.z / ep.nb1;
-    const size_t obase = (size_t)b1 * ep.o_s1 + (size_t)b2 * ep.o_s2;
-    const __half *__restrict__ residual = ep.residual ? ep.residual + obase : nullptr;
-    __half *__restrict__ out16 = ep.out16 ? ep.out16 + obase : nullptr;
-    float *__restrict__ out32 = ep.out32 ? ep.out32 + obase : nullptr;
+                       const GemmEpilogue ep, const ConvGeom cg, const TileSched ts) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = G_BM * G_BK * 2, B_BYTES = BN * G_BK * 2;
-    uint8_t *sA = smem, *sB = smem + G_STAGES * A_BYTES;
-    uint64_t *full = reinterpret_cast<uint64_t *>(sB + G_STAGES * B_BYTES);
-    uint64_t *empty = full + G_STAGES;
-    uint64_t *tmem_full = empty + G_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint8_t *sA = smem, *sB = smem + STAGES * A_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + STAGES * B_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;   // [2]
+    uint64_t *tmem_empty = tmem_full + 2;   // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * BN;
     const int num_k = (K + G_BK - 1) / G_BK;
-    int cx0 = 0, cy0 = 0, cb0 = 0;  // CONV: origin of this CTA's pixel tile
-    if (CONV) {
-        if (cg.TB > 1) {
-            cb0 = blockIdx.y * cg.TB;
-        } else {
-            const int per_img = cg.tiles_x * cg.tiles_y;
-            cb0 = blockIdx.y / per_img;
-            const int rem = blockIdx.y % per_img;
-            cy0 = (rem / cg.tiles_x) * cg.TH;
-            cx0 = (rem % cg.tiles_x) * cg.TW;
-        }
-    }
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;  // power of two >= 32
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);  // power of two >= 2*BN
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int i = 0; i < G_STAGES; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             mbar_init(full + i, 1);
             mbar_init(empty + i, 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tmem_full + i, 1);
+            mbar_init(tmem_empty + i, 128);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -167,110 +163,160 @@ __global__ void __launch_bounds__(G_THREADS, 2)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile id -> coordinates
+    auto decode = [&](int t, int &m0, int &n0, int &b1, int &b2, int &cx0, int &cy0, int &cb0) {
+        const int nt = t % ts.n_tiles;
+        const int r = t / ts.n_tiles;
+        const int mt = r % ts.m_tiles, z = r / ts.m_tiles;
+        n0 = nt * BN;
+        m0 = mt * G_BM;
+        b1 = z % ep.nb1;
+        b2 = z / ep.nb1;
+        cx0 = cy0 = cb0 = 0;
+        if (CONV) {
+            if (cg.TB > 1) {
+                cb0 = mt * cg.TB;
+            } else {
+                const int per_img = cg.tiles_x * cg.tiles_y;
+                cb0 = mt / per_img;
+                const int rem = mt % per_img;
+                cy0 = (rem / cg.tiles_x) * cg.TH;
+                cx0 = (rem % cg.tiles_x) * cg.TW;
+            }
+        }
+    };
+
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % G_STAGES;
-                const uint32_t ph = (kb / G_STAGES) & 1;
-                mbar_wait(empty + s, ph ^ 1);
-                mbar_expect_tx(full + s, A_BYTES + B_BYTES);
-                if (CONV) {
-                    const int tap = kb / cg.cblocks, cb = kb % cg.cblocks;
-                    tma_load_4d(sA + s * A_BYTES, &tmA, full + s, cb * G_BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb0);
-                } else {
-                    tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
+            int it = 0;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+                int m0, n0, b1, b2, cx0, cy0, cb0;
+                decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    mbar_expect_tx(full + s, A_BYTES + B_BYTES);
+                    if (CONV) {
+                        const int tap = kb / cg.cblocks, cb = kb % cg.cblocks;
+                        tma_load_4d(sA + s * A_BYTES, &tmA, full + s, cb * G_BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb0);
+                    } else {
+                        tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
+                    }
+                    tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0, b1, b2);
                 }
-                tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0, b1, b2);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N>>3, M>>4
             constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % G_STAGES;
-                const uint32_t ph = (kb / G_STAGES) & 1;
-                mbar_wait(full + s, ph);
+            int it = 0, i = 0;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+                const int acc = i & 1;
+                mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t da = umma_desc_sw128(smem_u32(sA + s * A_BYTES));
-                const uint64_t db = umma_desc_sw128(smem_u32(sB + s * B_BYTES));
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full + s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = umma_desc_sw128(smem_u32(sA + s * A_BYTES));
+                    const uint64_t db = umma_desc_sw128(smem_u32(sB + s * B_BYTES));
 #pragma unroll
-                for (int k = 0; k < G_BK / 16; ++k)  // advance 32 B (16 fp16) inside the 128 B swizzle atom: +2 in 16-B units
-                    umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                umma_commit(empty + s);  // frees the slab once the MMAs that read it have retired
+                    for (int k = 0; k < G_BK / 16; ++k)  // advance 32 B (16 fp16) inside the 128 B swizzle atom: +2 in 16-B units
+                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(empty + s);  // frees the slab once the MMAs that read it have retired
+                }
+                umma_commit(tmem_full + acc);
             }
-            umma_commit(tmem_full);
         }
     } else {
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float *__restrict__ bias = ep.bias;
+        const int act = ep.act, ldo = ep.ldo;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        int row = m0 + q * 32 + lane;
-        if (CONV) {  // TMEM lane -> pixel of the tile (x fastest, then y, then image)
-            const int r = q * 32 + lane;
-            const int tx = r % cg.TW, ty = (r / cg.TW) % cg.TH, tb = r / (cg.TW * cg.TH);
-            row = (cb0 + tb < cg.B) ? ((cb0 + tb) * cg.H + cy0 + ty) * cg.W + cx0 + tx : M;
-        }
+        int i = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+            int m0, n0, b1, b2, cx0, cy0, cb0;
+            decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
+            const size_t obase = (size_t)b1 * ep.o_s1 + (size_t)b2 * ep.o_s2;
+            const __half *__restrict__ residual = ep.residual ? ep.residual + obase : nullptr;
+            __half *__restrict__ out16 = ep.out16 ? ep.out16 + obase : nullptr;
+            float *__restrict__ out32 = ep.out32 ? ep.out32 + obase : nullptr;
+            const int acc = i & 1;
+            mbar_wait(tmem_full + acc, (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            int row = m0 + q * 32 + lane;
+            if (CONV) {  // TMEM lane -> pixel of the tile (x fastest, then y, then image)
+                const int r = q * 32 + lane;
+                const int tx = r % cg.TW, ty = (r / cg.TW) % cg.TH, tb = r / (cg.TW * cg.TH);
+                row = (cb0 + tb < cg.B) ? ((cb0 + tb) * cg.H + cy0 + ty) * cg.W + cx0 + tx : M;
+            }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (row < M) {
-                const int nb = n0 + c0;
-                const size_t off = (size_t)row * ldo + nb;
-                const float *brow = ep.bias_rows ? ep.bias_rows + (size_t)(row / ep.rows_per_bias) * N : nullptr;
-                if (nb + 32 <= N && (ldo % 8) == 0 && (obase % 8) == 0) {
-                    float f[32];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (row < M && n0 + c0 < N) {
+                    const int nb = n0 + c0;
+                    const size_t off = (size_t)row * ldo + nb;
+                    const float *brow = ep.bias_rows ? ep.bias_rows + (size_t)(row / ep.rows_per_bias) * N : nullptr;
+                    if (nb + 32 <= N && (ldo % 8) == 0 && (obase % 8) == 0) {
+                        float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        f[j] = __uint_as_float(v[j]) * ep.alpha + (bias ? __ldg(bias + nb + j) : 0.0f);
-                        if (brow) f[j] += __ldg(brow + nb + j);
-                    }
-                    if (residual) {
+                        for (int j = 0; j < 32; ++j) {
+                            f[j] = __uint_as_float(v[j]) * ep.alpha + (bias ? __ldg(bias + nb + j) : 0.0f);
+                            if (brow) f[j] += __ldg(brow + nb + j);
+                        }
+                        if (residual) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 r = *reinterpret_cast<const uint4 *>(residual + off + j);
-                            const __half2 *h = reinterpret_cast<const __half2 *>(&r);
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 r = *reinterpret_cast<const uint4 *>(residual + off + j);
+                                const __half2 *h = reinterpret_cast<const __half2 *>(&r);
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float2 x = __half22float2(h[t]);
-                                f[j + 2 * t] += x.x;
-                                f[j + 2 * t + 1] += x.y;
+                                for (int u = 0; u < 4; ++u) {
+                                    const float2 x = __half22float2(h[u]);
+                                    f[j + 2 * u] += x.x;
+                                    f[j + 2 * u + 1] += x.y;
+                                }
                             }
                         }
-                    }
-                    if (act == 1) {
+                        if (act == 1) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
-                    }
-                    if (out16) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 w;
-                            __half2 *h = reinterpret_cast<__half2 *>(&w);
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                            *reinterpret_cast<uint4 *>(out16 + off + j) = w;
+                            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
                         }
-                    }
-                    if (out32) {
+                        if (out16) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(out32 + off + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    }
-                } else {
-                    for (int j = 0; j < 32; ++j) {
-                        if (nb + j < N) {
-                            float x = __uint_as_float(v[j]) * ep.alpha + (bias ? bias[nb + j] : 0.0f);
-                            if (brow) x += brow[nb + j];
-                            if (residual) x += __half2float(residual[off + j]);
-                            if (act == 1) x = x / (1.0f + __expf(-x));
-                            if (out16) out16[off + j] = __float2half_rn(x);
-                            if (out32) out32[off + j] = x;
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 w;
+                                __half2 *h = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(f[j + 2 * u], f[j + 2 * u + 1]);
+                                *reinterpret_cast<uint4 *>(out16 + off + j) = w;
+                            }
+                        }
+                        if (out32) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(out32 + off + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j) {
+                            if (nb + j < N) {
+                                float x = __uint_as_float(v[j]) * ep.alpha + (bias ? bias[nb + j] : 0.0f);
+                                if (brow) x += brow[nb + j];
+                                if (residual) x += __half2float(residual[off + j]);
+                                if (act == 1) x = x / (1.0f + __expf(-x));
+                                if (out16) out16[off + j] = __float2half_rn(x);
+                                if (out32) out32[off + j] = x;
+                            }
                         }
                     }
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty + acc);  // 128 arrivals hand the accumulator back to the MMA warp
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -322,23 +368,59 @@ static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols,
 
 template <int BN, bool CONV>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const GemmEpilogue &ep, int nbatch,
-                       cudaStream_t st, const ConvGeom &cg = ConvGeom{}, int m_tiles = 0) {
-    constexpr size_t smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 256 + 1024;
+                       cudaStream_t st, const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
+    constexpr int STAGES = BN <= 128 ? 3 : 4;
+    constexpr size_t smem = (size_t)STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 256 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
             return (int)e;
         }
         attr[dev] = true;
     }
-    dim3 grid((N + BN - 1) / BN, CONV ? m_tiles : (M + G_BM - 1) / G_BM, nbatch);
-    gemm_f16_tn_kernel<BN, CONV><<<grid, G_THREADS, smem, st>>>(ta, tb, M, N, K, ep, cg);
+    TileSched ts;
+    ts.n_tiles = (N + BN - 1) / BN;
+    ts.m_tiles = CONV ? m_tiles_conv : (M + G_BM - 1) / G_BM;
+    const long long total = (long long)ts.n_tiles * ts.m_tiles * nbatch;
+    if (total >= (1LL << 31)) {
+        set_error("too many output tiles");
+        return COMA_E_BADARG;
+    }
+    ts.total = (int)total;
+    const int slots = kNumSM * (BN <= 128 ? 2 : 1);
+    const unsigned grid = (unsigned)(ts.total < slots ? ts.total : slots);
+    gemm_f16_tn_kernel<BN, CONV, STAGES><<<grid, G_THREADS, smem, st>>>(ta, tb, M, N, K, ep, cg, ts);
     return check_launch("gemm_f16_tn_kernel");
 }
+
+// Output-tile width: the candidate with the least padded work, ties to the wider tile.
+static int pick_bn(int64_t N) {
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    const int cands[3] = {256, 160, 128};
+    int best = 128;
+    int64_t best_pad = -1;
+    for (int c : cands) {
+        const int64_t pad = (N + c - 1) / c * c;
+        if (best_pad < 0 || pad < best_pad) {
+            best_pad = pad;
+            best = c;
+        }
+    }
+    return best;
+}
+
+#define COMA_DISPATCH_BN(bn, CONVF, ...)                               \
+    switch (bn) {                                                      \
+        case 64: return launch_gemm<64, CONVF>(__VA_ARGS__);           \
+        case 128: return launch_gemm<128, CONVF>(__VA_ARGS__);         \
+        case 160: return launch_gemm<160, CONVF>(__VA_ARGS__);         \
+        default: return launch_gemm<256, CONVF>(__VA_ARGS__);          \
+    }
 
 }  // namespace coma
 
@@ -347,7 +429,6 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     COMA_REQUIRE(g && g->A && g->W && (g->out_f16 || g->out_f32), "null pointer");
     const int64_t M = g->M, N = g->N, K = g->K, nb1 = g->nb1 > 0 ? g->nb1 : 1, nb2 = g->nb2 > 0 ? g->nb2 : 1;
     COMA_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "bad sizes");
-    COMA_REQUIRE(nb1 * nb2 <= 65535, "too many batches for one launch");
     COMA_REQUIRE(g->lda >= K && g->ldw >= K && g->ldo >= N, "leading dimensions smaller than the row length");
     COMA_REQUIRE(g->lda % 8 == 0 && g->ldw % 8 == 0, "lda / ldw must be multiples of 8 elements (16-byte TMA strides)");
     COMA_REQUIRE((nb1 == 1 || (g->a_s1 % 8 == 0 && g->w_s1 % 8 == 0)) && (nb2 == 1 || (g->a_s2 % 8 == 0 && g->w_s2 % 8 == 0)),
@@ -358,7 +439,7 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     COMA_REQUIRE(!g->out_f32 || (uintptr_t)g->out_f32 % 16 == 0, "out_f32 must be 16-byte aligned");
     COMA_REQUIRE(!g->residual || (uintptr_t)g->residual % 16 == 0, "residual must be 16-byte aligned");
     COMA_REQUIRE(!g->bias_rows || g->rows_per_bias > 0, "rows_per_bias must be positive");
-    const int bn = (N <= 64) ? 64 : 128;
+    const int bn = pick_bn(N);
     CUtensorMap ta, tb;
     if (int e = make_map(&ta, g->A, M, K, g->lda, G_BM, nb1, g->a_s1, nb2, g->a_s2)) return e;
     if (int e = make_map(&tb, g->W, N, K, g->ldw, bn, nb1, g->w_s1, nb2, g->w_s2)) return e;
@@ -376,8 +457,7 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     ep.act = g->act;
     ep.nb1 = (int)nb1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64) return launch_gemm<64, false>(ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st);
-    return launch_gemm<128, false>(ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st);
+    COMA_DISPATCH_BN(bn, false, ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st)
 }
 
 namespace coma {
@@ -421,9 +501,8 @@ extern "C" int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, 
     cg.H = (int)H; cg.W = (int)W; cg.B = (int)B; cg.TW = TW; cg.TH = TH; cg.TB = TB;
     cg.tiles_x = (int)(W / TW); cg.tiles_y = (int)(H / TH); cg.cblocks = (int)(C / 64);
     const int64_t m_tiles = TB > 1 ? (B + TB - 1) / TB : B * cg.tiles_x * cg.tiles_y;
-    COMA_REQUIRE(m_tiles <= 65535, "too many output tiles for one launch");
     const int64_t M = B * H * W, K = 9 * C;
-    const int bn = (N <= 64) ? 64 : 128;
+    const int bn = pick_bn(N);
     CUtensorMap ta, tb;
     if (int e = make_conv_map(&ta, x, B, H, W, C, ldx, TW, TH, TB)) return e;
     if (int e = make_map(&tb, Wt, N, K, ldw, bn, 1, 0, 1, 0)) return e;
@@ -432,8 +511,7 @@ extern "C" int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, 
     ep.out16 = (__half *)out_f16; ep.out32 = out_f32; ep.ldo = (int)ldo; ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = act;
     ep.nb1 = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64) return launch_gemm<64, true>(ta, tb, (int)M, (int)N, (int)K, ep, 1, st, cg, (int)m_tiles);
-    return launch_gemm<128, true>(ta, tb, (int)M, (int)N, (int)K, ep, 1, st, cg, (int)m_tiles);
+    COMA_DISPATCH_BN(bn, true, ta, tb, (int)M, (int)N, (int)K, ep, 1, st, cg, (int)m_tiles)
 }
 
 extern "C" int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,

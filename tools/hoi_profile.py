@@ -20,15 +20,23 @@ if what == "unet":
     x.t.copy_(torch.randn((2 * B * 4096, 9), device=dev, generator=g).half())
     ctx = (torch.randn((2 * B * 77, 768), device=dev, generator=g) * 0.02).half()
     tt = torch.full((2 * B,), 961.0, device=dev)
-    for _ in range(2):
-        net.forward(x, tt, ctx, 77)
+    net.forward(x, tt, ctx, 77)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push("fwd")
+    net.forward(x, tt, ctx, 77)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
 else:
     vae = VAE(so.make_vae_state_dict(1), device=dev)
     z = nn.new_act(B, 64, 64, 4, dev)
     z.t.copy_(torch.randn((B * 4096, 4), device=dev, generator=g).half())
     img = nn.new_act(B, 512, 512, 3, dev)
     img.t.copy_(torch.tanh(torch.randn((B * 512 * 512, 3), device=dev, generator=g)).half())
-    for _ in range(2):
-        vae.decode(z)
-        vae.encode_moments(img)
+    vae.decode(z)
+    vae.encode_moments(img)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push("fwd")
+    vae.decode(z)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
 torch.cuda.synchronize()
