@@ -93,6 +93,7 @@ struct GemmEpilogue {
     const float *bias;       // [N] or null
     const float *bias_rows;  // [ceil(M/rows_per_bias), N] or null (e.g. the per-sample time-embedding term of a ResnetBlock)
     int rows_per_bias;
+    long long bias_rows_ld;  // row stride of bias_rows (>= N)
     const __half *residual;  // same layout as the output, or null
     __half *out16;
     float *out32;
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(G_THREADS, (BN <= 128 ? 2 : 1))
                 if (row < M && n0 + c0 < N) {
                     const int nb = n0 + c0;
                     const size_t off = (size_t)row * ldo + nb;
-                    const float *brow = ep.bias_rows ? ep.bias_rows + (size_t)(row / ep.rows_per_bias) * N : nullptr;
+                    const float *brow = ep.bias_rows ? ep.bias_rows + (size_t)(row / ep.rows_per_bias) * ep.bias_rows_ld : nullptr;
                     if (nb + 32 <= N && (ldo % 8) == 0 && (obase % 8) == 0) {
                         float f[32];
 #pragma unroll
@@ -447,6 +448,7 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     ep.bias = g->bias;
     ep.bias_rows = g->bias_rows;
     ep.rows_per_bias = (int)(g->rows_per_bias > 0 ? g->rows_per_bias : 1);
+    ep.bias_rows_ld = g->bias_rows_ld > 0 ? g->bias_rows_ld : N;
     ep.residual = (const __half *)g->residual;
     ep.out16 = (__half *)g->out_f16;
     ep.out32 = g->out_f32;
@@ -485,8 +487,8 @@ static int make_conv_map(CUtensorMap *m, const void *ptr, int64_t B, int64_t H, 
 }  // namespace coma
 
 extern "C" int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const void *Wt, int64_t ldw,
-                                int64_t N, const float *bias, const float *bias_rows, const void *residual, int act, void *out_f16,
-                                float *out_f32, int64_t ldo, coma_stream_t stream) {
+                                int64_t N, const float *bias, const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act,
+                                void *out_f16, float *out_f32, int64_t ldo, coma_stream_t stream) {
     using namespace coma;
     COMA_REQUIRE(x && Wt && (out_f16 || out_f32), "null pointer");
     COMA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && N > 0, "bad sizes");
@@ -507,7 +509,7 @@ extern "C" int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, 
     if (int e = make_conv_map(&ta, x, B, H, W, C, ldx, TW, TH, TB)) return e;
     if (int e = make_map(&tb, Wt, N, K, ldw, bn, 1, 0, 1, 0)) return e;
     GemmEpilogue ep;
-    ep.bias = bias; ep.bias_rows = bias_rows; ep.rows_per_bias = (int)(H * W); ep.residual = (const __half *)residual;
+    ep.bias = bias; ep.bias_rows = bias_rows; ep.rows_per_bias = (int)(H * W); ep.bias_rows_ld = bias_rows_ld > 0 ? bias_rows_ld : N; ep.residual = (const __half *)residual;
     ep.out16 = (__half *)out_f16; ep.out32 = out_f32; ep.ldo = (int)ldo; ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = act;
     ep.nb1 = 1;
     cudaStream_t st = (cudaStream_t)stream;

@@ -19,10 +19,59 @@
 namespace coma {
 
 // ---------------------------------------------------------------------------------------------- GroupNorm statistics
-// grid (chunks, B), block 256. Thread t owns channels t, t+256, ...; sums over the chunk's pixels are coalesced.
+// grid (chunks, B), block 256. 16-byte loads: a thread owns 8 consecutive channels; when C/8 < 256 the spare threads
+// split the chunk's pixel rows. Partial sums go through shared memory, then one fp64 atomicAdd pair per (b, group).
 __global__ void __launch_bounds__(256)
     groupnorm_partial_kernel(const __half *__restrict__ x, int HW, int C, long long ldx, int G, int rows_per_chunk,
                              double *__restrict__ acc /* [B,G,2] */) {
+    extern __shared__ float sm[];  // [rg][2][C]
+    const int b = blockIdx.y, p0 = blockIdx.x * rows_per_chunk, p1 = min(HW, p0 + rows_per_chunk);
+    const __half *xb = x + (size_t)b * HW * ldx;
+    const int cgn = C / 8;                              // column groups of 8 channels
+    const int rg = cgn >= 256 ? 1 : 256 / cgn;          // row lanes
+    const int ry = threadIdx.x / cgn;                   // this thread's row lane (threads beyond rg*cgn idle)
+    if (ry < rg) {
+        for (int cg0 = threadIdx.x % cgn; cg0 < cgn; cg0 += (cgn >= 256 ? 256 : cgn)) {
+            float s[8], q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+            for (int p = p0 + ry; p < p1; p += rg) {
+                const uint4 raw = *reinterpret_cast<const uint4 *>(xb + (size_t)p * ldx + cg0 * 8);
+                const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 v = __half22float2(h[k]);
+                    s[2 * k] += v.x;
+                    s[2 * k + 1] += v.y;
+                    q[2 * k] = fmaf(v.x, v.x, q[2 * k]);
+                    q[2 * k + 1] = fmaf(v.y, v.y, q[2 * k + 1]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sm[(ry * 2 + 0) * C + cg0 * 8 + k] = s[k];
+                sm[(ry * 2 + 1) * C + cg0 * 8 + k] = q[k];
+            }
+        }
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int r = 0; r < rg; ++r)
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                s += (double)sm[(r * 2 + 0) * C + c];
+                q += (double)sm[(r * 2 + 1) * C + c];
+            }
+        atomicAdd(acc + ((size_t)b * G + g) * 2 + 0, s);
+        atomicAdd(acc + ((size_t)b * G + g) * 2 + 1, q);
+    }
+}
+
+// scalar fallback (C % 8 != 0 or unaligned rows): thread t owns channels t, t+256, ...
+__global__ void __launch_bounds__(256)
+    groupnorm_partial_scalar_kernel(const __half *__restrict__ x, int HW, int C, long long ldx, int G, int rows_per_chunk,
+                                    double *__restrict__ acc) {
     extern __shared__ float sm[];  // [2][C]
     const int b = blockIdx.y, p0 = blockIdx.x * rows_per_chunk, p1 = min(HW, p0 + rows_per_chunk);
     const __half *xb = x + (size_t)b * HW * ldx;
@@ -427,8 +476,15 @@ extern "C" int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, i
     long long rows = (HW + chunks - 1) / chunks;
     rows = rows < 16 ? 16 : rows;
     chunks = (HW + rows - 1) / rows;
-    groupnorm_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, sizeof(float) * 2 * C, st>>>(
-        (const __half *)x, (int)HW, (int)C, ldx, G, (int)rows, workspace);
+    const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && ((uintptr_t)x % 16 == 0);
+    if (vec) {
+        const int cgn = (int)(C / 8), rg = cgn >= 256 ? 1 : 256 / cgn;
+        groupnorm_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, sizeof(float) * 2 * C * rg, st>>>(
+            (const __half *)x, (int)HW, (int)C, ldx, G, (int)rows, workspace);
+    } else {
+        groupnorm_partial_scalar_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, sizeof(float) * 2 * C, st>>>(
+            (const __half *)x, (int)HW, (int)C, ldx, G, (int)rows, workspace);
+    }
     if (int e = check_launch("groupnorm_partial_kernel")) return e;
     groupnorm_finalize_kernel<<<(unsigned)((B * C + 255) / 256), 256, 0, st>>>(workspace, (int)B, (int)C, G, HW * (C / G), eps, gamma,
                                                                               beta, mean, rstd, scale, shift);

@@ -63,8 +63,8 @@ def gemm(a, w, bias=None, residual=None, act=0, out=None, out_dtype=F16, bias_ro
         g.residual = residual.data_ptr()
     g.bias = _ptr(bias)
     if bias_rows is not None:
-        assert bias_rows.dtype == F32 and bias_rows.stride(0) == N and rows_per_bias > 0
-        g.bias_rows, g.rows_per_bias = bias_rows.data_ptr(), rows_per_bias
+        assert bias_rows.dtype == F32 and bias_rows.stride(1) == 1 and bias_rows.shape[1] == N and rows_per_bias > 0
+        g.bias_rows, g.rows_per_bias, g.bias_rows_ld = bias_rows.data_ptr(), rows_per_bias, bias_rows.stride(0)
     g.alpha, g.act = alpha, act
     with torch.cuda.device(a.device):
         call("coma_gemm_f16_ex", ctypes.addressof(g), _stream())
@@ -147,7 +147,8 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
             assert residual.dtype == F16 and residual.stride(0) == out.t.stride(0)
         with torch.cuda.device(x.t.device):
             call("coma_conv3x3_f16", xa.t.data_ptr(), xa.B, xa.H, xa.W, xa.C, xa.ld, w.data_ptr(), w.stride(0), N, _ptr(bias),
-                 _ptr(bias_rows), None if residual is None else residual.data_ptr(), 0,
+                 None if bias_rows is None else bias_rows.data_ptr(), 0 if bias_rows is None else bias_rows.stride(0),
+                 None if residual is None else residual.data_ptr(), 0,
                  out.t.data_ptr() if out_dtype == F16 else None, out.t.data_ptr() if out_dtype == F32 else None, out.t.stride(0),
                  _stream())
         return out

@@ -44,7 +44,7 @@ class UNet:
         gn1 = nn.gn_affine(x, p[name + ".norm1.weight"], p[name + ".norm1.bias"], G, 1e-5)
         a, b = self.tproj_slices[name + ".time_emb_proj"]
         h = nn.conv3x3(x, p[name + ".conv1.weight"], p[name + ".conv1.bias"], gn=gn1, act=1,
-                       bias_rows=tproj[:, a:b].contiguous())
+                       bias_rows=tproj[:, a:b])
         gn2 = nn.gn_affine(h, p[name + ".norm2.weight"], p[name + ".norm2.bias"], G, 1e-5)
         if name + ".conv_shortcut.weight" in p:
             sc = nn.gemm(x.t, p[name + ".conv_shortcut.weight"], p[name + ".conv_shortcut.bias"])

@@ -123,7 +123,7 @@ typedef struct coma_gemm_args {
     void *out_f16; float *out_f32; int64_t ldo, o_s1, o_s2;
     const void *residual;
     const float *bias;
-    const float *bias_rows; int64_t rows_per_bias;
+    const float *bias_rows; int64_t rows_per_bias, bias_rows_ld; /* row stride of bias_rows, 0 = N */
     int64_t M, N, K, nb1, nb2;
     float alpha;
     int act;
@@ -135,8 +135,8 @@ COMA_API int coma_gemm_f16_ex(const coma_gemm_args *args, coma_stream_t stream);
  * matrix exists. x [B,H,W,C] NHWC f16 (row stride ldx, C % 64 == 0, H and W must tile into 128-pixel blocks);
  * W [N, ldw >= 9C] f16 with K order (ky, kx, c); epilogue as in coma_gemm_f16_ex with rows_per_bias = H*W. */
 COMA_API int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const void *Wt, int64_t ldw,
-                              int64_t N, const float *bias, const float *bias_rows, const void *residual, int act, void *out_f16,
-                              float *out_f32, int64_t ldo, coma_stream_t stream);
+                              int64_t N, const float *bias, const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act,
+                              void *out_f16, float *out_f32, int64_t ldo, coma_stream_t stream);
 
 COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
