@@ -12,6 +12,7 @@
 // thres (found on the host), so the verdict `sq < T` is identical and the hot loop needs no IEEE square root.
 // The proximity term exp(-d/size) only has to hold 1e-4: d = sq*rsqrt(sq) (MUFU) and exp via one MUFU.EX2.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -182,6 +183,51 @@ __global__ void __launch_bounds__(K2V_TX *K2V_TY, 4)
     }
 }
 
+// ---- streaming variant for S <= 4 samples per launch (the reference's one-sample-per-call form): no shared memory, no
+// barriers. A thread owns 4 object columns x 4 human rows; per sample it reads its 4 object vertices as three float4 (48
+// contiguous bytes) and the 4 human vertices as warp-uniform broadcast loads, everything else is the accumulator stream
+// (LDG.128 / STG.128, evict-first). With nothing to synchronise on, CTAs are pure load -> math -> store pipelines and the
+// SM keeps >100 KB of accumulator traffic in flight.
+template <int RH, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    pair_accumulate_stream_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float sq_thres,
+                                  float nl2e, float *__restrict__ count, float *__restrict__ nom) {
+    constexpr int K2V_RH = RH;
+    const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+    const int o = blockIdx.x * K2V_TO + 4 * tx, h0 = (blockIdx.y * 2 + ty) * RH;
+    if (o >= O) return;
+    float4 cnt[K2V_RH], acc[K2V_RH];
+#pragma unroll
+    for (int r = 0; r < K2V_RH; ++r) {
+        const bool ok = h0 + r < H;
+        const size_t q = (size_t)(h0 + r) * O + o;
+        cnt[r] = ok ? __ldcs(reinterpret_cast<const float4 *>(count + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[r] = ok ? __ldcs(reinterpret_cast<const float4 *>(nom + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int s = 0; s < S; ++s) {
+        const float4 *op = reinterpret_cast<const float4 *>(ov + ((size_t)s * O + o) * 3);  // 12 floats, 16-byte aligned (o % 4 == 0)
+        const float4 a = __ldg(op), b = __ldg(op + 1), c = __ldg(op + 2);  // x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3
+#pragma unroll
+        for (int r = 0; r < K2V_RH; ++r) {
+            const int h = min(h0 + r, H - 1);
+            const float *hp = hv + ((size_t)s * H + h) * 3;
+            const float hx = __ldg(hp), hy = __ldg(hp + 1), hz = __ldg(hp + 2);
+            pair_update(hx, hy, hz, a.x, a.y, a.z, sq_thres, nl2e, cnt[r].x, acc[r].x);
+            pair_update(hx, hy, hz, a.w, b.x, b.y, sq_thres, nl2e, cnt[r].y, acc[r].y);
+            pair_update(hx, hy, hz, b.z, b.w, c.x, sq_thres, nl2e, cnt[r].z, acc[r].z);
+            pair_update(hx, hy, hz, c.y, c.z, c.w, sq_thres, nl2e, cnt[r].w, acc[r].w);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < K2V_RH; ++r) {
+        if (h0 + r < H) {
+            const size_t q = (size_t)(h0 + r) * O + o;
+            __stcs(reinterpret_cast<float4 *>(count + q), cnt[r]);
+            __stcs(reinterpret_cast<float4 *>(nom + q), acc[r]);
+        }
+    }
+}
+
 // Smallest float T with sqrtf_rn(T) >= thres, so that  sqrtf_rn(x) < thres  <=>  x < T  for every x >= 0.
 static float squared_threshold_f32(float thres) {
     if (!(thres > 0.0f)) return 0.0f;  // d < thres never holds for thres <= 0 or NaN (d >= 0)
@@ -209,6 +255,20 @@ extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_
     const float nl2e = (float)(-1.4426950408889634 / (double)grid_size);
     const float sq_thres = squared_threshold_f32(thres);
     const bool vec4 = (O % 4 == 0) && (((uintptr_t)count | (uintptr_t)nom) % 16 == 0);
+    if (vec4 && S <= 4 && ((uintptr_t)ov % 16 == 0)) {
+        // measured (tools/k2_stream_bench.py): 4 rows/thread at 3 CTAs/SM (80 registers, no spills) 5.79-5.97 TB/s;
+        // 4 CTAs/SM (64 registers, spills) 5.30; 2 rows/thread at 6 CTAs/SM 5.28.  COMA_B200_K2S selects the others.
+        const char *var = getenv("COMA_B200_K2S");
+        const int kind = var ? atoi(var) : 2;
+        const int rh = (kind == 1) ? 2 : 4;
+        dim3 vgrid((unsigned)((O + K2V_TO - 1) / K2V_TO), (unsigned)((H + 2 * rh - 1) / (2 * rh)));
+        COMA_REQUIRE(vgrid.y <= 65535u, "H too large for one launch");
+        cudaStream_t st = (cudaStream_t)stream;
+        if (kind == 1) pair_accumulate_stream_kernel<2, 6><<<vgrid, 256, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
+        else if (kind == 2) pair_accumulate_stream_kernel<4, 3><<<vgrid, 256, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
+        else pair_accumulate_stream_kernel<4, 4><<<vgrid, 256, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
+        return check_launch("pair_accumulate_stream_kernel");
+    }
     if (vec4) {
         dim3 vblock(K2V_TX, K2V_TY);
         dim3 vgrid((unsigned)((O + K2V_TO - 1) / K2V_TO), (unsigned)((H + K2V_TH - 1) / K2V_TH));
