@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcoma_b200.so")
+LIB_PATH = os.environ.get("COMA_B200_LIB") or os.path.join(_HERE, "libcoma_b200.so")
 
 _c = ctypes
 _vp, _i64, _f32, _f64, _int = _c.c_void_p, _c.c_int64, _c.c_float, _c.c_double, _c.c_int

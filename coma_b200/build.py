@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libcoma_b200.so")
+LIB = os.environ.get("COMA_B200_LIB") or os.path.join(HERE, "libcoma_b200.so")   # override: A/B builds for tuning runs
 SOURCES = ["capi.cu", "pair.cu", "orient.cu", "occupancy.cu", "nearest.cu", "readout.cu", "gemm.cu", "unet_ops.cu", "pipeline_ops.cu", "attention.cu"]
 
 NVCC_FLAGS = [
@@ -35,7 +35,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("COMA_NVCC_EXTRA", "").split() + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     env = dict(os.environ)
     env.pop("CC", None)  # the image's CC points at a wrapper nvcc should not use
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 ? 2 : 1))
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+    pdl_trigger();  // PDL: the prologue above overlapped the previous kernel's tail
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -361,7 +363,7 @@ static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const 
         attr[dev] = true;
     }
     dim3 grid((S + FA_BQ - 1) / FA_BQ, heads, B);
-    attention_fwd_kernel<DKB, DN, STAGES><<<grid, FA_THREADS, smem, st>>>(tq, tk, tv, S, L, d, scale_log2, out, ldo, o_bstride);
+    launch_pdl(attention_fwd_kernel<DKB, DN, STAGES>, grid, dim3(FA_THREADS), smem, st, tq, tk, tv, S, L, d, scale_log2, out, ldo, o_bstride);
     return check_launch("attention_fwd_kernel");
 }
 

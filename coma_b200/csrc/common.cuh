@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/coma_b200.h"
 
 namespace coma {
@@ -30,6 +32,28 @@ inline int check_launch(const char *what) {
             return COMA_E_BADARG;                        \
         }                                                \
     } while (0)
+
+// ---- programmatic dependent launch (PDL): the UNet / VAE forward is ~500 short dependent kernels replayed from a CUDA
+// graph; with the launch attribute below a kernel's CTAs are scheduled while its predecessor drains, run their prologue
+// (barrier init, TMEM allocation, descriptor prefetch) and block in pdl_wait() until the predecessor's memory is visible.
+// Every kernel launched through launch_pdl() calls pdl_trigger() and then pdl_wait() before it touches global memory.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

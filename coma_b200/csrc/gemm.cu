@@ -17,13 +17,22 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
 namespace coma {
 
 constexpr int G_BM = 128, G_BK = 64;
-constexpr int G_THREADS = 192;
+// warps: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue. One-CTA-per-SM tiles (BN > 128) run TWO epilogue warps per TMEM lane
+// quarter (they split the tile's 32-column panels): a lone warp per SM sub-partition is issue-latency bound (~150 dependent
+// instructions per panel) and cannot keep up with a short-K main loop. The BN <= 128 tiles get the same 8 warps per SM from
+// their two resident CTAs.
+#ifndef COMA_GEMM_WIDE_EPI_WARPS
+#define COMA_GEMM_WIDE_EPI_WARPS 8
+#endif
+__host__ __device__ constexpr int gemm_epi_warps(int BN) { return BN <= 128 ? 4 : COMA_GEMM_WIDE_EPI_WARPS; }
+__host__ __device__ constexpr int gemm_threads(int BN) { return 64 + 32 * gemm_epi_warps(BN); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -89,6 +98,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// warp-synchronous TMEM load whose completion is awaited separately (tmem_wait_ld ties the registers to the wait)
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t *v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+// TMA store of a shared-memory box (bulk async group) and its completion primitives
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int x, int y, int z, int w) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+                 "r"(x), "r"(y), "r"(z), "r"(w)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 struct GemmEpilogue {
     const float *bias;       // [N] or null
     const float *bias_rows;  // [ceil(M/rows_per_bias), N] or null (e.g. the per-sample time-embedding term of a ResnetBlock)
@@ -102,7 +144,11 @@ struct GemmEpilogue {
     float alpha;             // scales the accumulator (attention: 1/sqrt(d))
     int act;                 // 0 = identity, 1 = SiLU
     int nb1;                 // extent of batch dim 1 (blockIdx.z = b2 * nb1 + b1)
+    int tma;                 // 1: fp16 output (and residual) move as 32x32 boxes through shared memory + TMA (tmO / tmR)
 };
+
+constexpr int E_PANEL_BYTES = 32 * 32 * 2;  // one epilogue panel: 32 rows x 32 fp16 columns, 64-byte rows, 64B-swizzled
+__host__ __device__ constexpr int gemm_epi_bufs(int BN) { return 2; }
 
 // Implicit-GEMM 3x3 convolution (stride 1, pad 1) on an NHWC tensor: the A operand of K-slab (tap, channel block) is the
 // 128-pixel output tile shifted by (ky-1, kx-1), fetched by ONE 4-D TMA load whose out-of-image coordinates are
@@ -124,18 +170,27 @@ struct TileSched {
 // BN in {64, 128, 160, 256}: wider tiles raise the flop/byte of the operand stream (L2 -> SMEM is what bounds a 128x128
 // tile at ~0.75 PFLOP/s on this part: 32 KB per 2.1 MFLOP).
 template <int BN, bool CONV, int STAGES>
-__global__ void __launch_bounds__(G_THREADS, (BN <= 128 ? 2 : 1))
-    gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+__global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
+    gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, int M, int N, int K,
                        const GemmEpilogue ep, const ConvGeom cg, const TileSched ts) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // The two-CTA-per-SM configurations (BN <= 128) have no room for alignment slack: the dynamic window is requested
+    // 1024-byte aligned (128B-swizzle atoms) and the kernel traps if the toolchain ever places it otherwise.
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     constexpr int A_BYTES = G_BM * G_BK * 2, B_BYTES = BN * G_BK * 2;
+    constexpr int NBUF = gemm_epi_bufs(BN);
+    constexpr int EPI_WARPS = gemm_epi_warps(BN);
+    constexpr int PW = EPI_WARPS / 4;       // epilogue warps per TMEM lane quarter = panel stride of one warp
     uint8_t *sA = smem, *sB = smem + STAGES * A_BYTES;
-    uint64_t *full = reinterpret_cast<uint64_t *>(sB + STAGES * B_BYTES);
+    uint8_t *sE = sB + STAGES * B_BYTES;    // epilogue staging: EPI_WARPS warps x NBUF panels
+    uint64_t *full = reinterpret_cast<uint64_t *>(sE + EPI_WARPS * NBUF * E_PANEL_BYTES);
     uint64_t *empty = full + STAGES;
     uint64_t *tmem_full = empty + STAGES;   // [2]
     uint64_t *tmem_empty = tmem_full + 2;   // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *res_full = tmem_empty + 2;    // [EPI_WARPS][NBUF]: residual panel landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_full + EPI_WARPS * NBUF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (K + G_BK - 1) / G_BK;
@@ -144,14 +199,19 @@ __global__ void __launch_bounds__(G_THREADS, (BN <= 128 ? 2 : 1))
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (ep.tma) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+            if (ep.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+        }
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(full + i, 1);
             mbar_init(empty + i, 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tmem_full + i, 1);
-            mbar_init(tmem_empty + i, 128);
+            mbar_init(tmem_empty + i, 32 * EPI_WARPS);
         }
+        for (int i = 0; i < EPI_WARPS * NBUF; ++i) mbar_init(res_full + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -163,6 +223,9 @@ __global__ void __launch_bounds__(G_THREADS, (BN <= 128 ? 2 : 1))
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: everything above overlapped the previous kernel's tail; its results are visible after pdl_wait()
+    pdl_trigger();
+    pdl_wait();
 
     // tile id -> coordinates
     auto decode = [&](int t, int &m0, int &n0, int &b1, int &b2, int &cx0, int &cy0, int &cb0) {
@@ -233,6 +296,153 @@ __global__ void __launch_bounds__(G_THREADS, (BN <= 128 ? 2 : 1))
                 umma_commit(tmem_full + acc);
             }
         }
+    } else if (ep.tma) {
+        // ---- epilogue, TMA form: a warp owns TMEM lanes [32q, 32q+32) = 32 output rows (always contiguous in memory, also
+        // for the conv tiles: TW == W whenever a tile spans several image rows). Per 32-column panel: the residual panel
+        // arrives by TMA into a 64B-swizzled 2 KB buffer (prefetched NBUF-1 panels ahead, across tile boundaries), each
+        // thread folds accumulator + bias (+ residual, SiLU) for its row IN PLACE, and one lane hands the buffer to a TMA
+        // store, which also clips rows >= M / columns >= N. No per-thread global stores, no cross-warp synchronisation.
+        const float *__restrict__ bias = ep.bias;
+        const int act = ep.act;
+        const float alpha = ep.alpha;
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;  // which of the PW interleaved panel subsets this warp owns
+        const bool has_res = ep.residual != nullptr;
+        uint8_t *ebuf = sE + (warp - 2) * (NBUF * E_PANEL_BYTES);
+        uint64_t *rb = res_full + (warp - 2) * NBUF;
+        uint8_t *my_row = ebuf + lane * 64;
+        const int sw = (lane >> 1) & 3;  // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
+        // load cursor (lane 0 only): walks the same (tile, panel) stream as the consumer loop, NBUF-1 panels ahead
+        int lt = blockIdx.x, lp = 0, lP = 0, lrow0 = 0, ln0 = 0, lb1 = 0, lb2 = 0;
+        uint32_t lg = 0;
+        auto cursor_tile = [&]() {  // position the cursor on this warp's first panel of tile lt (skipping tiles without one)
+            while (lt < ts.total) {
+                int m0, n0, b1, b2, cx0, cy0, cb0;
+                decode(lt, m0, n0, b1, b2, cx0, cy0, cb0);
+                lrow0 = CONV ? ((cb0 * cg.H + cy0) * cg.W + cx0) : m0;
+                ln0 = n0; lb1 = b1; lb2 = b2; lp = half;
+                lP = (min(BN, N - n0) + 31) >> 5;
+                if (lp < lP) break;
+                lt += gridDim.x;
+            }
+        };
+        auto cursor_issue = [&]() {  // issue the residual load of the cursor's panel, then advance
+            if (lt >= ts.total) return;
+            const uint32_t buf = lg % NBUF;
+            mbar_expect_tx(rb + buf, E_PANEL_BYTES);
+            tma_load_4d(ebuf + buf * E_PANEL_BYTES, &tmR, rb + buf, ln0 + lp * 32, lrow0 + q * 32, lb1, lb2);
+            ++lg;
+            lp += PW;
+            if (lp >= lP) {
+                lt += gridDim.x;
+                cursor_tile();
+            }
+        };
+        if (has_res && lane == 0) {
+            cursor_tile();
+#pragma unroll 1
+            for (int i = 0; i < NBUF - 1; ++i) cursor_issue();
+        }
+        uint32_t g = 0;
+        int i = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+            int m0, n0, b1, b2, cx0, cy0, cb0;
+            decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
+            const int row0 = (CONV ? ((cb0 * cg.H + cy0) * cg.W + cx0) : m0) + q * 32;
+            const int P = (min(BN, N - n0) + 31) >> 5;
+            const int brow_row = min(row0 + lane, M - 1) / ep.rows_per_bias;
+            const float *brow = ep.bias_rows ? ep.bias_rows + (size_t)brow_row * ep.bias_rows_ld : nullptr;
+            const int acc = i & 1;
+            mbar_wait(tmem_full + acc, (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int p = half; p < P; p += PW, ++g) {
+                const uint32_t buf = g % NBUF;
+                uint8_t *prow = my_row + buf * E_PANEL_BYTES;
+                uint32_t v[32];
+                tmem_ld32_async(tmem_d + (uint32_t)(p * 32), v);
+                const int nb = n0 + p * 32;
+                float f[32];
+                if (nb + 32 <= N) {
+                    if (bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + nb + j));
+                            f[j] = b4.x; f[j + 1] = b4.y; f[j + 2] = b4.z; f[j + 3] = b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = 0.0f;
+                    }
+                    if (brow) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(brow + nb + j));
+                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        }
+                    }
+                } else {  // last, partial panel of the matrix
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const bool ok = nb + j < N;
+                        f[j] = (ok && bias) ? __ldg(bias + nb + j) : 0.0f;
+                        if (ok && brow) f[j] += __ldg(brow + nb + j);
+                    }
+                }
+                if (has_res) {
+                    mbar_wait(rb + buf, (g / NBUF) & 1);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 r = *reinterpret_cast<const uint4 *>(prow + ((c ^ sw) << 4));
+                        const __half2 *h = reinterpret_cast<const __half2 *>(&r);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float2 x = __half22float2(h[u]);
+                            f[c * 8 + 2 * u] += x.x;
+                            f[c * 8 + 2 * u + 1] += x.y;
+                        }
+                    }
+                } else {
+                    if (lane == 0) bulk_wait_read<NBUF - 1>();  // the store that last read this buffer has drained it
+                    __syncwarp();
+                }
+                tmem_wait_ld(v);
+                const float2 alpha2 = make_float2(alpha, alpha);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {  // packed FP32x2 FMAs
+                    const float2 r = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), alpha2,
+                                                make_float2(f[j], f[j + 1]));
+                    f[j] = r.x;
+                    f[j + 1] = r.y;
+                }
+                if (act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 w;
+                    __half2 *h = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(f[c * 8 + 2 * u], f[c * 8 + 2 * u + 1]);
+                    *reinterpret_cast<uint4 *>(prow + ((c ^ sw) << 4)) = w;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&tmO, ebuf + buf * E_PANEL_BYTES, nb, row0, b1, b2);
+                    bulk_commit();
+                    if (has_res) {
+                        bulk_wait_read<1>();  // the previous panel's store has finished reading its buffer: refill it
+                        cursor_issue();
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty + acc);
+        }
+        if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last stores' reads
     } else {
         const float *__restrict__ bias = ep.bias;
         const int act = ep.act, ldo = ep.ldo;
@@ -256,7 +466,7 @@ __global__ void __launch_bounds__(G_THREADS, (BN <= 128 ? 2 : 1))
                 row = (cb0 + tb < cg.B) ? ((cb0 + tb) * cg.H + cy0 + ty) * cg.W + cx0 + tx : M;
             }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN; c0 += 32 * PW) {
                 uint32_t v[32];
                 tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (row < M && n0 + c0 < N) {
@@ -367,11 +577,50 @@ static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols,
     return 0;
 }
 
+// fp16 [rows, cols] matrix (row stride ld, batch strides s1 / s2) as 32 x 32 boxes with 64-byte rows, 64B-swizzled: the
+// epilogue's staging panels (TMA store of the output, TMA load of the residual).
+static int make_panel_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int64_t nb1, int64_t s1, int64_t nb2,
+                          int64_t s2) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return COMA_E_NODEVICE;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nb1, (cuuint64_t)nb2};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(nb1 > 1 ? s1 : ld) * 2, (cuuint64_t)(nb2 > 1 ? s2 : ld) * 2};
+    cuuint32_t box[4] = {32, 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (epilogue panel) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
+                  (long long)rows, (long long)cols, (long long)ld);
+        return COMA_E_BADARG;
+    }
+    return 0;
+}
+
+// Decides whether the epilogue can run in its TMA form and builds the output / residual panel maps.
+static int setup_epilogue_maps(GemmEpilogue &ep, CUtensorMap *to, CUtensorMap *tr, int64_t M, int64_t N, int64_t nb1, int64_t nb2) {
+    memset(to, 0, sizeof(*to));
+    memset(tr, 0, sizeof(*tr));
+    const bool ok = ep.out16 && !ep.out32 && ep.ldo % 8 == 0 && (nb1 == 1 || ep.o_s1 % 8 == 0) && (nb2 == 1 || ep.o_s2 % 8 == 0) &&
+                    (uintptr_t)ep.out16 % 16 == 0 && (uintptr_t)ep.residual % 16 == 0 && (uintptr_t)ep.bias % 16 == 0 &&
+                    (uintptr_t)ep.bias_rows % 16 == 0 && ep.bias_rows_ld % 4 == 0;
+    ep.tma = ok ? 1 : 0;
+    if (!ok) return 0;
+    if (int e = make_panel_map(to, ep.out16, M, N, ep.ldo, nb1, ep.o_s1, nb2, ep.o_s2)) return e;
+    if (ep.residual)
+        if (int e = make_panel_map(tr, ep.residual, M, N, ep.ldo, nb1, ep.o_s1, nb2, ep.o_s2)) return e;
+    return 0;
+}
+
 template <int BN, bool CONV>
-static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K, const GemmEpilogue &ep, int nbatch,
-                       cudaStream_t st, const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
+static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr, int M, int N, int K,
+                       const GemmEpilogue &ep, int nbatch, cudaStream_t st, const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
     constexpr int STAGES = BN <= 128 ? 3 : 4;
-    constexpr size_t smem = (size_t)STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 256 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + gemm_epi_warps(BN) * gemm_epi_bufs(BN) * E_PANEL_BYTES + 256;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -394,7 +643,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, int M, int 
     ts.total = (int)total;
     const int slots = kNumSM * (BN <= 128 ? 2 : 1);
     const unsigned grid = (unsigned)(ts.total < slots ? ts.total : slots);
-    gemm_f16_tn_kernel<BN, CONV, STAGES><<<grid, G_THREADS, smem, st>>>(ta, tb, M, N, K, ep, cg, ts);
+    launch_pdl(gemm_f16_tn_kernel<BN, CONV, STAGES>, dim3(grid), dim3(gemm_threads(BN)), smem, st, ta, tb, to, tr, M, N, K, ep, cg, ts);
     return check_launch("gemm_f16_tn_kernel");
 }
 
@@ -458,8 +707,10 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     ep.alpha = g->alpha;
     ep.act = g->act;
     ep.nb1 = (int)nb1;
+    CUtensorMap to, tr;
+    if (int e = setup_epilogue_maps(ep, &to, &tr, M, N, nb1, nb2)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    COMA_DISPATCH_BN(bn, false, ta, tb, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st)
+    COMA_DISPATCH_BN(bn, false, ta, tb, to, tr, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st)
 }
 
 namespace coma {
@@ -512,8 +763,10 @@ extern "C" int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, 
     ep.bias = bias; ep.bias_rows = bias_rows; ep.rows_per_bias = (int)(H * W); ep.bias_rows_ld = bias_rows_ld > 0 ? bias_rows_ld : N; ep.residual = (const __half *)residual;
     ep.out16 = (__half *)out_f16; ep.out32 = out_f32; ep.ldo = (int)ldo; ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = act;
     ep.nb1 = 1;
+    CUtensorMap to, tr;
+    if (int e = setup_epilogue_maps(ep, &to, &tr, M, N, 1, 1)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    COMA_DISPATCH_BN(bn, true, ta, tb, (int)M, (int)N, (int)K, ep, 1, st, cg, (int)m_tiles)
+    COMA_DISPATCH_BN(bn, true, ta, tb, to, tr, (int)M, (int)N, (int)K, ep, 1, st, cg, (int)m_tiles)
 }
 
 extern "C" int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,

@@ -16,6 +16,8 @@ namespace coma {
 __global__ void cfg_ddim_kernel(const float *__restrict__ eps, long long half_rows, int ld, int C, float guidance,
                                 const float *__restrict__ x, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev,
                                 float sqrt_1m_a_prev, float *__restrict__ x_prev, float *__restrict__ x0) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half_rows * C) return;
     const long long r = i / C;
@@ -31,6 +33,8 @@ __global__ void cfg_ddim_kernel(const float *__restrict__ eps, long long half_ro
 // in9[(b', p), 0:4] = latents[b, p, :], [4] = mask64[b, p], [5:9] = masked_latents[b, p, :], b' in {b, b + B} (CFG duplicate)
 __global__ void assemble_input_kernel(const float *__restrict__ lat, const float *__restrict__ mask64,
                                       const float *__restrict__ masked_lat, long long rows, __half *__restrict__ out, int ldo) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * 9) return;
     const long long r = i / 9;
@@ -43,6 +47,8 @@ __global__ void assemble_input_kernel(const float *__restrict__ lat, const float
 
 // ---- adaptive mask --------------------------------------------------------------------------------------------------
 __global__ void mask_area_kernel(const uint8_t *__restrict__ seg, int n, unsigned long long *__restrict__ area) {
+    pdl_trigger();
+    pdl_wait();
     unsigned long long s = 0;
     const uint8_t *m = seg + (size_t)blockIdx.y * n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += m[i];
@@ -54,6 +60,8 @@ __global__ void mask_area_kernel(const uint8_t *__restrict__ seg, int n, unsigne
 // horizontal (dir = 0) or vertical (dir = 1) running max of radius k over a u8 image; pixels outside the image are
 // ignored — identical to k iterations of cv2.dilate with a 3x3 ones kernel (default border handling).
 __global__ void box_max_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int H, int W, int k, int dir) {
+    pdl_trigger();
+    pdl_wait();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
     const uint8_t *src = in + (size_t)b * H * W;
@@ -74,6 +82,8 @@ __global__ void mask_finalize_kernel(const uint8_t *__restrict__ dil, const uint
                                      int W, const float *__restrict__ image /* [B,H,W,3] in [-1,1] */, uint8_t *__restrict__ mask_out,
                                      __half *__restrict__ masked_image /* [B,H,W,ldm] */, int ldm, float *__restrict__ mask_small,
                                      int *__restrict__ used_default) {
+    pdl_trigger();
+    pdl_wait();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
     const bool use_def = force_default || ((float)area[b] < area_thres);            // :1130
@@ -90,6 +100,8 @@ __global__ void mask_finalize_kernel(const uint8_t *__restrict__ dil, const uint
 }
 
 __global__ void image_to_u8_kernel(const float *__restrict__ img, long long rows, int ld, uint8_t *__restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * 3) return;
     const float v = fminf(fmaxf(img[(i / 3) * ld + (i % 3)] * 0.5f + 0.5f, 0.0f), 1.0f);
@@ -98,6 +110,8 @@ __global__ void image_to_u8_kernel(const float *__restrict__ img, long long rows
 
 __global__ void sample_latents_kernel(const float *__restrict__ mean, const float *__restrict__ logvar,
                                       const float *__restrict__ noise, long long n, float scaling, float *__restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (mean[i] + expf(0.5f * logvar[i]) * noise[i]) * scaling;
 }
@@ -112,7 +126,7 @@ extern "C" int coma_cfg_ddim_step_f32(const float *eps, int64_t half_rows, int64
     COMA_REQUIRE(half_rows > 0 && C > 0 && ld >= C, "bad sizes");
     COMA_REQUIRE(alpha_t > 0.0 && alpha_t <= 1.0 && alpha_prev > 0.0 && alpha_prev <= 1.0, "alphas_cumprod out of range");
     const long long n = half_rows * C;
-    cfg_ddim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(cfg_ddim_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         eps, half_rows, (int)ld, (int)C, guidance, x, (float)sqrt(alpha_t), (float)sqrt(1.0 - alpha_t), (float)sqrt(alpha_prev),
         (float)sqrt(1.0 - alpha_prev), x_prev, x0);
     return check_launch("cfg_ddim_kernel");
@@ -122,7 +136,7 @@ extern "C" int coma_assemble_unet_input_f16(const float *latents, const float *m
                                             void *out, int64_t ldo, coma_stream_t stream) {
     COMA_REQUIRE(latents && mask64 && masked_latents && out, "null pointer");
     COMA_REQUIRE(rows > 0 && ldo >= 9, "bad sizes");
-    assemble_input_kernel<<<(unsigned)((rows * 9 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(latents, mask64, masked_latents, rows,
+    launch_pdl(assemble_input_kernel, dim3((unsigned)((rows * 9 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, latents, mask64, masked_latents, rows,
                                                                                              (__half *)out, (int)ldo);
     return check_launch("assemble_input_kernel");
 }
@@ -136,33 +150,33 @@ extern "C" int coma_adaptive_mask_u8(const uint8_t *seg, const uint8_t *default_
                  "bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(area_ws, 0, sizeof(unsigned long long) * B, st);
-    mask_area_kernel<<<dim3(32, (unsigned)B), 256, 0, st>>>(seg, (int)(H * W), area_ws);
+    launch_pdl(mask_area_kernel, dim3(dim3(32, (unsigned)B)), dim3(256), 0, st, seg, (int)(H * W), area_ws);
     if (int e = check_launch("mask_area_kernel")) return e;
     const uint8_t *dil = seg;
     if (dilate_iters > 0) {  // separable (2k+1)^2 box max: rows into scratch[0], columns into scratch[1]
         uint8_t *t0 = scratch, *t1 = scratch + (size_t)B * H * W;
         dim3 grid((unsigned)((W + 127) / 128), (unsigned)H, (unsigned)B);
-        box_max_kernel<<<grid, 128, 0, st>>>(seg, t0, (int)H, (int)W, dilate_iters, 0);
+        launch_pdl(box_max_kernel, dim3(grid), dim3(128), 0, st, seg, t0, (int)H, (int)W, dilate_iters, 0);
         if (int e = check_launch("box_max_kernel")) return e;
-        box_max_kernel<<<grid, 128, 0, st>>>(t0, t1, (int)H, (int)W, dilate_iters, 1);
+        launch_pdl(box_max_kernel, dim3(grid), dim3(128), 0, st, t0, t1, (int)H, (int)W, dilate_iters, 1);
         if (int e = check_launch("box_max_kernel")) return e;
         dil = t1;
     }
     dim3 grid((unsigned)((W + 127) / 128), (unsigned)H, (unsigned)B);
-    mask_finalize_kernel<<<grid, 128, 0, st>>>(dil, default_mask, area_ws, area_thres, force_default, (int)H, (int)W, image, mask_out,
+    launch_pdl(mask_finalize_kernel, dim3(grid), dim3(128), 0, st, dil, default_mask, area_ws, area_thres, force_default, (int)H, (int)W, image, mask_out,
                                               (__half *)masked_image, (int)ldm, mask_small, used_default);
     return check_launch("mask_finalize_kernel");
 }
 
 extern "C" int coma_image_to_u8(const float *img, int64_t rows, int64_t ld, uint8_t *out, coma_stream_t stream) {
     COMA_REQUIRE(img && out && rows > 0 && ld >= 3, "bad arguments");
-    image_to_u8_kernel<<<(unsigned)((rows * 3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, rows, (int)ld, out);
+    launch_pdl(image_to_u8_kernel, dim3((unsigned)((rows * 3 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, rows, (int)ld, out);
     return check_launch("image_to_u8_kernel");
 }
 
 extern "C" int coma_sample_latents_f32(const float *mean, const float *logvar, const float *noise, int64_t n, float scaling,
                                        float *out, coma_stream_t stream) {
     COMA_REQUIRE(mean && logvar && noise && out && n > 0, "bad arguments");
-    sample_latents_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mean, logvar, noise, n, scaling, out);
+    launch_pdl(sample_latents_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, mean, logvar, noise, n, scaling, out);
     return check_launch("sample_latents_kernel");
 }

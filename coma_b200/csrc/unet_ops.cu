@@ -24,6 +24,8 @@ namespace coma {
 __global__ void __launch_bounds__(256)
     groupnorm_partial_kernel(const __half *__restrict__ x, int HW, int C, long long ldx, int G, int rows_per_chunk,
                              double *__restrict__ acc /* [B,G,2] */) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];  // [rg][2][C]
     const int b = blockIdx.y, p0 = blockIdx.x * rows_per_chunk, p1 = min(HW, p0 + rows_per_chunk);
     const __half *xb = x + (size_t)b * HW * ldx;
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     groupnorm_partial_scalar_kernel(const __half *__restrict__ x, int HW, int C, long long ldx, int G, int rows_per_chunk,
                                     double *__restrict__ acc) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];  // [2][C]
     const int b = blockIdx.y, p0 = blockIdx.x * rows_per_chunk, p1 = min(HW, p0 + rows_per_chunk);
     const __half *xb = x + (size_t)b * HW * ldx;
@@ -102,6 +106,8 @@ __global__ void __launch_bounds__(256)
 __global__ void groupnorm_finalize_kernel(const double *__restrict__ acc, int B, int C, int G, long long count, float eps,
                                           const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ mean,
                                           float *__restrict__ rstd, float *__restrict__ scale, float *__restrict__ shift) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * C) return;
     const int b = i / C, c = i % C, g = c / (C / G);
@@ -125,6 +131,8 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)
 __global__ void __launch_bounds__(256)
     affine_act_kernel(const __half *__restrict__ x, long long rows, int HW, int C, long long ldx, const float *__restrict__ scale,
                       const float *__restrict__ shift, int act, __half *__restrict__ y, long long ldy) {
+    pdl_trigger();
+    pdl_wait();
     const int c8n = C / 8;
     const long long total = rows * c8n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -156,6 +164,8 @@ __global__ void __launch_bounds__(256)
     upsample2x_affine_act_kernel(const __half *__restrict__ x, int B, int H, int W, int C, long long ldx,
                                  const float *__restrict__ scale, const float *__restrict__ shift, int act, __half *__restrict__ y,
                                  long long ldy) {
+    pdl_trigger();
+    pdl_wait();
     const int c8n = C / 8;
     const long long total = (long long)B * 4 * H * W * c8n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -190,6 +200,8 @@ __global__ void __launch_bounds__(256)
     im2col3x3_kernel(const __half *__restrict__ x, int B, int H, int W, int C, long long ldx, int Ho, int Wo, int stride, int pad,
                      int up, const float *__restrict__ scale, const float *__restrict__ shift, int act, __half *__restrict__ out,
                      long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     const int Hin = up ? 2 * H : H, Win = up ? 2 * W : W;  // logical input extent
     const int cv = VEC8 ? C / 8 : C;
     const long long total = (long long)B * Ho * Wo * 9 * cv;
@@ -241,6 +253,8 @@ __global__ void __launch_bounds__(256)
 
 // zero the K-padding columns [K, ldo) of an im2col matrix (only when 9C is not a multiple of 8)
 __global__ void zero_cols_kernel(__half *__restrict__ out, long long rows, int K, long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     const int padc = (int)(ldo - K);
     const long long total = rows * padc;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -251,6 +265,8 @@ __global__ void zero_cols_kernel(__half *__restrict__ out, long long rows, int K
 __global__ void __launch_bounds__(256)
     layernorm_kernel(const __half *__restrict__ x, long long M, int C, long long ldx, const float *__restrict__ gamma,
                      const float *__restrict__ beta, float eps, __half *__restrict__ y, long long ldy) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -274,6 +290,8 @@ __global__ void __launch_bounds__(256)
 //   L <= 4096 and 16-byte aligned rows: one 256-thread CTA per row, 16 values per thread as two 16-byte loads
 //   otherwise : three-pass fallback
 __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(__half *__restrict__ s, long long R, int L, long long ld) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= R) return;
@@ -303,6 +321,8 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(__half *__restri
 }
 
 __global__ void __launch_bounds__(256) softmax_rows_block_kernel(__half *__restrict__ s, int L, long long ld) {
+    pdl_trigger();
+    pdl_wait();
     __half *row = s + (long long)blockIdx.x * ld;
     __shared__ float red[8];
     __shared__ float bc;
@@ -365,6 +385,8 @@ __global__ void __launch_bounds__(256) softmax_rows_block_kernel(__half *__restr
 }
 
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__half *__restrict__ s, int L, long long ld) {
+    pdl_trigger();
+    pdl_wait();
     __half *row = s + (long long)blockIdx.x * ld;
     __shared__ float red[8];
     __shared__ float bc;
@@ -402,6 +424,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half *__restrict__ 
 // ---------------------------------------------------------------------------------------------- GEGLU
 __global__ void __launch_bounds__(256)
     geglu_kernel(const __half *__restrict__ h, long long M, int C, long long ldh, __half *__restrict__ y, long long ldy) {
+    pdl_trigger();
+    pdl_wait();
     const int c2n = C / 2;
     const long long total = M * c2n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -419,6 +443,8 @@ __global__ void __launch_bounds__(256)
 // v [B, L, heads*d] (row stride ldv) -> vt [B, heads, d, Lpad], zero padded. 32x32 smem tiles.
 __global__ void __launch_bounds__(256)
     transpose_heads_kernel(const __half *__restrict__ v, int L, int heads, int d, long long ldv, __half *__restrict__ vt, int Lpad) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __half tile[32][33];
     const int bh = blockIdx.z, b = bh / heads, hd = bh % heads;
     const int l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -437,6 +463,8 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------- timestep embedding
 // diffusers get_timestep_embedding(t, dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i) | sin(t f_i)]
 __global__ void timestep_embedding_kernel(const float *__restrict__ t, int B, int dim, __half *__restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = dim / 2;
     if (i >= B * half) return;
@@ -449,6 +477,8 @@ __global__ void timestep_embedding_kernel(const float *__restrict__ t, int B, in
 
 // elementwise SiLU on fp16 (time-embedding MLP input of every ResnetBlock)
 __global__ void silu_kernel(const __half *__restrict__ x, long long n, __half *__restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __float2half_rn(silu_f(__half2float(x[i])));
 }
@@ -479,14 +509,14 @@ extern "C" int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, i
     const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && ((uintptr_t)x % 16 == 0);
     if (vec) {
         const int cgn = (int)(C / 8), rg = cgn >= 256 ? 1 : 256 / cgn;
-        groupnorm_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, sizeof(float) * 2 * C * rg, st>>>(
+        launch_pdl(groupnorm_partial_kernel, dim3(dim3((unsigned)chunks, (unsigned)B)), dim3(256), sizeof(float) * 2 * C * rg, st, 
             (const __half *)x, (int)HW, (int)C, ldx, G, (int)rows, workspace);
     } else {
-        groupnorm_partial_scalar_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, sizeof(float) * 2 * C, st>>>(
+        launch_pdl(groupnorm_partial_scalar_kernel, dim3(dim3((unsigned)chunks, (unsigned)B)), dim3(256), sizeof(float) * 2 * C, st, 
             (const __half *)x, (int)HW, (int)C, ldx, G, (int)rows, workspace);
     }
     if (int e = check_launch("groupnorm_partial_kernel")) return e;
-    groupnorm_finalize_kernel<<<(unsigned)((B * C + 255) / 256), 256, 0, st>>>(workspace, (int)B, (int)C, G, HW * (C / G), eps, gamma,
+    launch_pdl(groupnorm_finalize_kernel, dim3((unsigned)((B * C + 255) / 256)), dim3(256), 0, st, workspace, (int)B, (int)C, G, HW * (C / G), eps, gamma,
                                                                               beta, mean, rstd, scale, shift);
     return check_launch("groupnorm_finalize_kernel");
 }
@@ -496,7 +526,7 @@ extern "C" int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t
     COMA_REQUIRE(x && y && scale && shift, "null pointer");
     COMA_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "C, ldx, ldy must be multiples of 8");
     COMA_REQUIRE(((uintptr_t)x | (uintptr_t)y) % 16 == 0, "x / y must be 16-byte aligned");
-    affine_act_kernel<<<blocks_for(B * HW * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __half *)x, B * HW, (int)HW, (int)C, ldx,
+    launch_pdl(affine_act_kernel, dim3(blocks_for(B * HW * (C / 8))), dim3(256), 0, (cudaStream_t)stream, (const __half *)x, B * HW, (int)HW, (int)C, ldx,
                                                                                     scale, shift, act, (__half *)y, ldy);
     return check_launch("affine_act_kernel");
 }
@@ -507,7 +537,7 @@ extern "C" int coma_upsample2x_affine_act_f16(const void *x, int64_t B, int64_t 
     COMA_REQUIRE(x && y, "null pointer");
     COMA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "C, ldx, ldy must be multiples of 8");
     COMA_REQUIRE(((uintptr_t)x | (uintptr_t)y) % 16 == 0 && !scale == !shift, "bad arguments");
-    upsample2x_affine_act_kernel<<<blocks_for(B * 4 * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(upsample2x_affine_act_kernel, dim3(blocks_for(B * 4 * H * W * (C / 8))), dim3(256), 0, (cudaStream_t)stream, 
         (const __half *)x, (int)B, (int)H, (int)W, (int)C, ldx, scale, shift, act, (__half *)y, ldy);
     return check_launch("upsample2x_affine_act_kernel");
 }
@@ -529,16 +559,16 @@ extern "C" int coma_im2col3x3_f16(const void *x, int64_t B, int64_t H, int64_t W
     const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && (((uintptr_t)x | (uintptr_t)out) % 16 == 0);
     const long long rows = B * Ho * Wo;
     if (vec)
-        im2col3x3_kernel<true><<<blocks_for(rows * 9 * (C / 8)), 256, 0, st>>>((const __half *)x, (int)B, (int)H, (int)W, (int)C, ldx,
+        launch_pdl(im2col3x3_kernel<true>, dim3(blocks_for(rows * 9 * (C / 8))), dim3(256), 0, st, (const __half *)x, (int)B, (int)H, (int)W, (int)C, ldx,
                                                                             (int)Ho, (int)Wo, stride, pad, upsample, scale, shift, act,
                                                                             (__half *)out, ldo);
     else
-        im2col3x3_kernel<false><<<blocks_for(rows * 9 * C), 256, 0, st>>>((const __half *)x, (int)B, (int)H, (int)W, (int)C, ldx, (int)Ho,
+        launch_pdl(im2col3x3_kernel<false>, dim3(blocks_for(rows * 9 * C)), dim3(256), 0, st, (const __half *)x, (int)B, (int)H, (int)W, (int)C, ldx, (int)Ho,
                                                                        (int)Wo, stride, pad, upsample, scale, shift, act,
                                                                        (__half *)out, ldo);
     if (int e = check_launch("im2col3x3_kernel")) return e;
     if (ldo > 9 * C) {
-        zero_cols_kernel<<<blocks_for(rows * (ldo - 9 * C)), 256, 0, st>>>((__half *)out, rows, (int)(9 * C), ldo);
+        launch_pdl(zero_cols_kernel, dim3(blocks_for(rows * (ldo - 9 * C))), dim3(256), 0, st, (__half *)out, rows, (int)(9 * C), ldo);
         return check_launch("zero_cols_kernel");
     }
     return 0;
@@ -548,7 +578,7 @@ extern "C" int coma_layernorm_f16(const void *x, int64_t M, int64_t C, int64_t l
                                   void *y, int64_t ldy, coma_stream_t stream) {
     COMA_REQUIRE(x && y && gamma && beta, "null pointer");
     COMA_REQUIRE(M > 0 && C > 0 && ldx >= C && ldy >= C, "bad sizes");
-    layernorm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const __half *)x, M, (int)C, ldx, gamma, beta, eps,
+    launch_pdl(layernorm_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, (const __half *)x, M, (int)C, ldx, gamma, beta, eps,
                                                                               (__half *)y, ldy);
     return check_launch("layernorm_kernel");
 }
@@ -558,21 +588,21 @@ extern "C" int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, 
     COMA_REQUIRE(R > 0 && L > 0 && ld >= L && R < (1LL << 31), "bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     if (ld <= 1024) {
-        softmax_rows_warp_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>((__half *)s, R, (int)L, ld);
+        launch_pdl(softmax_rows_warp_kernel, dim3((unsigned)((R + 7) / 8)), dim3(256), 0, st, (__half *)s, R, (int)L, ld);
         return check_launch("softmax_rows_warp_kernel");
     }
     if (ld <= 4096 && ld % 8 == 0 && (uintptr_t)s % 16 == 0) {
-        softmax_rows_block_kernel<<<(unsigned)R, 256, 0, st>>>((__half *)s, (int)L, ld);
+        launch_pdl(softmax_rows_block_kernel, dim3((unsigned)R), dim3(256), 0, st, (__half *)s, (int)L, ld);
         return check_launch("softmax_rows_block_kernel");
     }
-    softmax_rows_kernel<<<(unsigned)R, 256, 0, st>>>((__half *)s, (int)L, ld);
+    launch_pdl(softmax_rows_kernel, dim3((unsigned)R), dim3(256), 0, st, (__half *)s, (int)L, ld);
     return check_launch("softmax_rows_kernel");
 }
 
 extern "C" int coma_geglu_f16(const void *h, int64_t M, int64_t C, int64_t ldh, void *y, int64_t ldy, coma_stream_t stream) {
     COMA_REQUIRE(h && y, "null pointer");
     COMA_REQUIRE(M > 0 && C > 0 && C % 2 == 0 && ldh >= 2 * C && ldy >= C && ldh % 2 == 0 && ldy % 2 == 0, "bad sizes");
-    geglu_kernel<<<blocks_for(M * (C / 2)), 256, 0, (cudaStream_t)stream>>>((const __half *)h, M, (int)C, ldh, (__half *)y, ldy);
+    launch_pdl(geglu_kernel, dim3(blocks_for(M * (C / 2))), dim3(256), 0, (cudaStream_t)stream, (const __half *)h, M, (int)C, ldh, (__half *)y, ldy);
     return check_launch("geglu_kernel");
 }
 
@@ -581,7 +611,7 @@ extern "C" int coma_transpose_heads_f16(const void *v, int64_t B, int64_t L, int
     COMA_REQUIRE(v && vt, "null pointer");
     COMA_REQUIRE(B > 0 && L > 0 && heads > 0 && d > 0 && Lpad >= L && ldv >= heads * d && B * heads <= 65535, "bad sizes");
     dim3 grid((unsigned)((Lpad + 31) / 32), (unsigned)((d + 31) / 32), (unsigned)(B * heads));
-    transpose_heads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half *)v, (int)L, (int)heads, (int)d, ldv, (__half *)vt,
+    launch_pdl(transpose_heads_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __half *)v, (int)L, (int)heads, (int)d, ldv, (__half *)vt,
                                                                  (int)Lpad);
     return check_launch("transpose_heads_kernel");
 }
@@ -589,12 +619,12 @@ extern "C" int coma_transpose_heads_f16(const void *v, int64_t B, int64_t L, int
 extern "C" int coma_timestep_embedding_f16(const float *t, int64_t B, int64_t dim, void *out, coma_stream_t stream) {
     COMA_REQUIRE(t && out, "null pointer");
     COMA_REQUIRE(B > 0 && dim > 0 && dim % 2 == 0, "bad sizes");
-    timestep_embedding_kernel<<<(unsigned)((B * dim / 2 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(t, (int)B, (int)dim, (__half *)out);
+    launch_pdl(timestep_embedding_kernel, dim3((unsigned)((B * dim / 2 + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, t, (int)B, (int)dim, (__half *)out);
     return check_launch("timestep_embedding_kernel");
 }
 
 extern "C" int coma_silu_f16(const void *x, int64_t n, void *y, coma_stream_t stream) {
     COMA_REQUIRE(x && y && n > 0, "bad arguments");
-    silu_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>((const __half *)x, n, (__half *)y);
+    launch_pdl(silu_kernel, dim3(blocks_for(n)), dim3(256), 0, (cudaStream_t)stream, (const __half *)x, n, (__half *)y);
     return check_launch("silu_kernel");
 }

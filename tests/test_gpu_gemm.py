@@ -55,3 +55,47 @@ def test_gemm_epilogue(dev, act):
     wide = torch.randn((M, K + 64), device=dev, generator=g).half()
     out = ops.gemm_f16(wide[:, :K], w, out_dtype=torch.float32)
     assert (out - _ref(wide[:, :K], w, None, None, 0)).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 320, 320), (4096, 320, 320), (1000, 72, 88), (2048, 1280, 640), (77, 640, 768),
+                                   (8192 + 40, 2560, 320), (512, 1288, 128)])
+@pytest.mark.parametrize("res", [False, True])
+def test_gemm_f16_out_tma_epilogue(dev, M, N, K, res):
+    """fp16 outputs leave through the TMA epilogue (32x32 panels staged in swizzled shared memory, residual fetched by TMA):
+    row / column tails are clipped by the tensor map, every panel of every tile must land exactly once."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(M * 3 + N + K)
+    a = (torch.randn((M, K), device=dev, generator=g) * 0.5).half()
+    w = (torch.randn((N, K), device=dev, generator=g) * K ** -0.5).half()
+    bias = torch.randn(N, device=dev, generator=g)
+    r = torch.randn((M, N), device=dev, generator=g).half() if res else None
+    rows_per_bias = 64
+    brows = torch.randn(((M + rows_per_bias - 1) // rows_per_bias, N), device=dev, generator=g)
+    out = torch.full((M + 2, N), 7.0, dtype=torch.float16, device=dev)      # guard rows: nothing may be written past M
+    nn.gemm(a, w, bias, r, act=1, out=out[:M], bias_rows=brows, rows_per_bias=rows_per_bias, alpha=0.5)
+    ref = 0.5 * (a.float() @ w.float().t()) + bias + brows.repeat_interleave(rows_per_bias, 0)[:M]
+    if res:
+        ref = ref + r.float()
+    ref = torch.nn.functional.silu(ref)
+    torch.testing.assert_close(out[:M].float(), ref, rtol=2e-3, atol=2e-3)
+    assert (out[M:] == 7.0).all()
+
+
+def test_gemm_f16_out_strided_and_batched(dev):
+    """Output written into a column slice of a wider buffer (skip-concat target) and the batched form (nb1 x nb2)."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(5)
+    M, N, K = 640, 320, 192
+    a = torch.randn((M, K), device=dev, generator=g).half()
+    w = (torch.randn((N, K), device=dev, generator=g) * K ** -0.5).half()
+    wide = torch.zeros((M, N + 64), dtype=torch.float16, device=dev)
+    nn.gemm(a, w, out=wide[:, 64:])
+    torch.testing.assert_close(wide[:, 64:].float(), a.float() @ w.float().t(), rtol=2e-3, atol=2e-3)
+    assert (wide[:, :64] == 0).all()
+    B, Hh, S, L, d = 2, 3, 200, 136, 64
+    q = torch.randn((B, S, Hh * d), device=dev, generator=g).half()
+    k = torch.randn((B, L, Hh * d), device=dev, generator=g).half()
+    scores = torch.zeros((B, Hh, S, L), dtype=torch.float16, device=dev)
+    nn.gemm_batched(q, Hh * d, d, S * Hh * d, k, Hh * d, d, L * Hh * d, scores, L, S * L, Hh * S * L, S, L, d, Hh, B, alpha=0.125)
+    ref = 0.125 * torch.einsum("bshd,blhd->bhsl", q.float().view(B, S, Hh, d), k.float().view(B, L, Hh, d))
+    torch.testing.assert_close(scores.float(), ref, rtol=2e-3, atol=2e-3)

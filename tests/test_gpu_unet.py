@@ -70,6 +70,23 @@ def test_conv3x3_with_groupnorm_prologue(dev, C, Cout, H, stride, pad, up, B):
     _close(_nchw(out.t, B, out.H, out.W), ref, 2e-3 if use_gn else 1e-4)
 
 
+
+@pytest.mark.parametrize("C,Cout,H,B", [(64, 96, 16, 2), (128, 320, 8, 3), (64, 160, 32, 2), (64, 40, 64, 1), (128, 128, 128, 1)])
+def test_conv3x3_f16_out_tma_epilogue(dev, C, Cout, H, B):
+    """Implicit-GEMM conv with the fp16 TMA epilogue: bias + per-sample bias rows (time embedding) + residual, all tile
+    geometries (several image rows per tile, two images per tile with an odd batch, one row segment per tile)."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(C + H + Cout)
+    x = torch.randn((B, C, H, H), device=dev, generator=g).half().float()
+    w = (torch.randn((Cout, C, 3, 3), device=dev, generator=g) * (9 * C) ** -0.5).half().float()
+    b = torch.randn(Cout, device=dev, generator=g)
+    brows = torch.randn((B, Cout), device=dev, generator=g)
+    res = torch.randn((B * H * H, Cout), device=dev, generator=g).half()
+    out = nn.conv3x3(_nhwc(x), nn.prep_conv3x3(w, dev), b, residual=res, bias_rows=brows)
+    ref = F.conv2d(x, w, b, padding=1) + brows[:, :, None, None] + _nchw(res, B, H, H)
+    _close(_nchw(out.t, B, H, H), ref, 2e-3)
+
+
 def test_groupnorm_layernorm_geglu_softmax(dev):
     from coma_b200.inpaint import nn
     g = torch.Generator(device=dev).manual_seed(0)
