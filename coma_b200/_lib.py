@@ -27,6 +27,7 @@ SIGNATURES = {
     "coma_gemm_f16_tn": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp, _i64, _vp],
     "coma_gemm_f16_ex": [_vp, _vp],
     "coma_conv3x3_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp],
+    "coma_conv3x3_f16_ws": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp, _i64, _vp],
     "coma_attention_fwd_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
     "coma_groupnorm_affine_f16": [_vp, _i64, _i64, _i64, _i64, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "coma_affine_act_f16": [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _vp],
@@ -53,7 +54,7 @@ class GemmArgs(ctypes.Structure):
                 ("out_f16", _vp), ("out_f32", _vp), ("ldo", _i64), ("o_s1", _i64), ("o_s2", _i64),
                 ("residual", _vp), ("bias", _vp), ("bias_rows", _vp), ("rows_per_bias", _i64), ("bias_rows_ld", _i64),
                 ("M", _i64), ("N", _i64), ("K", _i64), ("nb1", _i64), ("nb2", _i64),
-                ("alpha", _f32), ("act", _int)]
+                ("alpha", _f32), ("act", _int), ("workspace", _vp), ("workspace_elems", _i64)]
 
 _LIB = None
 

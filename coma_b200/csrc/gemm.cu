@@ -161,7 +161,11 @@ struct ConvGeom {
 };
 
 struct TileSched {
-    int n_tiles, m_tiles, total;  // total = n_tiles * m_tiles * batches; tile id = (z * m_tiles + mt) * n_tiles + nt
+    int n_tiles, m_tiles, total;  // total = n_tiles * m_tiles * batches * ksplit
+    // split-K: work item id = tile id * ksplit + ks; slice ks reduces K-slabs [ks*kb_per, (ks+1)*kb_per) into its own fp32
+    // slab of the workspace (out32 + ks * split_stride) — a fixed-order finishing pass sums the slabs (deterministic)
+    int ksplit, kb_per;
+    long long split_stride;
 };
 
 // Persistent, warp-specialised kernel: gridDim.x CTAs walk the tile list with stride gridDim.x. The fp32 accumulator is
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
 
     // tile id -> coordinates
     auto decode = [&](int t, int &m0, int &n0, int &b1, int &b2, int &cx0, int &cy0, int &cb0) {
+        t /= ts.ksplit;
         const int nt = t % ts.n_tiles;
         const int r = t / ts.n_tiles;
         const int mt = r % ts.m_tiles, z = r / ts.m_tiles;
@@ -256,7 +261,8 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
             for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
                 int m0, n0, b1, b2, cx0, cy0, cb0;
                 decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int kb0 = (t % ts.ksplit) * ts.kb_per, kb1 = min(num_k, kb0 + ts.kb_per);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty + s, ph ^ 1);
@@ -281,7 +287,8 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int kb0 = (t % ts.ksplit) * ts.kb_per, kb1 = min(num_k, kb0 + ts.kb_per);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(full + s, ph);
@@ -290,7 +297,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                     const uint64_t db = umma_desc_sw128(smem_u32(sB + s * B_BYTES));
 #pragma unroll
                     for (int k = 0; k < G_BK / 16; ++k)  // advance 32 B (16 fp16) inside the 128 B swizzle atom: +2 in 16-B units
-                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
                     umma_commit(empty + s);  // frees the slab once the MMAs that read it have retired
                 }
                 umma_commit(tmem_full + acc);
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
             int m0, n0, b1, b2, cx0, cy0, cb0;
             decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
-            const size_t obase = (size_t)b1 * ep.o_s1 + (size_t)b2 * ep.o_s2;
+            const size_t obase = (size_t)b1 * ep.o_s1 + (size_t)b2 * ep.o_s2 + (size_t)(t % ts.ksplit) * ts.split_stride;
             const __half *__restrict__ residual = ep.residual ? ep.residual + obase : nullptr;
             __half *__restrict__ out16 = ep.out16 ? ep.out16 + obase : nullptr;
             float *__restrict__ out32 = ep.out32 ? ep.out32 + obase : nullptr;
@@ -618,7 +625,8 @@ static int setup_epilogue_maps(GemmEpilogue &ep, CUtensorMap *to, CUtensorMap *t
 
 template <int BN, bool CONV>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr, int M, int N, int K,
-                       const GemmEpilogue &ep, int nbatch, cudaStream_t st, const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
+                       const GemmEpilogue &ep, int nbatch, cudaStream_t st, int ksplit, long long split_stride,
+                       const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
     constexpr int STAGES = BN <= 128 ? 3 : 4;
     constexpr size_t smem = (size_t)STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + gemm_epi_warps(BN) * gemm_epi_bufs(BN) * E_PANEL_BYTES + 256;
     static bool attr[16] = {false};
@@ -635,7 +643,11 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
     TileSched ts;
     ts.n_tiles = (N + BN - 1) / BN;
     ts.m_tiles = CONV ? m_tiles_conv : (M + G_BM - 1) / G_BM;
-    const long long total = (long long)ts.n_tiles * ts.m_tiles * nbatch;
+    const int num_k = (K + G_BK - 1) / G_BK;
+    ts.kb_per = (num_k + ksplit - 1) / ksplit;
+    ts.ksplit = (num_k + ts.kb_per - 1) / ts.kb_per;  // every slice owns at least one K-slab
+    ts.split_stride = split_stride;
+    const long long total = (long long)ts.n_tiles * ts.m_tiles * nbatch * ts.ksplit;
     if (total >= (1LL << 31)) {
         set_error("too many output tiles");
         return COMA_E_BADARG;
@@ -647,29 +659,124 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
     return check_launch("gemm_f16_tn_kernel");
 }
 
-// Output-tile width: the candidate with the least padded work, ties to the wider tile.
-static int pick_bn(int64_t N) {
-    if (N <= 64) return 64;
-    if (N <= 128) return 128;
-    const int cands[3] = {256, 160, 128};
-    int best = 128;
-    int64_t best_pad = -1;
-    for (int c : cands) {
-        const int64_t pad = (N + c - 1) / c * c;
-        if (best_pad < 0 || pad < best_pad) {
-            best_pad = pad;
-            best = c;
+// ---- tile width and split-K factor from a small cost model (microseconds, calibrated on B200 with tools/gemm_bench.py) --
+// A work item = one (128 x BN tile, K slice). The SM count quantises the schedule: 80 tiles of a deep-K problem leave 68 SMs
+// idle, which a narrower tile or a K split repairs. Split slices write fp32 slabs that a finishing pass reduces.
+struct GemmPlan {
+    int bn, ksplit;
+};
+
+static GemmPlan plan_gemm(int64_t m_tiles, int64_t N, int64_t K, int64_t nbatch, int64_t M, bool can_split, int64_t ws_elems) {
+    const int cands[4] = {256, 160, 128, 64};
+    const double t_kb[4] = {0.41, 0.27, 0.22, 0.14};   // one 64-deep K slab of a 128 x BN tile on one SM
+    const double t_epi[4] = {0.9, 0.6, 0.5, 0.35};     // epilogue of one tile (hidden behind the next tile's main loop)
+    const double t_fixed = 3.0, t_finish = 2.5;
+    const int64_t num_k = (K + G_BK - 1) / G_BK;
+    GemmPlan best = {128, 1};
+    double best_t = 1e30;
+    for (int c = 0; c < 4; ++c) {
+        const int bn = cands[c];
+        if (bn > 64 && N <= bn / 2 && N <= 128) continue;  // do not pad a narrow problem into a wide tile
+        const int64_t tiles = m_tiles * ((N + bn - 1) / bn) * nbatch;
+        const int max_split = (can_split && bn >= 128) ? 16 : 1;
+        for (int ks = 1; ks <= max_split; ++ks) {
+            const int64_t kb = (num_k + ks - 1) / ks;
+            if (ks > 1 && (kb < 8 || (int64_t)ks * M * N > ws_elems)) break;
+            const int64_t items = tiles * ((num_k + kb - 1) / kb);
+            const int64_t waves = (items + kNumSM - 1) / kNumSM;
+            const double body = (double)kb * t_kb[c];
+            double t = t_fixed + (double)waves * (body > t_epi[c] ? body : t_epi[c]) + t_epi[c];
+            if (ks > 1) t += t_finish + 8.0 * (double)ks * (double)M * (double)N / 5.0e6;  // slab write + read at ~5 TB/s
+            if (t < best_t - 1e-9) {
+                best_t = t;
+                best = {bn, ks};
+            }
         }
     }
     return best;
 }
 
-#define COMA_DISPATCH_BN(bn, CONVF, ...)                               \
+// Split-K finishing pass: out = act(alpha * sum_ks slab[ks] + bias + bias_rows[row / rows_per_bias] + residual), slabs summed
+// in index order (bit-reproducible). One thread per 8 consecutive columns.
+__global__ void splitk_finish_kernel(const float *__restrict__ ws, int ksplit, long long slab, long long M, int N, float alpha,
+                                     const float *__restrict__ bias, const float *__restrict__ bias_rows, int rows_per_bias,
+                                     long long bias_rows_ld, const __half *__restrict__ residual, int act, __half *__restrict__ out16,
+                                     float *__restrict__ out32, int ldo) {
+    pdl_trigger();
+    pdl_wait();
+    const int n8 = N / 8;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * n8) return;
+    const long long row = i / n8;
+    const int col = (int)(i % n8) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.0f;
+    const float *p = ws + row * N + col;
+    for (int k = 0; k < ksplit; ++k, p += slab) {
+        const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+        f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    const float *brow = bias_rows ? bias_rows + (row / rows_per_bias) * bias_rows_ld : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        f[j] = f[j] * alpha + (bias ? __ldg(bias + col + j) : 0.0f);
+        if (brow) f[j] += __ldg(brow + col + j);
+    }
+    const long long off = row * ldo + col;
+    if (residual) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(residual + off);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&r);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 x = __half22float2(h[u]);
+            f[2 * u] += x.x;
+            f[2 * u + 1] += x.y;
+        }
+    }
+    if (act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+    }
+    if (out16) {
+        uint4 w;
+        __half2 *h = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(f[2 * u], f[2 * u + 1]);
+        *reinterpret_cast<uint4 *>(out16 + off) = w;
+    }
+    if (out32) {
+        *reinterpret_cast<float4 *>(out32 + off) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4 *>(out32 + off + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+}
+
+static bool split_eligible(const GemmEpilogue &ep, int64_t N, int64_t nbatch, const float *ws) {
+    return ws && nbatch == 1 && N % 8 == 0 && ep.ldo % 8 == 0 && (uintptr_t)ws % 16 == 0 && (uintptr_t)ep.residual % 16 == 0 &&
+           (uintptr_t)ep.out16 % 16 == 0 && (uintptr_t)ep.out32 % 16 == 0;
+}
+
+// Rewrites the epilogue of a split launch (raw fp32 partial slabs) and returns the one the finishing pass applies.
+static GemmEpilogue split_epilogue(GemmEpilogue &ep, float *ws, int64_t N) {
+    const GemmEpilogue fin = ep;
+    ep.bias = nullptr; ep.bias_rows = nullptr; ep.residual = nullptr; ep.out16 = nullptr; ep.out32 = ws; ep.ldo = (int)N;
+    ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = 0; ep.tma = 0; ep.rows_per_bias = 1;
+    return fin;
+}
+
+static int launch_split_finish(const GemmEpilogue &fin, const float *ws, int ksplit, int64_t M, int64_t N, cudaStream_t st) {
+    const long long n = M * (N / 8);
+    launch_pdl(splitk_finish_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, ws, ksplit, (long long)(M * N), (long long)M, (int)N,
+               fin.alpha, fin.bias, fin.bias_rows, fin.rows_per_bias, fin.bias_rows_ld, fin.residual, fin.act, fin.out16, fin.out32, fin.ldo);
+    return check_launch("splitk_finish_kernel");
+}
+
+#define COMA_DISPATCH_BN(rc, bn, CONVF, ...)                           \
     switch (bn) {                                                      \
-        case 64: return launch_gemm<64, CONVF>(__VA_ARGS__);           \
-        case 128: return launch_gemm<128, CONVF>(__VA_ARGS__);         \
-        case 160: return launch_gemm<160, CONVF>(__VA_ARGS__);         \
-        default: return launch_gemm<256, CONVF>(__VA_ARGS__);          \
+        case 64: rc = launch_gemm<64, CONVF>(__VA_ARGS__); break;      \
+        case 128: rc = launch_gemm<128, CONVF>(__VA_ARGS__); break;    \
+        case 160: rc = launch_gemm<160, CONVF>(__VA_ARGS__); break;    \
+        default: rc = launch_gemm<256, CONVF>(__VA_ARGS__); break;     \
     }
 
 }  // namespace coma
@@ -689,10 +796,6 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     COMA_REQUIRE(!g->out_f32 || (uintptr_t)g->out_f32 % 16 == 0, "out_f32 must be 16-byte aligned");
     COMA_REQUIRE(!g->residual || (uintptr_t)g->residual % 16 == 0, "residual must be 16-byte aligned");
     COMA_REQUIRE(!g->bias_rows || g->rows_per_bias > 0, "rows_per_bias must be positive");
-    const int bn = pick_bn(N);
-    CUtensorMap ta, tb;
-    if (int e = make_map(&ta, g->A, M, K, g->lda, G_BM, nb1, g->a_s1, nb2, g->a_s2)) return e;
-    if (int e = make_map(&tb, g->W, N, K, g->ldw, bn, nb1, g->w_s1, nb2, g->w_s2)) return e;
     GemmEpilogue ep;
     ep.bias = g->bias;
     ep.bias_rows = g->bias_rows;
@@ -707,10 +810,20 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     ep.alpha = g->alpha;
     ep.act = g->act;
     ep.nb1 = (int)nb1;
-    CUtensorMap to, tr;
+    const bool can_split = split_eligible(ep, N, nb1 * nb2, g->workspace);
+    const GemmPlan plan = plan_gemm((M + G_BM - 1) / G_BM, N, K, nb1 * nb2, M, can_split, g->workspace_elems);
+    const int bn = plan.bn;
+    CUtensorMap ta, tb, to, tr;
+    if (int e = make_map(&ta, g->A, M, K, g->lda, G_BM, nb1, g->a_s1, nb2, g->a_s2)) return e;
+    if (int e = make_map(&tb, g->W, N, K, g->ldw, bn, nb1, g->w_s1, nb2, g->w_s2)) return e;
+    GemmEpilogue fin = ep;
+    if (plan.ksplit > 1) fin = split_epilogue(ep, g->workspace, N);
     if (int e = setup_epilogue_maps(ep, &to, &tr, M, N, nb1, nb2)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    COMA_DISPATCH_BN(bn, false, ta, tb, to, tr, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st)
+    int rc = 0;
+    COMA_DISPATCH_BN(rc, bn, false, ta, tb, to, tr, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st, plan.ksplit, (long long)(M * N))
+    if (rc == 0 && plan.ksplit > 1) rc = launch_split_finish(fin, g->workspace, plan.ksplit, M, N, st);
+    return rc;
 }
 
 namespace coma {
@@ -740,6 +853,14 @@ static int make_conv_map(CUtensorMap *m, const void *ptr, int64_t B, int64_t H, 
 extern "C" int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const void *Wt, int64_t ldw,
                                 int64_t N, const float *bias, const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act,
                                 void *out_f16, float *out_f32, int64_t ldo, coma_stream_t stream) {
+    return coma_conv3x3_f16_ws(x, B, H, W, C, ldx, Wt, ldw, N, bias, bias_rows, bias_rows_ld, residual, act, out_f16, out_f32, ldo, nullptr, 0,
+                               stream);
+}
+
+extern "C" int coma_conv3x3_f16_ws(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const void *Wt, int64_t ldw,
+                                   int64_t N, const float *bias, const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act,
+                                   void *out_f16, float *out_f32, int64_t ldo, float *workspace, int64_t workspace_elems,
+                                   coma_stream_t stream) {
     using namespace coma;
     COMA_REQUIRE(x && Wt && (out_f16 || out_f32), "null pointer");
     COMA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && N > 0, "bad sizes");
@@ -755,18 +876,25 @@ extern "C" int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, 
     cg.tiles_x = (int)(W / TW); cg.tiles_y = (int)(H / TH); cg.cblocks = (int)(C / 64);
     const int64_t m_tiles = TB > 1 ? (B + TB - 1) / TB : B * cg.tiles_x * cg.tiles_y;
     const int64_t M = B * H * W, K = 9 * C;
-    const int bn = pick_bn(N);
-    CUtensorMap ta, tb;
-    if (int e = make_conv_map(&ta, x, B, H, W, C, ldx, TW, TH, TB)) return e;
-    if (int e = make_map(&tb, Wt, N, K, ldw, bn, 1, 0, 1, 0)) return e;
     GemmEpilogue ep;
     ep.bias = bias; ep.bias_rows = bias_rows; ep.rows_per_bias = (int)(H * W); ep.bias_rows_ld = bias_rows_ld > 0 ? bias_rows_ld : N; ep.residual = (const __half *)residual;
     ep.out16 = (__half *)out_f16; ep.out32 = out_f32; ep.ldo = (int)ldo; ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = act;
     ep.nb1 = 1;
-    CUtensorMap to, tr;
+    // split-K needs every slab row < M to be written: tiles never straddle M except with an odd image count at TB > 1
+    const bool can_split = split_eligible(ep, N, 1, workspace) && (TB == 1 || B % TB == 0);
+    const GemmPlan plan = plan_gemm(m_tiles, N, K, 1, M, can_split, workspace_elems);
+    const int bn = plan.bn;
+    CUtensorMap ta, tb, to, tr;
+    if (int e = make_conv_map(&ta, x, B, H, W, C, ldx, TW, TH, TB)) return e;
+    if (int e = make_map(&tb, Wt, N, K, ldw, bn, 1, 0, 1, 0)) return e;
+    GemmEpilogue fin = ep;
+    if (plan.ksplit > 1) fin = split_epilogue(ep, workspace, N);
     if (int e = setup_epilogue_maps(ep, &to, &tr, M, N, 1, 1)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    COMA_DISPATCH_BN(bn, true, ta, tb, to, tr, (int)M, (int)N, (int)K, ep, 1, st, cg, (int)m_tiles)
+    int rc = 0;
+    COMA_DISPATCH_BN(rc, bn, true, ta, tb, to, tr, (int)M, (int)N, (int)K, ep, 1, st, plan.ksplit, (long long)(M * N), cg, (int)m_tiles)
+    if (rc == 0 && plan.ksplit > 1) rc = launch_split_finish(fin, workspace, plan.ksplit, M, N, st);
+    return rc;
 }
 
 extern "C" int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,

@@ -45,6 +45,21 @@ def new_act(B, H, W, C, device, dtype=F16):
     return Act(buf[:, :C], B, H, W)
 
 
+SPLITK_WS_ELEMS = 8 << 20   # 32 MB of fp32 partial slabs per device: enough for the 8x8 / 16x16 levels, small enough for L2
+_SPLITK_WS = {}
+
+
+def splitk_workspace(device):
+    """Per-device fp32 scratch for the deterministic split-K schedule (deep-K problems with too few tiles for 148 SMs).
+    Allocated once, outside any CUDA-graph capture (the eager warm-up of `Graphed` runs first); launches on one stream
+    serialise on it."""
+    key = torch.device(device).index
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = _SPLITK_WS[key] = torch.empty(SPLITK_WS_ELEMS, dtype=F32, device=device)
+    return ws
+
+
 def gemm(a, w, bias=None, residual=None, act=0, out=None, out_dtype=F16, bias_rows=None, rows_per_bias=0, alpha=1.0, K=None):
     """out[M,N] = act(alpha * a @ w[:, :K].T + bias + bias_rows[m // rows_per_bias] + residual). a [M,K] f16, w [N,>=K] f16."""
     M = a.shape[0]
@@ -66,6 +81,8 @@ def gemm(a, w, bias=None, residual=None, act=0, out=None, out_dtype=F16, bias_ro
         assert bias_rows.dtype == F32 and bias_rows.stride(1) == 1 and bias_rows.shape[1] == N and rows_per_bias > 0
         g.bias_rows, g.rows_per_bias, g.bias_rows_ld = bias_rows.data_ptr(), rows_per_bias, bias_rows.stride(0)
     g.alpha, g.act = alpha, act
+    ws = splitk_workspace(a.device)
+    g.workspace, g.workspace_elems = ws.data_ptr(), ws.numel()
     with torch.cuda.device(a.device):
         call("coma_gemm_f16_ex", ctypes.addressof(g), _stream())
     return out
@@ -145,12 +162,13 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
         out = new_act(x.B, Ho, Wo, N, x.t.device, out_dtype)
         if residual is not None:
             assert residual.dtype == F16 and residual.stride(0) == out.t.stride(0)
+        ws = splitk_workspace(x.t.device)
         with torch.cuda.device(x.t.device):
-            call("coma_conv3x3_f16", xa.t.data_ptr(), xa.B, xa.H, xa.W, xa.C, xa.ld, w.data_ptr(), w.stride(0), N, _ptr(bias),
+            call("coma_conv3x3_f16_ws", xa.t.data_ptr(), xa.B, xa.H, xa.W, xa.C, xa.ld, w.data_ptr(), w.stride(0), N, _ptr(bias),
                  None if bias_rows is None else bias_rows.data_ptr(), 0 if bias_rows is None else bias_rows.stride(0),
                  None if residual is None else residual.data_ptr(), 0,
                  out.t.data_ptr() if out_dtype == F16 else None, out.t.data_ptr() if out_dtype == F32 else None, out.t.stride(0),
-                 _stream())
+                 ws.data_ptr(), ws.numel(), _stream())
         return out
     K = 9 * x.C
     cols = torch.empty((x.B * Ho * Wo, rup(K)), dtype=F16, device=x.t.device)

@@ -127,6 +127,8 @@ typedef struct coma_gemm_args {
     int64_t M, N, K, nb1, nb2;
     float alpha;
     int act;
+    float *workspace; int64_t workspace_elems; /* optional fp32 scratch (>= ksplit*M*N floats) enabling split-K on problems with
+                                                * too few output tiles for 148 SMs; NULL = never split */
 } coma_gemm_args;
 COMA_API int coma_gemm_f16_ex(const coma_gemm_args *args, coma_stream_t stream);
 
@@ -137,6 +139,12 @@ COMA_API int coma_gemm_f16_ex(const coma_gemm_args *args, coma_stream_t stream);
 COMA_API int coma_conv3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const void *Wt, int64_t ldw,
                               int64_t N, const float *bias, const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act,
                               void *out_f16, float *out_f32, int64_t ldo, coma_stream_t stream);
+
+/* Same, with an fp32 workspace that allows a deterministic split-K schedule (deep-K convolutions at 8x8 / 16x16). */
+COMA_API int coma_conv3x3_f16_ws(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const void *Wt, int64_t ldw,
+                                 int64_t N, const float *bias, const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act,
+                                 void *out_f16, float *out_f32, int64_t ldo, float *workspace, int64_t workspace_elems,
+                                 coma_stream_t stream);
 
 COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,

@@ -99,3 +99,22 @@ def test_gemm_f16_out_strided_and_batched(dev):
     nn.gemm_batched(q, Hh * d, d, S * Hh * d, k, Hh * d, d, L * Hh * d, scores, L, S * L, Hh * S * L, S, L, d, Hh, B, alpha=0.125)
     ref = 0.125 * torch.einsum("bshd,blhd->bhsl", q.float().view(B, S, Hh, d), k.float().view(B, L, Hh, d))
     torch.testing.assert_close(scores.float(), ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,K,out_dtype", [(512, 1280, 11520, torch.float16), (256, 640, 5760, torch.float32), (2048, 1280, 23040, torch.float16)])
+def test_gemm_split_k(dev, M, N, K, out_dtype):
+    """Deep-K problems with few output tiles run a deterministic split-K schedule (fp32 slabs + fixed-order finishing pass):
+    same epilogue contract, bit-identical across repeats."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(K)
+    a = (torch.randn((M, K), device=dev, generator=g) * 0.5).half()
+    w = (torch.randn((N, K), device=dev, generator=g) * K ** -0.5).half()
+    bias = torch.randn(N, device=dev, generator=g)
+    res = torch.randn((M, N), device=dev, generator=g).half()
+    brows = torch.randn((M // 64, N), device=dev, generator=g)
+    out = nn.gemm(a, w, bias, res, act=1, out_dtype=out_dtype, bias_rows=brows, rows_per_bias=64)
+    ref = torch.nn.functional.silu(a.float() @ w.float().t() + bias + brows.repeat_interleave(64, 0) + res.float())
+    tol = 2e-3 if out_dtype == torch.float16 else 1e-4
+    assert (out.float() - ref).abs().max().item() <= tol * ref.abs().max().item()
+    again = nn.gemm(a, w, bias, res, act=1, out_dtype=out_dtype, bias_rows=brows, rows_per_bias=64)
+    assert torch.equal(out, again)

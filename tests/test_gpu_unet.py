@@ -71,7 +71,8 @@ def test_conv3x3_with_groupnorm_prologue(dev, C, Cout, H, stride, pad, up, B):
 
 
 
-@pytest.mark.parametrize("C,Cout,H,B", [(64, 96, 16, 2), (128, 320, 8, 3), (64, 160, 32, 2), (64, 40, 64, 1), (128, 128, 128, 1)])
+@pytest.mark.parametrize("C,Cout,H,B", [(64, 96, 16, 2), (128, 320, 8, 3), (64, 160, 32, 2), (64, 40, 64, 1), (128, 128, 128, 1),
+                                        (1280, 1280, 8, 8), (2560, 1280, 8, 2), (1280, 640, 16, 2)])   # deep K, few tiles: split-K
 def test_conv3x3_f16_out_tma_epilogue(dev, C, Cout, H, B):
     """Implicit-GEMM conv with the fp16 TMA epilogue: bias + per-sample bias rows (time embedding) + residual, all tile
     geometries (several image rows per tile, two images per tile with an odd batch, one row segment per tile)."""
