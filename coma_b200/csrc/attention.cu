@@ -4,12 +4,16 @@
 //
 //   O[b, s, h*d : (h+1)*d] = softmax(Q_h K_h^T / sqrt(d)) V_h        Q [B,S,heads*d], K [B,L,heads*d], V^T [B,heads,d,Lp]
 //
-// One CTA per (128-query tile, head, batch), 6 warps:
-//   warp 0    TMA producer: Q tile once; K tiles [128 keys x d] and V^T tiles [d x 128 keys] through a 2-stage ring
-//   warp 1    MMA issuer (one thread): S = Q K^T  (M128 x N128 x K16 steps) into TMEM, then O_j = P V (M128 x Nd x K16)
-//   warps 2-5 softmax: tcgen05.ld S (one query row per thread), online max / sum in base 2, P -> fp16 into shared memory
-//             in the 128B-swizzled K-major layout the MMA reads, then O = O*alpha + O_j with the running output in registers
-// Scores never leave the SM: HBM traffic is Q, K, V once per tile and O once.
+// One CTA per (128-query tile, head, batch), 6 warps, 64 keys per step:
+//   warp 0    TMA producer: Q tile once; K tiles [64 keys x d] and V^T tiles [d x 64 keys] through a STAGES-deep ring
+//   warp 1    MMA issuer (one thread): S_{j+1} = Q K_{j+1}^T (M128 x N64) into the OTHER of two TMEM score buffers as soon as
+//             the softmax warps have drained it, then O += P_j V_j (M128 x Nd x K64) accumulating IN TMEM
+//   warps 2-5 softmax, one query row per thread: tcgen05.ld S_j, row max, exp2, P_j -> fp16 into one of two swizzled shared
+//             memory buffers. The running maximum is LAZY: it only moves (and O / l are only rescaled, tcgen05.ld -> mul ->
+//             tcgen05.st) when a tile's maximum exceeds it by more than 2^8, so the steady-state loop has no dependence on
+//             the P V product at all — the tensor core runs a full step behind / ahead of the exponentials.
+// Scores never leave the SM: HBM traffic is Q, K, V once per tile and O once. TMEM: 2 x 64 score columns + d output
+// columns (<= 256 for d <= 128: two CTAs per SM at d = 40).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -91,6 +95,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float *v) {
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]),
+        "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -98,36 +111,38 @@ __device__ __forceinline__ float ex2(float x) {
 }
 }  // namespace fa
 
-constexpr int FA_BQ = 128, FA_BKV = 128, FA_THREADS = 192;
+constexpr int FA_BQ = 128, FA_BKV = 64, FA_THREADS = 192;
+constexpr float FA_LAZY = 8.0f;  // log2 headroom before the running maximum (and O, l) is moved: P <= 2^8 stays exact enough in fp16
+
+__host__ __device__ constexpr int fa_ctas_per_sm(int DKB, int DN) { return (DKB == 1 && DN <= 64) ? 2 : 1; }
 
 // DKB = number of 64-wide K blocks of the head dimension (d <= 64*DKB); DN = head dim rounded up to a multiple of 16
 template <int DKB, int DN, int STAGES>
-__global__ void __launch_bounds__(FA_THREADS, (DKB == 1 ? 2 : 1))
+__global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
                          long long ldo, long long o_bstride) {
     using namespace fa;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int QK_BLOCK = FA_BQ * 64 * 2;     // one [128 x 64] fp16 K-block, 16 KB
-    constexpr int Q_BYTES = DKB * QK_BLOCK, K_BYTES = DKB * QK_BLOCK;
-    constexpr int VT_BLOCK = DN * 64 * 2;        // one [DN x 64 keys] block
-    constexpr int VT_BYTES = ((2 * VT_BLOCK + 1023) / 1024) * 1024;
-    constexpr int VT_BLOCK_AL = VT_BYTES / 2;    // keep every block 1024-byte aligned (DN*128 is a multiple of 1024 for DN%8==0)
-    constexpr int P_BYTES = 2 * QK_BLOCK;        // P [128 x 128] fp16 as two K-blocks
+    constexpr int Q_BLOCK = FA_BQ * 64 * 2;      // one [128 x 64] fp16 K-block of Q, 16 KB
+    constexpr int K_BLOCK = FA_BKV * 64 * 2;     // one [64 keys x 64] K-block of K, 8 KB
+    constexpr int Q_BYTES = DKB * Q_BLOCK, K_BYTES = DKB * K_BLOCK;
+    constexpr int VT_BYTES = ((DN * 128 + 1023) / 1024) * 1024;  // [DN x 64 keys], 128-byte rows
+    constexpr int P_BYTES = FA_BQ * 64 * 2;      // P [128 x 64] fp16, one K-block, 16 KB (two buffers)
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + Q_BYTES;
     uint8_t *sVt = sK + STAGES * K_BYTES;
     uint8_t *sP = sVt + STAGES * VT_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sP + P_BYTES);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sP + 2 * P_BYTES);
     uint64_t *q_full = bar, *k_full = bar + 1, *k_empty = k_full + STAGES, *v_full = k_empty + STAGES, *v_empty = v_full + STAGES;
-    uint64_t *s_full = v_empty + STAGES, *s_empty = s_full + 1, *p_full = s_empty + 1, *o_full = p_full + 1, *o_empty = o_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 1);
+    uint64_t *s_full = v_empty + STAGES, *s_empty = s_full + 2, *p_full = s_empty + 2, *p_empty = p_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = (L + FA_BKV - 1) / FA_BKV;
-    constexpr uint32_t TMEM_COLS = (128 + DN <= 256) ? 256 : 512;  // S: 128 columns at 0, O_j: DN columns at 128 (power of two)
+    constexpr uint32_t TMEM_COLS = (128 + DN <= 256) ? 256 : 512;  // S0: 64 columns at 0, S1 at 64, O: DN columns at 128
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -140,11 +155,12 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 ? 2 : 1))
             mbar_init(v_full + i, 1);
             mbar_init(v_empty + i, 1);
         }
-        mbar_init(s_full, 1);
-        mbar_init(s_empty, 128);
-        mbar_init(p_full, 128);
-        mbar_init(o_full, 1);
-        mbar_init(o_empty, 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(s_full + i, 1);
+            mbar_init(s_empty + i, 128);
+            mbar_init(p_full + i, 128);
+            mbar_init(p_empty + i, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -164,19 +180,17 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 ? 2 : 1))
         if (lane == 0) {
             mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
-            for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sQ + kb * QK_BLOCK, &tmQ, q_full, kb * 64, q0, h, b);
+            for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sQ + kb * Q_BLOCK, &tmQ, q_full, kb * 64, q0, h, b);
             for (int j = 0; j < n_kv; ++j) {
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
                 mbar_wait(k_empty + s, ph ^ 1);
                 mbar_expect_tx(k_full + s, K_BYTES);
 #pragma unroll
-                for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sK + s * K_BYTES + kb * QK_BLOCK, &tmK, k_full + s, kb * 64, j * FA_BKV, h, b);
+                for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sK + s * K_BYTES + kb * K_BLOCK, &tmK, k_full + s, kb * 64, j * FA_BKV, h, b);
                 mbar_wait(v_empty + s, ph ^ 1);
-                mbar_expect_tx(v_full + s, 2 * VT_BLOCK);
-#pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
-                    tma_load_4d(sVt + s * VT_BYTES + kb * VT_BLOCK_AL, &tmVt, v_full + s, j * FA_BKV + kb * 64, 0, h, b);
+                mbar_expect_tx(v_full + s, DN * 128);
+                tma_load_4d(sVt + s * VT_BYTES, &tmVt, v_full + s, j * FA_BKV, 0, h, b);
             }
         }
     } else if (warp == 1) {
@@ -184,60 +198,59 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 ? 2 : 1))
             constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(FA_BKV >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
             constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
             const int ksteps = (d + 15) / 16;  // columns d..63 of the Q / K blocks are TMA zero-filled
-            mbar_wait(q_full, 0);
-            for (int j = 0; j < n_kv; ++j) {
+            auto issue_qk = [&](int j) {       // S_j = Q K_j^T into score buffer j & 1
                 const int s = j % STAGES;
-                const uint32_t ph = (j / STAGES) & 1;
-                // ---- S = Q K_j^T
-                mbar_wait(k_full + s, ph);
-                mbar_wait(s_empty, (j & 1) ^ 1);  // softmax warps have drained S_{j-1}
+                mbar_wait(k_full + s, (j / STAGES) & 1);
+                if (j >= 2) mbar_wait(s_empty + (j & 1), ((j >> 1) & 1) ^ 1);  // softmax has drained S_{j-2}
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ts = tmem_S + (uint32_t)((j & 1) * 64);
                 for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t off = (uint32_t)(k / 4) * QK_BLOCK + (uint32_t)(k % 4) * 32;
-                    umma_f16(tmem_S, umma_desc_sw128(smem_u32(sQ) + off), umma_desc_sw128(smem_u32(sK + s * K_BYTES) + off), idesc_s, k != 0);
+                    const uint32_t offq = (uint32_t)(k / 4) * Q_BLOCK + (uint32_t)(k % 4) * 32;
+                    const uint32_t offk = (uint32_t)(k / 4) * K_BLOCK + (uint32_t)(k % 4) * 32;
+                    umma_f16(ts, umma_desc_sw128(smem_u32(sQ) + offq), umma_desc_sw128(smem_u32(sK + s * K_BYTES) + offk), idesc_s, k != 0);
                 }
                 umma_commit(k_empty + s);
-                umma_commit(s_full);
-                // ---- O_j = P V_j  (fresh accumulator: the running output lives in the softmax warps' registers)
-                mbar_wait(v_full + s, ph);
-                mbar_wait(p_full, j & 1);         // P_j is in shared memory (and O_{j-1} has been read: same warps)
-                mbar_wait(o_empty, (j & 1) ^ 1);
+                umma_commit(s_full + (j & 1));
+            };
+            mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_qk(j + 1);  // the next scores are produced while the softmax warps work on S_j
+                // ---- O (+)= P_j V_j, accumulated in TMEM
+                const int s = j % STAGES;
+                mbar_wait(v_full + s, (j / STAGES) & 1);
+                mbar_wait(p_full + (j & 1), (j >> 1) & 1);  // P_j is in shared memory (and any rescale of O has been stored)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < FA_BKV / 16; ++k) {
-                    const uint32_t offp = (uint32_t)(k / 4) * QK_BLOCK + (uint32_t)(k % 4) * 32;
-                    const uint32_t offv = (uint32_t)(k / 4) * VT_BLOCK_AL + (uint32_t)(k % 4) * 32;
-                    umma_f16(tmem_O, umma_desc_sw128(smem_u32(sP) + offp), umma_desc_sw128(smem_u32(sVt + s * VT_BYTES) + offv), idesc_o,
-                             k != 0);
-                }
+                for (int k = 0; k < FA_BKV / 16; ++k)
+                    umma_f16(tmem_O, umma_desc_sw128(smem_u32(sP + (j & 1) * P_BYTES) + (uint32_t)k * 32),
+                             umma_desc_sw128(smem_u32(sVt + s * VT_BYTES) + (uint32_t)k * 32), idesc_o, (j | k) != 0);
                 umma_commit(v_empty + s);
-                umma_commit(o_full);
+                umma_commit(p_empty + (j & 1));  // P_j consumed; O includes tile j
             }
         }
     } else {
-        // ---- softmax / accumulate: thread owns query row r of the tile
+        // ---- softmax: thread owns query row r of the tile
         const int q = warp & 3, r = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float2 o_acc[DN / 2];  // running output, packed pairs (FP32x2 FMAs)
-#pragma unroll
-        for (int c = 0; c < DN / 2; ++c) o_acc[c] = make_float2(0.f, 0.f);
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_used = -INFINITY, l_run = 0.f;
         // P row r inside a [128 x 64] K-major 128B-swizzled block: atom (r/8)*1024 + (r%8)*128, 16-byte chunk index ^ (r%8)
-        uint8_t *p_row = sP + (r >> 3) * 1024 + (r & 7) * 128;
+        uint8_t *p_row0 = sP + (r >> 3) * 1024 + (r & 7) * 128;
         const int xr = r & 7;
         const float2 scale2 = make_float2(scale_log2, scale_log2);
         for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(s_full, j & 1);
+            const int bsel = j & 1;
+            mbar_wait(s_full + bsel, (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tS = tmem_S + lane_addr + (uint32_t)(bsel * 64);
             const int valid = min(FA_BKV, L - j * FA_BKV);  // keys beyond L are masked out (last tile only)
             const bool full_tile = valid == FA_BKV;          // warp-uniform
-            // pass 1 over S: row maximum (TMEM reads are cheap; keeping all 128 scores live next to the running output
-            // would cost the second resident CTA)
+            // pass 1 over S: row maximum
             float mx = -INFINITY;
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = 0; c0 < FA_BKV; c0 += 32) {
                 float sv[32];
-                tmem_ld32(tmem_S + lane_addr + c0, sv);
+                tmem_ld32(tS + c0, sv);
                 if (full_tile) {
 #pragma unroll
                     for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(sv[c], sv[c + 1]));
@@ -247,15 +260,35 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 ? 2 : 1))
                 }
             }
             mx *= scale_log2;  // scale > 0: the max commutes with the scaling
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-            const float2 negm2 = make_float2(-m_new, -m_new);
-            float2 rs2 = make_float2(0.f, 0.f);
-            // pass 2: probabilities -> fp16 -> shared memory. P_{j-1} has been consumed (o_full_{j-1} was waited on below).
+            if (j == 0) {
+                m_used = mx;
+            } else if (__any_sync(0xffffffffu, mx > m_used + FA_LAZY)) {
+                // rare: some row's maximum moved by more than 2^8 -> rescale that row of O (in TMEM) and its running sum
+                const float m_new = (mx > m_used + FA_LAZY) ? mx : m_used;
+                const float alpha = ex2(m_used - m_new);
+                m_used = m_new;
+                l_run *= alpha;
+                mbar_wait(p_empty + ((j - 1) & 1), ((j - 1) >> 1) & 1);  // every P V product issued so far has landed in O
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+                for (int c0 = 0; c0 < DN; c0 += 16) {
+                    float t16[16];
+                    tmem_ld16(tmem_O + lane_addr + c0, t16);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) t16[c] *= alpha;
+                    tmem_st16(tmem_O + lane_addr + c0, t16);
+                }
+                tmem_wait_st();
+            }
+            if (j >= 2) mbar_wait(p_empty + bsel, ((j >> 1) & 1) ^ 1);  // P_{j-2} has been consumed: its buffer is free
+            const float2 negm2 = make_float2(-m_used, -m_used);
+            float2 rs2 = make_float2(0.f, 0.f);
+            uint8_t *p_row = p_row0 + bsel * P_BYTES;
+            // pass 2: probabilities -> fp16 -> shared memory
+#pragma unroll
+            for (int c0 = 0; c0 < FA_BKV; c0 += 32) {
                 float sv[32];
-                tmem_ld32(tmem_S + lane_addr + c0, sv);
+                tmem_ld32(tS + c0, sv);
 #pragma unroll
                 for (int c8 = 0; c8 < 32; c8 += 8) {
                     uint4 w;
@@ -272,43 +305,35 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 ? 2 : 1))
                         hp[t] = __floats2half2_rn(pr.x, pr.y);
                         rs2 = __fadd2_rn(rs2, pr);
                     }
-                    const int cc = c0 + c8, blk = cc >> 6, chunk = (cc & 63) >> 3;
-                    *reinterpret_cast<uint4 *>(p_row + blk * QK_BLOCK + ((chunk ^ xr) << 4)) = w;
+                    const int chunk = (c0 + c8) >> 3;
+                    *reinterpret_cast<uint4 *>(p_row + ((chunk ^ xr) << 4)) = w;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(s_empty);  // S may be overwritten by the next QK^T
-            l_run = l_run * alpha + (rs2.x + rs2.y);
-            m_run = m_new;
+            mbar_arrive(s_empty + bsel);  // this score buffer may be overwritten by Q K_{j+2}^T
+            l_run += rs2.x + rs2.y;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-            mbar_arrive(p_full);
-            // ---- O = O*alpha + O_j
-            mbar_wait(o_full, j & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float2 alpha2 = make_float2(alpha, alpha);
-#pragma unroll
-            for (int c0 = 0; c0 < DN; c0 += 16) {
-                float t16[16];
-                tmem_ld16(tmem_O + lane_addr + c0, t16);
-#pragma unroll
-                for (int c = 0; c < 16; c += 2)
-                    o_acc[(c0 + c) / 2] = __ffma2_rn(o_acc[(c0 + c) / 2], alpha2, make_float2(t16[c], t16[c + 1]));
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(o_empty);
+            mbar_arrive(p_full + bsel);
         }
+        // ---- O / l
+        mbar_wait(p_empty + ((n_kv - 1) & 1), ((n_kv - 1) >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = q0 + r;
-        if (row < S) {
-            const float inv = 1.0f / l_run;
-            __half *dst = out + (size_t)b * o_bstride + (size_t)row * ldo + (size_t)h * d;
+        const float inv = 1.0f / l_run;
+        __half *dst = out + (size_t)b * o_bstride + (size_t)row * ldo + (size_t)h * d;
 #pragma unroll
-            for (int c = 0; c < DN; c += 8) {  // static indices keep o_acc in registers; d % 8 == 0
-                if (c >= d) break;
-                uint4 w;
-                __half2 *hp = reinterpret_cast<__half2 *>(&w);
+        for (int c0 = 0; c0 < DN; c0 += 16) {
+            float t16[16];
+            tmem_ld16(tmem_O + lane_addr + c0, t16);  // warp-collective: no early exit for rows beyond S
 #pragma unroll
-                for (int t = 0; t < 4; ++t) hp[t] = __floats2half2_rn(o_acc[c / 2 + t].x * inv, o_acc[c / 2 + t].y * inv);
-                *reinterpret_cast<uint4 *>(dst + c) = w;
+            for (int c = 0; c < 16; c += 8) {
+                if (row < S && c0 + c < d) {  // d % 8 == 0
+                    uint4 w;
+                    __half2 *hp = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) hp[t] = __floats2half2_rn(t16[c + 2 * t] * inv, t16[c + 2 * t + 1] * inv);
+                    *reinterpret_cast<uint4 *>(dst + c0 + c) = w;
+                }
             }
         }
     }
@@ -350,7 +375,7 @@ static int make_map4(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], 
 template <int DKB, int DN, int STAGES>
 static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads, int S, int L, int d,
                             float scale_log2, __half *out, long long ldo, long long o_bstride, cudaStream_t st) {
-    constexpr size_t smem = (size_t)DKB * 16384 * (1 + STAGES) + (size_t)STAGES * (((2 * DN * 128 + 1023) / 1024) * 1024) + 32768 + 256 + 1024;
+    constexpr size_t smem = (size_t)DKB * 16384 + (size_t)STAGES * (DKB * 8192 + ((DN * 128 + 1023) / 1024) * 1024) + 2 * 16384 + 256 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -393,7 +418,7 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
     {
         cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)L, (cuuint64_t)heads, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)ldk * 2, (cuuint64_t)d * 2, (cuuint64_t)(L * ldk) * 2};
-        cuuint32_t box[4] = {64, 128, 1, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)FA_BKV, 1, 1};
         if (int e = make_map4(&tk, k, dims, str, box)) return e;
     }
     {
@@ -407,14 +432,14 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
     __half *o = (__half *)out;
     const long long obs = (long long)S * ldo;
     if (d <= 64) {
-        if (DN == 48) return launch_attention<1, 48, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
-        if (DN == 32) return launch_attention<1, 32, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
-        return launch_attention<1, 64, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        if (DN == 48) return launch_attention<1, 48, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        if (DN == 32) return launch_attention<1, 32, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        return launch_attention<1, 64, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
     }
     if (d <= 128) {
-        if (DN == 80) return launch_attention<2, 80, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
-        return launch_attention<2, 128, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        if (DN == 80) return launch_attention<2, 80, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        return launch_attention<2, 128, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
     }
-    if (DN == 160) return launch_attention<3, 160, 1>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
-    return launch_attention<3, 192, 1>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+    if (DN == 160) return launch_attention<3, 160, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+    return launch_attention<3, 192, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
 }
