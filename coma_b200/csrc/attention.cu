@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -59,6 +60,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+// K-major operand with 64-byte rows (32 fp16 of K per row), 64B swizzle: 8-row atoms of 512 B
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
     return d;
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -111,14 +122,19 @@ __device__ __forceinline__ float ex2(float x) {
 }
 }  // namespace fa
 
-constexpr int FA_BQ = 128, FA_BKV = 64, FA_THREADS = 192;
+constexpr int FA_BQ = 128, FA_THREADS = 192;
 constexpr float FA_LAZY = 8.0f;  // log2 headroom before the running maximum (and O, l) is moved: P <= 2^8 stays exact enough in fp16
 
-__host__ __device__ constexpr int fa_ctas_per_sm(int DKB, int DN) { return (DKB == 1 && DN <= 64) ? 2 : 1; }
+__host__ __device__ constexpr int fa_ctas_per_sm(int DKB, int DN, int BKV) {
+    return (DKB == 1 && DN <= 64) ? (BKV == 32 ? 4 : 2) : 1;
+}
 
-// DKB = number of 64-wide K blocks of the head dimension (d <= 64*DKB); DN = head dim rounded up to a multiple of 16
-template <int DKB, int DN, int STAGES>
-__global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
+// DKB = number of 64-wide K blocks of the head dimension (d <= 64*DKB); DN = head dim rounded up to a multiple of 16;
+// FA_BKV = keys per step: 64, or 32 for small heads — 2 x 32 score columns + DN output columns fit 128 TMEM columns and
+// ~54 KB of shared memory, so FOUR CTAs share an SM (4 softmax warps per sub-partition hide the exp2 / cvt / TMEM-load
+// latencies that two warps cannot: ncu showed `stall_wait` as the top stall at two CTAs per SM).
+template <int DKB, int DN, int STAGES, int FA_BKV>
+__global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
                          long long ldo, long long o_bstride) {
@@ -126,10 +142,11 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int Q_BLOCK = FA_BQ * 64 * 2;      // one [128 x 64] fp16 K-block of Q, 16 KB
-    constexpr int K_BLOCK = FA_BKV * 64 * 2;     // one [64 keys x 64] K-block of K, 8 KB
+    constexpr int K_BLOCK = FA_BKV * 64 * 2;     // one [FA_BKV keys x 64] K-block of K
     constexpr int Q_BYTES = DKB * Q_BLOCK, K_BYTES = DKB * K_BLOCK;
-    constexpr int VT_BYTES = ((DN * 128 + 1023) / 1024) * 1024;  // [DN x 64 keys], 128-byte rows
-    constexpr int P_BYTES = FA_BQ * 64 * 2;      // P [128 x 64] fp16, one K-block, 16 KB (two buffers)
+    constexpr int PV_ROW = FA_BKV * 2;           // bytes per row of the P / V^T tiles (keys are the K dimension of P V)
+    constexpr int VT_BYTES = ((DN * PV_ROW + 1023) / 1024) * 1024;  // [DN x FA_BKV keys]
+    constexpr int P_BYTES = FA_BQ * PV_ROW;      // P [128 x FA_BKV] fp16 (two buffers)
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + Q_BYTES;
     uint8_t *sVt = sK + STAGES * K_BYTES;
@@ -142,7 +159,8 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = (L + FA_BKV - 1) / FA_BKV;
-    constexpr uint32_t TMEM_COLS = (128 + DN <= 256) ? 256 : 512;  // S0: 64 columns at 0, S1 at 64, O: DN columns at 128
+    // S0: FA_BKV columns at 0, S1 at FA_BKV, O: DN columns at 2*FA_BKV
+    constexpr uint32_t TMEM_COLS = (2 * FA_BKV + DN <= 128) ? 128 : ((2 * FA_BKV + DN <= 256) ? 256 : 512);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -172,7 +190,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * FA_BKV;
     pdl_trigger();  // PDL: the prologue above overlapped the previous kernel's tail
     pdl_wait();
 
@@ -189,7 +207,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
 #pragma unroll
                 for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sK + s * K_BYTES + kb * K_BLOCK, &tmK, k_full + s, kb * 64, j * FA_BKV, h, b);
                 mbar_wait(v_empty + s, ph ^ 1);
-                mbar_expect_tx(v_full + s, DN * 128);
+                mbar_expect_tx(v_full + s, DN * PV_ROW);
                 tma_load_4d(sVt + s * VT_BYTES, &tmVt, v_full + s, j * FA_BKV, 0, h, b);
             }
         }
@@ -203,7 +221,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
                 mbar_wait(k_full + s, (j / STAGES) & 1);
                 if (j >= 2) mbar_wait(s_empty + (j & 1), ((j >> 1) & 1) ^ 1);  // softmax has drained S_{j-2}
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t ts = tmem_S + (uint32_t)((j & 1) * 64);
+                const uint32_t ts = tmem_S + (uint32_t)((j & 1) * FA_BKV);
                 for (int k = 0; k < ksteps; ++k) {
                     const uint32_t offq = (uint32_t)(k / 4) * Q_BLOCK + (uint32_t)(k % 4) * 32;
                     const uint32_t offk = (uint32_t)(k / 4) * K_BLOCK + (uint32_t)(k % 4) * 32;
@@ -222,9 +240,11 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
                 mbar_wait(p_full + (j & 1), (j >> 1) & 1);  // P_j is in shared memory (and any rescale of O has been stored)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < FA_BKV / 16; ++k)
-                    umma_f16(tmem_O, umma_desc_sw128(smem_u32(sP + (j & 1) * P_BYTES) + (uint32_t)k * 32),
-                             umma_desc_sw128(smem_u32(sVt + s * VT_BYTES) + (uint32_t)k * 32), idesc_o, (j | k) != 0);
+                for (int k = 0; k < FA_BKV / 16; ++k) {
+                    const uint32_t pa = smem_u32(sP + (j & 1) * P_BYTES) + (uint32_t)k * 32, va = smem_u32(sVt + s * VT_BYTES) + (uint32_t)k * 32;
+                    umma_f16(tmem_O, FA_BKV == 64 ? umma_desc_sw128(pa) : umma_desc_sw64(pa),
+                             FA_BKV == 64 ? umma_desc_sw128(va) : umma_desc_sw64(va), idesc_o, (j | k) != 0);
+                }
                 umma_commit(v_empty + s);
                 umma_commit(p_empty + (j & 1));  // P_j consumed; O includes tile j
             }
@@ -234,31 +254,33 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
         const int q = warp & 3, r = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float m_used = -INFINITY, l_run = 0.f;
-        // P row r inside a [128 x 64] K-major 128B-swizzled block: atom (r/8)*1024 + (r%8)*128, 16-byte chunk index ^ (r%8)
-        uint8_t *p_row0 = sP + (r >> 3) * 1024 + (r & 7) * 128;
-        const int xr = r & 7;
+        // P row r inside the K-major swizzled [128 x FA_BKV] tile: 8-row atoms; 128-byte rows: 16-byte chunk index ^ (r%8),
+        // 64-byte rows: chunk index ^ ((r/2)%4)
+        uint8_t *p_row0 = sP + (r >> 3) * (8 * PV_ROW) + (r & 7) * PV_ROW;
+        const int xr = FA_BKV == 64 ? (r & 7) : ((r >> 1) & 3);
         const float2 scale2 = make_float2(scale_log2, scale_log2);
         for (int j = 0; j < n_kv; ++j) {
             const int bsel = j & 1;
             mbar_wait(s_full + bsel, (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tS = tmem_S + lane_addr + (uint32_t)(bsel * 64);
+            const uint32_t tS = tmem_S + lane_addr + (uint32_t)(bsel * FA_BKV);
             const int valid = min(FA_BKV, L - j * FA_BKV);  // keys beyond L are masked out (last tile only)
             const bool full_tile = valid == FA_BKV;          // warp-uniform
             // pass 1 over S: row maximum
-            float mx = -INFINITY;
-#pragma unroll
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains (a single dependent
+#pragma unroll                                                                   // FMNMX3 chain costs ~8 clk per link)
             for (int c0 = 0; c0 < FA_BKV; c0 += 32) {
                 float sv[32];
                 tmem_ld32(tS + c0, sv);
                 if (full_tile) {
 #pragma unroll
-                    for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(sv[c], sv[c + 1]));
+                    for (int c = 0; c < 32; c += 2) mx4[(c >> 1) & 3] = fmaxf(mx4[(c >> 1) & 3], fmaxf(sv[c], sv[c + 1]));
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (c0 + c < valid) ? sv[c] : -INFINITY);
+                    for (int c = 0; c < 32; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], (c0 + c < valid) ? sv[c] : -INFINITY);
                 }
             }
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             mx *= scale_log2;  // scale > 0: the max commutes with the scaling
             if (j == 0) {
                 m_used = mx;
@@ -282,7 +304,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
             }
             if (j >= 2) mbar_wait(p_empty + bsel, ((j >> 1) & 1) ^ 1);  // P_{j-2} has been consumed: its buffer is free
             const float2 negm2 = make_float2(-m_used, -m_used);
-            float2 rs2 = make_float2(0.f, 0.f);
+            float2 rs2 = make_float2(0.f, 0.f), rs2b = make_float2(0.f, 0.f);  // two row-sum chains
             uint8_t *p_row = p_row0 + bsel * P_BYTES;
             // pass 2: probabilities -> fp16 -> shared memory
 #pragma unroll
@@ -303,7 +325,8 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
                             pr.y = (c + 1 < valid) ? pr.y : 0.f;
                         }
                         hp[t] = __floats2half2_rn(pr.x, pr.y);
-                        rs2 = __fadd2_rn(rs2, pr);
+                        if (t & 1) rs2b = __fadd2_rn(rs2b, pr);
+                        else rs2 = __fadd2_rn(rs2, pr);
                     }
                     const int chunk = (c0 + c8) >> 3;
                     *reinterpret_cast<uint4 *>(p_row + ((chunk ^ xr) << 4)) = w;
@@ -311,7 +334,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN))
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(s_empty + bsel);  // this score buffer may be overwritten by Q K_{j+2}^T
-            l_run += rs2.x + rs2.y;
+            l_run += (rs2.x + rs2.y) + (rs2b.x + rs2b.y);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
             mbar_arrive(p_full + bsel);
         }
@@ -349,7 +372,7 @@ typedef CUresult (*EncodeTiledFnA)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_map4(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3],
-                     const cuuint32_t box[4]) {
+                     const cuuint32_t box[4], CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     static EncodeTiledFnA fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -363,7 +386,7 @@ static int make_map4(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], 
     }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r);
@@ -372,15 +395,16 @@ static int make_map4(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], 
     return 0;
 }
 
-template <int DKB, int DN, int STAGES>
+template <int DKB, int DN, int STAGES, int BKV>
 static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads, int S, int L, int d,
                             float scale_log2, __half *out, long long ldo, long long o_bstride, cudaStream_t st) {
-    constexpr size_t smem = (size_t)DKB * 16384 + (size_t)STAGES * (DKB * 8192 + ((DN * 128 + 1023) / 1024) * 1024) + 2 * 16384 + 256 + 1024;
+    constexpr size_t smem = (size_t)DKB * 16384 + (size_t)STAGES * (DKB * BKV * 128 + ((DN * BKV * 2 + 1023) / 1024) * 1024) + 2 * 128 * BKV * 2 +
+                            256 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<DKB, DN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<DKB, DN, STAGES, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
             return (int)e;
@@ -388,7 +412,7 @@ static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const 
         attr[dev] = true;
     }
     dim3 grid((S + FA_BQ - 1) / FA_BQ, heads, B);
-    launch_pdl(attention_fwd_kernel<DKB, DN, STAGES>, grid, dim3(FA_THREADS), smem, st, tq, tk, tv, S, L, d, scale_log2, out, ldo, o_bstride);
+    launch_pdl(attention_fwd_kernel<DKB, DN, STAGES, BKV>, grid, dim3(FA_THREADS), smem, st, tq, tk, tv, S, L, d, scale_log2, out, ldo, o_bstride);
     return check_launch("attention_fwd_kernel");
 }
 
@@ -408,6 +432,11 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
     // (rows >= d are zero-filled) or the producer's expect_tx byte count never completes.
     const int d16 = (int)((d + 15) / 16 * 16);
     const int DN = d <= 64 ? (d16 == 48 ? 48 : (d16 <= 32 ? 32 : 64)) : (d <= 128 ? (d16 == 80 ? 80 : 128) : (d16 == 160 ? 160 : 192));
+    // keys per step: 32 for small heads with SHORT key sequences (cross-attention over 77 tokens: four CTAs per SM and no
+    // half-empty 64-key step), 64 otherwise (measured: 2.23 vs 2.46 ms over the five 4096-token self-attention layers);
+    // COMA_ATTN_BKV = 32 | 64 forces one of them (tuning)
+    static const int forced_bkv = getenv("COMA_ATTN_BKV") ? atoi(getenv("COMA_ATTN_BKV")) : 0;
+    const int BKV = (d <= 64 && (forced_bkv ? forced_bkv == 32 : L <= 128)) ? 32 : 64;
     CUtensorMap tq, tk, tv;
     {
         cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)S, (cuuint64_t)heads, (cuuint64_t)B};
@@ -418,28 +447,35 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
     {
         cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)L, (cuuint64_t)heads, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)ldk * 2, (cuuint64_t)d * 2, (cuuint64_t)(L * ldk) * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)FA_BKV, 1, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)BKV, 1, 1};
         if (int e = make_map4(&tk, k, dims, str, box)) return e;
     }
     {
         cuuint64_t dims[4] = {(cuuint64_t)Lp, (cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)Lp * 2, (cuuint64_t)(d * Lp) * 2, (cuuint64_t)(heads * d * Lp) * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)DN, 1, 1};
-        if (int e = make_map4(&tv, vt, dims, str, box)) return e;
+        cuuint32_t box[4] = {(cuuint32_t)BKV, (cuuint32_t)DN, 1, 1};
+        if (int e = make_map4(&tv, vt, dims, str, box, BKV == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     }
     const float scale_log2 = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
     __half *o = (__half *)out;
     const long long obs = (long long)S * ldo;
+#define COMA_FA_ARGS tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st
     if (d <= 64) {
-        if (DN == 48) return launch_attention<1, 48, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
-        if (DN == 32) return launch_attention<1, 32, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
-        return launch_attention<1, 64, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        if (BKV == 32) {
+            if (DN == 48) return launch_attention<1, 48, 3, 32>(COMA_FA_ARGS);
+            if (DN == 32) return launch_attention<1, 32, 3, 32>(COMA_FA_ARGS);
+            return launch_attention<1, 64, 3, 32>(COMA_FA_ARGS);
+        }
+        if (DN == 48) return launch_attention<1, 48, 3, 64>(COMA_FA_ARGS);
+        if (DN == 32) return launch_attention<1, 32, 3, 64>(COMA_FA_ARGS);
+        return launch_attention<1, 64, 3, 64>(COMA_FA_ARGS);
     }
     if (d <= 128) {
-        if (DN == 80) return launch_attention<2, 80, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
-        return launch_attention<2, 128, 3>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+        if (DN == 80) return launch_attention<2, 80, 3, 64>(COMA_FA_ARGS);
+        return launch_attention<2, 128, 3, 64>(COMA_FA_ARGS);
     }
-    if (DN == 160) return launch_attention<3, 160, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
-    return launch_attention<3, 192, 2>(tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st);
+    if (DN == 160) return launch_attention<3, 160, 2, 64>(COMA_FA_ARGS);
+    return launch_attention<3, 192, 2, 64>(COMA_FA_ARGS);
+#undef COMA_FA_ARGS
 }
