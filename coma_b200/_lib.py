@@ -54,7 +54,7 @@ class GemmArgs(ctypes.Structure):
                 ("out_f16", _vp), ("out_f32", _vp), ("ldo", _i64), ("o_s1", _i64), ("o_s2", _i64),
                 ("residual", _vp), ("bias", _vp), ("bias_rows", _vp), ("rows_per_bias", _i64), ("bias_rows_ld", _i64),
                 ("M", _i64), ("N", _i64), ("K", _i64), ("nb1", _i64), ("nb2", _i64),
-                ("alpha", _f32), ("act", _int), ("workspace", _vp), ("workspace_elems", _i64)]
+                ("alpha", _f32), ("act", _int), ("workspace", _vp), ("workspace_elems", _i64), ("geglu", _int)]
 
 _LIB = None
 

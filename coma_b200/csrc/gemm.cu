@@ -173,7 +173,11 @@ struct TileSched {
 // ids share the A tile (N fastest), which keeps the activation slab L2-resident while its N-tiles are produced.
 // BN in {64, 128, 160, 256}: wider tiles raise the flop/byte of the operand stream (L2 -> SMEM is what bounds a 128x128
 // tile at ~0.75 PFLOP/s on this part: 32 KB per 2.1 MFLOP).
-template <int BN, bool CONV, int STAGES>
+// GEGLU (BN = 256 plain GEMM only): the weight rows of the feed-forward projection are interleaved in blocks of 32 (32 value
+// rows, then their 32 gate rows: prep_geglu in nn.py), so accumulator columns [64p, 64p+32) / [64p+32, 64p+64) of a tile are
+// value / gate of the same 32 features and the epilogue writes value * gelu(gate) — half as many output columns, no
+// [M, 8C] intermediate and no separate GEGLU pass (diffusers GEGLU inside BasicTransformerBlock.ff).
+template <int BN, bool CONV, int STAGES, bool GEGLU = false>
 __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
     gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, int M, int N, int K,
@@ -356,7 +360,8 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
             int m0, n0, b1, b2, cx0, cy0, cb0;
             decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
             const int row0 = (CONV ? ((cb0 * cg.H + cy0) * cg.W + cx0) : m0) + q * 32;
-            const int P = (min(BN, N - n0) + 31) >> 5;
+            constexpr int PCOLS = GEGLU ? 64 : 32;  // accumulator columns behind one 32-column output panel
+            const int P = (min(BN, N - n0) + PCOLS - 1) / PCOLS;
             const int brow_row = min(row0 + lane, M - 1) / ep.rows_per_bias;
             const float *brow = ep.bias_rows ? ep.bias_rows + (size_t)brow_row * ep.bias_rows_ld : nullptr;
             const int acc = i & 1;
@@ -368,9 +373,30 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 const uint32_t buf = g % NBUF;
                 uint8_t *prow = my_row + buf * E_PANEL_BYTES;
                 uint32_t v[32];
-                tmem_ld32_async(tmem_d + (uint32_t)(p * 32), v);
-                const int nb = n0 + p * 32;
+                tmem_ld32_async(tmem_d + (uint32_t)(p * PCOLS), v);
+                const int nb = n0 + p * PCOLS;
                 float f[32];
+                if constexpr (GEGLU) {
+                    uint32_t gt[32];
+                    tmem_ld32_async(tmem_d + (uint32_t)(p * PCOLS + 32), gt);
+                    if (lane == 0) bulk_wait_read<NBUF - 1>();
+                    __syncwarp();
+                    tmem_wait_ld(v);
+                    tmem_wait_ld(gt);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = bias ? __ldg(reinterpret_cast<const float4 *>(bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 bg = bias ? __ldg(reinterpret_cast<const float4 *>(bias + nb + 32 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float bvs[4] = {bv.x, bv.y, bv.z, bv.w}, bgs[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            // value and gate pass through fp16 like the unfused projection output did (same roundings)
+                            const float a = __half2float(__float2half_rn(fmaf(__uint_as_float(v[j + u]), alpha, bvs[u])));
+                            const float x = __half2float(__float2half_rn(fmaf(__uint_as_float(gt[j + u]), alpha, bgs[u])));
+                            f[j + u] = a * (0.5f * x * (1.0f + erff(x * 0.70710678118654752f)));
+                        }
+                    }
+                } else {
                 if (nb + 32 <= N) {
                     if (bias) {
 #pragma unroll
@@ -427,6 +453,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
                 }
+                }  // !GEGLU
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint4 w;
@@ -438,7 +465,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&tmO, ebuf + buf * E_PANEL_BYTES, nb, row0, b1, b2);
+                    tma_store_4d(&tmO, ebuf + buf * E_PANEL_BYTES, GEGLU ? (n0 >> 1) + p * 32 : nb, row0, b1, b2);
                     bulk_commit();
                     if (has_res) {
                         bulk_wait_read<1>();  // the previous panel's store has finished reading its buffer: refill it
@@ -623,7 +650,7 @@ static int setup_epilogue_maps(GemmEpilogue &ep, CUtensorMap *to, CUtensorMap *t
     return 0;
 }
 
-template <int BN, bool CONV>
+template <int BN, bool CONV, bool GEGLU = false>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr, int M, int N, int K,
                        const GemmEpilogue &ep, int nbatch, cudaStream_t st, int ksplit, long long split_stride,
                        const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
@@ -633,7 +660,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
             return (int)e;
@@ -655,7 +682,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
     ts.total = (int)total;
     const int slots = kNumSM * (BN <= 128 ? 2 : 1);
     const unsigned grid = (unsigned)(ts.total < slots ? ts.total : slots);
-    launch_pdl(gemm_f16_tn_kernel<BN, CONV, STAGES>, dim3(grid), dim3(gemm_threads(BN)), smem, st, ta, tb, to, tr, M, N, K, ep, cg, ts);
+    launch_pdl(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU>, dim3(grid), dim3(gemm_threads(BN)), smem, st, ta, tb, to, tr, M, N, K, ep, cg, ts);
     return check_launch("gemm_f16_tn_kernel");
 }
 
@@ -786,7 +813,7 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     COMA_REQUIRE(g && g->A && g->W && (g->out_f16 || g->out_f32), "null pointer");
     const int64_t M = g->M, N = g->N, K = g->K, nb1 = g->nb1 > 0 ? g->nb1 : 1, nb2 = g->nb2 > 0 ? g->nb2 : 1;
     COMA_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "bad sizes");
-    COMA_REQUIRE(g->lda >= K && g->ldw >= K && g->ldo >= N, "leading dimensions smaller than the row length");
+    COMA_REQUIRE(g->lda >= K && g->ldw >= K && g->ldo >= (g->geglu ? N / 2 : N), "leading dimensions smaller than the row length");
     COMA_REQUIRE(g->lda % 8 == 0 && g->ldw % 8 == 0, "lda / ldw must be multiples of 8 elements (16-byte TMA strides)");
     COMA_REQUIRE((nb1 == 1 || (g->a_s1 % 8 == 0 && g->w_s1 % 8 == 0)) && (nb2 == 1 || (g->a_s2 % 8 == 0 && g->w_s2 % 8 == 0)),
                  "batch strides of A / W must be multiples of 8 elements");
@@ -810,6 +837,18 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     ep.alpha = g->alpha;
     ep.act = g->act;
     ep.nb1 = (int)nb1;
+    if (g->geglu) {
+        // fused GEGLU: W / bias rows interleaved in blocks of 32 (value, gate); output [M, N/2] fp16
+        COMA_REQUIRE(N % 256 == 0 && g->out_f16 && !g->out_f32 && !g->residual && !g->bias_rows && g->act == 0 && nb1 * nb2 == 1,
+                     "geglu: needs N % 256 == 0, fp16 output only, no residual / bias rows / activation / batching");
+        COMA_REQUIRE(g->ldo >= N / 2 && g->ldo % 8 == 0 && (uintptr_t)g->bias % 16 == 0, "geglu: bad output stride or bias alignment");
+        CUtensorMap ta, tb, to, tr;
+        if (int e = make_map(&ta, g->A, M, K, g->lda, G_BM, 1, 0, 1, 0)) return e;
+        if (int e = make_map(&tb, g->W, N, K, g->ldw, 256, 1, 0, 1, 0)) return e;
+        if (int e = setup_epilogue_maps(ep, &to, &tr, M, N / 2, 1, 1)) return e;
+        COMA_REQUIRE(ep.tma == 1, "geglu: output not eligible for the TMA epilogue");
+        return launch_gemm<256, false, true>(ta, tb, to, tr, (int)M, (int)N, (int)K, ep, 1, (cudaStream_t)stream, 1, 0);
+    }
     const bool can_split = split_eligible(ep, N, nb1 * nb2, g->workspace);
     const GemmPlan plan = plan_gemm((M + G_BM - 1) / G_BM, N, K, nb1 * nb2, M, can_split, g->workspace_elems);
     const int bn = plan.bn;

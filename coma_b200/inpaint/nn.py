@@ -190,6 +190,32 @@ def layernorm(x2d, gamma, beta, eps=1e-5):
     return y
 
 
+def prep_geglu(w, b, device):
+    """Feed-forward projection [2F, C] (rows: F values, then F gates) -> rows interleaved in blocks of 32 (32 values, their 32
+    gates, ...) so one 64-column accumulator group of the GEMM holds value and gate of the same features (fused GEGLU
+    epilogue). Returns (weight [2F, rup(C)] f16, bias [2F] f32) or None when the fused kernel does not apply."""
+    F = w.shape[0] // 2
+    if (2 * F) % 256 != 0:
+        return None
+    blocks = torch.arange(F // 32).view(-1, 1, 1) * 32 + torch.arange(32).view(1, 1, 32)   # feature index per slot
+    src = torch.cat([blocks, blocks + F], dim=1).reshape(-1)       # new row r <- old row src[r]
+    return prep_linear(w[src], device), prep_vec(b[src], device)
+
+
+def gemm_geglu(a, w_il, b_il):
+    """out[M, F] = value * gelu(gate) of the interleaved projection (see prep_geglu), one kernel."""
+    M, K = a.shape
+    N = w_il.shape[0]
+    out = torch.empty((M, N // 2), dtype=F16, device=a.device)
+    g = GemmArgs()
+    g.A, g.lda, g.W, g.ldw = a.data_ptr(), a.stride(0), w_il.data_ptr(), w_il.stride(0)
+    g.M, g.N, g.K, g.nb1, g.nb2 = M, N, K, 1, 1
+    g.out_f16, g.ldo, g.bias, g.alpha, g.geglu = out.data_ptr(), out.stride(0), _ptr(b_il), 1.0, 1
+    with torch.cuda.device(a.device):
+        call("coma_gemm_f16_ex", ctypes.addressof(g), _stream())
+    return out
+
+
 def geglu(h):
     C = h.shape[1] // 2
     y = torch.empty((h.shape[0], C), dtype=F16, device=h.device)

@@ -22,6 +22,11 @@ class UNet:
         for k, v in sd.items():
             base = k.rsplit(".", 1)[0]
             if k.endswith(".weight"):
+                if k.endswith(".ff.net.0.proj.weight"):
+                    fused = nn.prep_geglu(v, sd[base + ".bias"], self.dev)
+                    if fused is not None:
+                        self.p[base.rsplit(".net.0.proj", 1)[0] + ".geglu"] = fused
+                        continue
                 if ".time_emb_proj" in k:      # all 22 projections run as ONE GEMM per step
                     tproj_w.append(v)
                     tproj_b.append(sd[base + ".bias"])
@@ -65,7 +70,10 @@ class UNet:
         h = nn.attention(n2, ctx, B, S, L, p[t + ".attn2.to_q.weight"], p[t + ".attn2.to_k.weight"], p[t + ".attn2.to_v.weight"],
                          p[t + ".attn2.to_out.0.weight"], p[t + ".attn2.to_out.0.bias"], heads, h)
         n3 = nn.layernorm(h, p[t + ".norm3.weight"], p[t + ".norm3.bias"])
-        ff = nn.geglu(nn.gemm(n3, p[t + ".ff.net.0.proj.weight"], p[t + ".ff.net.0.proj.bias"]))
+        if t + ".ff.geglu" in p:     # projection + GEGLU in one kernel (interleaved weight rows)
+            ff = nn.gemm_geglu(n3, *p[t + ".ff.geglu"])
+        else:
+            ff = nn.geglu(nn.gemm(n3, p[t + ".ff.net.0.proj.weight"], p[t + ".ff.net.0.proj.bias"]))
         h = nn.gemm(ff, p[t + ".ff.net.2.weight"], p[t + ".ff.net.2.bias"], residual=h)
         out = nn.gemm(h, p[name + ".proj_out.weight"], p[name + ".proj_out.bias"], residual=x.t)
         return Act(out, x.B, x.H, x.W)

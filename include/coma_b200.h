@@ -129,6 +129,8 @@ typedef struct coma_gemm_args {
     int act;
     float *workspace; int64_t workspace_elems; /* optional fp32 scratch (>= ksplit*M*N floats) enabling split-K on problems with
                                                 * too few output tiles for 148 SMs; NULL = never split */
+    int geglu; /* 1: W / bias rows are interleaved in blocks of 32 (32 value rows, their 32 gate rows, ...) and the epilogue writes
+                * out[M, N/2] = value * gelu(gate) (diffusers GEGLU fused into its projection); needs N % 256 == 0 */
 } coma_gemm_args;
 COMA_API int coma_gemm_f16_ex(const coma_gemm_args *args, coma_stream_t stream);
 

@@ -118,3 +118,23 @@ def test_gemm_split_k(dev, M, N, K, out_dtype):
     assert (out.float() - ref).abs().max().item() <= tol * ref.abs().max().item()
     again = nn.gemm(a, w, bias, res, act=1, out_dtype=out_dtype, bias_rows=brows, rows_per_bias=64)
     assert torch.equal(out, again)
+
+
+@pytest.mark.parametrize("M,C", [(1000, 320), (4096, 640), (300, 1280)])
+def test_gemm_geglu_fused(dev, M, C):
+    """Feed-forward projection with the GEGLU folded into the GEMM epilogue (interleaved weight rows) == projection (fp16) then
+    value * gelu(gate), the diffusers GEGLU."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(C)
+    F = 4 * C
+    x = torch.randn((M, C), device=dev, generator=g).half()
+    w = (torch.randn((2 * F, C), device=dev, generator=g) * C ** -0.5).half()
+    b = torch.randn(2 * F, device=dev, generator=g) * 0.1
+    fused = nn.prep_geglu(w.cpu(), b.cpu(), dev)
+    assert fused is not None
+    out = nn.gemm_geglu(x, *fused)
+    h = (x.float() @ w.float().t() + b).half().float()
+    ref = h[:, :F] * torch.nn.functional.gelu(h[:, F:])
+    torch.testing.assert_close(out.float(), ref, rtol=2e-3, atol=2e-3)
+    unfused = nn.geglu(nn.gemm(x, nn.prep_linear(w, dev), b))
+    torch.testing.assert_close(out.float(), unfused.float(), rtol=2e-3, atol=2e-3)
