@@ -29,7 +29,8 @@ SIGNATURES = {
     "coma_conv3x3_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp],
     "coma_conv3x3_f16_ws": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp, _i64, _vp],
     "coma_attention_fwd_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
-    "coma_groupnorm_affine_f16": [_vp, _i64, _i64, _i64, _i64, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "coma_groupnorm_workspace_doubles": [_i64, _int],
+    "coma_groupnorm_affine_f16": [_vp, _i64, _i64, _i64, _i64, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "coma_affine_act_f16": [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _vp],
     "coma_upsample2x_affine_act_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _vp],
     "coma_im2col3x3_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp, _int, _vp, _i64, _vp],
@@ -78,7 +79,7 @@ def load():
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = args
-            fn.restype = _int
+            fn.restype = _i64 if name == "coma_groupnorm_workspace_doubles" else _int
         _LIB = lib
     return _LIB
 

@@ -19,11 +19,84 @@
 namespace coma {
 
 // ---------------------------------------------------------------------------------------------- GroupNorm statistics
+// Tail of the statistics kernels: CTA (chunk, b) has written its per-group partial sums; the LAST CTA of sample b to
+// arrive (ticket counter, self-resetting) adds the chunks in index order (bit-reproducible, fp64) and writes the folded
+// affine  scale[b,c] = rstd*gamma[c],  shift[b,c] = beta[c] - mean*rstd*gamma[c]  — no memset, no finalize launch.
+__device__ __forceinline__ void groupnorm_finish(double *__restrict__ partial, unsigned *__restrict__ counter, int b, int C, int G,
+                                                 long long count, float eps, const float *__restrict__ gamma,
+                                                 const float *__restrict__ beta, float *__restrict__ mean, float *__restrict__ rstd,
+                                                 float *__restrict__ scale, float *__restrict__ shift, float *sm /* >= 2*G floats */) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(counter + b, 1u);
+        is_last = (ticket == gridDim.x - 1);
+        if (is_last) counter[b] = 0;  // ready for the next launch on this stream
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // all 256 threads: thread (slice, g) adds every NS-th chunk of group g, then the NS slices are combined in index order —
+    // fixed association, independent of scheduling
+    const int chunks = gridDim.x;
+    double *dsm = reinterpret_cast<double *>(sm);
+    const int NS = G <= 128 ? (int)blockDim.x / G : 1;  // slices per group
+    for (int g0 = 0; g0 < G; g0 += (int)blockDim.x / NS) {
+        const int g = g0 + (int)threadIdx.x % ((int)blockDim.x / NS), sl = (int)threadIdx.x / ((int)blockDim.x / NS);
+        double s = 0.0, q = 0.0;
+        if (g < G) {
+            const double *p = partial + ((size_t)b * chunks * G + g) * 2;
+#pragma unroll 4
+            for (int k = sl; k < chunks; k += NS) {
+                s += __ldcg(p + (size_t)k * G * 2);
+                q += __ldcg(p + (size_t)k * G * 2 + 1);
+            }
+        }
+        __syncthreads();
+        if (g < G) {
+            dsm[(sl * G + g) * 2] = s;       // [NS][G][2] doubles <= 2 * 256 doubles = 4 KB (host sizes smem accordingly)
+            dsm[(sl * G + g) * 2 + 1] = q;
+        }
+        __syncthreads();
+        if (sl == 0 && g < G) {
+            for (int k = 1; k < NS; ++k) {
+                s += dsm[(k * G + g) * 2];
+                q += dsm[(k * G + g) * 2 + 1];
+            }
+            const double m = s / (double)count;
+            double var = q / (double)count - m * m;
+            var = var < 0.0 ? 0.0 : var;
+            const double r = 1.0 / sqrt(var + (double)eps);
+            if (mean) mean[b * G + g] = (float)m;
+            if (rstd) rstd[b * G + g] = (float)r;
+            s = m;
+            q = r;
+        }
+        __syncthreads();
+        if (sl == 0 && g < G) {
+            dsm[2 * g] = s;      // slot (0, g): mean, rstd
+            dsm[2 * g + 1] = q;
+        }
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double m = reinterpret_cast<double *>(sm)[2 * (c / cpg)], r = reinterpret_cast<double *>(sm)[2 * (c / cpg) + 1];
+        const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+        scale[(size_t)b * C + c] = (float)(r * ga);
+        shift[(size_t)b * C + c] = (float)(be - m * r * ga);
+    }
+}
+
+
 // grid (chunks, B), block 256. 16-byte loads: a thread owns 8 consecutive channels; when C/8 < 256 the spare threads
 // split the chunk's pixel rows. Partial sums go through shared memory, then one fp64 atomicAdd pair per (b, group).
 __global__ void __launch_bounds__(256)
     groupnorm_partial_kernel(const __half *__restrict__ x, int HW, int C, long long ldx, int G, int rows_per_chunk,
-                             double *__restrict__ acc /* [B,G,2] */) {
+                             double *__restrict__ partial /* [B,chunks,G,2] */, unsigned *__restrict__ counter, long long count, float eps,
+                             const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ mean,
+                             float *__restrict__ rstd, float *__restrict__ scale, float *__restrict__ shift) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float sm[];  // [rg][2][C]
@@ -37,16 +110,23 @@ __global__ void __launch_bounds__(256)
             float s[8], q[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
-            for (int p = p0 + ry; p < p1; p += rg) {
-                const uint4 raw = *reinterpret_cast<const uint4 *>(xb + (size_t)p * ldx + cg0 * 8);
-                const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+            // 8 independent 16-byte loads in flight per thread (a one-load-per-iteration loop is pure L2 latency)
+            for (int p = p0 + ry; p < p1; p += 8 * rg) {
+                uint4 raw[8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 v = __half22float2(h[k]);
-                    s[2 * k] += v.x;
-                    s[2 * k + 1] += v.y;
-                    q[2 * k] = fmaf(v.x, v.x, q[2 * k]);
-                    q[2 * k + 1] = fmaf(v.y, v.y, q[2 * k + 1]);
+                for (int u = 0; u < 8; ++u)
+                    raw[u] = (p + u * rg < p1) ? *reinterpret_cast<const uint4 *>(xb + (size_t)(p + u * rg) * ldx + cg0 * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&raw[u]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 v = __half22float2(h[k]);
+                        s[2 * k] += v.x;
+                        s[2 * k + 1] += v.y;
+                        q[2 * k] = fmaf(v.x, v.x, q[2 * k]);
+                        q[2 * k + 1] = fmaf(v.y, v.y, q[2 * k + 1]);
+                    }
                 }
             }
 #pragma unroll
@@ -65,15 +145,20 @@ __global__ void __launch_bounds__(256)
                 s += (double)sm[(r * 2 + 0) * C + c];
                 q += (double)sm[(r * 2 + 1) * C + c];
             }
-        atomicAdd(acc + ((size_t)b * G + g) * 2 + 0, s);
-        atomicAdd(acc + ((size_t)b * G + g) * 2 + 1, q);
+        double *dst = partial + (((size_t)b * gridDim.x + blockIdx.x) * G + g) * 2;
+        dst[0] = s;
+        dst[1] = q;
     }
+    __syncthreads();  // sm is reused by the finishing block
+    groupnorm_finish(partial, counter, b, C, G, count, eps, gamma, beta, mean, rstd, scale, shift, sm);
 }
 
 // scalar fallback (C % 8 != 0 or unaligned rows): thread t owns channels t, t+256, ...
 __global__ void __launch_bounds__(256)
     groupnorm_partial_scalar_kernel(const __half *__restrict__ x, int HW, int C, long long ldx, int G, int rows_per_chunk,
-                                    double *__restrict__ acc) {
+                                    double *__restrict__ partial, unsigned *__restrict__ counter, long long count, float eps,
+                                    const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ mean,
+                                    float *__restrict__ rstd, float *__restrict__ scale, float *__restrict__ shift) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float sm[];  // [2][C]
@@ -97,32 +182,12 @@ __global__ void __launch_bounds__(256)
             s += (double)sm[c];
             q += (double)sm[C + c];
         }
-        atomicAdd(acc + ((size_t)b * G + g) * 2 + 0, s);
-        atomicAdd(acc + ((size_t)b * G + g) * 2 + 1, q);
+        double *dst = partial + (((size_t)b * gridDim.x + blockIdx.x) * G + g) * 2;
+        dst[0] = s;
+        dst[1] = q;
     }
-}
-
-// mean/rstd per (b,g) and the per-(b,c) affine  y = x*scale + shift  (scale = rstd*gamma, shift = beta - mean*rstd*gamma)
-__global__ void groupnorm_finalize_kernel(const double *__restrict__ acc, int B, int C, int G, long long count, float eps,
-                                          const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ mean,
-                                          float *__restrict__ rstd, float *__restrict__ scale, float *__restrict__ shift) {
-    pdl_trigger();
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * C) return;
-    const int b = i / C, c = i % C, g = c / (C / G);
-    const double s = acc[((size_t)b * G + g) * 2], q = acc[((size_t)b * G + g) * 2 + 1];
-    const double m = s / (double)count;
-    double var = q / (double)count - m * m;
-    var = var < 0.0 ? 0.0 : var;
-    const double r = 1.0 / sqrt(var + (double)eps);
-    if (c % (C / G) == 0) {
-        if (mean) mean[b * G + g] = (float)m;
-        if (rstd) rstd[b * G + g] = (float)r;
-    }
-    const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
-    scale[i] = (float)(r * ga);
-    shift[i] = (float)(be - m * r * ga);
+    __syncthreads();
+    groupnorm_finish(partial, counter, b, C, G, count, eps, gamma, beta, mean, rstd, scale, shift, sm);
 }
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
@@ -140,15 +205,18 @@ __global__ void __launch_bounds__(256)
         const int c = (int)(i % c8n) * 8;
         const int b = (int)(r / HW);
         const uint4 raw = *reinterpret_cast<const uint4 *>(x + r * ldx + c);
+        // scale / shift rows are [B, C] fp32 with C % 8 == 0: two 16-byte loads each instead of eight scalar ones
+        const float4 *sp = reinterpret_cast<const float4 *>(scale + (size_t)b * C + c), *tp = reinterpret_cast<const float4 *>(shift + (size_t)b * C + c);
+        const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), t0 = __ldg(tp), t1 = __ldg(tp + 1);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
         const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
         uint4 o;
         __half2 *oh = reinterpret_cast<__half2 *>(&o);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             float2 v = __half22float2(h[t]);
-            const int cc = b * C + c + 2 * t;
-            v.x = fmaf(v.x, scale[cc], shift[cc]);
-            v.y = fmaf(v.y, scale[cc + 1], shift[cc + 1]);
+            v.x = fmaf(v.x, sc[2 * t], sh[2 * t]);
+            v.y = fmaf(v.y, sc[2 * t + 1], sh[2 * t + 1]);
             if (act == 1) {
                 v.x = silu_f(v.x);
                 v.y = silu_f(v.y);
@@ -282,6 +350,67 @@ __global__ void __launch_bounds__(256)
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     __half *yr = y + row * ldy;
     for (int c = lane; c < C; c += 32) yr[c] = __float2half_rn((__half2float(xr[c]) - mean) * rstd * gamma[c] + beta[c]);
+}
+
+// vectorised form (C % 8 == 0, C <= 256*NCH, 16-byte aligned rows): the row is read ONCE as 16-byte chunks into registers
+// (lane owns chunks lane, lane+32, ...), mean and centred variance come from the registers, one 16-byte store per chunk.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+    layernorm_vec_kernel(const __half *__restrict__ x, long long M, int C, long long ldx, const float *__restrict__ gamma,
+                         const float *__restrict__ beta, float eps, __half *__restrict__ y, long long ldy) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nch = C / 8;
+    const __half *xr = x + row * ldx;
+    float v[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int ch = lane + 32 * j;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (ch < nch) raw = *reinterpret_cast<const uint4 *>(xr + ch * 8);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(h[t]);
+            v[j][2 * t] = f.x;
+            v[j][2 * t + 1] = f.y;
+            s += f.x + f.y;
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        if (lane + 32 * j < nch) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float d = v[j][t] - mean;
+                q = fmaf(d, d, q);
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    __half *yr = y + row * ldy;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int ch = lane + 32 * j;
+        if (ch < nch) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + ch * 8)), g1 = __ldg(reinterpret_cast<const float4 *>(gamma + ch * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(beta + ch * 8)), b1 = __ldg(reinterpret_cast<const float4 *>(beta + ch * 8 + 4));
+            const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 o;
+            __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                oh[t] = __floats2half2_rn((v[j][2 * t] - mean) * rstd * ga[2 * t] + be[2 * t],
+                                          (v[j][2 * t + 1] - mean) * rstd * ga[2 * t + 1] + be[2 * t + 1]);
+            *reinterpret_cast<uint4 *>(yr + ch * 8) = o;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- row softmax (in place)
@@ -493,39 +622,42 @@ static inline unsigned blocks_for(long long total, int threads = 256) {
 
 using namespace coma;
 
+extern "C" int64_t coma_groupnorm_workspace_doubles(int64_t B, int G) { return 2LL * G * (4LL * coma::kNumSM + B); }
+
 extern "C" int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, int G, float eps,
-                                         const float *gamma, const float *beta, double *workspace, float *mean, float *rstd,
-                                         float *scale, float *shift, coma_stream_t stream) {
-    COMA_REQUIRE(x && workspace && scale && shift, "null pointer");
+                                         const float *gamma, const float *beta, double *workspace, unsigned *counters, float *mean,
+                                         float *rstd, float *scale, float *shift, coma_stream_t stream) {
+    COMA_REQUIRE(x && workspace && counters && scale && shift, "null pointer");
     COMA_REQUIRE(B > 0 && HW > 0 && C > 0 && G > 0 && C % G == 0 && ldx >= C, "bad sizes");
-    COMA_REQUIRE(C <= 8192 && B <= 65535, "C or B too large");
+    COMA_REQUIRE(C <= 8192 && B <= 65535 && G <= 1024, "C, B or G too large");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * B * G, st);
-    // enough chunks to fill the machine, each at least 16 pixel rows
+    // enough chunks to fill the machine, each at least 16 pixel rows; B * chunks <= 4 * 148 + B (the workspace bound)
     long long chunks = (4LL * kNumSM + B - 1) / B;
     long long rows = (HW + chunks - 1) / chunks;
-    rows = rows < 16 ? 16 : rows;
+    rows = rows < 8 ? 8 : rows;
     chunks = (HW + rows - 1) / rows;
     const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && ((uintptr_t)x % 16 == 0);
+    const long long count = HW * (C / G);
     if (vec) {
         const int cgn = (int)(C / 8), rg = cgn >= 256 ? 1 : 256 / cgn;
-        launch_pdl(groupnorm_partial_kernel, dim3(dim3((unsigned)chunks, (unsigned)B)), dim3(256), sizeof(float) * 2 * C * rg, st, 
-            (const __half *)x, (int)HW, (int)C, ldx, G, (int)rows, workspace);
+        size_t smem = sizeof(float) * 2 * C * rg;
+        if (smem < sizeof(double) * 2 * (256 + G)) smem = sizeof(double) * 2 * (256 + G);
+        launch_pdl(groupnorm_partial_kernel, dim3((unsigned)chunks, (unsigned)B), dim3(256), smem, st, (const __half *)x, (int)HW, (int)C, ldx, G,
+                   (int)rows, workspace, counters, count, eps, gamma, beta, mean, rstd, scale, shift);
     } else {
-        launch_pdl(groupnorm_partial_scalar_kernel, dim3(dim3((unsigned)chunks, (unsigned)B)), dim3(256), sizeof(float) * 2 * C, st, 
-            (const __half *)x, (int)HW, (int)C, ldx, G, (int)rows, workspace);
+        size_t smem = sizeof(float) * 2 * C;
+        if (smem < sizeof(double) * 2 * (256 + G)) smem = sizeof(double) * 2 * (256 + G);
+        launch_pdl(groupnorm_partial_scalar_kernel, dim3((unsigned)chunks, (unsigned)B), dim3(256), smem, st, (const __half *)x, (int)HW, (int)C,
+                   ldx, G, (int)rows, workspace, counters, count, eps, gamma, beta, mean, rstd, scale, shift);
     }
-    if (int e = check_launch("groupnorm_partial_kernel")) return e;
-    launch_pdl(groupnorm_finalize_kernel, dim3((unsigned)((B * C + 255) / 256)), dim3(256), 0, st, workspace, (int)B, (int)C, G, HW * (C / G), eps, gamma,
-                                                                              beta, mean, rstd, scale, shift);
-    return check_launch("groupnorm_finalize_kernel");
+    return check_launch("groupnorm_partial_kernel");
 }
 
 extern "C" int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, const float *scale,
                                    const float *shift, int act, void *y, int64_t ldy, coma_stream_t stream) {
     COMA_REQUIRE(x && y && scale && shift, "null pointer");
     COMA_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "C, ldx, ldy must be multiples of 8");
-    COMA_REQUIRE(((uintptr_t)x | (uintptr_t)y) % 16 == 0, "x / y must be 16-byte aligned");
+    COMA_REQUIRE(((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift) % 16 == 0, "x / y / scale / shift must be 16-byte aligned");
     launch_pdl(affine_act_kernel, dim3(blocks_for(B * HW * (C / 8))), dim3(256), 0, (cudaStream_t)stream, (const __half *)x, B * HW, (int)HW, (int)C, ldx,
                                                                                     scale, shift, act, (__half *)y, ldy);
     return check_launch("affine_act_kernel");
@@ -578,8 +710,18 @@ extern "C" int coma_layernorm_f16(const void *x, int64_t M, int64_t C, int64_t l
                                   void *y, int64_t ldy, coma_stream_t stream) {
     COMA_REQUIRE(x && y && gamma && beta, "null pointer");
     COMA_REQUIRE(M > 0 && C > 0 && ldx >= C && ldy >= C, "bad sizes");
-    launch_pdl(layernorm_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, (const __half *)x, M, (int)C, ldx, gamma, beta, eps,
-                                                                              (__half *)y, ldy);
+    const bool vec = C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldy % 8 == 0 &&
+                     ((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) % 16 == 0;
+    const dim3 grid((unsigned)((M + 7) / 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec && C <= 512)
+        launch_pdl(layernorm_vec_kernel<2>, grid, dim3(256), 0, st, (const __half *)x, M, (int)C, ldx, gamma, beta, eps, (__half *)y, ldy);
+    else if (vec && C <= 1024)
+        launch_pdl(layernorm_vec_kernel<4>, grid, dim3(256), 0, st, (const __half *)x, M, (int)C, ldx, gamma, beta, eps, (__half *)y, ldy);
+    else if (vec)
+        launch_pdl(layernorm_vec_kernel<8>, grid, dim3(256), 0, st, (const __half *)x, M, (int)C, ldx, gamma, beta, eps, (__half *)y, ldy);
+    else
+        launch_pdl(layernorm_kernel, grid, dim3(256), 0, st, (const __half *)x, M, (int)C, ldx, gamma, beta, eps, (__half *)y, ldy);
     return check_launch("layernorm_kernel");
 }
 

@@ -101,15 +101,21 @@ def gemm_batched(A, lda, a_s1, a_s2, W, ldw, w_s1, w_s2, out, ldo, o_s1, o_s2, M
     return out
 
 
+_GN_COUNTERS = {}
+
+
 def gn_affine(x: Act, gamma, beta, groups, eps):
-    """GroupNorm statistics folded with the affine: gn(x) = x*scale[b,c] + shift[b,c] (fp32 [B,C] each)."""
+    """GroupNorm statistics folded with the affine: gn(x) = x*scale[b,c] + shift[b,c] (fp32 [B,C] each). One launch."""
     dev = x.t.device
-    ws = torch.empty(2 * x.B * groups, dtype=torch.float64, device=dev)
+    ws = torch.empty(2 * groups * (4 * 148 + x.B), dtype=torch.float64, device=dev)
+    cnt = _GN_COUNTERS.get(dev.index)
+    if cnt is None or cnt.numel() < x.B:   # ticket counters: zero once, every launch leaves them zero
+        cnt = _GN_COUNTERS[dev.index] = torch.zeros(max(1024, x.B), dtype=torch.int32, device=dev)
     scale = torch.empty((x.B, x.C), dtype=F32, device=dev)
     shift = torch.empty((x.B, x.C), dtype=F32, device=dev)
     with torch.cuda.device(dev):
         call("coma_groupnorm_affine_f16", x.t.data_ptr(), x.B, x.H * x.W, x.C, x.ld, groups, float(eps), _ptr(gamma), _ptr(beta),
-             ws.data_ptr(), None, None, scale.data_ptr(), shift.data_ptr(), _stream())
+             ws.data_ptr(), cnt.data_ptr(), None, None, scale.data_ptr(), shift.data_ptr(), _stream())
     return scale, shift
 
 

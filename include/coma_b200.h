@@ -165,11 +165,14 @@ COMA_API int coma_attention_fwd_f16(const void *q, const void *k, const void *vt
  * (diffusers UNet2DConditionModel / AutoencoderKL layers reached from utils/adaptive_mask_inpainting.py:1001, :680, :1086) */
 
 /* GroupNorm statistics + folded affine: scale[b,c] = rstd*gamma[c], shift[b,c] = beta[c] - mean*rstd*gamma[c] so that
- * gn(x) = x*scale + shift. workspace: 2*B*G doubles. mean / rstd ([B,G] f32) may be NULL. */
+ * gn(x) = x*scale + shift. ONE launch: per-chunk partial sums, the last CTA of each sample reduces them in index order
+ * (fp64, bit-reproducible). workspace: coma_groupnorm_workspace_doubles(B, G) doubles (contents irrelevant); counters: B
+ * unsigned ints that must be ZERO before the first call and are left zero by every call (per-stream persistent scratch).
+ * mean / rstd ([B,G] f32) may be NULL. */
+COMA_API int64_t coma_groupnorm_workspace_doubles(int64_t B, int G);
 COMA_API int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, int G, float eps,
-                                       const float *gamma, const float *beta, double *workspace, float *mean, float *rstd,
-                                       float *scale, float *shift, coma_stream_t stream);
-/* y = act(x*scale[b,c] + shift[b,c]); act 0 none / 1 SiLU. C, ldx, ldy multiples of 8. */
+                                       const float *gamma, const float *beta, double *workspace, unsigned *counters, float *mean,
+                                       float *rstd, float *scale, float *shift, coma_stream_t stream);
 COMA_API int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, const float *scale,
                                  const float *shift, int act, void *y, int64_t ldy, coma_stream_t stream);
 /* Nearest x2 upsampling fused with the affine + activation (input of the Upsample2D convolutions): y [B,2H,2W,C]. */
