@@ -247,22 +247,57 @@ def timestep_embedding(t, dim):
 FUSED_ATTENTION = True
 
 
-def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual):
-    """softmax(Q K^T / sqrt(d)) V followed by the output projection (+bias +residual). xq [B*S, C], xkv [B*L, Ckv] f16.
-    Scores and probabilities are materialised in fp16 ([B,heads,S,Lp]); the products run as batched tensor-core GEMMs."""
-    dev = xq.device
-    C = wq.shape[0]
+def project_kv(xkv, B, L, wkv, heads):
+    """K and V^T of an attention layer from ONE projection GEMM over the concatenated [2C, Ckv] weight: returns
+    (k [B*L, C] view with row stride 2C, vt [B, heads, d, Lp]). The UNet's cross-attention context is constant over the
+    denoising loop, so the pipeline computes these once per call instead of once per step."""
+    C = wkv.shape[0] // 2
     d = C // heads
-    q, k, v = gemm(xq, wq), gemm(xkv, wk), gemm(xkv, wv)
+    kv = gemm(xkv, wkv)
+    Lp = rup(L)
+    vt = torch.empty((B, heads, d, Lp), dtype=F16, device=xkv.device)
+    v = kv[:, C:]
+    with torch.cuda.device(xkv.device):
+        call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
+    return kv[:, :C], vt
+
+
+def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual, wqkv=None, wkv=None, kv=None):
+    """softmax(Q K^T / sqrt(d)) V followed by the output projection (+bias +residual). xq [B*S, C], xkv [B*L, Ckv] f16.
+    wqkv ([3C, C], self-attention) / wkv ([2C, Ckv]) are the row-concatenated projection weights: one GEMM instead of three /
+    two; kv = (k, vt) supplies precomputed keys / transposed values (see project_kv)."""
+    dev = xq.device
+    C = wo.shape[1] if wq is None else wq.shape[0]
+    d = C // heads
     Lp = rup(L)
     if FUSED_ATTENTION and d % 8 == 0 and d <= 192:
-        vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)
+        if kv is not None:
+            q = gemm(xq, wq)
+            k, vt = kv
+        elif wqkv is not None:
+            qkv = gemm(xq, wqkv)
+            q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+            vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)
+            with torch.cuda.device(dev):
+                call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
+        else:
+            q = gemm(xq, wq)
+            k, vt = project_kv(xkv, B, L, wkv, heads) if wkv is not None else (gemm(xkv, wk), None)
+            if vt is None:
+                v = gemm(xkv, wv)
+                vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)
+                with torch.cuda.device(dev):
+                    call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
         o = torch.empty((B * S, C), dtype=F16, device=dev)
         with torch.cuda.device(dev):
-            call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
             call("coma_attention_fwd_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, q.stride(0), k.stride(0), Lp,
                  float(d ** -0.5), o.data_ptr(), o.stride(0), _stream())
         return gemm(o, wo, bo, residual)
+    if wq is None:
+        wq, wk, wv = wqkv[:C], wqkv[C:2 * C], wqkv[2 * C:]
+    elif wk is None:
+        wk, wv = wkv[:C], wkv[C:]
+    q, k, v = gemm(xq, wq), gemm(xkv, wk), gemm(xkv, wv)
     scores = torch.empty((B, heads, S, Lp), dtype=F16, device=dev)
     gemm_batched(q, C, d, S * C, k, C, d, L * C, scores, Lp, S * Lp, heads * S * Lp, S, L, d, heads, B, alpha=d ** -0.5)
     vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)

@@ -242,6 +242,8 @@ class AdaptiveMaskInpaintPipeline:
         tt = self._static(ukey + ("t",), lambda: torch.zeros((2 * B,), dtype=F32, device=dev))
         ctx_static = self._static(ukey + ("ctx",), lambda: torch.empty_like(ctx))
         ctx_static.copy_(ctx)
+        # cross-attention keys / values depend on the prompt only: projected once per call, reused by all UNet evaluations
+        ctx_kv = self._graphed(ukey + ("kv",), lambda c: self.unet.context_kv(c, L, 2 * B), ctx_static)
         trace = [] if return_trace else None
         settings = self.adaptive_mask_settings
         for i, t in enumerate(timesteps):
@@ -249,7 +251,7 @@ class AdaptiveMaskInpaintPipeline:
                 call("coma_assemble_unet_input_f16", latents.data_ptr(), mask64.data_ptr(), masked_latents.data_ptr(), rows,
                      x_in.t.data_ptr(), x_in.ld, _stream())
             tt.fill_(float(t))
-            eps = self._graphed(ukey, lambda a, b, c: self.unet.forward(a, b, c, L), x_in, tt, ctx_static)  # fp32 [2*rows, 4 (ld 8)]
+            eps = self._graphed(ukey, lambda a, b, c: self.unet.forward(a, b, c, L, ctx_kv=ctx_kv), x_in, tt, ctx_static)  # fp32 [2*rows, 4 (ld 8)]
             a_t, a_prev = self.scheduler.alphas(t, ratio)
             new_latents, x0 = torch.empty_like(latents), torch.empty_like(latents)
             with torch.cuda.device(dev):

@@ -42,6 +42,16 @@ class UNet:
                 self.p[k] = nn.prep_vec(v, self.dev)
         self.tproj_w = nn.prep_linear(torch.cat(tproj_w, 0), self.dev)
         self.tproj_b = nn.prep_vec(torch.cat(tproj_b, 0), self.dev)
+        # row-concatenated projection weights: self-attention q|k|v in one GEMM, cross-attention k|v in one GEMM
+        self.cross_layers = []
+        for k in [k for k in self.p if k.endswith(".attn1.to_q.weight")]:
+            a = k[: -len(".to_q.weight")]
+            self.p[a + ".to_qkv.weight"] = torch.cat([self.p.pop(a + ".to_q.weight"), self.p.pop(a + ".to_k.weight"),
+                                                      self.p.pop(a + ".to_v.weight")], 0).contiguous()
+        for k in [k for k in self.p if k.endswith(".attn2.to_k.weight")]:
+            a = k[: -len(".to_k.weight")]
+            self.p[a + ".to_kv.weight"] = torch.cat([self.p.pop(a + ".to_k.weight"), self.p.pop(a + ".to_v.weight")], 0).contiguous()
+            self.cross_layers.append(a)
 
     # ------------------------------------------------------------------------------------------------
     def _resnet(self, x: Act, name, tproj):
@@ -57,18 +67,25 @@ class UNet:
             sc = x.t
         return nn.conv3x3(h, p[name + ".conv2.weight"], p[name + ".conv2.bias"], gn=gn2, act=1, residual=sc)
 
-    def _transformer(self, x: Act, ctx, L, name):
+    def context_kv(self, ctx, L, B):
+        """Keys / transposed values of every cross-attention layer for a context [B*L, cross_dim] f16 — constant over the
+        denoising loop (the prompt embeddings do not change between steps), so the pipeline calls this once per image batch."""
+        heads = self.cfg["heads"]
+        return {a: nn.project_kv(ctx, B, L, self.p[a + ".to_kv.weight"], heads) for a in self.cross_layers}
+
+    def _transformer(self, x: Act, ctx, L, name, ctx_kv=None):
         p, G, heads = self.p, self.cfg["groups"], self.cfg["heads"]
         B, S = x.B, x.H * x.W
         s, sh = nn.gn_affine(x, p[name + ".norm.weight"], p[name + ".norm.bias"], G, 1e-6)
         h = nn.gemm(nn.affine_act(x, s, sh, 0).t, p[name + ".proj_in.weight"], p[name + ".proj_in.bias"])
         t = name + ".transformer_blocks.0"
         n1 = nn.layernorm(h, p[t + ".norm1.weight"], p[t + ".norm1.bias"])
-        h = nn.attention(n1, n1, B, S, S, p[t + ".attn1.to_q.weight"], p[t + ".attn1.to_k.weight"], p[t + ".attn1.to_v.weight"],
-                         p[t + ".attn1.to_out.0.weight"], p[t + ".attn1.to_out.0.bias"], heads, h)
+        h = nn.attention(n1, n1, B, S, S, None, None, None, p[t + ".attn1.to_out.0.weight"], p[t + ".attn1.to_out.0.bias"], heads, h,
+                         wqkv=p[t + ".attn1.to_qkv.weight"])
         n2 = nn.layernorm(h, p[t + ".norm2.weight"], p[t + ".norm2.bias"])
-        h = nn.attention(n2, ctx, B, S, L, p[t + ".attn2.to_q.weight"], p[t + ".attn2.to_k.weight"], p[t + ".attn2.to_v.weight"],
-                         p[t + ".attn2.to_out.0.weight"], p[t + ".attn2.to_out.0.bias"], heads, h)
+        h = nn.attention(n2, ctx, B, S, L, p[t + ".attn2.to_q.weight"], None, None, p[t + ".attn2.to_out.0.weight"],
+                         p[t + ".attn2.to_out.0.bias"], heads, h, wkv=p[t + ".attn2.to_kv.weight"],
+                         kv=None if ctx_kv is None else ctx_kv[t + ".attn2"])
         n3 = nn.layernorm(h, p[t + ".norm3.weight"], p[t + ".norm3.bias"])
         if t + ".ff.geglu" in p:     # projection + GEGLU in one kernel (interleaved weight rows)
             ff = nn.gemm_geglu(n3, *p[t + ".ff.geglu"])
@@ -86,8 +103,9 @@ class UNet:
         e = nn.gemm(e, p["time_embedding.linear_2.weight"], p["time_embedding.linear_2.bias"])
         return nn.gemm(nn.silu(e), self.tproj_w, self.tproj_b, out_dtype=F32)
 
-    def forward(self, x: Act, t, ctx, L=77, taps=None):
-        """x: Act [B, h, w, 9]; t [B] f32 (cuda); ctx [B*L, cross_dim] f16 -> eps: fp32 tensor [B*h*w, 4]."""
+    def forward(self, x: Act, t, ctx, L=77, taps=None, ctx_kv=None):
+        """x: Act [B, h, w, 9]; t [B] f32 (cuda); ctx [B*L, cross_dim] f16 -> eps: fp32 tensor [B*h*w, 4].
+        ctx_kv = context_kv(ctx, L, B) skips the per-step cross-attention key / value projections."""
         cfg, p = self.cfg, self.p
         ch, nl = cfg["block_out_channels"], cfg["layers_per_block"]
         tproj = self.time_projections(t)
@@ -97,7 +115,7 @@ class UNet:
             for j in range(nl):
                 h = self._resnet(h, f"down_blocks.{i}.resnets.{j}", tproj)
                 if cfg["attn_levels"][i]:
-                    h = self._transformer(h, ctx, L, f"down_blocks.{i}.attentions.{j}")
+                    h = self._transformer(h, ctx, L, f"down_blocks.{i}.attentions.{j}", ctx_kv)
                 skips.append(h)
             if i < len(ch) - 1:
                 h = nn.conv3x3(h, p[f"down_blocks.{i}.downsamplers.0.conv.weight"], p[f"down_blocks.{i}.downsamplers.0.conv.bias"], stride=2)
@@ -105,7 +123,7 @@ class UNet:
         if taps is not None:
             taps["down"] = h
         h = self._resnet(h, "mid_block.resnets.0", tproj)
-        h = self._transformer(h, ctx, L, "mid_block.attentions.0")
+        h = self._transformer(h, ctx, L, "mid_block.attentions.0", ctx_kv)
         h = self._resnet(h, "mid_block.resnets.1", tproj)
         if taps is not None:
             taps["mid"] = h
@@ -118,7 +136,7 @@ class UNet:
                 cat[:, h.C:].copy_(s.t)
                 h = self._resnet(Act(cat, h.B, h.H, h.W), f"up_blocks.{i}.resnets.{j}", tproj)
                 if ral[i]:
-                    h = self._transformer(h, ctx, L, f"up_blocks.{i}.attentions.{j}")
+                    h = self._transformer(h, ctx, L, f"up_blocks.{i}.attentions.{j}", ctx_kv)
             if i < len(ch) - 1:
                 h = nn.conv3x3(h, p[f"up_blocks.{i}.upsamplers.0.conv.weight"], p[f"up_blocks.{i}.upsamplers.0.conv.bias"], up=True)
         if taps is not None:

@@ -60,7 +60,8 @@ def run():
         x.t.copy_(torch.randn((2 * B * 4096, 9), device=dev, generator=g).half())
         ctx = (torch.randn((2 * B * 77, 768), device=dev, generator=g) * 0.02).half()
         tt = torch.full((2 * B,), 961.0, device=dev)
-        return lambda: net.forward(x, tt, ctx, 77)
+        kv = net.context_kv(ctx, 77, 2 * B)     # as in the pipeline: cross-attention K / V once per call, not per step
+        return lambda: net.forward(x, tt, ctx, 77, ctx_kv=kv)
     vae = VAE(so.make_vae_state_dict(1), device=dev)
     if what == "vae_decode":
         z = nn.new_act(B, 64, 64, 4, dev)
