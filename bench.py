@@ -91,6 +91,12 @@ def cpu_reference_rate(target_seconds=12.0):
     """Oracle port (C + OpenMP, all host cores) on a bounded sample of the workload: rows [0, Hs) of ONE cfg-4 sample."""
     from coma_b200 import synth
     from oracle import oracle
+    # all host cores this process may run on — torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    oracle.set_num_threads(avail)
     cores = oracle.num_threads()
     hv, hn, ov, on = synth.make_sample_arrays(1, H, O, seed=123)
     grid = oracle.fibonacci_sphere(N)
