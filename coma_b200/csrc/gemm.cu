@@ -158,6 +158,7 @@ struct ConvGeom {
     int TW, TH, TB;      // tile = TB images x TH rows x TW columns = 128 output pixels
     int tiles_x, tiles_y;
     int cblocks;         // input channels / 64
+    int stride, pad;     // input pixel of output (y, x), tap (ky, kx): (y*stride + ky - pad, x*stride + kx - pad)
 };
 
 struct TileSched {
@@ -273,7 +274,8 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                     mbar_expect_tx(full + s, A_BYTES + B_BYTES);
                     if (CONV) {
                         const int tap = kb / cg.cblocks, cb = kb % cg.cblocks;
-                        tma_load_4d(sA + s * A_BYTES, &tmA, full + s, cb * G_BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb0);
+                        tma_load_4d(sA + s * A_BYTES, &tmA, full + s, cb * G_BK, cx0 * cg.stride + tap % 3 - cg.pad,
+                                    cy0 * cg.stride + tap / 3 - cg.pad, cb0);
                     } else {
                         tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
                     }
@@ -868,7 +870,7 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
 namespace coma {
 // NHWC tensor map {C, W, H, B} with box {64, TW, TH, TB}
 static int make_conv_map(CUtensorMap *m, const void *ptr, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, int TW, int TH,
-                         int TB) {
+                         int TB, int stride) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -876,8 +878,9 @@ static int make_conv_map(CUtensorMap *m, const void *ptr, int64_t B, int64_t H, 
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)(W * ldx) * 2, (cuuint64_t)(H * W * ldx) * 2};
-    cuuint32_t box[4] = {(cuuint32_t)G_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // strided convolution: the box TRAVERSES stride*T pixels with element stride `stride`, i.e. lands T pixels in shared memory
+    cuuint32_t box[4] = {(cuuint32_t)G_BK, (cuuint32_t)(TW * stride), (cuuint32_t)(TH * stride), (cuuint32_t)TB};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -900,9 +903,22 @@ extern "C" int coma_conv3x3_f16_ws(const void *x, int64_t B, int64_t H, int64_t 
                                    int64_t N, const float *bias, const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act,
                                    void *out_f16, float *out_f32, int64_t ldo, float *workspace, int64_t workspace_elems,
                                    coma_stream_t stream) {
+    return coma_conv3x3_strided_f16(x, B, H, W, C, ldx, 1, 1, Wt, ldw, N, bias, bias_rows, bias_rows_ld, residual, act, out_f16, out_f32, ldo,
+                                    workspace, workspace_elems, stream);
+}
+
+extern "C" int coma_conv3x3_strided_f16(const void *x, int64_t B, int64_t Hin, int64_t Win, int64_t C, int64_t ldx, int stride, int pad,
+                                        const void *Wt, int64_t ldw, int64_t N, const float *bias, const float *bias_rows,
+                                        int64_t bias_rows_ld, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
+                                        float *workspace, int64_t workspace_elems, coma_stream_t stream) {
     using namespace coma;
     COMA_REQUIRE(x && Wt && (out_f16 || out_f32), "null pointer");
-    COMA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && N > 0, "bad sizes");
+    COMA_REQUIRE(B > 0 && Hin > 0 && Win > 0 && C > 0 && N > 0, "bad sizes");
+    COMA_REQUIRE((stride == 1 && pad == 1) || (stride == 2 && (pad == 0 || pad == 1)), "stride 1 / pad 1, or stride 2 with pad 1 (both sides) or pad 0 (one zero row / column after the image)");
+    // output extent: stride 1: same; stride 2, pad 1: floor((n - 1) / 2) + 1; stride 2, pad 0 with (0, 1) padding: floor((n - 2) / 2) + 1
+    const int64_t H = stride == 1 ? Hin : (pad ? (Hin - 1) / 2 + 1 : (Hin - 2) / 2 + 1);
+    const int64_t W = stride == 1 ? Win : (pad ? (Win - 1) / 2 + 1 : (Win - 2) / 2 + 1);
+    COMA_REQUIRE(H > 0 && W > 0, "image too small");
     COMA_REQUIRE(C % 64 == 0 && ldx % 8 == 0 && ldx >= C, "implicit-GEMM conv needs C % 64 == 0 (use im2col otherwise)");
     COMA_REQUIRE(ldw >= 9 * C && ldw % 8 == 0 && ldo >= N, "bad leading dimensions");
     COMA_REQUIRE(((uintptr_t)x | (uintptr_t)Wt) % 16 == 0, "x and W must be 16-byte aligned");
@@ -912,7 +928,7 @@ extern "C" int coma_conv3x3_f16_ws(const void *x, int64_t B, int64_t H, int64_t 
     COMA_REQUIRE(TW * TH * TB == 128 && W % TW == 0 && H % TH == 0, "image extent does not tile into 128-pixel blocks (use im2col)");
     ConvGeom cg;
     cg.H = (int)H; cg.W = (int)W; cg.B = (int)B; cg.TW = TW; cg.TH = TH; cg.TB = TB;
-    cg.tiles_x = (int)(W / TW); cg.tiles_y = (int)(H / TH); cg.cblocks = (int)(C / 64);
+    cg.tiles_x = (int)(W / TW); cg.tiles_y = (int)(H / TH); cg.cblocks = (int)(C / 64); cg.stride = stride; cg.pad = pad;
     const int64_t m_tiles = TB > 1 ? (B + TB - 1) / TB : B * cg.tiles_x * cg.tiles_y;
     const int64_t M = B * H * W, K = 9 * C;
     GemmEpilogue ep;
@@ -924,7 +940,8 @@ extern "C" int coma_conv3x3_f16_ws(const void *x, int64_t B, int64_t H, int64_t 
     const GemmPlan plan = plan_gemm(m_tiles, N, K, 1, M, can_split, workspace_elems);
     const int bn = plan.bn;
     CUtensorMap ta, tb, to, tr;
-    if (int e = make_conv_map(&ta, x, B, H, W, C, ldx, TW, TH, TB)) return e;
+    COMA_REQUIRE(stride == 1 || TB == 1, "strided implicit conv: the output must have at least 128 pixels per image");
+    if (int e = make_conv_map(&ta, x, B, Hin, Win, C, ldx, TW, TH, TB, stride)) return e;
     if (int e = make_map(&tb, Wt, N, K, ldw, bn, 1, 0, 1, 0)) return e;
     GemmEpilogue fin = ep;
     if (plan.ksplit > 1) fin = split_epilogue(ep, workspace, N);

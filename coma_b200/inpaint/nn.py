@@ -156,7 +156,8 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
     stride 1, Cin % 64 == 0: implicit GEMM (shifted TMA tiles, no im2col matrix) on the pre-activated tensor;
     otherwise (stride 2, tiny Cin): im2col with the GroupNorm affine + SiLU applied while gathering, then GEMM."""
     Ho, Wo = conv_out_hw(x.H, x.W, stride, pad, up)
-    if IMPLICIT_CONV and stride == 1 and pad == 1 and x.C % 64 == 0 and _tiles_128(Ho, Wo):
+    strided_ok = stride == 2 and not up and gn is None and Ho * Wo >= 128   # element-strided TMA tiles
+    if IMPLICIT_CONV and ((stride == 1 and pad == 1) or strided_ok) and x.C % 64 == 0 and _tiles_128(Ho, Wo):
         scale, shift = gn if gn is not None else (None, None)
         if up:
             xa = upsample2x_affine_act(x, scale, shift, act if gn is not None else 0)
@@ -170,7 +171,8 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
             assert residual.dtype == F16 and residual.stride(0) == out.t.stride(0)
         ws = splitk_workspace(x.t.device)
         with torch.cuda.device(x.t.device):
-            call("coma_conv3x3_f16_ws", xa.t.data_ptr(), xa.B, xa.H, xa.W, xa.C, xa.ld, w.data_ptr(), w.stride(0), N, _ptr(bias),
+            call("coma_conv3x3_strided_f16", xa.t.data_ptr(), xa.B, xa.H, xa.W, xa.C, xa.ld, stride, 1 if stride == 1 else int(bool(pad)),
+                 w.data_ptr(), w.stride(0), N, _ptr(bias),
                  None if bias_rows is None else bias_rows.data_ptr(), 0 if bias_rows is None else bias_rows.stride(0),
                  None if residual is None else residual.data_ptr(), 0,
                  out.t.data_ptr() if out_dtype == F16 else None, out.t.data_ptr() if out_dtype == F32 else None, out.t.stride(0),

@@ -148,6 +148,14 @@ COMA_API int coma_conv3x3_f16_ws(const void *x, int64_t B, int64_t H, int64_t W,
                                  void *out_f16, float *out_f32, int64_t ldo, float *workspace, int64_t workspace_elems,
                                  coma_stream_t stream);
 
+/* Strided form: stride 2 with pad 1 (UNet downsamplers) or pad 0 + one zero row / column after the image (VAE encoder
+ * downsamplers, diffusers F.pad (0,1,0,1)); the shifted TMA tiles use an element stride of 2, still no im2col matrix.
+ * Hin / Win are the INPUT extent; the output [B, Ho, Wo, N] must tile into 128-pixel blocks with >= 128 pixels per image. */
+COMA_API int coma_conv3x3_strided_f16(const void *x, int64_t B, int64_t Hin, int64_t Win, int64_t C, int64_t ldx, int stride, int pad,
+                                      const void *Wt, int64_t ldw, int64_t N, const float *bias, const float *bias_rows,
+                                      int64_t bias_rows_ld, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
+                                      float *workspace, int64_t workspace_elems, coma_stream_t stream);
+
 COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
                               coma_stream_t stream);

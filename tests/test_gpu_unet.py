@@ -88,6 +88,25 @@ def test_conv3x3_f16_out_tma_epilogue(dev, C, Cout, H, B):
     _close(_nchw(out.t, B, H, H), ref, 2e-3)
 
 
+
+@pytest.mark.parametrize("C,Cout,H,pad,B", [(64, 64, 32, 1, 2), (128, 96, 64, 0, 1), (64, 128, 256, 0, 1), (320, 320, 64, 1, 2)])
+def test_conv3x3_stride2_implicit(dev, C, Cout, H, pad, B):
+    """Stride-2 convolutions (UNet downsamplers: pad 1; VAE encoder downsamplers: F.pad (0,1,0,1) then pad 0) as implicit GEMMs
+    over element-strided TMA tiles — no im2col matrix."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(C + H + pad)
+    x = torch.randn((B, C, H, H), device=dev, generator=g).half().float()
+    w = (torch.randn((Cout, C, 3, 3), device=dev, generator=g) * (9 * C) ** -0.5).half().float()
+    b = torch.randn(Cout, device=dev, generator=g)
+    xin = x if pad else F.pad(x, (0, 1, 0, 1))
+    ref = F.conv2d(xin, w, b, stride=2, padding=pad)
+    out = nn.conv3x3(_nhwc(x), nn.prep_conv3x3(w, dev), b, stride=2, pad=pad, out_dtype=torch.float32)
+    assert (out.H, out.W) == tuple(ref.shape[-2:])
+    _close(_nchw(out.t, B, out.H, out.W), ref, 1e-4)
+    out16 = nn.conv3x3(_nhwc(x), nn.prep_conv3x3(w, dev), b, stride=2, pad=pad)
+    _close(_nchw(out16.t, B, out.H, out.W), ref, 2e-3)
+
+
 def test_groupnorm_layernorm_geglu_softmax(dev):
     from coma_b200.inpaint import nn
     g = torch.Generator(device=dev).manual_seed(0)

@@ -33,6 +33,9 @@ def signature(name, args):
         g = ctypes.cast(args[0], ctypes.POINTER(GemmArgs)).contents
         nb = max(g.nb1, 1) * max(g.nb2, 1)
         return f"M={g.M} N={g.N} K={g.K} nb={nb}", 2.0 * g.M * g.N * g.K * nb
+    if name == "coma_conv3x3_strided_f16":
+        _, Bn, H, W, C, _, st, _, _, _, N = args[:11]
+        return f"B={Bn} HWin={H}x{W} Cin={C} Cout={N} stride={st}", 2.0 * Bn * (H // st) * (W // st) * 9 * C * N
     if name in ("coma_conv3x3_f16", "coma_conv3x3_f16_ws"):
         _, Bn, H, W, C, _, _, _, N = args[:9]
         return f"B={Bn} HW={H}x{W} Cin={C} Cout={N}", 2.0 * Bn * H * W * 9 * C * N
