@@ -20,10 +20,11 @@ if what == "unet":
     x.t.copy_(torch.randn((2 * B * 4096, 9), device=dev, generator=g).half())
     ctx = (torch.randn((2 * B * 77, 768), device=dev, generator=g) * 0.02).half()
     tt = torch.full((2 * B,), 961.0, device=dev)
-    net.forward(x, tt, ctx, 77)
+    kv = net.context_kv(ctx, 77, 2 * B)
+    net.forward(x, tt, ctx, 77, ctx_kv=kv)
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_push("fwd")
-    net.forward(x, tt, ctx, 77)
+    net.forward(x, tt, ctx, 77, ctx_kv=kv)
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_pop()
 else:
