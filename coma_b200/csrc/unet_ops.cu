@@ -192,38 +192,52 @@ __global__ void __launch_bounds__(256)
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
-// y[b,p,c] = act(x*scale[b,c] + shift[b,c]); 8 channels (16 B) per thread. act: 0 none, 1 SiLU
+// y[b,p,c] = act(x*scale[b,c] + shift[b,c]); act: 0 none, 1 SiLU. grid (row blocks, B): a thread owns ONE 16-byte channel chunk
+// (its 8 scale / shift values live in registers for the whole CTA: no per-element index division, no reloads) and walks
+// the sample's pixel rows with a stride of 256 / (C/8) rows, four independent 16-byte loads in flight.
 __global__ void __launch_bounds__(256)
-    affine_act_kernel(const __half *__restrict__ x, long long rows, int HW, int C, long long ldx, const float *__restrict__ scale,
-                      const float *__restrict__ shift, int act, __half *__restrict__ y, long long ldy) {
+    affine_act_kernel(const __half *__restrict__ x, int HW, int C, long long ldx, const float *__restrict__ scale,
+                      const float *__restrict__ shift, int act, __half *__restrict__ y, long long ldy, int rows_per_cta) {
     pdl_trigger();
     pdl_wait();
     const int c8n = C / 8;
-    const long long total = rows * c8n;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / c8n;
-        const int c = (int)(i % c8n) * 8;
-        const int b = (int)(r / HW);
-        const uint4 raw = *reinterpret_cast<const uint4 *>(x + r * ldx + c);
-        // scale / shift rows are [B, C] fp32 with C % 8 == 0: two 16-byte loads each instead of eight scalar ones
+    const int b = blockIdx.y;
+    const int lanes = c8n >= 256 ? 1 : 256 / c8n;       // row lanes per pass
+    const int ry = threadIdx.x / c8n;
+    if (ry >= lanes) return;
+    const int p0 = blockIdx.x * rows_per_cta, p1 = min(HW, p0 + rows_per_cta);
+    const __half *xb = x + (size_t)b * HW * ldx;
+    __half *yb = y + (size_t)b * HW * ldy;
+    for (int ch = threadIdx.x % c8n; ch < c8n; ch += (c8n >= 256 ? 256 : c8n)) {
+        const int c = ch * 8;
         const float4 *sp = reinterpret_cast<const float4 *>(scale + (size_t)b * C + c), *tp = reinterpret_cast<const float4 *>(shift + (size_t)b * C + c);
         const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), t0 = __ldg(tp), t1 = __ldg(tp + 1);
         const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-        const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
-        uint4 o;
-        __half2 *oh = reinterpret_cast<__half2 *>(&o);
+        for (int p = p0 + ry; p < p1; p += 4 * lanes) {
+            uint4 raw[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            float2 v = __half22float2(h[t]);
-            v.x = fmaf(v.x, sc[2 * t], sh[2 * t]);
-            v.y = fmaf(v.y, sc[2 * t + 1], sh[2 * t + 1]);
-            if (act == 1) {
-                v.x = silu_f(v.x);
-                v.y = silu_f(v.y);
+            for (int u = 0; u < 4; ++u)
+                if (p + u * lanes < p1) raw[u] = *reinterpret_cast<const uint4 *>(xb + (size_t)(p + u * lanes) * ldx + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (p + u * lanes >= p1) break;
+                const __half2 *h = reinterpret_cast<const __half2 *>(&raw[u]);
+                uint4 o;
+                __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float2 v = __half22float2(h[t]);
+                    v.x = fmaf(v.x, sc[2 * t], sh[2 * t]);
+                    v.y = fmaf(v.y, sc[2 * t + 1], sh[2 * t + 1]);
+                    if (act == 1) {
+                        v.x = silu_f(v.x);
+                        v.y = silu_f(v.y);
+                    }
+                    oh[t] = __floats2half2_rn(v.x, v.y);
+                }
+                *reinterpret_cast<uint4 *>(yb + (size_t)(p + u * lanes) * ldy + c) = o;
             }
-            oh[t] = __floats2half2_rn(v.x, v.y);
         }
-        *reinterpret_cast<uint4 *>(y + r * ldy + c) = o;
     }
 }
 
@@ -658,8 +672,15 @@ extern "C" int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t
     COMA_REQUIRE(x && y && scale && shift, "null pointer");
     COMA_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "C, ldx, ldy must be multiples of 8");
     COMA_REQUIRE(((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift) % 16 == 0, "x / y / scale / shift must be 16-byte aligned");
-    launch_pdl(affine_act_kernel, dim3(blocks_for(B * HW * (C / 8))), dim3(256), 0, (cudaStream_t)stream, (const __half *)x, B * HW, (int)HW, (int)C, ldx,
-                                                                                    scale, shift, act, (__half *)y, ldy);
+    COMA_REQUIRE(B <= 65535 && HW < (1LL << 31), "B or HW too large");
+    // ~8 CTAs per SM in flight, each at least one unrolled pass (4 rows per row lane)
+    const long long c8n = C / 8, lanes = c8n >= 256 ? 1 : 256 / c8n;
+    long long chunks = (8LL * kNumSM + B - 1) / B;
+    long long rows = (HW + chunks - 1) / chunks;
+    rows = rows < 4 * lanes ? 4 * lanes : rows;
+    chunks = (HW + rows - 1) / rows;
+    launch_pdl(affine_act_kernel, dim3((unsigned)chunks, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const __half *)x, (int)HW, (int)C, ldx,
+               scale, shift, act, (__half *)y, ldy, (int)rows);
     return check_launch("affine_act_kernel");
 }
 
