@@ -656,7 +656,7 @@ template <int BN, bool CONV, bool GEGLU = false>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr, int M, int N, int K,
                        const GemmEpilogue &ep, int nbatch, cudaStream_t st, int ksplit, long long split_stride,
                        const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
-    constexpr int STAGES = BN <= 128 ? 3 : 4;
+    constexpr int STAGES = BN <= 128 ? 3 : (BN == 160 ? 5 : 4);  // short-K problems are TMA-latency bound: as many slabs in flight as shared memory allows
     constexpr size_t smem = (size_t)STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + gemm_epi_warps(BN) * gemm_epi_bufs(BN) * E_PANEL_BYTES + 256;
     static bool attr[16] = {false};
     int dev = 0;
