@@ -14,6 +14,7 @@ _f32p = _c.POINTER(_c.c_float)
 
 # name -> argtypes, exactly the prototypes of include/coma_b200.h (device pointers travel as void*)
 SIGNATURES = {
+    "coma_vertex_normals_f64": [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _f64, _vp, _vp],
     "coma_nearest_vertex_f64": [_vp, _i64, _vp, _i64, _vp, _vp],
     "coma_pair_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp],
     "coma_orient_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _vp, _vp],

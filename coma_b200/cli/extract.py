@@ -21,6 +21,7 @@ import numpy as np
 
 from coma_b200 import dist as cdist
 from coma_b200.cli.io import jet_rgb, vertex_normals, write_point_cloud_ply
+from coma_b200 import ingest
 from coma_b200.misc import normalize_vectors_np
 
 ERROR_SENTINELS = ["NOT ALLOWED VIEWPOINT PROMPTS", "ERRONEOUS SAMPLE DUE TO TOO SMALL HUMAN", "TOO LITTLE INLIERS",
@@ -35,7 +36,8 @@ def prepare_affordance_extraction_inputs(human_mesh_pth, human_downsample_metada
     with open(human_mesh_pth, "rb") as handle:
         human_data = pickle.load(handle)
     human_verts_orig, human_faces_orig = human_data["verts"], human_data["faces"]
-    human_vertex_normals_orig = normalize_vectors_np(vertex_normals(human_verts_orig, human_faces_orig), eps=eps)
+    # K6: area-weighted vertex normals + normalize_vectors_np(., eps) on the GPU (fixed SMPL-X topology, cached corner list)
+    human_vertex_normals_orig = ingest.vertex_normals(human_verts_orig, human_faces_orig, eps=eps)
     obj_verts_orig = object_downsample_metadata["obj_vertices_original"]
     obj_vertex_normals_orig = normalize_vectors_np(np.asarray(object_downsample_metadata["obj_vertex_normals_original"]))
     hidx = human_downsample_metadata["downsample_indices"]

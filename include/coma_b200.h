@@ -37,6 +37,16 @@ COMA_API const char *coma_b200_last_error(void);
 /* Number of kernel launches enqueued by this library in the calling process (bench.py's `gpu_launches`). */
 COMA_API int64_t coma_b200_launch_count(void);
 
+/* ---- K6: per-vertex normals of a fixed-topology mesh, batched over samples (sample ingest) -------------------
+ * Replaces open3d TriangleMesh.compute_vertex_normals() + normalize_vectors_np(., eps) on every fitted SMPL-X mesh
+ * (utils/coma.py:665-686): area-weighted sum of the face normals (v1-v0)x(v2-v0) over incident faces, normalised, (0,0,1) where
+ * no finite direction exists; eps >= 0 additionally applies v/(||v||+eps), eps < 0 skips it.
+ * verts [S,V,3] f64, faces [F,3] i32; corner_off [V+1] / corner_face [3F] = CSR of the faces incident to each vertex ordered
+ * (corner index, face index) — the accumulation order of the numpy restatement, which makes the result bit-identical. */
+COMA_API int coma_vertex_normals_f64(const double *verts, int64_t S, int64_t V, const int32_t *faces, int64_t F,
+                                     const int32_t *corner_off, const int32_t *corner_face, double eps, double *out,
+                                     coma_stream_t stream);
+
 /* ---- K1: nearest mesh vertex of each sampled point --------------------------------------------------------------
  * Replaces utils/coma.py:88-91 (dup. utils/coma_occupancy.py:70-74): idx[n] = argmin_v ((p0-v0)^2+(p1-v1)^2)+(p2-v2)^2
  * evaluated in fp64 with separately rounded products/sums; first minimum wins (np.argmin). Bit-exact.

@@ -101,6 +101,31 @@ def to_f32(x):
 
 
 # ----------------------------------------------------------------------------------------------- accumulation
+def vertex_normals(verts, faces, eps=None):
+    """Sample ingest, reference utils/coma.py:665-686: open3d `TriangleMesh.compute_vertex_normals()` — the sum
+    over incident faces of the UN-normalised face normals (v1-v0)x(v2-v0), normalised, (0,0,1) where the sum has no finite
+    direction [open3d 0.17 TriangleMesh.cpp ComputeVertexNormals; open3d is not installed here: PARITY UNPINNED against
+    open3d itself] — optionally followed by `normalize_vectors_np(., eps)` (utils/transformations.py:8-11). fp64, [.., V, 3]."""
+    v = np.asarray(verts, dtype=np.float64)
+    f = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+    lead = v.shape[:-2]
+    v = v.reshape(-1, v.shape[-2], 3)
+    out = np.empty_like(v)
+    for s in range(v.shape[0]):
+        fn = np.cross(v[s][f[:, 1]] - v[s][f[:, 0]], v[s][f[:, 2]] - v[s][f[:, 0]])
+        vn = np.zeros_like(v[s])
+        for k in range(3):
+            np.add.at(vn, f[:, k], fn)
+        n = np.sqrt(np.sum(np.square(vn), axis=-1, keepdims=True))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            o = vn / np.where(n > 0, n, 1.0)
+        o[(n[:, 0] == 0) | ~np.isfinite(o).all(-1)] = (0.0, 0.0, 1.0)
+        if eps is not None:
+            o = o / (np.sqrt(np.sum(np.square(o), axis=-1, keepdims=True)) + eps)
+        out[s] = o
+    return out.reshape(*lead, v.shape[-2], 3)
+
+
 def nearest_vertex(pts, verts):
     pts, verts = _c(pts, np.float64), _c(verts, np.float64)
     out = np.empty(len(pts), dtype=np.int64)

@@ -336,3 +336,56 @@ def test_orient_property_mass_and_symmetry(dev):
     assert torch.equal(PH, QO.permute(1, 0, 2)) and torch.equal(PO, QH.permute(1, 0, 2))
     mass = PH.sum(-1) / S
     assert (mass.max() - mass.min()) / mass.mean() < 0.05
+
+
+def _icosphere(subdiv, rng):
+    """Closed triangle mesh (subdivided icosahedron, randomly perturbed radially) — SMPL-X-like valence-5/6 topology."""
+    t = (1 + 5 ** 0.5) / 2
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2),
+         (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdiv):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[k] = len(v) - 1
+            return cache[k]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    v = np.stack(v) * (1 + 0.2 * rng.standard_normal((len(v), 1)))
+    return v, np.array(f, dtype=np.int64)
+
+
+@pytest.mark.parametrize("subdiv,S", [(1, 1), (3, 5), (5, 3)])
+def test_vertex_normals_bit_exact(dev, subdiv, S):
+    """K6 (sample ingest): batched area-weighted vertex normals == the numpy restatement of open3d's
+    compute_vertex_normals (+ normalize_vectors_np), bit for bit (fp64, same accumulation order), including an isolated
+    vertex, a degenerate (zero-area) face and NaN coordinates, which all fall back to (0, 0, 1)."""
+    from coma_b200.ingest import MeshNormals
+    from oracle import oracle
+    rng = np.random.default_rng(subdiv)
+    v0, f = _icosphere(subdiv, rng)
+    V = v0.shape[0] + 2
+    verts = np.stack([np.vstack([v0 * (1 + 0.05 * s) + rng.standard_normal(v0.shape) * 0.01, [[9.0, 9.0, 9.0], [1.0, 2.0, 3.0]]]) for s in range(S)])
+    f = np.vstack([f, [[V - 1, V - 1, V - 1]]])           # degenerate face on an otherwise unused vertex; vertex V-2 is isolated
+    if S > 1:
+        verts[1, 5] = np.nan                               # poisons the faces around vertex 5 of sample 1
+    mn = MeshNormals(f, V, dev)
+    for eps in (None, 1e-10):
+        ref = oracle.vertex_normals(verts, f, eps)
+        out = mn(verts, -1.0 if eps is None else eps).cpu().numpy()
+        assert out.shape == ref.shape
+        assert np.array_equal(out, ref, equal_nan=True), np.abs(out - ref).max()
+        assert np.array_equal(out[:, V - 2], np.broadcast_to(np.array([0, 0, 1.0]) / (1.0 + (eps or 0.0)), (S, 3)))
+    # SMPL-X-sized: 10 475 vertices, unit normals, consistent with the radial direction of the perturbed sphere
+    if subdiv == 5:
+        n = mn(verts[0]).cpu().numpy()[: V - 2]
+        np.testing.assert_allclose(np.linalg.norm(n, axis=-1), 1.0, atol=1e-12)
+        assert (np.sum(n * verts[0][: V - 2], -1) > 0).mean() > 0.99
