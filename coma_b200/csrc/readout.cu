@@ -34,6 +34,52 @@ __global__ void __launch_bounds__(K5_WARPS * 32)
     }
 }
 
+// K5a, N <= 256 (the reference's 250 normal bins): a lane keeps its <= 8 row entries in registers, so a row is read ONCE and
+// written once (the generic kernel re-reads it for the second pass); two rows per warp iteration keep 16 independent
+// 4-byte loads per lane in flight. Same per-lane accumulation order as the generic kernel -> identical results.
+__global__ void __launch_bounds__(K5_WARPS * 32)
+    normalize_contact_reg_kernel(float *__restrict__ P, long long HO, int N, float eps, const float *__restrict__ w,
+                                 const float *__restrict__ nom, const float *__restrict__ denom, float *__restrict__ cmap) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * K5_WARPS + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * K5_WARPS;
+    float wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[j] = (cmap && lane + 32 * j < N) ? w[lane + 32 * j] : 0.f;
+    for (long long q0 = 2 * warp0; q0 < HO; q0 += 2 * nwarps) {
+        float v[2][8];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float *row = P + (size_t)(q0 + r) * N;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[r][j] = (q0 + r < HO && lane + 32 * j < N) ? __ldcs(row + lane + 32 * j) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (q0 + r >= HO) break;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (lane + 32 * j < N) s += v[r][j];
+            s = warp_sum(s);
+            const float d = __fadd_rn(s, eps);
+            float acc = 0.f;
+            float *row = P + (size_t)(q0 + r) * N;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (lane + 32 * j < N) {
+                    const float x = __fdiv_rn(v[r][j], d);
+                    __stcs(row + lane + 32 * j, x);
+                    acc = fmaf(x, wv[j], acc);
+                }
+            }
+            if (cmap) {
+                acc = warp_sum(acc);
+                if (lane == 0) cmap[q0 + r] = acc * __fdiv_rn(nom[q0 + r], denom[q0 + r]);
+            }
+        }
+    }
+}
+
 // K5b: entropy read-out of a normalised grid
 __global__ void __launch_bounds__(K5_WARPS * 32)
     entropy_kernel(const float *__restrict__ P, long long HO, int N, float n_bin, float log_n_bin, float *__restrict__ out) {
@@ -108,6 +154,24 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256) occupancy_rowsum_kernel(const float *__restrict__ grids, long long V, float *__restrict__ sums) {
     const float *row = grids + (size_t)blockIdx.x * V;
     float s = 0.f;
+    if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(grids) & 15) == 0) {  // 16-byte loads, four in flight per thread
+        const float4 *r4 = reinterpret_cast<const float4 *>(row);
+        const long long V4 = V >> 2;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        long long i = threadIdx.x;
+        for (; i + 3 * 256 < V4; i += 4 * 256) {
+            float4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = __ldcs(r4 + i + u * 256);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s4[u] += (a[u].x + a[u].y) + (a[u].z + a[u].w);
+        }
+        for (; i < V4; i += 256) {
+            const float4 a = __ldcs(r4 + i);
+            s4[0] += (a.x + a.y) + (a.z + a.w);
+        }
+        s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    } else
     for (long long i = threadIdx.x; i < V; i += blockDim.x) s += row[i];
     s = warp_sum(s);
     __shared__ float part[8];
@@ -142,6 +206,45 @@ __global__ void __launch_bounds__(256)
     if (m != 0) atomicMax(reinterpret_cast<int *>(field) + v, m);
 }
 
+// float4 form (V % 4 == 0): a thread owns four consecutive voxels, two vertex rows in flight
+__global__ void __launch_bounds__(256)
+    occupancy_norm_max4_kernel(float *__restrict__ grids, int H, long long V, const float *__restrict__ sums,
+                               const uint8_t *__restrict__ sel, float *__restrict__ field) {
+    const long long v4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long V4 = V >> 2;
+    if (v4 >= V4) return;
+    const int per = (H + gridDim.y - 1) / gridDim.y;
+    const int h_lo = blockIdx.y * per, h_hi = min(H, h_lo + per);
+    int m[4] = {0, 0, 0, 0};
+    float4 *g4 = reinterpret_cast<float4 *>(grids);
+    auto fold = [&](float4 &a, float sm, bool use) {
+        a.x = __fdiv_rn(a.x, sm); a.y = __fdiv_rn(a.y, sm); a.z = __fdiv_rn(a.z, sm); a.w = __fdiv_rn(a.w, sm);
+        if (use) {
+            m[0] = max(m[0], __float_as_int(a.x) & 0x7fffffff); m[1] = max(m[1], __float_as_int(a.y) & 0x7fffffff);
+            m[2] = max(m[2], __float_as_int(a.z) & 0x7fffffff); m[3] = max(m[3], __float_as_int(a.w) & 0x7fffffff);
+        }
+    };
+    int h = h_lo;
+    for (; h + 1 < h_hi; h += 2) {
+        const size_t i0 = (size_t)h * V4 + v4, i1 = i0 + V4;
+        float4 a = __ldcs(g4 + i0), b = __ldcs(g4 + i1);
+        fold(a, sums[h], !sel || sel[h]);
+        fold(b, sums[h + 1], !sel || sel[h + 1]);
+        __stcs(g4 + i0, a);
+        __stcs(g4 + i1, b);
+    }
+    if (h < h_hi) {
+        const size_t i0 = (size_t)h * V4 + v4;
+        float4 a = __ldcs(g4 + i0);
+        fold(a, sums[h], !sel || sel[h]);
+        __stcs(g4 + i0, a);
+    }
+    int *f = reinterpret_cast<int *>(field) + 4 * v4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (m[k] != 0) atomicMax(f + k, m[k]);
+}
+
 __global__ void mark_selected_kernel(const long long *__restrict__ idx, long long n, int H, uint8_t *__restrict__ sel) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -161,7 +264,10 @@ extern "C" int coma_normalize_contact_readout_f32(float *P, int64_t HO, int64_t 
     COMA_REQUIRE(HO > 0 && N > 0 && N < (int64_t)1 << 30, "bad sizes");
     const long long blocks = (HO + K5_WARPS - 1) / K5_WARPS;
     const unsigned grid = (unsigned)(blocks < kNumSM * 8 ? blocks : kNumSM * 8);
-    normalize_contact_kernel<<<grid, K5_WARPS * 32, 0, (cudaStream_t)stream>>>(P, HO, (int)N, eps, w, nom, denom, cmap);
+    if (N <= 256)
+        normalize_contact_reg_kernel<<<grid, K5_WARPS * 32, 0, (cudaStream_t)stream>>>(P, HO, (int)N, eps, w, nom, denom, cmap);
+    else
+        normalize_contact_kernel<<<grid, K5_WARPS * 32, 0, (cudaStream_t)stream>>>(P, HO, (int)N, eps, w, nom, denom, cmap);
     return check_launch("normalize_contact_kernel");
 }
 
@@ -228,11 +334,15 @@ extern "C" int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, co
         }
     }
     if (!rc) {
-        const long long vb = (V + 255) / 256;
-        long long hsplit = (4LL * kNumSM + vb - 1) / vb;
+        const bool vec = (V & 3) == 0 && (reinterpret_cast<uintptr_t>(grids) & 15) == 0 && (reinterpret_cast<uintptr_t>(field) & 15) == 0;
+        const long long vb = ((vec ? V / 4 : V) + 255) / 256;
+        long long hsplit = (8LL * kNumSM + vb - 1) / vb;
         hsplit = hsplit < 1 ? 1 : (hsplit > H ? H : (hsplit > 65535 ? 65535 : hsplit));
         cudaMemsetAsync(field, 0, sizeof(float) * (size_t)V, st);
-        occupancy_norm_max_kernel<<<dim3((unsigned)vb, (unsigned)hsplit), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
+        if (vec)
+            occupancy_norm_max4_kernel<<<dim3((unsigned)vb, (unsigned)hsplit), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
+        else
+            occupancy_norm_max_kernel<<<dim3((unsigned)vb, (unsigned)hsplit), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
         rc = check_launch("occupancy_norm_max_kernel");
     }
     cudaFreeAsync(sums, st);

@@ -78,6 +78,14 @@ def main():
     pts = torch.randn((2048, 3), dtype=torch.float64, device=dev)
     ms = timeit(lambda: ops.nearest_vertex(pts, verts))
     out["k1"] = dict(ms=ms, pairs_per_s=2048 * 10475 / ms * 1e3)
+    from coma_b200.ingest import MeshNormals
+    rng = np.random.default_rng(0)
+    Vn, Fn, Sn = 10475, 20908, 64                       # SMPL-X sized topology (random connectivity), 64 samples per launch
+    faces = rng.integers(0, Vn, (Fn, 3))
+    mn = MeshNormals(faces, Vn, dev)
+    vb = torch.randn((Sn, Vn, 3), dtype=torch.float64, device=dev)
+    ms = timeit(lambda: mn(vb, 1e-10))
+    out["k6"] = dict(ms=ms, meshes_per_s=Sn / ms * 1e3, vertices_per_s=Sn * Vn / ms * 1e3)
     print(json.dumps(out, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/microbench.json", "w"), indent=1)
