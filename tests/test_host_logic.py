@@ -150,3 +150,36 @@ def test_sharding_rules():
     sub = n // N + 1
     assert [items[a:b] for a, b in got] == [items[i * sub:(i + 1) * sub] for i in range(N)]
     assert sum(b - a for a, b in got) == n
+
+
+def test_geglu_weight_interleave():
+    """prep_geglu reorders the feed-forward projection rows into blocks of 32 values followed by their 32 gates (the layout
+    the fused GEGLU epilogue reads from one 64-column accumulator group)."""
+    import torch
+    from coma_b200.inpaint import nn
+    F, C = 128, 24
+    w = torch.arange(2 * F * C, dtype=torch.float32).reshape(2 * F, C) / 1024
+    b = torch.arange(2 * F, dtype=torch.float32)
+    wi, bi = nn.prep_geglu(w, b, "cpu")
+    assert wi.shape == (2 * F, C) and bi.shape == (2 * F,)
+    for j in range(F // 32):
+        assert torch.equal(bi[64 * j: 64 * j + 32], b[32 * j: 32 * j + 32])                  # values of features 32j..32j+31
+        assert torch.equal(bi[64 * j + 32: 64 * j + 64], b[F + 32 * j: F + 32 * j + 32])      # their gates
+        assert torch.equal(wi[64 * j + 5].float(), w[32 * j + 5].half().float())
+        assert torch.equal(wi[64 * j + 37].float(), w[F + 32 * j + 5].half().float())
+    assert nn.prep_geglu(torch.zeros((2 * 40, C)), torch.zeros(2 * 40), "cpu") is None        # 2F % 256 != 0 -> unfused path
+
+
+def test_oracle_vertex_normals_matches_cli_helper():
+    """The oracle restatement of open3d's vertex normals (K6 checker) agrees with the helper the CLI used before K6 existed,
+    and normalize_vectors_np is applied on top when eps is given."""
+    from coma_b200.cli.io import vertex_normals
+    from coma_b200.misc import normalize_vectors_np
+    from oracle import oracle
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((50, 3))
+    f = rng.integers(0, 49, (120, 3))          # vertex 49 is isolated -> (0, 0, 1)
+    a, b = oracle.vertex_normals(v, f), vertex_normals(v, f)
+    assert np.array_equal(a, b) and a[49].tolist() == [0.0, 0.0, 1.0]
+    assert np.array_equal(oracle.vertex_normals(v, f, 1e-10), normalize_vectors_np(b, eps=1e-10))
+    assert oracle.vertex_normals(np.stack([v, 2 * v]), f).shape == (2, 50, 3)
