@@ -36,6 +36,12 @@ H, O, N = 10475, 1500, 250
 S_PER_RANK = 256
 PRESET = dict(spatial_grid_size=0.15, spatial_grid_thres=0.05, normal_gaussian_sigma=0.25, eps=1e-10,
               significant_contact_ratio=0.1)  # constants/coma/qual.py "qual:backpack_object_contact"
+# DRAM traffic of one launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_k3_full.md, same
+# H x O x N, 32 samples: the grids are read and written once per launch whatever the sample count; inputs are 0.3 MB / sample)
+K3_NCU_DRAM_BYTES = 31.467172e9 + 31.378264e9
+# K2 streaming kernel (one sample per launch), profiles/r01_k2_full.md: 125.9 MB read + 70.2 MB written while the capture ran (the
+# rest of the 125.7 MB of accumulator writes is still dirty in the 126 MB L2 when the single profiled launch ends)
+K2_NCU_DRAM_BYTES = 125.852928e6 + 70.227456e6
 K3_MUFU_PER_EVAL = 2.0     # MUFU.SQRT + MUFU.EX2 per bin evaluation in the K3 inner loop (cuobjdump)
 MUFU_CLK_PER_WARP_INSTR = 8.05  # measured on B200 with tools/ubench_pipes.cu (4 lanes/clk per SM sub-partition)
 
@@ -85,6 +91,15 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: the loop runs for ~1 s)"
+    return 1410.0, "fallback (B200_PROFILING.md sustained dense bf16)"
 
 
 def cpu_reference_rate(target_seconds=12.0):
@@ -181,6 +196,12 @@ def hoi_leg(args, dev, rank, world, barrier):
     res = {"metric": "HOI images/s (512x512, 50-step DDIM, adaptive mask)", "value": world * B / t.item(), "unit": "images/s",
            "s_per_batch": t.item(), "batch_per_gpu": B, "n_gpus": world, "data": "synthetic render + random weights (SD-1.5 inpainting UNet, SD VAE architectures)",
            "flop_per_image_T": 159.7, "tensor_tflops_achieved": world * B * 159.7 / t.item(),
+           "roofline": {"bound": "tensor", "achieved": B * 159.7 / t.item(), "peak": tensor_peak()[0], "unit": "TFLOP/s",
+                        "frac": B * 159.7 / t.item() / tensor_peak()[0], "peak_source": tensor_peak()[1],
+                        "note": "per GPU; necessary work = 49 x 2 UNet evaluations + 22 VAE decodes + 23 VAE encodes per image (SURVEY 8d), whole "
+                                "pipeline call incl. GroupNorm / softmax / mask logic / host copies, sustained clocks"},
+           "e2e": {"api": "AdaptiveMaskInpaintPipeline.__call__ (host uint8 render + mask in, host uint8 images out)",
+                   "h2d_bytes_per_step": int(image.nbytes + default.nbytes), "d2h_bytes_per_step": int(out.images.nbytes) if hasattr(out.images, "nbytes") else None},
            "d2h_bytes": int(out.images.nbytes) if hasattr(out.images, "nbytes") else None,
            "launches_outside_graphs_per_batch": int(launches)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -352,8 +373,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": ck,
             "roofline": {"bound": "hbm", "kernel": "orient_accumulate_kernel_x2 (K3)", "achieved": k3_bytes / (k3_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "peak_source": peak_src, "ms": k3_ms,
+                         "peak": peak, "unit": "GB/s", "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / peak, "traffic": K3_NCU_DRAM_BYTES,
+                         "algorithmic_bytes": k3_bytes, "peak_source": peak_src, "ms": k3_ms,
                          "note": "K3 is SFU (MUFU) / FP32-pipe bound once samples are fused (500 bin evaluations per pair-sample, "
                                  "2 MUFU each): see roofline_sfu; the HBM fraction is reported because the schema asks for it"},
             "roofline_sfu": {"bound": "sfu", "kernel": "orient_accumulate_kernel_x2 (K3)", "achieved": evals_per_s * K3_MUFU_PER_EVAL / 1e9,
@@ -362,7 +383,8 @@ def main():
                              "bin_evals_per_s": evals_per_s, "mufu_per_eval": K3_MUFU_PER_EVAL,
                              "peak_source": "148 SMs x 4 sub-partitions x 32 lanes / 8.05 clk per MUFU warp-instr (tools/ubench_pipes.cu) x median SM clock under load"},
             "roofline_k2_stream": {"bound": "hbm", "kernel": "pair_accumulate_stream_kernel (K2, S=1)", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9,
-                                   "peak": peak, "unit": "GB/s", "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                                   "peak": peak, "unit": "GB/s", "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak, "traffic": K2_NCU_DRAM_BYTES,
+                                   "algorithmic_bytes": k2_bytes,
                                    "ms": k2_ms, "peak_source": peak_src},
         }
         if hoi is not None:
