@@ -14,10 +14,14 @@ class LuminanceSegmenter:
 
     def __init__(self, thres=140):
         self.thres = float(thres)
+        self._w = {}     # per-device luminance weights (built once: torch.tensor(..., device=cuda) is a synchronising copy)
 
     def __call__(self, image):
         if isinstance(image, torch.Tensor):
-            lum = image.float().mul(torch.tensor([0.299, 0.587, 0.114], device=image.device)).sum(-1)
+            w = self._w.get(image.device)
+            if w is None:
+                w = self._w[image.device] = torch.tensor([0.299, 0.587, 0.114], device=image.device)
+            lum = image.float().mul(w).sum(-1)
             return {"mask": (lum > self.thres).to(torch.uint8), "asset_mask": None, "vis": None}
         lum = image.astype(np.float32) @ np.array([0.299, 0.587, 0.114], dtype=np.float32)
         return {"mask": (lum > self.thres).astype(np.uint8), "asset_mask": None, "vis": None}
