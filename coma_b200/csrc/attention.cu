@@ -191,8 +191,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * FA_BKV;
-    pdl_trigger();  // PDL: the prologue above overlapped the previous kernel's tail
-    pdl_wait();
+    pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail (the trigger is raised by the producer, late)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -210,6 +209,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
                 mbar_expect_tx(v_full + s, DN * PV_ROW);
                 tma_load_4d(sVt + s * VT_BYTES, &tmVt, v_full + s, j * FA_BKV, 0, h, b);
             }
+            pdl_trigger();
         }
     } else if (warp == 1) {
         if (lane == 0) {

@@ -190,6 +190,66 @@ __global__ void __launch_bounds__(256)
     groupnorm_finish(partial, counter, b, C, G, count, eps, gamma, beta, mean, rstd, scale, shift, sm);
 }
 
+// GroupNorm affine from the per-(32-row block, channel) partial sums a convolution epilogue left behind (gemm.cu, `stats`):
+// grid (G, B), 256 threads. Thread t adds blocks t, t+256, ... of every channel of the group (fp64, fixed assignment), the 256
+// partials are combined in index order -> bit-reproducible; no pass over the activation tensor at all.
+__global__ void __launch_bounds__(256)
+    groupnorm_from_stats_kernel(const float *__restrict__ stats, int HW, int C, int G, float eps, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, float *__restrict__ mean, float *__restrict__ rstd,
+                                float *__restrict__ scale, float *__restrict__ shift) {
+    pdl_trigger();
+    pdl_wait();
+    const int g = blockIdx.x, b = blockIdx.y, cpg = C / G, nblk = HW / 32;
+    const float *base = stats + ((size_t)b * nblk * C + (size_t)g * cpg) * 2;
+    double s = 0.0, q = 0.0;
+    // four row blocks per iteration: their loads are independent (a one-row loop is pure L2 latency)
+    for (int r = threadIdx.x; r < nblk; r += 4 * 256) {
+        float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (r + u * 256 < nblk) {
+                const float2 *row = reinterpret_cast<const float2 *>(base + (size_t)(r + u * 256) * C * 2);
+                for (int c = 0; c < cpg; ++c) {  // <= 80 channels per group: fp32 is exact enough within one 32-row block row
+                    const float2 v = __ldcg(row + c);
+                    fs[u] += v.x;
+                    fq[u] += v.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            s += (double)fs[u];
+            q += (double)fq[u];
+        }
+    }
+    __shared__ double ss[256], qq[256];
+    ss[threadIdx.x] = s;
+    qq[threadIdx.x] = q;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {  // fixed-shape tree
+        if (threadIdx.x < w) {
+            ss[threadIdx.x] += ss[threadIdx.x + w];
+            qq[threadIdx.x] += qq[threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    const double count = (double)HW * cpg;
+    const double m = ss[0] / count;
+    double var = qq[0] / count - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    const double r = 1.0 / sqrt(var + (double)eps);
+    if (threadIdx.x == 0) {
+        if (mean) mean[b * G + g] = (float)m;
+        if (rstd) rstd[b * G + g] = (float)r;
+    }
+    for (int c = threadIdx.x; c < cpg; c += 256) {
+        const int ch = g * cpg + c;
+        const double ga = gamma ? (double)gamma[ch] : 1.0, be = beta ? (double)beta[ch] : 0.0;
+        scale[(size_t)b * C + ch] = (float)(r * ga);
+        shift[(size_t)b * C + ch] = (float)(be - m * r * ga);
+    }
+}
+
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
 // y[b,p,c] = act(x*scale[b,c] + shift[b,c]); act: 0 none, 1 SiLU. grid (row blocks, B): a thread owns ONE 16-byte channel chunk
@@ -665,6 +725,17 @@ extern "C" int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, i
                    ldx, G, (int)rows, workspace, counters, count, eps, gamma, beta, mean, rstd, scale, shift);
     }
     return check_launch("groupnorm_partial_kernel");
+}
+
+extern "C" int coma_groupnorm_from_stats_f32(const float *stats, int64_t B, int64_t HW, int64_t C, int G, float eps, const float *gamma,
+                                             const float *beta, float *mean, float *rstd, float *scale, float *shift,
+                                             coma_stream_t stream) {
+    COMA_REQUIRE(stats && scale && shift, "null pointer");
+    COMA_REQUIRE(B > 0 && HW > 0 && HW % 32 == 0 && C > 0 && G > 0 && C % G == 0 && B <= 65535 && G <= 65535, "bad sizes");
+    COMA_REQUIRE((uintptr_t)stats % 8 == 0, "stats must be 8-byte aligned");
+    launch_pdl(groupnorm_from_stats_kernel, dim3((unsigned)G, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, stats, (int)HW, (int)C, G, eps,
+               gamma, beta, mean, rstd, scale, shift);
+    return check_launch("groupnorm_from_stats_kernel");
 }
 
 extern "C" int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, const float *scale,

@@ -24,6 +24,7 @@ class Act:
     B: int
     H: int
     W: int
+    stats: torch.Tensor = None   # [B*H*W/32, C, 2] f32 partial (sum, sumsq) left by the producing conv's epilogue, or None
 
     @property
     def C(self):
@@ -102,11 +103,20 @@ def gemm_batched(A, lda, a_s1, a_s2, W, ldw, w_s1, w_s2, out, ldo, o_s1, o_s2, M
 
 
 _GN_COUNTERS = {}
+FUSED_GN_STATS = True   # convolutions leave GroupNorm partial sums for their consumer (A/B switch for tests and tuning)
 
 
 def gn_affine(x: Act, gamma, beta, groups, eps):
-    """GroupNorm statistics folded with the affine: gn(x) = x*scale[b,c] + shift[b,c] (fp32 [B,C] each). One launch."""
+    """GroupNorm statistics folded with the affine: gn(x) = x*scale[b,c] + shift[b,c] (fp32 [B,C] each). One launch — and no
+    pass over x at all when the convolution that produced x left its per-block partial sums (`x.stats`)."""
     dev = x.t.device
+    if FUSED_GN_STATS and x.stats is not None:
+        scale = torch.empty((x.B, x.C), dtype=F32, device=dev)
+        shift = torch.empty((x.B, x.C), dtype=F32, device=dev)
+        with torch.cuda.device(dev):
+            call("coma_groupnorm_from_stats_f32", x.stats.data_ptr(), x.B, x.H * x.W, x.C, groups, float(eps), _ptr(gamma), _ptr(beta),
+                 None, None, scale.data_ptr(), shift.data_ptr(), _stream())
+        return scale, shift
     ws = torch.empty(2 * groups * (4 * 148 + x.B), dtype=torch.float64, device=dev)
     cnt = _GN_COUNTERS.get(dev.index)
     if cnt is None or cnt.numel() < x.B:   # ticket counters: zero once, every launch leaves them zero
@@ -151,7 +161,7 @@ def upsample2x_affine_act(x: Act, scale, shift, act):
 IMPLICIT_CONV = True
 
 
-def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual=None, bias_rows=None, out_dtype=F16):
+def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual=None, bias_rows=None, out_dtype=F16, stats=False):
     """3x3 convolution on the tensor cores. w: [Cout, ld >= 9*Cin] f16 with K order (ky, kx, cin).
     stride 1, Cin % 64 == 0: implicit GEMM (shifted TMA tiles, no im2col matrix) on the pre-activated tensor;
     otherwise (stride 2, tiny Cin): im2col with the GroupNorm affine + SiLU applied while gathering, then GEMM."""
@@ -170,13 +180,18 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
         if residual is not None:
             assert residual.dtype == F16 and residual.stride(0) == out.t.stride(0)
         ws = splitk_workspace(x.t.device)
+        want = stats and FUSED_GN_STATS and out_dtype == F16 and (x.B * Ho * Wo) % 32 == 0 and (Ho * Wo) % 32 == 0
+        st = torch.empty((x.B * Ho * Wo // 32, N, 2), dtype=F32, device=x.t.device) if want else None
+        written = ctypes.c_int(0)
         with torch.cuda.device(x.t.device):
             call("coma_conv3x3_strided_f16", xa.t.data_ptr(), xa.B, xa.H, xa.W, xa.C, xa.ld, stride, 1 if stride == 1 else int(bool(pad)),
                  w.data_ptr(), w.stride(0), N, _ptr(bias),
                  None if bias_rows is None else bias_rows.data_ptr(), 0 if bias_rows is None else bias_rows.stride(0),
                  None if residual is None else residual.data_ptr(), 0,
                  out.t.data_ptr() if out_dtype == F16 else None, out.t.data_ptr() if out_dtype == F32 else None, out.t.stride(0),
-                 ws.data_ptr(), ws.numel(), _stream())
+                 ws.data_ptr(), ws.numel(), None if st is None else st.data_ptr(), ctypes.byref(written), _stream())
+        if st is not None and written.value:
+            out.stats = st
         return out
     K = 9 * x.C
     cols = torch.empty((x.B * Ho * Wo, rup(K)), dtype=F16, device=x.t.device)

@@ -58,14 +58,14 @@ class UNet:
         p, G = self.p, self.cfg["groups"]
         gn1 = nn.gn_affine(x, p[name + ".norm1.weight"], p[name + ".norm1.bias"], G, 1e-5)
         a, b = self.tproj_slices[name + ".time_emb_proj"]
-        h = nn.conv3x3(x, p[name + ".conv1.weight"], p[name + ".conv1.bias"], gn=gn1, act=1,
+        h = nn.conv3x3(x, p[name + ".conv1.weight"], p[name + ".conv1.bias"], gn=gn1, act=1, stats=True,
                        bias_rows=tproj[:, a:b])
         gn2 = nn.gn_affine(h, p[name + ".norm2.weight"], p[name + ".norm2.bias"], G, 1e-5)
         if name + ".conv_shortcut.weight" in p:
             sc = nn.gemm(x.t, p[name + ".conv_shortcut.weight"], p[name + ".conv_shortcut.bias"])
         else:
             sc = x.t
-        return nn.conv3x3(h, p[name + ".conv2.weight"], p[name + ".conv2.bias"], gn=gn2, act=1, residual=sc)
+        return nn.conv3x3(h, p[name + ".conv2.weight"], p[name + ".conv2.bias"], gn=gn2, act=1, residual=sc, stats=True)
 
     def context_kv(self, ctx, L, B):
         """Keys / transposed values of every cross-attention layer for a context [B*L, cross_dim] f16 — constant over the
@@ -118,7 +118,7 @@ class UNet:
                     h = self._transformer(h, ctx, L, f"down_blocks.{i}.attentions.{j}", ctx_kv)
                 skips.append(h)
             if i < len(ch) - 1:
-                h = nn.conv3x3(h, p[f"down_blocks.{i}.downsamplers.0.conv.weight"], p[f"down_blocks.{i}.downsamplers.0.conv.bias"], stride=2)
+                h = nn.conv3x3(h, p[f"down_blocks.{i}.downsamplers.0.conv.weight"], p[f"down_blocks.{i}.downsamplers.0.conv.bias"], stride=2, stats=True)
                 skips.append(h)
         if taps is not None:
             taps["down"] = h
@@ -138,7 +138,7 @@ class UNet:
                 if ral[i]:
                     h = self._transformer(h, ctx, L, f"up_blocks.{i}.attentions.{j}", ctx_kv)
             if i < len(ch) - 1:
-                h = nn.conv3x3(h, p[f"up_blocks.{i}.upsamplers.0.conv.weight"], p[f"up_blocks.{i}.upsamplers.0.conv.bias"], up=True)
+                h = nn.conv3x3(h, p[f"up_blocks.{i}.upsamplers.0.conv.weight"], p[f"up_blocks.{i}.upsamplers.0.conv.bias"], up=True, stats=True)
         if taps is not None:
             taps["up"] = h
         gn = nn.gn_affine(h, p["conv_norm_out.weight"], p["conv_norm_out.bias"], cfg["groups"], 1e-5)

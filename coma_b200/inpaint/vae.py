@@ -26,13 +26,13 @@ class VAE:
     def _resnet(self, x: Act, name):
         p, G = self.p, self.cfg["groups"]
         gn1 = nn.gn_affine(x, p[name + ".norm1.weight"], p[name + ".norm1.bias"], G, 1e-6)
-        h = nn.conv3x3(x, p[name + ".conv1.weight"], p[name + ".conv1.bias"], gn=gn1, act=1)
+        h = nn.conv3x3(x, p[name + ".conv1.weight"], p[name + ".conv1.bias"], gn=gn1, act=1, stats=True)
         gn2 = nn.gn_affine(h, p[name + ".norm2.weight"], p[name + ".norm2.bias"], G, 1e-6)
         if name + ".conv_shortcut.weight" in p:
             sc = nn.gemm(x.t, p[name + ".conv_shortcut.weight"], p[name + ".conv_shortcut.bias"])
         else:
             sc = x.t
-        return nn.conv3x3(h, p[name + ".conv2.weight"], p[name + ".conv2.bias"], gn=gn2, act=1, residual=sc)
+        return nn.conv3x3(h, p[name + ".conv2.weight"], p[name + ".conv2.bias"], gn=gn2, act=1, residual=sc, stats=True)
 
     def _attn(self, x: Act, name):
         p = self.p
@@ -67,7 +67,7 @@ class VAE:
             for j in range(nl + 1):
                 h = self._resnet(h, f"decoder.up_blocks.{i}.resnets.{j}")
             if i < len(ch) - 1:
-                h = nn.conv3x3(h, p[f"decoder.up_blocks.{i}.upsamplers.0.conv.weight"], p[f"decoder.up_blocks.{i}.upsamplers.0.conv.bias"], up=True)
+                h = nn.conv3x3(h, p[f"decoder.up_blocks.{i}.upsamplers.0.conv.weight"], p[f"decoder.up_blocks.{i}.upsamplers.0.conv.bias"], up=True, stats=True)
         gn = nn.gn_affine(h, p["decoder.conv_norm_out.weight"], p["decoder.conv_norm_out.bias"], self.cfg["groups"], 1e-6)
         return nn.conv3x3(h, p["decoder.conv_out.weight"], p["decoder.conv_out.bias"], gn=gn, act=1, out_dtype=out_dtype)
 
@@ -80,7 +80,7 @@ class VAE:
                 h = self._resnet(h, f"encoder.down_blocks.{i}.resnets.{j}")
             if i < len(ch) - 1:
                 h = nn.conv3x3(h, p[f"encoder.down_blocks.{i}.downsamplers.0.conv.weight"],
-                               p[f"encoder.down_blocks.{i}.downsamplers.0.conv.bias"], stride=2, pad=0)
+                               p[f"encoder.down_blocks.{i}.downsamplers.0.conv.bias"], stride=2, pad=0, stats=True)
         h = self._resnet(h, "encoder.mid_block.resnets.0")
         h = self._attn(h, "encoder.mid_block.attentions.0")
         h = self._resnet(h, "encoder.mid_block.resnets.1")

@@ -164,7 +164,15 @@ COMA_API int coma_conv3x3_f16_ws(const void *x, int64_t B, int64_t H, int64_t W,
 COMA_API int coma_conv3x3_strided_f16(const void *x, int64_t B, int64_t Hin, int64_t Win, int64_t C, int64_t ldx, int stride, int pad,
                                       const void *Wt, int64_t ldw, int64_t N, const float *bias, const float *bias_rows,
                                       int64_t bias_rows_ld, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
-                                      float *workspace, int64_t workspace_elems, coma_stream_t stream);
+                                      float *workspace, int64_t workspace_elems, float *stats, int *stats_written,
+                                      coma_stream_t stream);
+/* stats (optional, [B*Ho*Wo/32, N, 2] f32): the epilogue also leaves, per 32-row block and output channel, the sum and the sum
+ * of squares of the fp16 values it wrote, so the GroupNorm that consumes this tensor needs no pass over it
+ * (coma_groupnorm_from_stats_f32). *stats_written tells whether this launch could provide them (fp16 TMA epilogue, no
+ * split-K, M % 32 == 0); otherwise the caller falls back to coma_groupnorm_affine_f16. */
+COMA_API int coma_groupnorm_from_stats_f32(const float *stats, int64_t B, int64_t HW, int64_t C, int G, float eps, const float *gamma,
+                                           const float *beta, float *mean, float *rstd, float *scale, float *shift,
+                                           coma_stream_t stream);
 
 COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,

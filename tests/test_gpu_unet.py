@@ -194,3 +194,29 @@ def test_vae_tiny_decode_encode(dev):
     rm, rl = so.vae_encode_moments(sdd, x, cfg, emulate_fp16=True)
     _close(_nchw(mean, 2, 8, 8), rm, 1e-2)
     _close(_nchw(logvar, 2, 8, 8), rl, 1e-2)
+
+
+@pytest.mark.parametrize("C,Cout,H,B,groups,res", [(64, 96, 16, 2, 8, False), (128, 320, 32, 2, 32, True), (64, 72, 64, 1, 8, True),
+                                                   (128, 128, 128, 1, 32, False), (320, 320, 64, 2, 32, True)])
+def test_groupnorm_from_conv_epilogue_stats(dev, C, Cout, H, B, groups, res):
+    """A convolution's TMA epilogue leaves per-(32-row block, channel) sums of the fp16 values it writes; the GroupNorm that
+    consumes the tensor is computed from them without reading it — and must equal the stand-alone statistics kernel."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(C + Cout + H)
+    x = torch.randn((B, C, H, H), device=dev, generator=g).half().float()
+    w = (torch.randn((Cout, C, 3, 3), device=dev, generator=g) * (9 * C) ** -0.5).half().float()
+    b = torch.randn(Cout, device=dev, generator=g)
+    r = torch.randn((B * H * H, Cout), device=dev, generator=g).half() if res else None
+    gamma, beta = 1 + 0.1 * torch.randn(Cout, device=dev, generator=g), 0.1 * torch.randn(Cout, device=dev, generator=g)
+    out = nn.conv3x3(_nhwc(x), nn.prep_conv3x3(w, dev), b, residual=r, stats=True)
+    assert out.stats is not None and out.stats.shape == (B * H * H // 32, Cout, 2)
+    s1, t1 = nn.gn_affine(out, gamma, beta, groups, 1e-5)                       # from the epilogue's partial sums
+    plain = nn.Act(out.t, out.B, out.H, out.W)                                   # same tensor, no stats -> stand-alone kernel
+    s0, t0 = nn.gn_affine(plain, gamma, beta, groups, 1e-5)
+    torch.testing.assert_close(s1, s0, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(t1, t0, rtol=2e-5, atol=2e-6)
+    ref = F.group_norm(_nchw(out.t, B, H, H), groups, gamma, beta, 1e-5)
+    y = nn.affine_act(out, s1, t1, 0)
+    torch.testing.assert_close(_nchw(y.t, B, H, H), ref, rtol=2e-3, atol=2e-3)
+    again = nn.conv3x3(_nhwc(x), nn.prep_conv3x3(w, dev), b, residual=r, stats=True)
+    assert torch.equal(again.stats, out.stats)                                   # deterministic
