@@ -125,16 +125,18 @@ __device__ __forceinline__ float ex2(float x) {
 constexpr int FA_BQ = 128, FA_THREADS = 192;
 constexpr float FA_LAZY = 8.0f;  // log2 headroom before the running maximum (and O, l) is moved: P <= 2^8 stays exact enough in fp16
 
-__host__ __device__ constexpr int fa_ctas_per_sm(int DKB, int DN, int BKV) {
-    return (DKB == 1 && DN <= 64) ? (BKV == 32 ? 4 : 2) : 1;
+__host__ __device__ constexpr int fa_ctas_per_sm(int DKB, int DN, int BKV, int NSB) {
+    return (DKB == 1 && DN <= 64) ? (BKV == 32 ? 4 : (NSB == 1 ? 3 : 2)) : 1;
 }
 
 // DKB = number of 64-wide K blocks of the head dimension (d <= 64*DKB); DN = head dim rounded up to a multiple of 16;
 // FA_BKV = keys per step: 64, or 32 for small heads — 2 x 32 score columns + DN output columns fit 128 TMEM columns and
 // ~54 KB of shared memory, so FOUR CTAs share an SM (4 softmax warps per sub-partition hide the exp2 / cvt / TMEM-load
 // latencies that two warps cannot: ncu showed `stall_wait` as the top stall at two CTAs per SM).
-template <int DKB, int DN, int STAGES, int FA_BKV>
-__global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
+// NSB / NPB = number of score (TMEM) / probability (shared memory) buffers: 2 / 2 pipelines one CTA deeply; 1 / 1 gives up the
+// intra-CTA overlap for a THIRD resident CTA (64 + DN TMEM columns, ~61 KB of shared memory).
+template <int DKB, int DN, int STAGES, int FA_BKV, int NSB = 2, int NPB = 2>
+__global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NSB))
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
                          long long ldo, long long o_bstride) {
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
     uint8_t *sK = sQ + Q_BYTES;
     uint8_t *sVt = sK + STAGES * K_BYTES;
     uint8_t *sP = sVt + STAGES * VT_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sP + 2 * P_BYTES);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sP + NPB * P_BYTES);
     uint64_t *q_full = bar, *k_full = bar + 1, *k_empty = k_full + STAGES, *v_full = k_empty + STAGES, *v_empty = v_full + STAGES;
     uint64_t *s_full = v_empty + STAGES, *s_empty = s_full + 2, *p_full = s_empty + 2, *p_empty = p_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_empty + 2);
@@ -159,8 +161,8 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = (L + FA_BKV - 1) / FA_BKV;
-    // S0: FA_BKV columns at 0, S1 at FA_BKV, O: DN columns at 2*FA_BKV
-    constexpr uint32_t TMEM_COLS = (2 * FA_BKV + DN <= 128) ? 128 : ((2 * FA_BKV + DN <= 256) ? 256 : 512);
+    // S0: FA_BKV columns at 0, (S1 at FA_BKV,) O: DN columns at NSB*FA_BKV
+    constexpr uint32_t TMEM_COLS = (NSB * FA_BKV + DN <= 128) ? 128 : ((NSB * FA_BKV + DN <= 256) ? 256 : 512);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * FA_BKV;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + NSB * FA_BKV;
     pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail (the trigger is raised by the producer, late)
 
     if (warp == 0) {
@@ -219,16 +221,16 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
             auto issue_qk = [&](int j) {       // S_j = Q K_j^T into score buffer j & 1
                 const int s = j % STAGES;
                 mbar_wait(k_full + s, (j / STAGES) & 1);
-                if (j >= 2) mbar_wait(s_empty + (j & 1), ((j >> 1) & 1) ^ 1);  // softmax has drained S_{j-2}
+                if (j >= NSB) mbar_wait(s_empty + (j % NSB), ((j / NSB) & 1) ^ 1);  // softmax has drained S_{j-NSB}
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t ts = tmem_S + (uint32_t)((j & 1) * FA_BKV);
+                const uint32_t ts = tmem_S + (uint32_t)((j % NSB) * FA_BKV);
                 for (int k = 0; k < ksteps; ++k) {
                     const uint32_t offq = (uint32_t)(k / 4) * Q_BLOCK + (uint32_t)(k % 4) * 32;
                     const uint32_t offk = (uint32_t)(k / 4) * K_BLOCK + (uint32_t)(k % 4) * 32;
                     umma_f16(ts, umma_desc_sw128(smem_u32(sQ) + offq), umma_desc_sw128(smem_u32(sK + s * K_BYTES) + offk), idesc_s, k != 0);
                 }
                 umma_commit(k_empty + s);
-                umma_commit(s_full + (j & 1));
+                umma_commit(s_full + (j % NSB));
             };
             mbar_wait(q_full, 0);
             issue_qk(0);
@@ -237,16 +239,16 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
                 // ---- O (+)= P_j V_j, accumulated in TMEM
                 const int s = j % STAGES;
                 mbar_wait(v_full + s, (j / STAGES) & 1);
-                mbar_wait(p_full + (j & 1), (j >> 1) & 1);  // P_j is in shared memory (and any rescale of O has been stored)
+                mbar_wait(p_full + (j % NPB), (j / NPB) & 1);  // P_j is in shared memory (and any rescale of O has been stored)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < FA_BKV / 16; ++k) {
-                    const uint32_t pa = smem_u32(sP + (j & 1) * P_BYTES) + (uint32_t)k * 32, va = smem_u32(sVt + s * VT_BYTES) + (uint32_t)k * 32;
+                    const uint32_t pa = smem_u32(sP + (j % NPB) * P_BYTES) + (uint32_t)k * 32, va = smem_u32(sVt + s * VT_BYTES) + (uint32_t)k * 32;
                     umma_f16(tmem_O, FA_BKV == 64 ? umma_desc_sw128(pa) : umma_desc_sw64(pa),
                              FA_BKV == 64 ? umma_desc_sw128(va) : umma_desc_sw64(va), idesc_o, (j | k) != 0);
                 }
                 umma_commit(v_empty + s);
-                umma_commit(p_empty + (j & 1));  // P_j consumed; O includes tile j
+                umma_commit(p_empty + (j % NPB));  // P_j consumed; O includes tile j
             }
         }
     } else {
@@ -260,8 +262,8 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
         const int xr = FA_BKV == 64 ? (r & 7) : ((r >> 1) & 3);
         const float2 scale2 = make_float2(scale_log2, scale_log2);
         for (int j = 0; j < n_kv; ++j) {
-            const int bsel = j & 1;
-            mbar_wait(s_full + bsel, (j >> 1) & 1);
+            const int bsel = j % NSB, psel = j % NPB;
+            mbar_wait(s_full + bsel, (j / NSB) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tS = tmem_S + lane_addr + (uint32_t)(bsel * FA_BKV);
             const int valid = min(FA_BKV, L - j * FA_BKV);  // keys beyond L are masked out (last tile only)
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
                 const float alpha = ex2(m_used - m_new);
                 m_used = m_new;
                 l_run *= alpha;
-                mbar_wait(p_empty + ((j - 1) & 1), ((j - 1) >> 1) & 1);  // every P V product issued so far has landed in O
+                mbar_wait(p_empty + ((j - 1) % NPB), ((j - 1) / NPB) & 1);  // every P V product issued so far has landed in O
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int c0 = 0; c0 < DN; c0 += 16) {
@@ -302,10 +304,10 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
                 }
                 tmem_wait_st();
             }
-            if (j >= 2) mbar_wait(p_empty + bsel, ((j >> 1) & 1) ^ 1);  // P_{j-2} has been consumed: its buffer is free
+            if (j >= NPB) mbar_wait(p_empty + psel, ((j / NPB) & 1) ^ 1);  // P_{j-NPB} has been consumed: its buffer is free
             const float2 negm2 = make_float2(-m_used, -m_used);
             float2 rs2 = make_float2(0.f, 0.f), rs2b = make_float2(0.f, 0.f);  // two row-sum chains
-            uint8_t *p_row = p_row0 + bsel * P_BYTES;
+            uint8_t *p_row = p_row0 + psel * P_BYTES;
             // pass 2: probabilities -> fp16 -> shared memory
 #pragma unroll
             for (int c0 = 0; c0 < FA_BKV; c0 += 32) {
@@ -336,10 +338,10 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV))
             mbar_arrive(s_empty + bsel);  // this score buffer may be overwritten by Q K_{j+2}^T
             l_run += (rs2.x + rs2.y) + (rs2b.x + rs2b.y);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-            mbar_arrive(p_full + bsel);
+            mbar_arrive(p_full + psel);
         }
         // ---- O / l
-        mbar_wait(p_empty + ((n_kv - 1) & 1), ((n_kv - 1) >> 1) & 1);
+        mbar_wait(p_empty + ((n_kv - 1) % NPB), ((n_kv - 1) / NPB) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = q0 + r;
         const float inv = 1.0f / l_run;
@@ -395,16 +397,16 @@ static int make_map4(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], 
     return 0;
 }
 
-template <int DKB, int DN, int STAGES, int BKV>
+template <int DKB, int DN, int STAGES, int BKV, int NSB = 2, int NPB = 2>
 static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads, int S, int L, int d,
                             float scale_log2, __half *out, long long ldo, long long o_bstride, cudaStream_t st) {
-    constexpr size_t smem = (size_t)DKB * 16384 + (size_t)STAGES * (DKB * BKV * 128 + ((DN * BKV * 2 + 1023) / 1024) * 1024) + 2 * 128 * BKV * 2 +
+    constexpr size_t smem = (size_t)DKB * 16384 + (size_t)STAGES * (DKB * BKV * 128 + ((DN * BKV * 2 + 1023) / 1024) * 1024) + NPB * 128 * BKV * 2 +
                             256 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<DKB, DN, STAGES, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<DKB, DN, STAGES, BKV, NSB, NPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
             return (int)e;
@@ -412,7 +414,7 @@ static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const 
         attr[dev] = true;
     }
     dim3 grid((S + FA_BQ - 1) / FA_BQ, heads, B);
-    launch_pdl(attention_fwd_kernel<DKB, DN, STAGES, BKV>, grid, dim3(FA_THREADS), smem, st, tq, tk, tv, S, L, d, scale_log2, out, ldo, o_bstride);
+    launch_pdl(attention_fwd_kernel<DKB, DN, STAGES, BKV, NSB, NPB>, grid, dim3(FA_THREADS), smem, st, tq, tk, tv, S, L, d, scale_log2, out, ldo, o_bstride);
     return check_launch("attention_fwd_kernel");
 }
 
@@ -467,6 +469,8 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
             if (DN == 32) return launch_attention<1, 32, 3, 32>(COMA_FA_ARGS);
             return launch_attention<1, 64, 3, 32>(COMA_FA_ARGS);
         }
+        static const bool three = getenv("COMA_ATTN_3CTA") != nullptr;  // A/B: single-buffered S / P, three CTAs per SM
+        if (three && DN == 48) return launch_attention<1, 48, 2, 64, 1, 1>(COMA_FA_ARGS);
         if (DN == 48) return launch_attention<1, 48, 3, 64>(COMA_FA_ARGS);
         if (DN == 32) return launch_attention<1, 32, 3, 64>(COMA_FA_ARGS);
         return launch_attention<1, 64, 3, 64>(COMA_FA_ARGS);
