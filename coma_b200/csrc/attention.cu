@@ -36,19 +36,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-#if FA_SPIN
-    // non-blocking test_wait in a tight loop: lowest wake-up latency, costs issue slots
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -58,7 +45,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
-#endif
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z, int w) {
     asm volatile(
@@ -136,13 +122,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 }  // namespace fa
 
-#ifndef FA_SPIN
-#define FA_SPIN 0
-#endif
-#ifndef FA_EXP
-#define FA_EXP 0   // tuning experiments (timing only, WRONG results): 1 = no MUFU.EX2, 2 = no P stores, 4 = no max pass
-#endif
-constexpr int FA_BQ = 128, FA_THREADS = 224;  // warps: 0 TMA producer, 1 QK^T issuer, 2-5 softmax, 6 PV issuer
+constexpr int FA_BQ = 128, FA_THREADS = 192;
 constexpr float FA_LAZY = 8.0f;  // log2 headroom before the running maximum (and O, l) is moved: P <= 2^8 stays exact enough in fp16
 
 __host__ __device__ constexpr int fa_ctas_per_sm(int DKB, int DN, int BKV, int NSB) {
@@ -166,21 +146,17 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
     constexpr int Q_BLOCK = FA_BQ * 64 * 2;      // one [128 x 64] fp16 K-block of Q, 16 KB
     constexpr int K_BLOCK = FA_BKV * 64 * 2;     // one [FA_BKV keys x 64] K-block of K
     constexpr int Q_BYTES = DKB * Q_BLOCK, K_BYTES = DKB * K_BLOCK;
-    // P and V^T tiles: keys are the K dimension of P V; they are stored as KBP blocks of <= 64 keys (128-byte swizzled rows)
-    constexpr int KBP = FA_BKV > 64 ? FA_BKV / 64 : 1;
-    constexpr int PV_ROW = (FA_BKV > 64 ? 64 : FA_BKV) * 2;  // bytes per row inside one block
-    constexpr int VT_BLK = ((DN * PV_ROW + 1023) / 1024) * 1024;     // [DN x <=64 keys]
-    constexpr int VT_BYTES = KBP * VT_BLK;
-    constexpr int P_BLK = FA_BQ * PV_ROW;        // [128 x <=64 keys]
-    constexpr int P_BYTES = KBP * P_BLK;         // P [128 x FA_BKV] fp16
+    constexpr int PV_ROW = FA_BKV * 2;           // bytes per row of the P / V^T tiles (keys are the K dimension of P V)
+    constexpr int VT_BYTES = ((DN * PV_ROW + 1023) / 1024) * 1024;  // [DN x FA_BKV keys]
+    constexpr int P_BYTES = FA_BQ * PV_ROW;      // P [128 x FA_BKV] fp16 (two buffers)
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + Q_BYTES;
     uint8_t *sVt = sK + STAGES * K_BYTES;
     uint8_t *sP = sVt + STAGES * VT_BYTES;
     uint64_t *bar = reinterpret_cast<uint64_t *>(sP + NPB * P_BYTES);
     uint64_t *q_full = bar, *k_full = bar + 1, *k_empty = k_full + STAGES, *v_full = k_empty + STAGES, *v_empty = v_full + STAGES;
-    uint64_t *s_full = v_empty + STAGES, *s_empty = s_full + 4, *p_full = s_empty + 4, *p_empty = p_full + 4;  // up to 4 buffers each
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_empty + 4);
+    uint64_t *s_full = v_empty + STAGES, *s_empty = s_full + 2, *p_full = s_empty + 2, *p_empty = p_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ, h = blockIdx.y, b = blockIdx.z;
@@ -199,10 +175,10 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
             mbar_init(v_full + i, 1);
             mbar_init(v_empty + i, 1);
         }
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             mbar_init(s_full + i, 1);
-            mbar_init(s_empty + i, 4);   // one arrival per softmax warp (after __syncwarp): 128 per-thread arrivals on one
-            mbar_init(p_full + i, 4);    // shared-memory barrier serialise and sat on the critical path of every step
+            mbar_init(s_empty + i, 128);
+            mbar_init(p_full + i, 128);
             mbar_init(p_empty + i, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,25 +204,19 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
                 const int s = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
                 mbar_wait(k_empty + s, ph ^ 1);
-                if (FA_EXP & 64) mbar_arrive(k_full + s);
-                else {
                 mbar_expect_tx(k_full + s, K_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sK + s * K_BYTES + kb * K_BLOCK, &tmK, k_full + s, kb * 64, j * FA_BKV, h, b);
-                }
                 mbar_wait(v_empty + s, ph ^ 1);
-                if (FA_EXP & 128) mbar_arrive(v_full + s);
-                else {
-                mbar_expect_tx(v_full + s, KBP * DN * PV_ROW);
-#pragma unroll
-                for (int kb = 0; kb < KBP; ++kb) tma_load_4d(sVt + s * VT_BYTES + kb * VT_BLK, &tmVt, v_full + s, j * FA_BKV + kb * 64, 0, h, b);
-                }
+                mbar_expect_tx(v_full + s, DN * PV_ROW);
+                tma_load_4d(sVt + s * VT_BYTES, &tmVt, v_full + s, j * FA_BKV, 0, h, b);
             }
             pdl_trigger();
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(FA_BKV >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+            constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
             const int ksteps = (d + 15) / 16;  // columns d..63 of the Q / K blocks are TMA zero-filled
             auto issue_qk = [&](int j) {       // S_j = Q K_j^T into score buffer j & 1
                 const int s = j % STAGES;
@@ -254,7 +224,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
                 if (j >= NSB) mbar_wait(s_empty + (j % NSB), ((j / NSB) & 1) ^ 1);  // softmax has drained S_{j-NSB}
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ts = tmem_S + (uint32_t)((j % NSB) * FA_BKV);
-                for (int k = 0; k < ((FA_EXP & 32) ? 0 : ksteps); ++k) {
+                for (int k = 0; k < ksteps; ++k) {
                     const uint32_t offq = (uint32_t)(k / 4) * Q_BLOCK + (uint32_t)(k % 4) * 32;
                     const uint32_t offk = (uint32_t)(k / 4) * K_BLOCK + (uint32_t)(k % 4) * 32;
                     umma_f16(ts, umma_desc_sw128(smem_u32(sQ) + offq), umma_desc_sw128(smem_u32(sK + s * K_BYTES) + offk), idesc_s, k != 0);
@@ -263,32 +233,25 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
                 umma_commit(s_full + (j % NSB));
             };
             mbar_wait(q_full, 0);
-            // Two issuing threads: this one feeds the score tiles, warp 6 the P V products. A single thread walking both chains
-            // (4 barrier waits, 7 MMAs with their descriptor / uniform-register setup, 4 commits per step) is a ~1300-1900 clk
-            // serial instruction stream per step and was THE limiter of this kernel (measured by removing all other work).
-            for (int j = 0; j < n_kv; ++j) issue_qk(j);
-        }
-    } else if (warp == 6) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+            issue_qk(0);
             for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_qk(j + 1);  // the next scores are produced while the softmax warps work on S_j
                 // ---- O (+)= P_j V_j, accumulated in TMEM
                 const int s = j % STAGES;
                 mbar_wait(v_full + s, (j / STAGES) & 1);
                 mbar_wait(p_full + (j % NPB), (j / NPB) & 1);  // P_j is in shared memory (and any rescale of O has been stored)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < ((FA_EXP & 32) ? 0 : FA_BKV / 16); ++k) {
-                    const uint32_t pa = smem_u32(sP + (j % NPB) * P_BYTES) + (uint32_t)(k / 4) * P_BLK + (uint32_t)(k % 4) * 32;
-                    const uint32_t va = smem_u32(sVt + s * VT_BYTES) + (uint32_t)(k / 4) * VT_BLK + (uint32_t)(k % 4) * 32;
-                    umma_f16(tmem_O, FA_BKV >= 64 ? umma_desc_sw128(pa) : umma_desc_sw64(pa),
-                             FA_BKV >= 64 ? umma_desc_sw128(va) : umma_desc_sw64(va), idesc_o, (j | k) != 0);
+                for (int k = 0; k < FA_BKV / 16; ++k) {
+                    const uint32_t pa = smem_u32(sP + (j % NPB) * P_BYTES) + (uint32_t)k * 32, va = smem_u32(sVt + s * VT_BYTES) + (uint32_t)k * 32;
+                    umma_f16(tmem_O, FA_BKV == 64 ? umma_desc_sw128(pa) : umma_desc_sw64(pa),
+                             FA_BKV == 64 ? umma_desc_sw128(va) : umma_desc_sw64(va), idesc_o, (j | k) != 0);
                 }
                 umma_commit(v_empty + s);
                 umma_commit(p_empty + (j % NPB));  // P_j consumed; O includes tile j
             }
         }
-    } else if (warp >= 2 && warp <= 5) {
+    } else {
         // ---- softmax: thread owns query row r of the tile
         const int q = warp & 3, r = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -296,7 +259,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
         // P row r inside the K-major swizzled [128 x FA_BKV] tile: 8-row atoms; 128-byte rows: 16-byte chunk index ^ (r%8),
         // 64-byte rows: chunk index ^ ((r/2)%4)
         uint8_t *p_row0 = sP + (r >> 3) * (8 * PV_ROW) + (r & 7) * PV_ROW;
-        const int xr = FA_BKV >= 64 ? (r & 7) : ((r >> 1) & 3);
+        const int xr = FA_BKV == 64 ? (r & 7) : ((r >> 1) & 3);
         const float2 scale2 = make_float2(scale_log2, scale_log2);
         for (int j = 0; j < n_kv; ++j) {
             const int bsel = j % NSB, psel = j % NPB;
@@ -349,10 +312,6 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
 #pragma unroll
             for (int c0 = 0; c0 < FA_BKV; c0 += 32) {
                 float sv[32];
-                if (FA_EXP & 16) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) sv[c] = (float)(c + j) * 0.01f;
-                } else
                 tmem_ld32(tS + c0, sv);
 #pragma unroll
                 for (int c8 = 0; c8 < 32; c8 += 8) {
@@ -362,7 +321,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
                     for (int t = 0; t < 4; ++t) {
                         const int c = c0 + c8 + 2 * t;
                         const float2 x = __ffma2_rn(make_float2(sv[c8 + 2 * t], sv[c8 + 2 * t + 1]), scale2, negm2);
-                        float2 pr = (FA_EXP & 1) ? make_float2(x.x * 0.001f, x.y * 0.001f) : make_float2(ex2(x.x), ex2(x.y));
+                        float2 pr = make_float2(ex2(x.x), ex2(x.y));
                         if (!full_tile) {
                             pr.x = (c < valid) ? pr.x : 0.f;
                             pr.y = (c + 1 < valid) ? pr.y : 0.f;
@@ -371,17 +330,15 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
                         if (t & 1) rs2b = __fadd2_rn(rs2b, pr);
                         else rs2 = __fadd2_rn(rs2, pr);
                     }
-                    const int cc = c0 + c8, chunk = (cc & 63) >> 3;   // 16-byte chunk inside the 64-key block cc / 64
-                    if (!(FA_EXP & 2) || w.x == 0x12345678u) *reinterpret_cast<uint4 *>(p_row + (cc >> 6) * P_BLK + ((chunk ^ xr) << 4)) = w;
+                    const int chunk = (c0 + c8) >> 3;
+                    *reinterpret_cast<uint4 *>(p_row + ((chunk ^ xr) << 4)) = w;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty + bsel);  // this score buffer may be overwritten by Q K_{j+2}^T
+            mbar_arrive(s_empty + bsel);  // this score buffer may be overwritten by Q K_{j+2}^T
             l_run += (rs2.x + rs2.y) + (rs2b.x + rs2b.y);
-            if (!(FA_EXP & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full + psel);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(p_full + psel);
         }
         // ---- O / l
         mbar_wait(p_empty + ((n_kv - 1) % NPB), ((n_kv - 1) / NPB) & 1);
@@ -443,9 +400,8 @@ static int make_map4(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], 
 template <int DKB, int DN, int STAGES, int BKV, int NSB = 2, int NPB = 2>
 static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads, int S, int L, int d,
                             float scale_log2, __half *out, long long ldo, long long o_bstride, cudaStream_t st) {
-    constexpr int KBP = BKV > 64 ? BKV / 64 : 1, ROWB = (BKV > 64 ? 64 : BKV) * 2;
-    constexpr size_t smem = (size_t)DKB * 16384 + (size_t)STAGES * (DKB * BKV * 128 + KBP * (((DN * ROWB + 1023) / 1024) * 1024)) +
-                            (size_t)NPB * 128 * BKV * 2 + 512 + 1024;
+    constexpr size_t smem = (size_t)DKB * 16384 + (size_t)STAGES * (DKB * BKV * 128 + ((DN * BKV * 2 + 1023) / 1024) * 1024) + NPB * 128 * BKV * 2 +
+                            256 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -482,10 +438,7 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
     // half-empty 64-key step), 64 otherwise (measured: 2.23 vs 2.46 ms over the five 4096-token self-attention layers);
     // COMA_ATTN_BKV = 32 | 64 forces one of them (tuning)
     static const int forced_bkv = getenv("COMA_ATTN_BKV") ? atoi(getenv("COMA_ATTN_BKV")) : 0;
-    // long key sequences with a small head: 128 keys per step, single-buffered scores (2 CTAs per SM) — every step costs a fixed
-    // ~1300 clk of barrier hand-offs between the producer, MMA and softmax warps (measured with all work removed), so fewer,
-    // fatter steps win
-    const int BKV = (d <= 64 && (forced_bkv ? forced_bkv == 32 : L <= 128)) ? 32 : ((d16 == 48 && L >= 512 && forced_bkv != 64) ? 128 : 64);
+    const int BKV = (d <= 64 && (forced_bkv ? forced_bkv == 32 : L <= 128)) ? 32 : 64;
     CUtensorMap tq, tk, tv;
     {
         cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)S, (cuuint64_t)heads, (cuuint64_t)B};
@@ -502,8 +455,8 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
     {
         cuuint64_t dims[4] = {(cuuint64_t)Lp, (cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)Lp * 2, (cuuint64_t)(d * Lp) * 2, (cuuint64_t)(heads * d * Lp) * 2};
-        cuuint32_t box[4] = {(cuuint32_t)(BKV > 64 ? 64 : BKV), (cuuint32_t)DN, 1, 1};
-        if (int e = make_map4(&tv, vt, dims, str, box, BKV >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+        cuuint32_t box[4] = {(cuuint32_t)BKV, (cuuint32_t)DN, 1, 1};
+        if (int e = make_map4(&tv, vt, dims, str, box, BKV == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     }
     const float scale_log2 = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
@@ -516,16 +469,9 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
             if (DN == 32) return launch_attention<1, 32, 3, 32>(COMA_FA_ARGS);
             return launch_attention<1, 64, 3, 32>(COMA_FA_ARGS);
         }
-        if (BKV == 128) return launch_attention<1, 48, 2, 128, 1, 1>(COMA_FA_ARGS);
         static const bool three = getenv("COMA_ATTN_3CTA") != nullptr;  // A/B: single-buffered S / P, three CTAs per SM
         if (three && DN == 48) return launch_attention<1, 48, 2, 64, 1, 1>(COMA_FA_ARGS);
-        static const bool deep = getenv("COMA_ATTN_DEEP") != nullptr;   // A/B: three score / probability buffers
-        if (deep && DN == 48) return launch_attention<1, 48, 3, 64, 3, 3>(COMA_FA_ARGS);
-#ifndef FA_ST
-#define FA_ST 3
-#define FA_NPB 2
-#endif
-        if (DN == 48) return launch_attention<1, 48, FA_ST, 64, 2, FA_NPB>(COMA_FA_ARGS);
+        if (DN == 48) return launch_attention<1, 48, 3, 64>(COMA_FA_ARGS);
         if (DN == 32) return launch_attention<1, 32, 3, 64>(COMA_FA_ARGS);
         return launch_attention<1, 64, 3, 64>(COMA_FA_ARGS);
     }
