@@ -5,14 +5,19 @@
 // W = weights ([N,K], K contiguous). Reference call sites: utils/adaptive_mask_inpainting.py:1001-1007 (UNet),
 // :680,:1086,:1112 (VAE) — the arithmetic itself lives in diffusers' UNet2DConditionModel / AutoencoderKL [ext].
 //
-// Blackwell structure (one CTA per 128 x BN output tile, 6 warps, warp-specialised):
-//   warp 0    : TMA producer — cp.async.bulk.tensor.2d of the A (128 x 64) and W (BN x 64) K-slabs into a 4-stage
-//               128B-swizzled shared-memory ring, completion on `full` mbarriers
+// Blackwell structure (persistent CTAs walking 128 x BN output tiles, warp-specialised):
+//   warp 0    : TMA producer — cp.async.bulk.tensor.4d of the A (128 x 64) and W (BN x 64) K-slabs into a 3-5 stage
+//               128B-swizzled shared-memory ring, completion on `full` mbarriers; for CONV the A slab is the output tile shifted by
+//               one filter tap (implicit GEMM, hardware zero fill = padding, element stride 2 for strided convolutions)
 //   warp 1    : MMA issuer — one elected thread issues 4 x tcgen05.mma.kind::f16 (M128 x BN x K16) per slab from shared-memory
-//               descriptors, fp32 accumulator in TMEM; tcgen05.commit releases the slab (`empty`) and finally signals
-//               `tmem_full`
-//   warps 2-5 : epilogue — tcgen05.ld (32 lanes x 32 columns per warp-instruction) TMEM -> registers, + bias, + residual,
-//               optional SiLU, store fp16 and/or fp32
+//               descriptors into one of TWO fp32 TMEM accumulators; tcgen05.commit releases the slab (`empty`) and finally signals
+//               `tmem_full`, so the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2.. : epilogue (4 warps, 8 on the one-CTA-per-SM tiles) — tcgen05.ld of 32-column panels, + bias, + per-sample bias rows,
+//               + residual (fetched by TMA), optional SiLU or fused GEGLU, fp16 panel staged in 64B-swizzled shared memory and
+//               written by a TMA store (which clips the row / column tails); optionally the GroupNorm partial sums of the panel.
+//               fp32 outputs and split-K slabs take the direct-store path.
+// Host side: a small cost model picks the tile width and a split-K factor (deterministic slab reduction) for problems with too
+// few tiles for 148 SMs; every launch uses programmatic dependent launch with a late trigger.
 // Operands are fp16, accumulation fp32 (the reference runs the models in fp16, src/generation/inpaint.py:64).
 #include <cuda.h>
 #include <cuda_fp16.h>

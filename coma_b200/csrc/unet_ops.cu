@@ -2,7 +2,8 @@
 // Activations are NHWC fp16 ([B, H*W, C] matrices, the GEMM's A operand layout); statistics and epilogues are fp32.
 // Reference call sites: utils/adaptive_mask_inpainting.py:1001-1007 (unet), :680/:1086/:1112 (vae) — the layer
 // definitions themselves are diffusers' (UNet2DConditionModel / AutoencoderKL 0.20.2, not vendored).
-//   groupnorm_partial/finalize  GroupNorm(32) statistics (fp32 partial sums per channel, fp64 combination)
+//   groupnorm_partial           GroupNorm(32) statistics in ONE launch (fp32 partials per channel, last CTA combines in fp64, fixed order)
+//   groupnorm_from_stats        the same affine from the partial sums a convolution epilogue left behind (no pass over x)
 //   groupnorm_apply             y = act(gn(x))                        (Transformer2D / VAE attention inputs, conv_norm_out)
 //   im2col3x3                   [B,H,W,C] -> [B*Ho*Wo, 9C] with the GroupNorm affine + SiLU applied on the fly, stride 1/2,
 //                               nearest x2 upsampling and the VAE encoder's asymmetric (0,1,0,1) padding folded in
