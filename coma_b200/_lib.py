@@ -27,6 +27,7 @@ SIGNATURES = {
     "coma_occupancy_readout_f32": [_vp, _i64, _i64, _vp, _i64, _vp, _vp],
     "coma_gemm_f16_tn": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp, _i64, _vp],
     "coma_gemm_f16_ex": [_vp, _vp],
+    "coma_gemm_plan": [_i64, _i64, _i64, _i64, _int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)],
     "coma_conv3x3_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp],
     "coma_conv3x3_strided_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp,
                                  _i64, _vp, _c.POINTER(_c.c_int), _vp],

@@ -847,6 +847,17 @@ static int launch_split_finish(const GemmEpilogue &fin, const float *ws, int ksp
 
 }  // namespace coma
 
+// Host-only query of the schedule the planner would pick (no device work): tests and tuning tools read it.
+extern "C" int coma_gemm_plan(int64_t M, int64_t N, int64_t K, int64_t workspace_elems, int conv_m_tiles, int *tile_n, int *ksplit) {
+    using namespace coma;
+    COMA_REQUIRE(M > 0 && N > 0 && K > 0 && tile_n && ksplit, "bad arguments");
+    const int64_t m_tiles = conv_m_tiles > 0 ? conv_m_tiles : (M + G_BM - 1) / G_BM;
+    const GemmPlan p = plan_gemm(m_tiles, N, K, 1, M, workspace_elems > 0 && N % 8 == 0, workspace_elems);
+    *tile_n = p.bn;
+    *ksplit = p.ksplit;
+    return 0;
+}
+
 extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     using namespace coma;
     COMA_REQUIRE(g && g->A && g->W && (g->out_f16 || g->out_f32), "null pointer");

@@ -143,6 +143,9 @@ typedef struct coma_gemm_args {
                 * out[M, N/2] = value * gelu(gate) (diffusers GEGLU fused into its projection); needs N % 256 == 0 */
 } coma_gemm_args;
 COMA_API int coma_gemm_f16_ex(const coma_gemm_args *args, coma_stream_t stream);
+/* Host-only: the output-tile width (64 / 128 / 160 / 256) and split-K factor the scheduler picks for an M x N x K problem with
+ * `workspace_elems` floats of split-K scratch (0 = splitting not allowed); conv_m_tiles > 0 overrides ceil(M / 128). */
+COMA_API int coma_gemm_plan(int64_t M, int64_t N, int64_t K, int64_t workspace_elems, int conv_m_tiles, int *tile_n, int *ksplit);
 
 /* 3x3 convolution, stride 1, zero padding 1, as an IMPLICIT GEMM: the A operand of every (tap, 64-channel) K-slab is a
  * shifted 128-pixel tile fetched by one 4-D TMA load (out-of-image rows/columns are hardware zero-filled), so no im2col

@@ -183,3 +183,28 @@ def test_oracle_vertex_normals_matches_cli_helper():
     assert np.array_equal(a, b) and a[49].tolist() == [0.0, 0.0, 1.0]
     assert np.array_equal(oracle.vertex_normals(v, f, 1e-10), normalize_vectors_np(b, eps=1e-10))
     assert oracle.vertex_normals(np.stack([v, 2 * v]), f).shape == (2, 50, 3)
+
+
+def test_gemm_planner_choices():
+    """The tile-width / split-K cost model (host code, no GPU needed): problems with too few 128-row tiles for 148 SMs are narrowed
+    or split along K; big problems keep wide tiles and never split; no workspace -> never split."""
+    import ctypes
+    from coma_b200 import _lib
+    lib = _lib.load()
+
+    def plan(M, N, K, ws=8 << 20, conv_m_tiles=0):
+        bn, ks = ctypes.c_int(0), ctypes.c_int(0)
+        assert lib.coma_gemm_plan(M, N, K, ws, conv_m_tiles, ctypes.byref(bn), ctypes.byref(ks)) == 0
+        return bn.value, ks.value
+
+    assert plan(8192, 8192, 8192) == (256, 1)                      # plenty of tiles
+    bn, ks = plan(512, 1280, 11520)                                # 8x8-level 3x3 conv: 4 x 5 tiles of 180 K-slabs
+    assert ks >= 2 and bn in (128, 160, 256)                       # split along K (slab traffic caps the factor)
+    assert plan(512, 1280, 11520, ws=0)[1] == 1                    # no scratch, no split
+    assert plan(2048, 1280, 1280) == (160, 1)                      # 128 tiles in one wave instead of 80 wide ones
+    assert plan(32768, 320, 320) == (160, 1)                       # N = 320: two exact 160-wide tiles
+    assert plan(512, 1280, 1280)[0] == 64                          # short K: narrow tiles rather than a split
+    assert plan(1 << 20, 128, 1152) == (128, 1)
+    for M, N, K in [(77, 320, 768), (616, 640, 768), (32768, 2560, 320), (8192, 640, 2560)]:
+        bn, ks = plan(M, N, K)
+        assert bn in (64, 128, 160, 256) and 1 <= ks <= 16 and ks * M * N <= 8 << 20 or ks == 1
