@@ -12,6 +12,21 @@ import torch
 from ._lib import _ptr, _stream, call
 
 
+def build_corner_list(faces, num_verts):
+    """CSR of the faces incident to each vertex, ordered by (vertex, corner index, face index) — the order in which
+    `np.add.at(vn, f[:, k], fn)` for k = 0, 1, 2 adds the face normals, which is what makes K6 bit-identical to the numpy
+    restatement. Returns (faces int32 [F,3], corner_off int32 [V+1], corner_face int32 [3F])."""
+    f = np.ascontiguousarray(np.asarray(faces).reshape(-1, 3).astype(np.int64))
+    assert f.size and f.min() >= 0 and f.max() < num_verts, "face indices out of range"
+    F = int(f.shape[0])
+    corner_vertex = f.T.reshape(-1)                                   # [3F]: corner k of face j at k*F + j
+    order = np.argsort(corner_vertex, kind="stable")
+    counts = np.bincount(corner_vertex, minlength=num_verts)
+    off = np.zeros(num_verts + 1, dtype=np.int32)
+    np.cumsum(counts, out=off[1:])
+    return f.astype(np.int32), off, (order % F).astype(np.int32)
+
+
 class MeshNormals:
     """Vertex normals for meshes sharing `faces` [F,3]: `normals = MeshNormals(faces, V)(verts)` with verts [V,3] or [S,V,3]
     (numpy or CUDA tensor, any float dtype; computed in fp64 like the reference) -> same leading shape, fp64 CUDA tensor."""
@@ -20,18 +35,11 @@ class MeshNormals:
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("coma_b200.ingest runs on CUDA only (there is no CPU fallback)")
-        f = np.ascontiguousarray(np.asarray(faces).reshape(-1, 3).astype(np.int64))
-        assert f.min() >= 0 and f.max() < num_verts, "face indices out of range"
+        f, off, cf = build_corner_list(faces, num_verts)
         self.V, self.F = int(num_verts), int(f.shape[0])
-        # corner list ordered by (vertex, corner index, face index): np.add.at(vn, f[:, k], fn) for k = 0, 1, 2 adds in this order
-        corner_vertex = f.T.reshape(-1)                                   # [3F]: corner k of face j at k*F + j
-        order = np.argsort(corner_vertex, kind="stable")
-        self.corner_face = torch.from_numpy((order % self.F).astype(np.int32)).to(self.dev)
-        counts = np.bincount(corner_vertex, minlength=self.V)
-        off = np.zeros(self.V + 1, dtype=np.int32)
-        np.cumsum(counts, out=off[1:])
+        self.corner_face = torch.from_numpy(cf).to(self.dev)
         self.corner_off = torch.from_numpy(off).to(self.dev)
-        self.faces = torch.from_numpy(f.astype(np.int32)).to(self.dev)
+        self.faces = torch.from_numpy(f).to(self.dev)
 
     def __call__(self, verts, eps=-1.0):
         v = torch.as_tensor(np.asarray(verts) if not torch.is_tensor(verts) else verts).to(device=self.dev, dtype=torch.float64)

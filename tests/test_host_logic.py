@@ -208,3 +208,25 @@ def test_gemm_planner_choices():
     for M, N, K in [(77, 320, 768), (616, 640, 768), (32768, 2560, 320), (8192, 640, 2560)]:
         bn, ks = plan(M, N, K)
         assert bn in (64, 128, 160, 256) and 1 <= ks <= 16 and ks * M * N <= 8 << 20 or ks == 1
+
+
+def test_ingest_corner_list_reproduces_numpy_accumulation_order():
+    """K6's host side: gathering each vertex's faces in the corner-list order and adding sequentially gives bit-for-bit what
+    np.add.at(vn, f[:, k], fn), k = 0, 1, 2 gives (the oracle's accumulation) — including vertices without faces."""
+    from coma_b200.ingest import build_corner_list
+    rng = np.random.default_rng(1)
+    V, F = 60, 200
+    faces = rng.integers(0, V - 1, (F, 3))                 # vertex V-1 has no faces
+    fn = rng.standard_normal((F, 3)) * np.exp(rng.uniform(-8, 8, (F, 1)))   # wide dynamic range: order matters in fp64
+    f32, off, cf = build_corner_list(faces, V)
+    assert off[0] == 0 and off[-1] == 3 * F and f32.dtype == np.int32 and off[V] == off[V - 1]
+    ref = np.zeros((V, 3))
+    for k in range(3):
+        np.add.at(ref, faces[:, k], fn)
+    mine = np.zeros((V, 3))
+    for v in range(V):
+        for i in range(off[v], off[v + 1]):
+            mine[v] = mine[v] + fn[cf[i]]
+    assert np.array_equal(mine, ref)
+    # every corner appears exactly once
+    assert sorted(cf.tolist()) == sorted(np.repeat(np.arange(F), 3).tolist())
