@@ -81,6 +81,7 @@ def load():
         lib.coma_b200_version.restype = _int
         lib.coma_b200_last_error.restype = _c.c_char_p
         lib.coma_b200_launch_count.restype = _i64
+        lib.coma_b200_last_kernel.restype = _c.c_char_p
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = args
@@ -91,6 +92,11 @@ def load():
 
 def launch_count():
     return int(load().coma_b200_launch_count())
+
+
+def last_kernel():
+    """Name of the kernel variant the last entry point called from this thread launched."""
+    return load().coma_b200_last_kernel().decode()
 
 
 def _ptr(t):

@@ -6,14 +6,18 @@ and `src/coma/inference.py` (:26-147, flags :152-160) with the same directory la
                                                          orientational_tendency.npy,occupancy.npy}
   output/<sc>/<c>/{...}                                  (inference)
 
-The per-sample host work (pickle IO, vertex normals, index gather) stays on the CPU as in the reference; aggregation and
-read-outs run on the GPU through `utils.coma.ComA` / `utils.coma_occupancy.ComA_Occupancy` (coma_b200 kernels).
-With torchrun (WORLD_SIZE > 1) the samples of each SCAM are sharded over the ranks and the accumulators are summed with
-one all-reduce before rank 0 writes the outputs.
+Sample ingest: the pickles of a SCAM are read by a thread pool, the vertex normals of ALL its samples are
+one K6 launch and the downsample index gather runs on the GPU (`prepare_affordance_extraction_inputs_batch`); aggregation
+and read-outs run through `utils.coma.ComA` / `utils.coma_occupancy.ComA_Occupancy` (coma_b200 kernels).
+With torchrun (WORLD_SIZE > 1) every rank owns a block of HUMAN-VERTEX rows of the accumulators (`human_slice`), loads
+1/world of the sample files and the staged fp32 samples are all-gathered, so no accumulator ever crosses GPUs; the
+read-outs exchange per-vertex maps only, and `export` assembles the pickle on rank 0. Every rank takes part in the
+(collective) read-outs; only rank 0 writes files.
 """
 import json
 import os
 import pickle
+from concurrent.futures import ThreadPoolExecutor
 from copy import deepcopy
 from glob import glob
 
@@ -66,45 +70,109 @@ def prepare_affordance_extraction_inputs(human_mesh_pth, human_downsample_metada
                 obj_verts=np.asarray(obj_verts), obj_vertex_normals=np.asarray(obj_vertex_normals))
 
 
-def _build_coma(visualize_type, H, O, hp, scale_tolerance, device="cuda"):
+def _load_pickle(pth):
+    with open(pth, "rb") as handle:
+        return pickle.load(handle)
+
+
+def prepare_affordance_extraction_inputs_batch(human_mesh_pths, human_downsample_metadata, object_downsample_metadata,
+                                               human_use_downsample_pcd_raw, object_use_downsample_pcd_raw, eps,
+                                               standardize_human_scale=False, scaler_range=None, camera_pth=None,
+                                               human_params_pths=None, io_threads=8):
+    """utils/coma.py:649-791 for a LIST of sample pickles sharing one topology (one SCAM): threaded pickle IO, ONE K6 launch for
+    the vertex normals of every sample, the `downsample_indices` gather on the GPU. Returns a list (one entry per path, None for
+    samples the scale filter drops) of the same dicts `prepare_affordance_extraction_inputs` returns — bit-identical values."""
+    import torch
+    assert not human_use_downsample_pcd_raw, "Human must use 'mesh' for Representation. You'll know why"
+    if not human_mesh_pths:
+        return []
+    with ThreadPoolExecutor(max_workers=io_threads) as ex:
+        datas = list(ex.map(_load_pickle, human_mesh_pths))
+    keep = [True] * len(datas)
+    if standardize_human_scale:
+        cam_scale = _load_pickle(camera_pth)["scale"]
+        for i, pp in enumerate(human_params_pths):
+            hp_ = _load_pickle(pp)
+            scaler = (512 / cam_scale) * (hp_["convert_data"]["z_mean"] / hp_["convert_data"]["focals"][0])
+            keep[i] = scaler_range is None or (scaler_range[0] <= scaler <= scaler_range[1])
+    obj_verts_orig = object_downsample_metadata["obj_vertices_original"]
+    obj_vertex_normals_orig = normalize_vectors_np(np.asarray(object_downsample_metadata["obj_vertex_normals_original"]))
+    hidx = np.asarray(human_downsample_metadata["downsample_indices"], dtype=np.int64)
+    oidx = object_downsample_metadata["downsample_indices"]
+    if object_use_downsample_pcd_raw:
+        obj_verts = np.asarray(object_downsample_metadata["downsampled_pcd_points_raw"])
+        obj_vertex_normals = np.asarray(object_downsample_metadata["downsampled_pcd_normal_raw"])
+        assert len(obj_verts) == object_downsample_metadata["N_raw"]
+    else:
+        obj_verts = np.asarray(obj_verts_orig).copy()[oidx]
+        obj_vertex_normals = obj_vertex_normals_orig.copy()[oidx]
+        assert len(obj_verts) == object_downsample_metadata["N"]
+    out = [None] * len(datas)
+    kept = [i for i, k in enumerate(keep) if k]
+    # group by topology (all SMPL-X samples share one face array; be robust to a stray different one)
+    groups = {}
+    for i in kept:
+        f = np.asarray(datas[i]["faces"])
+        groups.setdefault((f.shape, hash(np.ascontiguousarray(f).tobytes())), []).append(i)
+    for members in groups.values():
+        verts = np.stack([np.asarray(datas[i]["verts"], dtype=np.float64) for i in members])           # [S,V,3]
+        mn = ingest.mesh_normals_for(datas[members[0]]["faces"], verts.shape[1])
+        vt = torch.from_numpy(verts).to(mn.dev)
+        normals = mn(vt, eps)                                                                          # one K6 launch, fp64
+        it = torch.from_numpy(hidx).to(mn.dev)
+        hv = vt.index_select(1, it).cpu().numpy()
+        hn = normals.index_select(1, it).cpu().numpy()
+        assert hv.shape[1] == human_downsample_metadata["N"]
+        for j, i in enumerate(members):
+            out[i] = dict(human_verts=hv[j], human_vertex_normals=hn[j], obj_verts=obj_verts, obj_vertex_normals=obj_vertex_normals)
+    return out
+
+
+def _build_coma(visualize_type, H, O, hp, scale_tolerance, device="cuda", human_slice=None):
     from utils.coma import ComA
     from utils.coma_occupancy import ComA_Occupancy
     common = dict(human_res=H, obj_res=O, normal_res=hp["normal_res"], spatial_res=hp["spatial_res"],
                   proximity_settings=dict(spatial_grid_size=hp["spatial_grid_size"], spatial_grid_thres=hp["spatial_grid_thres"]),
                   principle_vec=hp["principle_vec"], sub_principle_vec=hp["sub_principle_vec"],
                   rel_dist_method=hp["rel_dist_method"], normal_gaussian_sigma=hp["normal_gaussian_sigma"], eps=hp["eps"],
-                  device=device)
+                  device=device, human_slice=human_slice)
     if visualize_type == "occupancy":
         return ComA_Occupancy(scale_tolerance=scale_tolerance, **common)
     return ComA(**common)
 
 
-def write_affordance(coma, visualize_type, hp, out_dir, object_downsample_metadata):
-    """The four read-outs of src/coma/extract_coma.py:428-483 == src/coma/inference.py:95-147."""
+def write_affordance(coma, visualize_type, hp, out_dir, object_downsample_metadata, save=True):
+    """The four read-outs of src/coma/extract_coma.py:428-483 == src/coma/inference.py:95-147.
+    On a row-sharded instance the read-outs are COLLECTIVE: every rank must call this; only `save=True` ranks write."""
     from utils.coma import get_aggregated_contact
-    os.makedirs(out_dir, exist_ok=True)
+    if save:
+        os.makedirs(out_dir, exist_ok=True)
     if visualize_type == "aggr-human-contact":
         agg, _ = get_aggregated_contact(coma=coma, contact_map_type="human", significant_contact_ratio=hp["significant_contact_ratio"])
-        np.save(f"{out_dir}/human_contact.npy", agg / agg.max())
+        if save:
+            np.save(f"{out_dir}/human_contact.npy", agg / agg.max())
     elif visualize_type == "aggr-object-contact":
         agg, _ = get_aggregated_contact(coma=coma, contact_map_type="obj", significant_contact_ratio=hp["significant_contact_ratio"])
         score = agg / agg.max()
-        write_point_cloud_ply(f"{out_dir}/object_contact.ply", object_downsample_metadata["downsampled_pcd_points_raw"],
-                              object_downsample_metadata["downsampled_pcd_normal_raw"], jet_rgb(score))
+        if save:
+            write_point_cloud_ply(f"{out_dir}/object_contact.ply", object_downsample_metadata["downsampled_pcd_points_raw"],
+                                  object_downsample_metadata["downsampled_pcd_normal_raw"], jet_rgb(score))
     elif visualize_type == "orientation":
         s = coma.compute_nonphysical_response_sphere(n_bin=1e6, nonphysical_type="human", as_numpy=True)["human"][:, 0]
-        np.save(f"{out_dir}/orientational_tendency.npy", (s - s.min()) / (s.max() - s.min()))
+        if save:
+            np.save(f"{out_dir}/orientational_tendency.npy", (s - s.min()) / (s.max() - s.min()))
     elif visualize_type == "occupancy":
         prob_field = coma.return_aggregated_spatial_grids(human_indices=None).cpu().numpy()
         prob_field /= prob_field.max()
         prob_field = 0.7 * prob_field
-        np.save(f"{out_dir}/occupancy.npy", dict(prob_field=prob_field, spatial_grid_metadata=coma.spatial_grid_metadata))
+        if save:
+            np.save(f"{out_dir}/occupancy.npy", dict(prob_field=prob_field, spatial_grid_metadata=coma.spatial_grid_metadata))
 
 
 def run_affordance_extraction(supercategories, categories, prompts, camera_dir, human_params_dir, asset_downsample_dir,
                               human_postfilter_dir, human_sample_dir, coma_save_dir, affordance_save_dir, hyperparams,
                               hyperparams_key, scale_tolerance=3.0, skip_done=False,
-                              smplx_downsample_dir="./constants/mesh", **_unused):
+                              smplx_downsample_dir="./constants/mesh", device="cuda", **_unused):
     hp = hyperparams
     visualize_type, quant_mode = hp["visualize_type"], hp["quant_mode"]
     rank, world, _ = cdist.init_process_group()
@@ -166,30 +234,32 @@ def run_affordance_extraction(supercategories, categories, prompts, camera_dir, 
             with open(json_pth, "w") as wf:
                 json.dump(info, wf, indent=1)
 
-        coma = _build_coma(visualize_type, H, O, hp, scale_tolerance)
-        if skip_done and os.path.exists(save_pth):
-            coma.load(save_pth)  # the ComA pickle is the checkpoint (:350-351)
+        # multi-GPU: this rank owns a block of human-vertex rows of every accumulator and loads 1/world of the sample files
+        coma = _build_coma(visualize_type, H, O, hp, scale_tolerance, device=device,
+                           human_slice=cdist.human_slice(H, rank, world) if world > 1 else None)
+        done = skip_done and os.path.exists(save_pth)
+        if done:
+            coma.load(save_pth)  # the ComA pickle is the checkpoint (:350-351); a sharded rank keeps its rows only
         else:
-            occupancy = visualize_type == "occupancy"
-            mine = inputs if (occupancy or world == 1) else [inputs[i] for i in cdist.sample_shard(len(inputs), rank, world)]
+            mine = [inputs[i] for i in cdist.sample_shard(len(inputs), rank, world)]
+            hparams = []
             for pth in mine:
                 sc_s2, c_s2, asset2, view_id, mask_id, prompt, id_ext = pth.split("/")[-7:]
-                hparams = f"{human_params_dir}/{sc_s2}/{c_s2}/{asset2}/{view_id}/{mask_id}/{prompt.replace('total:', '')}/{id_ext}"
-                x = prepare_affordance_extraction_inputs(pth, human_md, object_md, hp["human_use_downsample_pcd_raw"],
-                                                         hp["object_use_downsample_pcd_raw"], hp["eps"], hp["standardize_human_scale"],
-                                                         hp["scaler_range"], camera_pth, hparams)
+                hparams.append(f"{human_params_dir}/{sc_s2}/{c_s2}/{asset2}/{view_id}/{mask_id}/{prompt.replace('total:', '')}/{id_ext}")
+            xs = prepare_affordance_extraction_inputs_batch(mine, human_md, object_md, hp["human_use_downsample_pcd_raw"],
+                                                            hp["object_use_downsample_pcd_raw"], hp["eps"], hp["standardize_human_scale"],
+                                                            hp["scaler_range"], camera_pth, hparams)
+            for x in xs:
                 if x is None:
                     continue
                 coma.register_sample_to_cache(human_verts=x["human_verts"], human_normals=x["human_vertex_normals"],
                                               obj_verts=x["obj_verts"], obj_normals=x["obj_vertex_normals"])
-            coma.aggregate_all_samples()
-            if not occupancy:
-                coma.all_reduce()
+            coma.aggregate_all_samples(exchange=world > 1)
             if rank == 0:
                 os.makedirs(save_dir, exist_ok=True)
-                coma.export(save_pth=save_pth)
-        if rank == 0:
-            write_affordance(coma, visualize_type, hp, f"{affordance_save_dir}/{sc}/{c}/{asset}/{hyperparams_key}:{main}", object_md)
+            coma.export(save_pth=save_pth)       # collective on a sharded instance; rank 0 writes
+        write_affordance(coma, visualize_type, hp, f"{affordance_save_dir}/{sc}/{c}/{asset}/{hyperparams_key}:{main}", object_md,
+                         save=rank == 0)
         del coma
 
 

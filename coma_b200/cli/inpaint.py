@@ -132,22 +132,44 @@ def load_state_dict(path):
     return torch.load(os.path.join(path, "diffusion_pytorch_model.bin"), map_location="cpu")
 
 
-def set_pipeline(model_dir, adaptive_mask_model_type, default_ddim_steps, default_pointrend_threshold=0.2, device="cuda"):
+def build_segmenter(adaptive_mask_model_type, segmenter=None, default_pointrend_threshold=0.2):
+    """The in-loop human segmenter (src/generation/inpaint.py:66-110) is a PLUG-IN here: detectron2 PointRend / SAM and their
+    weights live outside this repository.
+      --segmenter module:factory   import `module`, call `factory(adaptive_mask_model_type=..., pointrend_threshold=...)` and use
+                                   the returned callable `(np.uint8 [H,W,3]) -> {"mask": np.uint8 [H,W], ...}` (the contract of
+                                   PointRendPredictor.__call__, utils/adaptive_mask_inpainting.py:1225-1236);
+      --adaptive_mask_model_type stub   the deterministic LuminanceSegmenter (benchmarks / smoke runs, clearly not a detector).
+    Resolved BEFORE any weights are loaded, so a missing plug-in fails in milliseconds, not after the checkpoint is on the GPU."""
+    if segmenter:
+        import importlib
+        mod, _, fn = segmenter.partition(":")
+        if not mod or not fn:
+            raise ValueError(f"--segmenter expects 'module:factory', got '{segmenter}'")
+        factory = getattr(importlib.import_module(mod), fn)
+        model = factory(adaptive_mask_model_type=adaptive_mask_model_type, pointrend_threshold=default_pointrend_threshold)
+        if not callable(model):
+            raise TypeError(f"{segmenter} returned {type(model).__name__}, expected a callable segmenter")
+        return model
+    if adaptive_mask_model_type == "stub":
+        from coma_b200.inpaint.segmenter import LuminanceSegmenter
+        return LuminanceSegmenter(128)
+    raise NotImplementedError(
+        f"--adaptive_mask_model_type {adaptive_mask_model_type}: the PointRend / SAM human segmenters of the reference need detectron2 / "
+        "segment-anything and their weights, which are plug-ins outside this repository. Pass `--segmenter module:factory` (a factory "
+        "returning a callable image -> {'mask': uint8 [H,W]}) or, for smoke runs, `--adaptive_mask_model_type stub`.")
+
+
+def set_pipeline(model_dir, adaptive_mask_model_type, default_ddim_steps, default_pointrend_threshold=0.2, device="cuda", segmenter=None):
     """src/generation/inpaint.py:33-137: DDIM scheduler, fp16 inpainting checkpoint, segmenter, dilate / provoke schedules.
     `model_dir` is a local diffusers-layout directory (unet/, vae/, text_encoder/, tokenizer/); there is no network access."""
     from coma_b200.inpaint.pipeline import (AdaptiveMaskInpaintPipeline, AdaptiveMaskSettings, MaskDilateScheduler, ProvokeScheduler,
                                             default_adaptive_mask_settings)
-    from coma_b200.inpaint.segmenter import LuminanceSegmenter
+    seg_model = build_segmenter(adaptive_mask_model_type, segmenter, default_pointrend_threshold)   # fails fast, before the weights
     from coma_b200.inpaint.unet import UNet
     from coma_b200.inpaint.vae import VAE
     pipe = AdaptiveMaskInpaintPipeline(UNet(load_state_dict(os.path.join(model_dir, "unet")), device=device),
                                        VAE(load_state_dict(os.path.join(model_dir, "vae")), device=device))
-    if adaptive_mask_model_type == "stub":
-        pipe.register_adaptive_mask_model(LuminanceSegmenter(128))
-    else:
-        raise NotImplementedError(
-            f"segmenter '{adaptive_mask_model_type}' needs detectron2 PointRend / SAM weights, which are plug-ins outside this "
-            "repository: build the predictor and pass it to pipeline.register_adaptive_mask_model(), or use --adaptive_mask_model_type stub")
+    pipe.register_adaptive_mask_model(seg_model)
     n = int(default_ddim_steps * 0.1)
     if adaptive_mask_model_type in ("p", "stub"):
         settings = default_adaptive_mask_settings(default_ddim_steps)

@@ -6,7 +6,12 @@ the reference (`ComA`, utils/coma.py:176-610; `get_aggregated_contact` :614-641)
   * samples registered in the cache are aggregated in BATCHES: the fp32 rounding of utils/misc.py:47-54 happens while
     filling pinned staging buffers, copies run on a side stream, and one K2 + one K3 launch consume a whole batch with
     the accumulators held in registers (the reference re-reads and re-writes every grid once per sample);
-  * there is no CPU path: aggregation / read-outs on a non-CUDA device raise.
+  * there is no CPU path: aggregation / read-outs on a non-CUDA device raise;
+  * multi-GPU (one process per GPU): `ComA(..., human_slice=(h0, h1))` makes this rank own the rows [h0, h1) of every
+    accumulator ("zero-collective" alternative). Every rank sees ALL samples — `aggregate_all_samples(exchange=True)`
+    all-gathers the fp32 sample chunks each rank staged (a few hundred MB per job) — so the 31 GB histogram all-reduce of the
+    sample-sharded form disappears; the only collectives left are the per-vertex ones of the read-outs ([O] flags, [O] / [H]
+    maps). Sample-sharding + `all_reduce()` is kept for API parity with round 1.
 """
 import pickle
 from functools import partial
@@ -14,9 +19,10 @@ from functools import partial
 import numpy as np
 import torch
 
+from . import dist as cdist
 from . import ops
 from .misc import get_uniform_points_on_sphere, to_np_torch_recursive
-from .staging import BatchStager
+from .staging import BatchStager, exchanged_batches
 
 
 def negative_exp(x, spatial_grid_size, spatial_grid_thres, **kwargs):
@@ -48,8 +54,11 @@ def _require_cuda(t, what):
 class ComA:
     def __init__(self, human_res: int, obj_res: int, normal_res: int, spatial_res: int, proximity_settings=dict(),
                  principle_vec=[0, 0, 1], sub_principle_vec=[0, 1, 0], rel_dist_method: str = "dist",
-                 normal_gaussian_sigma: float = 0.1, eps: float = 1e-8, device: str = "cuda"):
+                 normal_gaussian_sigma: float = 0.1, eps: float = 1e-8, device: str = "cuda", human_slice=None):
         self.device = device
+        # B200 extension: this rank owns rows [h0, h1) of every accumulator (row-sharded multi-GPU); default = all rows
+        self._human_slice = (0, human_res) if human_slice is None else (int(human_slice[0]), int(human_slice[1]))
+        assert 0 <= self._human_slice[0] <= self._human_slice[1] <= human_res
         self.human_res, self.obj_res = human_res, obj_res
         self.normal_res, self.spatial_res = normal_res, spatial_res
 
@@ -57,7 +66,7 @@ class ComA:
         self.canon_normal_grid = torch.tensor(np.stack([x, y, z], axis=-1)).to(device)  # fp64 [N,3], :204-205
 
         if self.spatial_res == 0:
-            H, O, N = human_res, obj_res, normal_res
+            H, O, N = self._human_slice[1] - self._human_slice[0], obj_res, normal_res
             z32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
             self.prob_grid_canon_human_wrt_obj = z32(H, O, N)
             self.prob_grid_canon_obj_wrt_human = z32(H, O, N)
@@ -92,42 +101,62 @@ class ComA:
         self.cache[f"{self.cache_count:05}"] = kwargs
         self.cache_count = len(self.cache.keys())
 
-    def aggregate_all_samples(self):
-        """utils/coma.py:257-268 — but the whole cache goes through the GPU in a few batched launches."""
+    def aggregate_all_samples(self, exchange=False, group=None):
+        """utils/coma.py:257-268 — but the whole cache goes through the GPU in a few batched launches.
+        exchange=True (row-sharded multi-GPU): the cache holds only the samples THIS rank loaded; they are all-gathered so
+        that every rank aggregates all samples into its rows, and `used_count` becomes the global sample count."""
         keys = list(self.cache.keys())
         samples = [self.cache[k] for k in keys]
-        self._aggregate_samples(samples)
+        n_global = self._aggregate_samples(samples, exchange=exchange, group=group)
+        first = self.used_count
         for k in keys:  # bookkeeping identical to the reference: cache -> used, counters
-            self.used[f"{self.used_count:05}"] = self.cache[k]
-            self.used_count = len(self.used.keys())
+            self.used[f"{len(self.used):05}"] = self.cache[k]
+        self.used_count = first + n_global
         self.cache = {}
         self.cache_count = 0
 
     def aggregate_single_sample(self, **kwargs):
         if self.spatial_res == 0:
-            self._aggregate_samples([kwargs])
+            self._aggregate_samples([kwargs])   # NB like the reference, this does not touch `used_count` (:270-277)
         else:
             print("Please implement the spatial grid and aggregation in spatial grid")
             raise NotImplementedError
 
-    def _aggregate_samples(self, samples):
+    def _aggregate_samples(self, samples, exchange=False, group=None):
+        """-> number of samples aggregated (the global count in exchange mode)."""
         if self.rel_dist_method == "sdf":
             raise NotImplementedError  # utils/coma.py:325-326
-        if not samples:
-            return
+        exchange = exchange and cdist.is_distributed(group)
+        if not samples and not exchange:
+            return 0
         for s in samples:
             self.assert_inputs(**s)
         _require_cuda(self.significant_contact_count, "ComA.aggregate")
-        H, O = self.human_res, self.obj_res
-        per_sample = (H + O) * 3 * 4 * 2
+        O = self.obj_res
+        h0, h1 = self._human_slice
+        Hs = self.human_res if exchange else h1 - h0        # rows staged per sample: all of them if they are to be exchanged
+        rows = slice(None) if exchange else slice(h0, h1)
+        per_sample = (Hs + O) * 3 * 4 * 2
         chunk = max(32, min(4096, (_STAGING_BYTES // per_sample) // 32 * 32))
-        chunk = min(chunk, (len(samples) + 31) // 32 * 32)
-        stager = BatchStager(dict(hv=H, hn=H, ov=O, on=O), chunk, self.significant_contact_count.device)
-        getters = dict(hv=lambda i: samples[i]["human_verts"], hn=lambda i: samples[i]["human_normals"],
+        if exchange:
+            chunk = min(chunk, 128)                          # world x chunk samples per launch
+        else:
+            chunk = min(chunk, (len(samples) + 31) // 32 * 32)
+        stager = BatchStager(dict(hv=Hs, hn=Hs, ov=O, on=O), chunk, self.significant_contact_count.device)
+        getters = dict(hv=lambda i: samples[i]["human_verts"][rows], hn=lambda i: samples[i]["human_normals"][rows],
                        ov=lambda i: samples[i]["obj_verts"], on=lambda i: samples[i]["obj_normals"])
-        for n, b in stager.batches(getters, len(samples)):
-            self.aggregate_batch_for_contact(b["hv"], b["hn"], b["ov"], b["on"])
+        total = 0
+        if exchange:
+            for n, b in exchanged_batches(stager, getters, len(samples), group):
+                if n:
+                    self.aggregate_batch_for_contact(b["hv"][:, h0:h1].contiguous(), b["hn"][:, h0:h1].contiguous(), b["ov"], b["on"])
+                total += n
+        else:
+            for n, b in stager.batches(getters, len(samples)):
+                self.aggregate_batch_for_contact(b["hv"], b["hn"], b["ov"], b["on"])
+                total += n
         self.last_h2d_bytes = stager.h2d_bytes
+        return total
 
     def aggregate_batch_for_contact(self, human_verts, human_normals, obj_verts, obj_normals):
         """Device-resident batched form of aggregate_single_sample_for_contact (utils/coma.py:279-323):
@@ -163,20 +192,35 @@ class ComA:
         want_h, want_o = contact_map_type in ["human", "both"], contact_map_type in ["obj", "both"]
         on_human = ops.normalize_contact_readout(self.prob_grid_canon_human_wrt_obj, self.eps, *((w, nom, den) if want_h else ()))
         on_obj = ops.normalize_contact_readout(self.prob_grid_canon_obj_wrt_human, self.eps, *((w, nom, den) if want_o else ()))
-        contact_map_dict = {"human": on_human, "obj": on_obj}
+        contact_map_dict = {"human": on_human, "obj": on_obj}   # row-sharded instance: this rank's rows [h0, h1)
         if as_numpy:
+            contact_map_dict = {k: (None if v is None else self._full_rows(v)) for k, v in contact_map_dict.items()}
             return to_np_torch_recursive(contact_map_dict, use_torch=False, device="cpu")
         return contact_map_dict
 
-    def _significant(self, significant_contact_ratio):
+    # -- row-sharded instances: local blocks <-> full tensors (no-ops on an unsharded instance) --------------------------------
+    def _sharded(self):
+        return self._human_slice != (0, self.human_res)
+
+    def _full_rows(self, t, group=None):
+        return cdist.gather_rows(t, self.human_res, group) if self._sharded() else t
+
+    def _significant(self, significant_contact_ratio, group=None):
+        """-> (sig [H_local,O], any_o [H_local], any_h [O]); `any_h` is OR-ed over all ranks' rows on a sharded instance."""
         num = significant_contact_ratio * self.used_count
-        return ops.significant_pairs(self.significant_contact_count, num)
+        sig, any_o, any_h = ops.significant_pairs(self.significant_contact_count, num)
+        if self._sharded() and cdist.is_distributed(group):
+            import torch.distributed as dist
+            flags = any_h.to(torch.int32)
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+            any_h = flags > 0
+        return sig, any_o, any_h
 
     def significant_contact_pairs(self, significant_contact_ratio: float, as_numpy: bool = True):
         """utils/coma.py:369-382."""
         sig = self._significant(significant_contact_ratio)[0]
         if as_numpy:
-            return to_np_torch_recursive(sig, use_torch=False, device="cpu")
+            return to_np_torch_recursive(self._full_rows(sig.to(torch.uint8)).to(torch.bool), use_torch=False, device="cpu")
         return sig
 
     def aggregate_contact_for_significant_pairs(self, contact_map_dict: dict, contact_map_type: str,
@@ -191,8 +235,14 @@ class ComA:
         if contact_map_type in ["obj", "both"]:
             assert contact_map_dict["obj"] is not None, "If 'contact_map_type' is 'obj' or 'both', contact_map_dict['obj'] must not be None"
             agg_o = ops.masked_max(contact_map_dict["obj"].to(torch.float32), any_o, axis=0)     # :421-427
+        if self._sharded():
+            # the per-vertex maps are the only data that crosses GPUs: [H] rows gathered, [O] MAX-reduced (contact >= 0, and a
+            # rank without significant rows contributes the reference's zero fallback, the identity of that max)
+            agg_h = None if agg_h is None else self._full_rows(agg_h)
+            agg_o = None if agg_o is None else cdist.all_reduce_max_nan(agg_o)
         out = {"human": agg_h, "obj": agg_o, "significant_contact_pairs": sig}
         if as_numpy:
+            out["significant_contact_pairs"] = self._full_rows(sig.to(torch.uint8)).to(torch.bool)
             return to_np_torch_recursive(out, use_torch=False, device="cpu")
         return out
 
@@ -207,6 +257,7 @@ class ComA:
             so = ops.entropy_readout(self.prob_grid_canon_obj_wrt_human, n_bin)
         out = {"human": sh, "obj": so, "n_bin": n_bin}
         if as_numpy:
+            out = {k: (self._full_rows(v) if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
             return to_np_torch_recursive(out, use_torch=False, device="cpu")
         return out
 
@@ -231,6 +282,7 @@ class ComA:
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
+        assert not self._sharded(), "all_reduce() sums SAMPLE-sharded accumulators; a row-sharded instance needs no reduction"
         for name in ("significant_contact_count", "contact_dist_expectation_grid_nom",
                      "contact_dist_expectation_grid_denom", "prob_grid_canon_human_wrt_obj",
                      "prob_grid_canon_obj_wrt_human"):
@@ -241,12 +293,25 @@ class ComA:
         self.used_count = int(n.item())
 
     # ------------------------------------------------------------------------------------------------- persistence
-    def export(self, save_pth=None):
-        """utils/coma.py:582-597: every tensor -> numpy fp32/int64, same keys, grids stored un-normalised."""
+    _ROW_SHARDED_KEYS = ("prob_grid_canon_human_wrt_obj", "prob_grid_canon_obj_wrt_human", "contact_dist_expectation_grid_nom",
+                         "contact_dist_expectation_grid_denom", "significant_contact_count", "cross_contact_scores_nom",
+                         "cross_contact_scores_denom")
+
+    def export(self, save_pth=None, group=None):
+        """utils/coma.py:582-597: every tensor -> numpy fp32/int64, same keys, grids stored un-normalised.
+        Row-sharded instance: a COLLECTIVE call — every rank sends its row blocks to rank 0, which assembles the full
+        [H, ...] arrays on the host and returns / writes them; the other ranks return None."""
         to_export = {}
+        sharded = self._sharded() and cdist.is_distributed(group)
         for k in _EXPORT_KEYS:
             v = getattr(self, k)
+            if sharded and k in self._ROW_SHARDED_KEYS:
+                v = cdist.gather_rows(v, self.human_res, group, dst=0)
             to_export[k] = v.detach().clone() if isinstance(v, torch.Tensor) else v
+        if sharded:
+            import torch.distributed as dist
+            if dist.get_rank(group) != 0:
+                return None
         to_export["proximity_settings"] = dict(self.proximity_settings)
         to_export["contact_dist_func"] = _portable_partial(self.proximity_settings)
         to_export = to_np_torch_recursive(to_export, use_torch=False, device="cpu")
@@ -259,6 +324,11 @@ class ComA:
         """utils/coma.py:600-610."""
         with open(load_pth, "rb") as handle:
             loadables = pickle.load(handle)
+        h0, h1 = self._human_slice
+        if self._sharded():   # keep only this rank's rows (sliced on the host, before anything reaches the device)
+            for k in self._ROW_SHARDED_KEYS:
+                if k in loadables:
+                    loadables[k] = np.ascontiguousarray(loadables[k][h0:h1])
         loadables = to_np_torch_recursive(loadables, use_torch=True, device=self.device)
         for k, v in loadables.items():
             setattr(self, k, v)

@@ -10,9 +10,10 @@ import pickle
 import numpy as np
 import torch
 
+from . import dist as cdist
 from . import ops
 from .misc import get_3d_indexgrid_ijk, to_np_torch_recursive
-from .staging import BatchStager
+from .staging import BatchStager, exchanged_batches
 
 _EXPORT_KEYS = (
     "device", "human_res", "obj_res", "normal_res", "spatial_res", "spatial_grid", "spatial_indexgrid",
@@ -22,6 +23,11 @@ _EXPORT_KEYS = (
 )
 
 _STAGING_BYTES = 64 << 20
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: coma_b200 runs on CUDA (sm_100a) only — no CPU fallback")
 
 
 def load_voxelgrid(gridsize=3.0, resolution=24, center=[0, 0, 0]):
@@ -83,19 +89,22 @@ class ComA_Occupancy:
         self.cache[f"{self.cache_count:05}"] = kwargs
         self.cache_count = len(self.cache.keys())
 
-    def aggregate_all_samples(self):
+    def aggregate_all_samples(self, exchange=False, group=None):
+        """exchange=True (H-sharded multi-GPU): the cache holds only the samples THIS rank loaded; the canonicalised vertices
+        are all-gathered so every rank scatters all samples into its rows, and `used_count` becomes the global count."""
         keys = list(self.cache.keys())
-        self._aggregate_samples([self.cache[k] for k in keys])
+        n_global = self._aggregate_samples([self.cache[k] for k in keys], exchange=exchange, group=group)
+        first = self.used_count
         for k in keys:
-            self.used[f"{self.used_count:05}"] = self.cache[k]
-            self.used_count = len(self.used.keys())
+            self.used[f"{len(self.used):05}"] = self.cache[k]
+        self.used_count = first + n_global
         self.cache = {}
         self.cache_count = 0
 
     def aggregate_single_sample(self, **kwargs):
         self._aggregate_samples([kwargs])
 
-    def _canonical_human_verts(self, sample):
+    def _canonical_human_verts(self, sample, all_rows=False):
         """Host part of aggregate_single_sample_for_occupancy (:274-288): invariants + subtraction in the input dtype."""
         human_verts, obj_verts, obj_normals = sample["human_verts"], sample["obj_verts"], sample["obj_normals"]
         out = None
@@ -112,22 +121,33 @@ class ComA_Occupancy:
             out = human_verts - obj_vert[None]
             assert out.shape[0] == self.human_res
         h0, h1 = self._human_slice
-        return out[h0:h1]
+        return out if all_rows else out[h0:h1]
 
-    def _aggregate_samples(self, samples):
-        if not samples:
-            return
-        if not self.spatial_occupancy_grids.is_cuda:
-            raise RuntimeError("ComA_Occupancy.aggregate: coma_b200 runs on CUDA (sm_100a) only — no CPU fallback")
+    def _aggregate_samples(self, samples, exchange=False, group=None):
+        exchange = exchange and cdist.is_distributed(group)
+        if not samples and not exchange:
+            return 0
+        _require_cuda(self.spatial_occupancy_grids, "ComA_Occupancy.aggregate")
         assert len(self.selected_obj_idxs) == 1
-        h_local = self._human_slice[1] - self._human_slice[0]
-        chunk = max(32, min(8192, (_STAGING_BYTES // (h_local * 12)) // 32 * 32))
-        chunk = min(chunk, (len(samples) + 31) // 32 * 32)
-        stager = BatchStager(dict(hvc=h_local), chunk, self.spatial_occupancy_grids.device)
-        getters = dict(hvc=lambda i: self._canonical_human_verts(samples[i]))
-        for n, b in stager.batches(getters, len(samples)):
-            self.aggregate_batch_for_occupancy(b["hvc"])
+        h0, h1 = self._human_slice
+        rows = self.human_res if exchange else max(h1 - h0, 1)
+        chunk = max(32, min(8192, (_STAGING_BYTES // (rows * 12)) // 32 * 32))
+        chunk = min(chunk, 256) if exchange else min(chunk, (len(samples) + 31) // 32 * 32)
+        stager = BatchStager(dict(hvc=self.human_res if exchange else h1 - h0), chunk, self.spatial_occupancy_grids.device)
+        getters = dict(hvc=lambda i: self._canonical_human_verts(samples[i], all_rows=exchange))
+        total = 0
+        if exchange:
+            for n, b in exchanged_batches(stager, getters, len(samples), group):
+                if n and h1 > h0:
+                    self.aggregate_batch_for_occupancy(b["hvc"][:, h0:h1].contiguous())
+                total += n
+        else:
+            for n, b in stager.batches(getters, len(samples)):
+                if h1 > h0:
+                    self.aggregate_batch_for_occupancy(b["hvc"])
+                total += n
         self.last_h2d_bytes = stager.h2d_bytes
+        return total
 
     def aggregate_batch_for_occupancy(self, human_verts_canon):
         """Device-resident batched form of :289-295: human_verts_canon [S,H_local,3] fp32 (already minus obj vertex 0)."""
@@ -144,19 +164,34 @@ class ComA_Occupancy:
         """:305-312 -> torch tensor [N,N,N] on the device. With an H-sharded instance the per-rank fields are combined
         by one MAX all-reduce (NaN-propagating, like torch.max over the full vertex axis)."""
         sel = None
+        h0, h1 = self._human_slice
         if human_indices is not None:
-            h0, h1 = self._human_slice
-            idx = np.asarray(list(human_indices), dtype=np.int64)
+            idx = np.asarray(list(human_indices), dtype=np.int64).reshape(-1)
+            if idx.size == 0:   # the reference's `grids[[]].max(dim=0)` raises on an empty selection
+                raise IndexError("max(): Expected reduction dim 0 to have non-zero size (empty human_indices)")
             idx = np.where(idx < 0, idx + self.human_res, idx)
             idx = idx[(idx >= h0) & (idx < h1)] - h0
+            # an H-sharded rank may own none of the selected vertices: an EMPTY selection (not "no selection") -> zero field,
+            # the identity of the MAX all-reduce below (normalised occupancies are >= 0)
             sel = torch.tensor(idx, dtype=torch.int64, device=self.spatial_occupancy_grids.device)
-        field = ops.occupancy_readout(self.spatial_occupancy_grids, sel)
-        return _all_reduce_max_nan(field, group)
+        if h1 > h0:
+            field = ops.occupancy_readout(self.spatial_occupancy_grids, sel)
+        else:
+            field = torch.zeros((self.N_x, self.N_y, self.N_z), dtype=torch.float32, device=self.spatial_occupancy_grids.device)
+        sharded = self._human_slice != (0, self.human_res)
+        return cdist.all_reduce_max_nan(field, group) if sharded else field
 
-    def export(self, save_pth=None):
+    def export(self, save_pth=None, group=None):
+        """utils/coma_occupancy.py:314-330. H-sharded instance: a COLLECTIVE call — rank 0 assembles the full
+        [H, Sg, Sg, Sg] grid on the host from the ranks' row blocks and returns / writes it; other ranks return None."""
         to_export = {}
+        sharded = self._human_slice != (0, self.human_res) and cdist.is_distributed(group)
         for k in _EXPORT_KEYS:
             v = getattr(self, k)
+            if sharded and k == "spatial_occupancy_grids":
+                v = cdist.gather_rows(v, self.human_res, group, dst=0)
+                if v is None:
+                    continue
             if isinstance(v, torch.Tensor):
                 v = v.detach().clone()
             elif isinstance(v, np.ndarray):
@@ -164,6 +199,10 @@ class ComA_Occupancy:
             elif isinstance(v, dict):
                 v = {kk: (vv.copy() if isinstance(vv, np.ndarray) else vv) for kk, vv in v.items()}
             to_export[k] = v
+        if sharded:
+            import torch.distributed as dist
+            if dist.get_rank(group) != 0:
+                return None
         to_export = to_np_torch_recursive(to_export, use_torch=False, device="cpu")
         if save_pth is None:
             return to_export
@@ -173,17 +212,12 @@ class ComA_Occupancy:
     def load(self, load_pth):
         with open(load_pth, "rb") as handle:
             loadables = pickle.load(handle)
+        h0, h1 = self._human_slice
+        if self._human_slice != (0, self.human_res) and "spatial_occupancy_grids" in loadables:
+            loadables["spatial_occupancy_grids"] = np.ascontiguousarray(loadables["spatial_occupancy_grids"][h0:h1])
         loadables = to_np_torch_recursive(loadables, use_torch=True, device=self.device)
         for k, v in loadables.items():
             setattr(self, k, v)
 
 
-def _all_reduce_max_nan(field, group=None):
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return field
-    # NCCL/gloo MAX does not define NaN ordering: carry NaN as +inf through the collective
-    nan = torch.isnan(field)
-    carried = torch.where(nan, torch.full_like(field, float("inf")), field)
-    dist.all_reduce(carried, op=dist.ReduceOp.MAX, group=group)
-    return torch.where(torch.isinf(carried) & (carried > 0), torch.full_like(carried, float("nan")), carried)
+_all_reduce_max_nan = cdist.all_reduce_max_nan   # round-1 name, kept for callers / tests

@@ -7,6 +7,7 @@
 namespace coma {
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static thread_local const char *g_last_kernel = "";
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -14,6 +15,7 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+void note_kernel(const char *name) { g_last_kernel = name; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace coma
 
@@ -21,4 +23,5 @@ extern "C" {
 int coma_b200_version(void) { return 100; }
 const char *coma_b200_last_error(void) { return coma::g_err; }
 int64_t coma_b200_launch_count(void) { return coma::g_launches.load(std::memory_order_relaxed); }
+const char *coma_b200_last_kernel(void) { return coma::g_last_kernel; }
 }

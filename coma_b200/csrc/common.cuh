@@ -15,6 +15,7 @@ constexpr int kNumSM = 148;  // B200
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+void note_kernel(const char *name);
 
 inline int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -23,6 +24,7 @@ inline int check_launch(const char *what) {
         return (int)e;
     }
     count_launch();
+    note_kernel(what);
     return 0;
 }
 

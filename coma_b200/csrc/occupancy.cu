@@ -118,7 +118,7 @@ extern "C" int coma_occupancy_accumulate(const float *hvc, int64_t S, int64_t H,
     const size_t V = (size_t)Sg * Sg * Sg;
     const size_t smem_small = 3 * sizeof(double) * Sg + sizeof(float) * V;
     cudaStream_t st = (cudaStream_t)stream;
-    const char *force = getenv("COMA_B200_OCC_PATH");  // experiments only: "smem" | "global"
+    static const char *const force = getenv("COMA_B200_OCC_PATH");  // experiments only ("smem" | "global"), read once per process
     // measured on B200 (tools/microbench.py, Sg = 30): RED.ADD into the L2-resident grid beats the shared-memory
     // histogram (5.0 vs 7.4 ms per 256 x 10475 vertex-samples), so the global path is the default for every size
     const bool use_smem = smem_small <= 200 * 1024 && (force && force[0] == 's');

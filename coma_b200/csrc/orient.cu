@@ -295,7 +295,7 @@ extern "C" int coma_orient_accumulate_f32(const float *hn, const float *on, int6
     const Vec3 p = normalize_host(p_host, epsf), sp = normalize_host(sub_p_host, epsf);
     const double sk = sqrt(1.4426950408889634) / sigma;
     const float skf = (float)sk, hp = (float)(sk * 1.5707963267948966);
-    const char *variant = getenv("COMA_B200_K3");  // experiments only: "v1" selects the scalar-FP32 kernel
+    static const char *const variant = getenv("COMA_B200_K3");  // experiments only (read once): "v1" selects the scalar-FP32 kernel
     const bool use_x2 = !(variant && variant[0] == 'v' && variant[1] == '1');
     // x3 (default: 8 bins/lane, 80 regs, 3 CTAs/SM) | x2 (128 regs, 2 CTAs/SM) | x4 (4 bins/lane, 4 CTAs/SM, two passes)
     const int x2_kind = (variant && variant[0] == 'x') ? atoi(variant + 1) : 3;

@@ -258,7 +258,7 @@ extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_
     if (vec4 && S <= 4 && ((uintptr_t)ov % 16 == 0)) {
         // measured (tools/k2_stream_bench.py): 4 rows/thread at 3 CTAs/SM (80 registers, no spills) 5.79-5.97 TB/s;
         // 4 CTAs/SM (64 registers, spills) 5.30; 2 rows/thread at 6 CTAs/SM 5.28.  COMA_B200_K2S selects the others.
-        const char *var = getenv("COMA_B200_K2S");
+        static const char *const var = getenv("COMA_B200_K2S");   // tuning switch, read once per process
         const int kind = var ? atoi(var) : 2;
         const int rh = (kind == 1) ? 2 : 4;
         dim3 vgrid((unsigned)((O + K2V_TO - 1) / K2V_TO), (unsigned)((H + 2 * rh - 1) / (2 * rh)));

@@ -55,12 +55,19 @@ class MeshNormals:
 _CACHE = {}
 
 
-def vertex_normals(verts, faces, eps=-1.0, device="cuda"):
-    """Convenience wrapper with a topology cache (keyed by the face array's bytes): numpy in, numpy fp64 out."""
+def mesh_normals_for(faces, num_verts, device="cuda"):
+    """Topology cache (keyed by the face array's bytes and the device): SMPL-X's corner list is built once per process."""
     f = np.ascontiguousarray(np.asarray(faces).reshape(-1, 3).astype(np.int64))
-    V = int(np.asarray(verts).shape[-2])
-    key = (hash(f.tobytes()), V, str(device))
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    key = (hash(f.tobytes()), int(num_verts), str(dev))
     mn = _CACHE.get(key)
     if mn is None:
-        mn = _CACHE[key] = MeshNormals(f, V, device)
-    return mn(verts, eps).cpu().numpy()
+        mn = _CACHE[key] = MeshNormals(f, int(num_verts), dev)
+    return mn
+
+
+def vertex_normals(verts, faces, eps=-1.0, device="cuda"):
+    """Convenience wrapper around `mesh_normals_for`: numpy in ([V,3] or [S,V,3]), numpy fp64 out."""
+    return mesh_normals_for(faces, int(np.asarray(verts).shape[-2]), device)(verts, eps).cpu().numpy()

@@ -112,6 +112,11 @@ class AdaptiveMaskInpaintPipeline:
                                  "`negative_prompt_embeds` [77, cross_dim]")
             prompt_embeds = self.text_encoder(prompt)
             negative_prompt_embeds = self.text_encoder(negative_prompt or "")
+        elif negative_prompt_embeds is None:
+            if self.text_encoder is None:
+                raise ValueError("`prompt_embeds` was given without `negative_prompt_embeds`: classifier-free guidance needs both "
+                                 "(or a registered text encoder to embed `negative_prompt`)")
+            negative_prompt_embeds = self.text_encoder(negative_prompt or "")
         pe = torch.as_tensor(prompt_embeds, device=self.dev).to(F16).reshape(1, L, -1)
         ne = torch.as_tensor(negative_prompt_embeds, device=self.dev).to(F16).reshape(1, L, -1)
         return torch.cat([ne.expand(B, -1, -1), pe.expand(B, -1, -1)], 0).reshape(2 * B * L, -1).contiguous()  # :536-552 order
@@ -203,7 +208,13 @@ class AdaptiveMaskInpaintPipeline:
         if H % 8 or W % 8:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {H} and {W}.")
         h, w = H // 8, W // 8
-        default_np = np.asarray(default_mask_image.convert("L") if hasattr(default_mask_image, "convert") else default_mask_image).astype(np.uint8)
+        if hasattr(default_mask_image, "convert"):
+            default_mask_image = default_mask_image.convert("L")
+            if default_mask_image.size != (W, H):   # the reference resizes the PIL mask with the image (prepare_mask_and_masked_image)
+                default_mask_image = default_mask_image.resize((W, H))
+        default_np = np.asarray(default_mask_image).astype(np.uint8)
+        if default_np.shape != (H, W):
+            raise ValueError(f"`default_mask_image` must be a single-channel [H, W] = [{H}, {W}] mask matching `image`, got {default_np.shape}")
         gens = generator if isinstance(generator, (list, tuple)) else [generator] * B
         if len(gens) != B:
             raise ValueError(f"You have passed a list of generators of length {len(gens)}, but requested an effective batch size of {B}.")

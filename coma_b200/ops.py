@@ -115,6 +115,10 @@ def occupancy_readout(grids, sel_idx=None):
     V = grids[0].numel()
     field = torch.empty(grids.shape[1:], dtype=torch.float32, device=grids.device)
     nsel = 0 if sel_idx is None else sel_idx.numel()
+    if sel_idx is not None and nsel == 0:
+        # an EMPTY selection: a 0-element tensor has a NULL data pointer, which the C ABI reads as "no selection, use every
+        # vertex" — pass a non-null dummy so the kernel really selects nothing (field = 0, grids still normalised in place)
+        sel_idx = torch.zeros(1, dtype=torch.int64, device=grids.device)
     with torch.cuda.device(grids.device):
         call("coma_occupancy_readout_f32", _ptr(grids), H, V, _ptr(sel_idx), nsel, _ptr(field), _stream())
     return field

@@ -27,11 +27,15 @@ class BatchStager:
             self.free = [torch.cuda.Event() for _ in range(2)]
             self.used_once = [False, False]
 
-    def batches(self, getters, S):
-        """getters = {name: callable(sample_index) -> array-like [rows,3]}; yields (n, {name: tensor[:n]})."""
+    def batches(self, getters, S, n_chunks=None, full=False):
+        """getters = {name: callable(sample_index) -> array-like [rows,3]}; yields (n, {name: tensor[:n]}).
+        `n_chunks` forces that many iterations (trailing ones with n = 0: a rank that ran out of samples still has to
+        take part in the exchange collectives); `full` yields the whole [chunk, rows, 3] buffers (fixed-size all-gather)."""
         compute = torch.cuda.current_stream(self.device) if self.is_cuda else None
-        for i, s0 in enumerate(range(0, S, self.chunk)):
-            b, n = i & 1, min(self.chunk, S - s0)
+        total = (S + self.chunk - 1) // self.chunk if n_chunks is None else int(n_chunks)
+        for i in range(total):
+            s0 = i * self.chunk
+            b, n = i & 1, max(0, min(self.chunk, S - s0))
             if self.is_cuda and self.used_once[b]:
                 self.free[b].synchronize()       # kernels that read dev[b] are done -> both buffers reusable
             for k in self.specs:
@@ -48,7 +52,30 @@ class BatchStager:
             else:
                 for k in self.specs:
                     self.dev[b][k][:n].copy_(self.pinned[b][k][:n])
-            yield n, {k: self.dev[b][k][:n] for k in self.specs}
+            yield n, {k: (self.dev[b][k] if full else self.dev[b][k][:n]) for k in self.specs}
             if self.is_cuda:
                 self.free[b].record(compute)
                 self.used_once[b] = True
+
+
+def exchanged_batches(stager, getters, n_local, group=None):
+    """Sample exchange for the ROW-sharded accumulators (ComA / ComA_Occupancy with `human_slice`): every rank stages the
+    samples IT loaded (full rows), the staged fp32 chunks are all-gathered over NVLink (a few hundred MB for a whole job)
+    and every rank receives all samples. Yields {name: [n_total, rows, 3]} with the ranks' samples concatenated in rank
+    order; the caller slices its rows. All ranks must iterate in lock-step (the chunk count is agreed by a MAX all-reduce)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = stager.device
+    chunk = stager.chunk
+    nmax = torch.tensor([(n_local + chunk - 1) // chunk], dtype=torch.int64, device=dev)
+    dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=group)
+    for n, bufs in stager.batches(getters, n_local, n_chunks=int(nmax.item()), full=True):
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
+        counts = [int(c.item()) for c in counts]
+        out = {}
+        for k, buf in bufs.items():
+            parts = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(parts, buf, group=group)
+            out[k] = torch.cat([parts[r][:counts[r]] for r in range(world) if counts[r] > 0]) if sum(counts) else buf[:0]
+        yield sum(counts), out

@@ -36,6 +36,9 @@ COMA_API int coma_b200_version(void);
 COMA_API const char *coma_b200_last_error(void);
 /* Number of kernel launches enqueued by this library in the calling process (bench.py's `gpu_launches`). */
 COMA_API int64_t coma_b200_launch_count(void);
+/* Name of the kernel (variant) the calling thread's most recent successful entry point enqueued — lets the parity tests
+ * assert WHICH kernel a shape was routed to (e.g. the S <= 4 streaming form of K2). Static storage, never NULL. */
+COMA_API const char *coma_b200_last_kernel(void);
 
 /* ---- K6: per-vertex normals of a fixed-topology mesh, batched over samples (sample ingest) -------------------
  * Replaces open3d TriangleMesh.compute_vertex_normals() + normalize_vectors_np(., eps) on every fitted SMPL-X mesh

@@ -86,7 +86,7 @@ def run_loop(unet_sd, vae_sd, ucfg, vcfg, image_u8, default_u8, ctx2, timesteps,
     return out, final
 
 
-def time_reference_loop(device, steps=50, strength=0.98, guidance=11.0, seed=0, dtype=torch.float16):
+def time_reference_loop(device, steps=50, strength=0.98, guidance=11.0, seed=0, dtype=torch.float16, sdpa=False):
     """Times the REFERENCE-SHAPED loop (batch 1 per call, fp16 torch eager: cuDNN convolutions, unfused
     baddbmm+softmax+bmm attention as under torch 1.13, VAE decode on EVERY step (:1028), cv2.dilate on the host with the
     D2H/H2D round trips) with the full-size restated models and seeded random weights — the 'reference single-GPU PyTorch
@@ -141,10 +141,14 @@ def time_reference_loop(device, steps=50, strength=0.98, guidance=11.0, seed=0, 
         out = so.vae_decode(vsd, latents / scal)
         return out
 
-    with torch.no_grad():
-        one_image()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        one_image()
-        torch.cuda.synchronize()
-        return time.perf_counter() - t0
+    so.USE_SDPA = bool(sdpa)   # True: F.scaled_dot_product_attention; False: torch-1.13-style unfused attention
+    try:
+        with torch.no_grad():
+            one_image()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            one_image()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+    finally:
+        so.USE_SDPA = False

@@ -24,6 +24,9 @@ VAE_CFG = dict(in_channels=3, latent_channels=4, block_out_channels=(128, 256, 5
                scaling_factor=0.18215)
 
 
+USE_SDPA = False   # set by inpaint_loop_oracle.time_reference_loop(sdpa=True)
+
+
 def tiny_unet_cfg():
     """Same topology at toy width — for fast tests."""
     return dict(in_channels=9, out_channels=4, block_out_channels=(32, 64, 64, 64), layers_per_block=2, heads=2,
@@ -210,6 +213,9 @@ def attention(xq, xkv, sd, name, heads, r, bias_out=True):
     q, k, v = r(_lin(xq, sd, name + ".to_q")), r(_lin(xkv, sd, name + ".to_k")), r(_lin(xkv, sd, name + ".to_v"))
     d = C // heads
     sp = lambda t: t.view(B, -1, heads, d).permute(0, 2, 1, 3)
+    if USE_SDPA and not r.on:   # timing baseline only (bench.py hoi reference arm, "sdpa" variant)
+        o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).permute(0, 2, 1, 3).reshape(B, S, C)
+        return _lin(o, sd, name + ".to_out.0")
     s = r(torch.matmul(sp(q), sp(k).transpose(-1, -2)) * d ** -0.5)
     p = r(torch.softmax(s, dim=-1))
     o = r(torch.matmul(p, sp(v)).permute(0, 2, 1, 3).reshape(B, S, C))

@@ -2,12 +2,14 @@
 # Multi-GPU fan-out of the inpainting stage — same role and flags as the reference's scripts/generation/inpaint.sh
 # (:72-196 flags, :207-268 one process per GPU with --parallel_idx i --parallel_num N). Here the fan-out is torchrun:
 # RANK / WORLD_SIZE become --parallel_idx / --parallel_num, so every rank takes the reference's contiguous work-list slice.
+# Every other flag is forwarded to src/generation/inpaint.py, including --no_skip_done, --segmenter module:factory (the
+# plug-in human segmenter) and --adaptive_mask_model_type stub.
 gpus=()
 pass=()
 while [[ $# -gt 0 ]]; do
   case $1 in
     --gpus) shift; while [[ $# -gt 0 && $1 != --* ]]; do gpus+=("$1"); shift; done ;;
-    --no_skip_done) shift ;;
+    --no_skip_done) pass+=("--no_skip_done"); shift ;;
     *) pass+=("$1"); shift ;;
   esac
 done

@@ -35,6 +35,10 @@ if __name__ == "__main__":
     p.add_argument("--enable_safety_checker", action="store_true")
     p.add_argument("--use_visualizer", action="store_true")
     p.add_argument("--skip_done", action="store_true", default=True)
+    p.add_argument("--no_skip_done", dest="skip_done", action="store_false", help="regenerate images that already exist")
+    p.add_argument("--segmenter", type=str, default=None,
+                   help="plug-in human segmenter 'module:factory' (see coma_b200.cli.inpaint.build_segmenter); required unless "
+                        "--adaptive_mask_model_type stub")
     p.add_argument("--verbose", action="store_true")
     p.add_argument("--seed", type=int, default=DEFAULT_SEED)
     p.add_argument("--parallel_num", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
@@ -50,7 +54,7 @@ if __name__ == "__main__":
     seed_everything(a.seed)
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     model_dir = a.model_dir or os.path.join("checkpoints", HF_MODEL_KEYS[a.ldm_model_key].replace("/", "--"))
-    pipe = set_pipeline(model_dir, a.adaptive_mask_model_type, a.default_ddim_steps, a.default_pointrend_threshold)
+    pipe = set_pipeline(model_dir, a.adaptive_mask_model_type, a.default_ddim_steps, a.default_pointrend_threshold, segmenter=a.segmenter)
     inpaint_human(pipe, clip_embedder(model_dir), a.num_img_per_combination, low(a.supercategories), low(a.categories), a.asset_render_dir,
                   a.asset_mask_dir, a.asset_seg_dir, a.prompts_dir, a.save_dir, a.negative_prompt,
                   dict(ddim_steps=a.default_ddim_steps, cfg_scale=a.default_cfg_scale, strength=a.default_strength,

@@ -71,6 +71,32 @@ def contact_case(name, H, O, N, S, size, thres, sigma, eps, ratio, adversarial, 
     print(name, "count sum", out["count"].sum(), "PH max", out["PH"].max(), "sig", out["sig_pairs"].sum())
 
 
+def pickle_case():
+    """Checkpoints WRITTEN BY THE REFERENCE (`export(save_pth)`, utils/coma.py:582-597 / utils/coma_occupancy.py:314-330) for
+    the contact_sigma02 / occupancy_small cases: the drop-in classes must load them (`--skip_done`, src/coma/inference.py) —
+    including the `functools.partial(utils.coma.negative_exp)` the reference pickles by reference."""
+    g = dict(np.load(os.path.join(HERE, "contact_sigma02.npz")))
+    size, thres, sigma, eps, ratio = (float(v) for v in g["params"])
+    S, H, _ = g["hv"].shape
+    coma = ComA(human_res=H, obj_res=g["ov"].shape[1], normal_res=int(g["N"]), spatial_res=0,
+                proximity_settings=dict(spatial_grid_size=size, spatial_grid_thres=thres), normal_gaussian_sigma=sigma, eps=eps, device="cpu")
+    for s in range(S):
+        coma.register_sample_to_cache(human_verts=g["hv"][s].copy(), human_normals=g["hn"][s].copy(), obj_verts=g["ov"][s].copy(),
+                                      obj_normals=g["on"][s].copy())
+    coma.aggregate_all_samples()
+    coma.export(save_pth=os.path.join(HERE, "ref_coma_sigma02.pickle"))
+    g = dict(np.load(os.path.join(HERE, "occupancy_small.npz")))
+    S, H, _ = g["hv"].shape
+    occ = ComA_Occupancy(scale_tolerance=float(g["tol"]), human_res=H, obj_res=g["ov"].shape[1], normal_res=0, spatial_res=int(g["Sg"]), device="cpu")
+    for s in range(S):
+        occ.register_sample_to_cache(human_verts=g["hv"][s].copy(), human_normals=g["hn"][s].copy(), obj_verts=g["ov"][s].copy(),
+                                     obj_normals=g["on"][s].copy())
+    occ.aggregate_all_samples()
+    occ.export(save_pth=os.path.join(HERE, "ref_occupancy_small.pickle"))
+    print("reference-written pickles:", os.path.getsize(os.path.join(HERE, "ref_coma_sigma02.pickle")),
+          os.path.getsize(os.path.join(HERE, "ref_occupancy_small.pickle")), "bytes")
+
+
 def occupancy_case(name, H, O, Sg, S, tol, seed):
     samples = synth.make_samples(S, H, O, seed)
     occ = ComA_Occupancy(scale_tolerance=tol, human_res=H, obj_res=O, normal_res=0, spatial_res=Sg, device="cpu")
@@ -108,6 +134,9 @@ def nearest_case(name, V, N, seed):
 
 
 if __name__ == "__main__":
+    if "--pickles-only" in sys.argv:
+        pickle_case()
+        sys.exit(0)
     contact_case("contact_small", H=24, O=12, N=250, S=5, size=0.07, thres=0.03, sigma=0.25, eps=1e-10, ratio=0.1,
                  adversarial=True, seed=42)
     contact_case("contact_sigma02", H=20, O=9, N=64, S=4, size=0.06, thres=0.24, sigma=0.2, eps=1e-10, ratio=0.3,
@@ -115,3 +144,4 @@ if __name__ == "__main__":
     occupancy_case("occupancy_small", H=40, O=6, Sg=12, S=4, tol=3.0, seed=5)
     occupancy_case("occupancy_s30", H=6, O=4, Sg=30, S=3, tol=3.0, seed=6)
     nearest_case("nearest_small", V=700, N=96, seed=11)
+    pickle_case()

@@ -1,4 +1,4 @@
-"""bench.py contract, CPU side: the reference arm runs without a GPU (it times the CPU restatement of the reference) and prints
+"""bench.py contract, CPU side: the reference arm runs without a GPU (it times the reference's own classes on the host cores) and prints
 ONE JSON line with the keys the driver reads; ranks other than 0 print nothing."""
 import json
 import os
@@ -6,6 +6,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def _run(env_extra):
@@ -24,7 +26,9 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["n_gpus"] == 2 and d["steps"] == 1
     assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["sample"]
+    from oracle import ref_loader
+    # the UNMODIFIED reference classes when they are staged (oracle/_ref; always in the dev container), else the C port
+    assert cb["kind"] == ("reference" if ref_loader.available() else "port") and cb["value"] == d["value"] and cb["sample"]
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     assert cb["cores"] == avail                                  # every available core despite OMP_NUM_THREADS=1
     assert "workload" in d["config"] and d["gpu_launches"] == 0

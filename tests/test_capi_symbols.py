@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(lib_path):
 
 def test_python_binding_covers_header(lib_path):
     from coma_b200 import _lib
-    bound = set(_lib.SIGNATURES) | {"coma_b200_version", "coma_b200_last_error", "coma_b200_launch_count"}
+    bound = set(_lib.SIGNATURES) | {"coma_b200_version", "coma_b200_last_error", "coma_b200_launch_count", "coma_b200_last_kernel"}
     assert bound == set(_declared())
     assert _lib.load() is not None
 

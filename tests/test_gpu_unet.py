@@ -196,6 +196,61 @@ def test_vae_tiny_decode_encode(dev):
     _close(_nchw(logvar, 2, 8, 8), rl, 1e-2)
 
 
+def test_unet_full_size_forward(dev):
+    """The SD-1.5-inpainting architecture at the benchmarked shape (9x64x64 latents, 77x768 context, 859.5 M parameters),
+    B = 2 (one CFG pair, different timesteps) against the fp16-emulating torch restatement, with the per-stage taps."""
+    from coma_b200.inpaint.unet import UNet
+    from oracle import sd_oracle as so
+    cfg = so.UNET_CFG
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = so.round_weights_fp16(so.make_unet_state_dict(0, cfg))
+    assert abs(sum(v.numel() for v in sd.values()) / 1e6 - 859.5) < 0.1
+    B, hw = 2, 64
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((B, 9, hw, hw), generator=g).half().float()
+    ctx = (torch.randn((B, 77, 768), generator=g)).half().float()
+    t = torch.tensor([981.0, 21.0])
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    with torch.no_grad():
+        ref, rtaps = so.unet_forward(sdd, x.to(dev), t.to(dev), ctx.to(dev), cfg, emulate_fp16=True, return_taps=True)
+    del sdd
+    net = UNet(sd, cfg, dev)
+    taps = {}
+    out = net.forward(_nhwc(x.to(dev)), t.to(dev), ctx.to(dev).reshape(B * 77, -1).half().contiguous(), 77, taps)
+    for k in ("down", "mid", "up"):
+        _close(_nchw(taps[k].t, B, taps[k].H, taps[k].W), rtaps[k], 1e-2)
+    _close(_nchw(out, B, hw, hw), ref, 1e-2)
+    rel_rms = ((_nchw(out, B, hw, hw) - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rel_rms < 2e-3, rel_rms
+
+
+def test_vae_full_size_decode_encode(dev):
+    """SD VAE (83.65 M parameters) at 64x64 latents <-> 512x512 images, B = 1, against the fp16-emulating restatement."""
+    from coma_b200.inpaint.vae import VAE
+    from oracle import sd_oracle as so
+    cfg = so.VAE_CFG
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = so.round_weights_fp16(so.make_vae_state_dict(1, cfg))
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn((1, 4, 64, 64), generator=g).half().float().to(dev)
+    vae = VAE(sd, cfg, dev)
+    img = vae.decode(_nhwc(z))
+    with torch.no_grad():
+        ref = so.vae_decode(sdd, z, cfg, emulate_fp16=True)
+    _close(_nchw(img.t, 1, 512, 512), ref, 1e-2)
+    rel_rms = ((_nchw(img.t, 1, 512, 512) - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rel_rms < 2e-3, rel_rms
+    x = torch.tanh(torch.randn((1, 3, 512, 512), generator=g)).half().float().to(dev)
+    mean, logvar = vae.encode_moments(_nhwc(x))
+    with torch.no_grad():
+        rm, rl = so.vae_encode_moments(sdd, x, cfg, emulate_fp16=True)
+    _close(_nchw(mean, 1, 64, 64), rm, 1e-2)
+    _close(_nchw(logvar, 1, 64, 64), rl, 1e-2)
+
+
 @pytest.mark.parametrize("C,Cout,H,B,groups,res", [(64, 96, 16, 2, 8, False), (128, 320, 32, 2, 32, True), (64, 72, 64, 1, 8, True),
                                                    (128, 128, 128, 1, 32, False), (320, 320, 64, 2, 32, True)])
 def test_groupnorm_from_conv_epilogue_stats(dev, C, Cout, H, B, groups, res):
