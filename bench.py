@@ -347,10 +347,11 @@ def occupancy_leg(args, dev, rank, world, barrier):
     occ = ComA_Occupancy(scale_tolerance=OCC["tol"], human_res=Hj, obj_res=4, normal_res=0, spatial_res=Sg, device=f"cuda:{dev.index}",
                          human_slice=(h0, h1))
     # device-resident canonical vertices of ALL samples for this rank's rows (fp32, already minus object vertex 0)
-    chunks = []
+    chunks, obj0 = [], None
     for c0 in range(0, S, 512):
         hv, _, ov, _ = synth.make_sample_arrays(min(512, S - c0), Hj, 4, seed=900 + c0 // 512, dtype=np.float64)
-        chunks.append(torch.from_numpy((hv[:, h0:h1] - ov[:, 0:1]).astype(np.float32)))
+        obj0 = ov[0, 0] if obj0 is None else obj0        # ONE object for the whole job (the reference asserts it never moves)
+        chunks.append(torch.from_numpy((hv[:, h0:h1] - obj0[None, None]).astype(np.float32)))
     hvc = torch.cat(chunks).to(dev)
     del chunks
 
@@ -392,10 +393,14 @@ def occupancy_leg(args, dev, rank, world, barrier):
     # end to end: host fp64 samples through the class API, 1/world of the samples loaded per rank
     S_e2e = min(S, args.occ_e2e_samples)
     mine_set = set(cdist.sample_shard(S_e2e, rank, world))
-    host = []
+    host, obj = [], None
     for c0 in range(0, S_e2e, 256):
         ss = synth.make_samples(min(256, S_e2e - c0), Hj, 4, seed=900 + c0 // 256)
-        host += [s for j, s in enumerate(ss) if (c0 + j) in mine_set]
+        obj = (ss[0]["obj_verts"], ss[0]["obj_normals"]) if obj is None else obj
+        for j, s in enumerate(ss):
+            if (c0 + j) in mine_set:
+                s["obj_verts"], s["obj_normals"] = obj
+                host.append(s)
     occ.spatial_occupancy_grids.zero_()
     occ.debug_obj_vert = occ.debug_obj_normal = None
     barrier()

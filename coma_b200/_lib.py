@@ -17,6 +17,7 @@ SIGNATURES = {
     "coma_vertex_normals_f64": [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _f64, _vp, _vp],
     "coma_nearest_vertex_f64": [_vp, _i64, _vp, _i64, _vp, _vp],
     "coma_pair_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp],
+    "coma_pair_accumulate_order_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _int, _vp, _vp, _vp],
     "coma_orient_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _vp, _vp],
     "coma_canonicalize_f32": [_vp, _i64, _vp, _i64, _f32p, _f32p, _f32, _vp, _vp],
     "coma_occupancy_accumulate": [_vp, _i64, _i64, _vp, _i64, _f64, _vp, _vp],

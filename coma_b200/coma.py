@@ -52,6 +52,11 @@ def _require_cuda(t, what):
 
 
 class ComA:
+    # Which device's arithmetic of the reference the bit-exact contact count follows: torch's CUDA reduction adds the squared
+    # distance as (x2+z2)+y2, its CPU reduction as (x2+y2)+z2 (include/coma_b200.h). The reference's production runs are
+    # device="cuda" (src/coma/extract_coma.py:329), hence the default; "cpu" reproduces a CPU run of the reference.
+    reference_sum_order = "cuda"
+
     def __init__(self, human_res: int, obj_res: int, normal_res: int, spatial_res: int, proximity_settings=dict(),
                  principle_vec=[0, 0, 1], sub_principle_vec=[0, 1, 0], rel_dist_method: str = "dist",
                  normal_gaussian_sigma: float = 0.1, eps: float = 1e-8, device: str = "cuda", human_slice=None):
@@ -164,7 +169,7 @@ class ComA:
         S = human_verts.shape[0]
         ps = self.proximity_settings
         ops.pair_accumulate(human_verts, obj_verts, ps["spatial_grid_thres"], ps["spatial_grid_size"],
-                            self.significant_contact_count, self.contact_dist_expectation_grid_nom)
+                            self.significant_contact_count, self.contact_dist_expectation_grid_nom, sum_order=self.reference_sum_order)
         self.contact_dist_expectation_grid_denom += float(S)  # `+= 1.0` per sample (:291): a scalar in disguise
         grid = self.canon_normal_grid
         if grid.dtype != torch.float64:  # after load() the reference's grid is fp32 (:606)

@@ -118,10 +118,10 @@ class ComA_Occupancy:
                 self.debug_obj_normal = obj_normal
             else:
                 assert np.allclose(self.debug_obj_normal, obj_normal)
-            out = human_verts - obj_vert[None]
-            assert out.shape[0] == self.human_res
-        h0, h1 = self._human_slice
-        return out if all_rows else out[h0:h1]
+            assert human_verts.shape[0] == self.human_res
+            h0, h1 = (0, self.human_res) if all_rows else self._human_slice
+            out = human_verts[h0:h1] - obj_vert[None]     # only the rows this rank owns (elementwise: same values as slicing after)
+        return out
 
     def _aggregate_samples(self, samples, exchange=False, group=None):
         exchange = exchange and cdist.is_distributed(group)

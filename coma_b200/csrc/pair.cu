@@ -18,12 +18,25 @@
 
 namespace coma {
 
+// Squared distance in the association of the reference's `torch.sum(torch.square(h - o), dim=-1)`:
+//   ORD = 0  ((x^2 + y^2) + z^2)  ATen's CPU reduction (and numpy);
+//   ORD = 1  ((x^2 + z^2) + y^2)  ATen's CUDA reduction over a contiguous last dimension of 3 — measured on B200 with torch 2.11
+//            for fp32 and fp64 and every shape tried (tools/probe_torch_cuda_semantics.py, profiles/r02_torch_cuda_semantics.json).
+// The reference's production runs are device="cuda" (src/coma/extract_coma.py:329), so ORD = 1 is what `ComA` uses by default;
+// ORD = 0 reproduces the CPU reference (the committed CPU-generated golden vectors) bit for bit.
+template <int ORD>
+__device__ __forceinline__ float sq_dist(float dx, float dy, float dz) {
+    const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
+    return ORD == 0 ? __fadd_rn(__fadd_rn(xx, yy), zz) : __fadd_rn(__fadd_rn(xx, zz), yy);
+}
+
 constexpr int K2_TO = 128;  // object columns per CTA (= blockDim.x)
 constexpr int K2_TY = 2;    // blockDim.y
 constexpr int K2_RH = 8;    // human rows per thread
 constexpr int K2_TH = K2_TY * K2_RH;
 constexpr int K2_CS = 16;   // samples staged per chunk
 
+template <int ORD>
 __global__ void __launch_bounds__(K2_TO *K2_TY, 4)
     pair_accumulate_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float sq_thres,
                            float neg_log2e_over_size, float *__restrict__ count, float *__restrict__ nom) {
@@ -73,7 +86,7 @@ __global__ void __launch_bounds__(K2_TO *K2_TY, 4)
             for (int r = 0; r < K2_RH; ++r) {
                 const float4 hvv = sh[cs][ty * K2_RH + r];
                 const float dx = __fsub_rn(hvv.x, ox), dy = __fsub_rn(hvv.y, oy), dz = __fsub_rn(hvv.z, oz);
-                const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                const float sq = sq_dist<ORD>(dx, dy, dz);
                 cnt[r] += (sq < sq_thres) ? 1.0f : 0.0f;
                 float d, e;
                 asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(sq));
@@ -106,10 +119,11 @@ constexpr int K2V_TH = K2V_TY * K2V_RH;
 constexpr int K2V_TO = K2V_TX * 4;
 constexpr int K2V_CS = 4;              // samples staged per chunk
 
+template <int ORD>
 __device__ __forceinline__ void pair_update(float hx, float hy, float hz, float ox, float oy, float oz, float sq_thres,
                                             float nl2e, float &cnt, float &acc) {
     const float dx = __fsub_rn(hx, ox), dy = __fsub_rn(hy, oy), dz = __fsub_rn(hz, oz);
-    const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const float sq = sq_dist<ORD>(dx, dy, dz);
     cnt += (sq < sq_thres) ? 1.0f : 0.0f;
     float d, e;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(sq));
@@ -117,6 +131,7 @@ __device__ __forceinline__ void pair_update(float hx, float hy, float hz, float 
     acc += e;
 }
 
+template <int ORD>
 __global__ void __launch_bounds__(K2V_TX *K2V_TY, 4)
     pair_accumulate_vec4_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float sq_thres,
                                 float nl2e, float *__restrict__ count, float *__restrict__ nom) {
@@ -162,10 +177,10 @@ __global__ void __launch_bounds__(K2V_TX *K2V_TY, 4)
 #pragma unroll
             for (int r = 0; r < K2V_RH; ++r) {
                 const float4 hvv = sh[cs][ty * K2V_RH + r];
-                pair_update(hvv.x, hvv.y, hvv.z, ox.x, oy.x, oz.x, sq_thres, nl2e, cnt[r].x, acc[r].x);
-                pair_update(hvv.x, hvv.y, hvv.z, ox.y, oy.y, oz.y, sq_thres, nl2e, cnt[r].y, acc[r].y);
-                pair_update(hvv.x, hvv.y, hvv.z, ox.z, oy.z, oz.z, sq_thres, nl2e, cnt[r].z, acc[r].z);
-                pair_update(hvv.x, hvv.y, hvv.z, ox.w, oy.w, oz.w, sq_thres, nl2e, cnt[r].w, acc[r].w);
+                pair_update<ORD>(hvv.x, hvv.y, hvv.z, ox.x, oy.x, oz.x, sq_thres, nl2e, cnt[r].x, acc[r].x);
+                pair_update<ORD>(hvv.x, hvv.y, hvv.z, ox.y, oy.y, oz.y, sq_thres, nl2e, cnt[r].y, acc[r].y);
+                pair_update<ORD>(hvv.x, hvv.y, hvv.z, ox.z, oy.z, oz.z, sq_thres, nl2e, cnt[r].z, acc[r].z);
+                pair_update<ORD>(hvv.x, hvv.y, hvv.z, ox.w, oy.w, oz.w, sq_thres, nl2e, cnt[r].w, acc[r].w);
             }
         }
         __syncthreads();
@@ -188,7 +203,7 @@ __global__ void __launch_bounds__(K2V_TX *K2V_TY, 4)
 // contiguous bytes) and the 4 human vertices as warp-uniform broadcast loads, everything else is the accumulator stream
 // (LDG.128 / STG.128, evict-first). With nothing to synchronise on, CTAs are pure load -> math -> store pipelines and the
 // SM keeps >100 KB of accumulator traffic in flight.
-template <int RH, int MINB>
+template <int RH, int MINB, int ORD>
 __global__ void __launch_bounds__(256, MINB)
     pair_accumulate_stream_kernel(const float *__restrict__ hv, const float *__restrict__ ov, int S, int H, int O, float sq_thres,
                                   float nl2e, float *__restrict__ count, float *__restrict__ nom) {
@@ -212,10 +227,10 @@ __global__ void __launch_bounds__(256, MINB)
             const int h = min(h0 + r, H - 1);
             const float *hp = hv + ((size_t)s * H + h) * 3;
             const float hx = __ldg(hp), hy = __ldg(hp + 1), hz = __ldg(hp + 2);
-            pair_update(hx, hy, hz, a.x, a.y, a.z, sq_thres, nl2e, cnt[r].x, acc[r].x);
-            pair_update(hx, hy, hz, a.w, b.x, b.y, sq_thres, nl2e, cnt[r].y, acc[r].y);
-            pair_update(hx, hy, hz, b.z, b.w, c.x, sq_thres, nl2e, cnt[r].z, acc[r].z);
-            pair_update(hx, hy, hz, c.y, c.z, c.w, sq_thres, nl2e, cnt[r].w, acc[r].w);
+            pair_update<ORD>(hx, hy, hz, a.x, a.y, a.z, sq_thres, nl2e, cnt[r].x, acc[r].x);
+            pair_update<ORD>(hx, hy, hz, a.w, b.x, b.y, sq_thres, nl2e, cnt[r].y, acc[r].y);
+            pair_update<ORD>(hx, hy, hz, b.z, b.w, c.x, sq_thres, nl2e, cnt[r].z, acc[r].z);
+            pair_update<ORD>(hx, hy, hz, c.y, c.z, c.w, sq_thres, nl2e, cnt[r].w, acc[r].w);
         }
     }
 #pragma unroll
@@ -241,12 +256,13 @@ static float squared_threshold_f32(float thres) {
 
 }  // namespace coma
 
-extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_t S, int64_t H, int64_t O, float thres,
-                                        float grid_size, float *count, float *nom, coma_stream_t stream) {
+extern "C" int coma_pair_accumulate_order_f32(const float *hv, const float *ov, int64_t S, int64_t H, int64_t O, float thres,
+                                              float grid_size, int sum_order, float *count, float *nom, coma_stream_t stream) {
     using namespace coma;
     COMA_REQUIRE(hv && ov && count && nom, "null pointer");
     COMA_REQUIRE(S >= 0 && H > 0 && O > 0, "bad sizes");
     COMA_REQUIRE(H * O < (int64_t)1 << 40 && S < (int64_t)1 << 30, "sizes out of range");
+    COMA_REQUIRE(sum_order == COMA_SUM_ORDER_TORCH_CPU || sum_order == COMA_SUM_ORDER_TORCH_CUDA, "sum_order must be 0 (torch CPU) or 1 (torch CUDA)");
     if (S == 0) return 0;
     dim3 block(K2_TO, K2_TY);
     dim3 grid((unsigned)((O + K2_TO - 1) / K2_TO), (unsigned)((H + K2_TH - 1) / K2_TH));
@@ -255,28 +271,31 @@ extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_
     const float nl2e = (float)(-1.4426950408889634 / (double)grid_size);
     const float sq_thres = squared_threshold_f32(thres);
     const bool vec4 = (O % 4 == 0) && (((uintptr_t)count | (uintptr_t)nom) % 16 == 0);
+    const bool cu = sum_order == COMA_SUM_ORDER_TORCH_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
     if (vec4 && S <= 4 && ((uintptr_t)ov % 16 == 0)) {
         // measured (tools/k2_stream_bench.py): 4 rows/thread at 3 CTAs/SM (80 registers, no spills) 5.79-5.97 TB/s;
-        // 4 CTAs/SM (64 registers, spills) 5.30; 2 rows/thread at 6 CTAs/SM 5.28.  COMA_B200_K2S selects the others.
-        static const char *const var = getenv("COMA_B200_K2S");   // tuning switch, read once per process
-        const int kind = var ? atoi(var) : 2;
-        const int rh = (kind == 1) ? 2 : 4;
-        dim3 vgrid((unsigned)((O + K2V_TO - 1) / K2V_TO), (unsigned)((H + 2 * rh - 1) / (2 * rh)));
+        // 4 CTAs/SM (64 registers, spills) 5.30; 2 rows/thread at 6 CTAs/SM 5.28.
+        dim3 vgrid((unsigned)((O + K2V_TO - 1) / K2V_TO), (unsigned)((H + 2 * 4 - 1) / (2 * 4)));
         COMA_REQUIRE(vgrid.y <= 65535u, "H too large for one launch");
-        cudaStream_t st = (cudaStream_t)stream;
-        if (kind == 1) pair_accumulate_stream_kernel<2, 6><<<vgrid, 256, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
-        else if (kind == 2) pair_accumulate_stream_kernel<4, 3><<<vgrid, 256, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
-        else pair_accumulate_stream_kernel<4, 4><<<vgrid, 256, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
+        if (cu) pair_accumulate_stream_kernel<4, 3, 1><<<vgrid, 256, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
+        else pair_accumulate_stream_kernel<4, 3, 0><<<vgrid, 256, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
         return check_launch("pair_accumulate_stream_kernel");
     }
     if (vec4) {
         dim3 vblock(K2V_TX, K2V_TY);
         dim3 vgrid((unsigned)((O + K2V_TO - 1) / K2V_TO), (unsigned)((H + K2V_TH - 1) / K2V_TH));
         COMA_REQUIRE(vgrid.y <= 65535u, "H too large for one launch (max 524280)");
-        pair_accumulate_vec4_kernel<<<vgrid, vblock, 0, (cudaStream_t)stream>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e,
-                                                                                count, nom);
+        if (cu) pair_accumulate_vec4_kernel<1><<<vgrid, vblock, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
+        else pair_accumulate_vec4_kernel<0><<<vgrid, vblock, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
         return check_launch("pair_accumulate_vec4_kernel");
     }
-    pair_accumulate_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
+    if (cu) pair_accumulate_kernel<1><<<grid, block, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
+    else pair_accumulate_kernel<0><<<grid, block, 0, st>>>(hv, ov, (int)S, (int)H, (int)O, sq_thres, nl2e, count, nom);
     return check_launch("pair_accumulate_kernel");
+}
+
+extern "C" int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_t S, int64_t H, int64_t O, float thres,
+                                        float grid_size, float *count, float *nom, coma_stream_t stream) {
+    return coma_pair_accumulate_order_f32(hv, ov, S, H, O, thres, grid_size, COMA_SUM_ORDER_TORCH_CPU, count, nom, stream);
 }

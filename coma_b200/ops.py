@@ -21,16 +21,21 @@ def nearest_vertex(pts, verts):
     return out
 
 
-def pair_accumulate(hv, ov, thres, grid_size, count, nom):
-    """utils/coma.py:284-291 over S samples. hv [S,H,3], ov [S,O,3] f32; count, nom [H,O] f32 updated in place."""
+SUM_ORDERS = {"cpu": 0, "cuda": 1}
+
+
+def pair_accumulate(hv, ov, thres, grid_size, count, nom, sum_order="cpu"):
+    """utils/coma.py:284-291 over S samples. hv [S,H,3], ov [S,O,3] f32; count, nom [H,O] f32 updated in place.
+    sum_order: which torch device's association of `sum(square(h - o), -1)` the squared distance follows ("cpu": (x2+y2)+z2,
+    "cuda": (x2+z2)+y2) — decides `count` for pairs within one ulp of the threshold (include/coma_b200.h)."""
     S, H, _ = hv.shape
     O = ov.shape[1]
     assert ov.shape[0] == S and count.shape == (H, O) and nom.shape == (H, O)
     for t, n in ((hv, "hv"), (ov, "ov"), (count, "count"), (nom, "nom")):
         _chk(t, torch.float32, n)
     with torch.cuda.device(hv.device):
-        call("coma_pair_accumulate_f32", _ptr(hv), _ptr(ov), S, H, O, float(thres), float(grid_size), _ptr(count), _ptr(nom),
-             _stream())
+        call("coma_pair_accumulate_order_f32", _ptr(hv), _ptr(ov), S, H, O, float(thres), float(grid_size), SUM_ORDERS[sum_order],
+             _ptr(count), _ptr(nom), _stream())
 
 
 def orient_accumulate(hn, on, grid, sigma, eps, p, sub_p, PH, PO):

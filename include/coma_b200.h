@@ -64,6 +64,15 @@ COMA_API int coma_nearest_vertex_f64(const double *pts, int64_t N, const double 
  * hv [S,H,3] f32, ov [S,O,3] f32; count, nom [H,O] f32 (accumulated in place). count is bit-exact. */
 COMA_API int coma_pair_accumulate_f32(const float *hv, const float *ov, int64_t S, int64_t H, int64_t O, float thres,
                              float grid_size, float *count, float *nom, coma_stream_t stream);
+/* Same, with the association of the 3-term sum chosen explicitly. The reference's `torch.sum(torch.square(.), dim=-1)` adds
+ * ((x^2+y^2)+z^2) on the CPU but ((x^2+z^2)+y^2) on CUDA (measured on B200, torch 2.11: tools/probe_torch_cuda_semantics.py);
+ * the two differ in the last bit of the squared distance for ~23 % of random pairs and hence in `count` for pairs within one
+ * ulp of the threshold. TORCH_CUDA is bit-exact against the reference run with device="cuda" (its production setting,
+ * src/coma/extract_coma.py:329), TORCH_CPU against device="cpu" (= coma_pair_accumulate_f32, the CPU-generated goldens). */
+#define COMA_SUM_ORDER_TORCH_CPU 0
+#define COMA_SUM_ORDER_TORCH_CUDA 1
+COMA_API int coma_pair_accumulate_order_f32(const float *hv, const float *ov, int64_t S, int64_t H, int64_t O, float thres,
+                                            float grid_size, int sum_order, float *count, float *nom, coma_stream_t stream);
 
 /* ---- K3: relative-orientation soft histograms --------------------------------------------------------------------
  * Replaces canonicalize_a_wrt_b_to_p (utils/coma.py:123-172, both calls :295-309) + geodesic_gaussian_scores

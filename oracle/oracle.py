@@ -51,6 +51,7 @@ def lib():
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.oracle_nearest_vertex_f64.argtypes = [_f64p, _i64, _f64p, _i64, _i64p]
         L.oracle_pair_accumulate_f32.argtypes = [_f32p, _f32p, _i64, _i64, _i64, ctypes.c_float, ctypes.c_float, _f32p, _f32p]
+        L.oracle_pair_accumulate_order_f32.argtypes = [_f32p, _f32p, _i64, _i64, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_int, _f32p, _f32p]
         L.oracle_canonicalize_f32.argtypes = [_f32p, _i64, _f32p, _i64, _f32p, _f32p, ctypes.c_float, _f32p]
         L.oracle_orient_accumulate.argtypes = [_f32p, _f32p, _i64, _i64, _i64, _f64p, _i64, ctypes.c_double, ctypes.c_double,
                                                _f32p, _f32p, _f32p, _f32p]
@@ -133,14 +134,16 @@ def nearest_vertex(pts, verts):
     return out
 
 
-def pair_accumulate(hv, ov, thres, grid_size, count=None, nom=None):
+def pair_accumulate(hv, ov, thres, grid_size, count=None, nom=None, sum_order="cpu"):
+    """utils/coma.py:284-291. sum_order: the association of torch.sum(torch.square(h - o), -1) — "cpu" ((xx+yy)+zz, also numpy) or
+    "cuda" ((xx+zz)+yy, ATen's CUDA reduction as measured on B200; pinned by tests/golden/cuda_*.npz)."""
     hv, ov = to_f32(hv), to_f32(ov)
     S, H, _ = hv.shape
     O = ov.shape[1]
     count = np.zeros((H, O), np.float32) if count is None else count
     nom = np.zeros((H, O), np.float32) if nom is None else nom
-    lib().oracle_pair_accumulate_f32(_p(hv, _f32p), _p(ov, _f32p), S, H, O, np.float32(thres), np.float32(grid_size),
-                                     _p(count, _f32p), _p(nom, _f32p))
+    lib().oracle_pair_accumulate_order_f32(_p(hv, _f32p), _p(ov, _f32p), S, H, O, np.float32(thres), np.float32(grid_size),
+                                           {"cpu": 0, "cuda": 1}[sum_order], _p(count, _f32p), _p(nom, _f32p))
     return count, nom
 
 

@@ -20,8 +20,8 @@ def install():
     def _np(t):
         return t.detach().cpu().numpy()
 
-    def pair_accumulate(hv, ov, thres, grid_size, count, nom):
-        c, n = oracle.pair_accumulate(_np(hv), _np(ov), thres, grid_size)
+    def pair_accumulate(hv, ov, thres, grid_size, count, nom, sum_order="cpu"):
+        c, n = oracle.pair_accumulate(_np(hv), _np(ov), thres, grid_size, sum_order=sum_order)
         count += torch.from_numpy(c)
         nom += torch.from_numpy(n)
 

@@ -102,7 +102,7 @@ def test_extract_and_inference_end_to_end(tmp_path):
     exp = pickle.load(open(f"{root}/extracted/BEHAVE/backpack/asset0/qual:backpack_human_contact:carrying a backpack.pickle", "rb"))
     hv = np.stack([s["human_verts"][hidx] for s in samples])
     ov = np.stack([s["obj_verts"] for s in samples])
-    cnt, nom = oracle.pair_accumulate(hv, ov, 0.24, 0.07)
+    cnt, nom = oracle.pair_accumulate(hv, ov, 0.24, 0.07, sum_order="cuda")   # ComA's default: the CUDA reference's association
     assert exp["used_count"] == 5
     np.testing.assert_array_equal(exp["significant_contact_count"], cnt)
     np.testing.assert_allclose(exp["contact_dist_expectation_grid_nom"], nom, rtol=1e-4)

@@ -112,9 +112,10 @@ def test_pair_threshold_boundary_ulps(dev):
 
 
 # K2 streaming form (S <= 4 samples per launch, O % 4 == 0): the kernel the north star's ">= 90 % of HBM" target is quoted on
+@pytest.mark.parametrize("order", ["cpu", "cuda"])
 @pytest.mark.parametrize("S", [1, 2, 3, 4])
 @pytest.mark.parametrize("H,O", [(37, 4), (1003, 180), (301, 1500), (8, 256)])
-def test_pair_accumulate_stream_kernel_oracle(dev, S, H, O):
+def test_pair_accumulate_stream_kernel_oracle(dev, S, H, O, order):
     """One to four samples per launch route to pair_accumulate_stream_kernel (asserted through the C ABI): counts bit-exact
     vs the oracle, proximity sums at 1e-4, ragged H (not a multiple of the 8-row CTA tile) and H*O tails included.
     Launch-by-launch accumulation over a longer sample list == the reference's one-sample-per-call loop (utils/coma.py:257-264)."""
@@ -124,11 +125,11 @@ def test_pair_accumulate_stream_kernel_oracle(dev, S, H, O):
     samples = synth.make_samples(3 * S + 1, H, O, seed=H + O + S) + synth.make_adversarial_samples(H, O, thres, seed=S)
     hv = np.stack([s["human_verts"] for s in samples]).astype(np.float32)
     ov = np.stack([s["obj_verts"] for s in samples]).astype(np.float32)
-    rc, rn = oracle.pair_accumulate(hv, ov, thres, 0.15)
+    rc, rn = oracle.pair_accumulate(hv, ov, thres, 0.15, sum_order=order)
     count = torch.zeros((H, O), device=dev)
     nom = torch.zeros((H, O), device=dev)
     for s0 in range(0, len(samples), S):
-        ops.pair_accumulate(_t(hv[s0:s0 + S], dev), _t(ov[s0:s0 + S], dev), thres, 0.15, count, nom)
+        ops.pair_accumulate(_t(hv[s0:s0 + S], dev), _t(ov[s0:s0 + S], dev), thres, 0.15, count, nom, sum_order=order)
         assert _lib.last_kernel() == "pair_accumulate_stream_kernel"
     np.testing.assert_array_equal(count.cpu().numpy(), rc)
     np.testing.assert_allclose(nom.cpu().numpy(), rn, rtol=RTOL, atol=0)
@@ -167,9 +168,16 @@ def test_pair_stream_kernel_threshold_boundary_ulps(dev, S, thres):
     rc, rn = oracle.pair_accumulate(hv, ov, thres, 0.07)
     np.testing.assert_array_equal(count.cpu().numpy(), rc)
     np.testing.assert_allclose(nom.cpu().numpy(), rn, rtol=RTOL, atol=0)
-    # and the same verdicts from torch's own fp32 evaluation (sqrt then compare), the reference's literal expression
+    # the same verdicts from torch's OWN fp32 evaluation of the reference's literal expression (sqrt, then compare): on the CPU it
+    # matches sum_order="cpu"; on this GPU ATen's reduction adds (x2+z2)+y2, which is sum_order="cuda"
+    hv_t, ov_t = torch.from_numpy(hv), torch.from_numpy(ov)
+    d_cpu = torch.sqrt(torch.sum(torch.square(hv_t[:, :, None, :] - ov_t[:, None, :, :]), dim=-1))
+    assert torch.equal(count.cpu(), (d_cpu < thres).sum(0).float())
+    c2, n2 = torch.zeros((H, 4), device=dev), torch.zeros((H, 4), device=dev)
+    ops.pair_accumulate(_t(hv, dev), _t(ov, dev), thres, 0.07, c2, n2, sum_order="cuda")
     d = torch.sqrt(torch.sum(torch.square(_t(hv, dev)[:, :, None, :] - _t(ov, dev)[:, None, :, :]), dim=-1))
-    assert torch.equal(count, (d < thres).sum(0).float())
+    assert torch.equal(c2, (d < thres).sum(0).float())
+    np.testing.assert_array_equal(c2.cpu().numpy(), oracle.pair_accumulate(hv, ov, thres, 0.07, sum_order="cuda")[0])
     assert 0 < rc.sum() < rc.size * S
 
 
@@ -270,9 +278,12 @@ def test_occupancy_oracle(dev, H, Sg, S, tol):
 
 
 # --------------------------------------------------------------------------------------------- classes / read-outs
-@pytest.mark.parametrize("name", ["contact_small", "contact_sigma02"])
+@pytest.mark.parametrize("name", ["contact_small", "contact_sigma02", "cuda_contact_small", "cuda_contact_sigma02", "cuda_contact_boundary"])
 def test_coma_class_matches_reference_golden(dev, golden_dir, name, tmp_path):
-    """The reference's call sequence of tests/golden/make_golden.py replayed through the drop-in class."""
+    """The reference's call sequence of tests/golden/make_golden.py (reference on the CPU) / make_golden_cuda.py (reference with
+    device="cuda" on a B200) replayed through the drop-in class."""
+    if not os.path.exists(os.path.join(golden_dir, name + ".npz")):
+        pytest.skip(f"{name}.npz not generated yet")
     from utils.coma import ComA, get_aggregated_contact
     g = _load(golden_dir, name)
     size, thres, sigma, eps, ratio = (float(v) for v in g["params"])
@@ -281,6 +292,7 @@ def test_coma_class_matches_reference_golden(dev, golden_dir, name, tmp_path):
     coma = ComA(human_res=H, obj_res=O, normal_res=N, spatial_res=0,
                 proximity_settings=dict(spatial_grid_size=size, spatial_grid_thres=thres),
                 normal_gaussian_sigma=sigma, eps=eps, device="cuda")
+    coma.reference_sum_order = "cuda" if name.startswith("cuda_") else "cpu"   # which device of the reference wrote the fixture
     for s in range(S):
         coma.register_sample_to_cache(human_verts=g["hv"][s], human_normals=g["hn"][s], obj_verts=g["ov"][s], obj_normals=g["on"][s])
     assert coma.cache_count == S
@@ -368,14 +380,14 @@ def test_full_size_properties(dev):
     H, O, S = 10475, 1500, 8
     hv, hn, ov, on = (torch.from_numpy(a).to(dev) for a in synth.make_sample_arrays(S, H, O, seed=1))
     c1, n1 = torch.zeros((H, O), device=dev), torch.zeros((H, O), device=dev)
-    ops.pair_accumulate(hv, ov, 0.05, 0.15, c1, n1)
+    ops.pair_accumulate(hv, ov, 0.05, 0.15, c1, n1, sum_order="cuda")
     # (1) integer histogram is invariant to the sample order; (2) additive over batches
     perm = torch.randperm(S, device=dev)
     c2, n2 = torch.zeros_like(c1), torch.zeros_like(n1)
-    ops.pair_accumulate(hv[perm].contiguous(), ov[perm].contiguous(), 0.05, 0.15, c2, n2)
+    ops.pair_accumulate(hv[perm].contiguous(), ov[perm].contiguous(), 0.05, 0.15, c2, n2, sum_order="cuda")
     assert torch.equal(c1, c2)
     torch.testing.assert_close(n1, n2, rtol=1e-5, atol=0)
-    # (3) against a direct torch evaluation of the same formula on a slice of rows (fp32 eager, same op order)
+    # (3) against a direct torch-CUDA evaluation of the reference's expression on a slice of rows (sum_order="cuda")
     rows = slice(5000, 5064)
     d = torch.sqrt(torch.sum(torch.square(hv[:, rows, None, :] - ov[:, None, :, :]), dim=-1))
     assert torch.equal(c1[rows], (d < 0.05).sum(0).float())

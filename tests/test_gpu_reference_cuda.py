@@ -46,9 +46,13 @@ def test_contact_reference_cpu_vs_cuda_vs_kernels(ref, H, O, N, S, thres, sigma)
     r_cuda = rc.export()
     mine_c = _run(ComA, samples, device="cuda", **kw)
     mine = mine_c.export()
-    # (1) the reference against itself: integer counts agree bit for bit across devices (recorded in DESIGN §4)
-    np.testing.assert_array_equal(r_cpu["significant_contact_count"], r_cuda["significant_contact_count"])
-    np.testing.assert_allclose(r_cpu["prob_grid_canon_human_wrt_obj"], r_cuda["prob_grid_canon_human_wrt_obj"], rtol=1e-5, atol=1e-30)
+    # (1) the reference against itself. ATen adds the 3-term sums as (x2+z2)+y2 on CUDA and (x2+y2)+z2 on the CPU, so the two runs
+    # of the SAME reference may disagree on `count` for pairs within an ulp of the threshold (tests/golden/cuda_contact_boundary.npz
+    # holds such pairs) and agree on the fp32 grids only to ~3e-5 relative (canonical normals differ in the last bit, amplified by
+    # 1/sigma^2). The drop-in class follows the CUDA run (ComA.reference_sum_order = "cuda"); "cpu" reproduces the CPU run.
+    np.testing.assert_allclose(r_cpu["prob_grid_canon_human_wrt_obj"], r_cuda["prob_grid_canon_human_wrt_obj"], rtol=1e-4, atol=1e-30)
+    mine_cpu = _run(type("ComACpuOrder", (ComA,), dict(reference_sum_order="cpu")), samples, device="cuda", **kw).export()
+    np.testing.assert_array_equal(mine_cpu["significant_contact_count"], r_cpu["significant_contact_count"])
     # (2) kernels against the CUDA reference
     np.testing.assert_array_equal(mine["significant_contact_count"], r_cuda["significant_contact_count"])
     np.testing.assert_array_equal(mine["contact_dist_expectation_grid_denom"], r_cuda["contact_dist_expectation_grid_denom"])
