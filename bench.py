@@ -495,12 +495,13 @@ def main():
     def step(timed):
         # K2 + K3 over all samples of the step, accumulators in registers, one launch each (== ComA.aggregate_batch_for_contact)
         ops.pair_accumulate(hv, ov, PRESET["spatial_grid_thres"], PRESET["spatial_grid_size"], coma.significant_contact_count,
-                            coma.contact_dist_expectation_grid_nom)
+                            coma.contact_dist_expectation_grid_nom, sum_order=coma.reference_sum_order)
         coma.contact_dist_expectation_grid_denom += float(S)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         ops.orient_accumulate(hn, on, grid, PRESET["normal_gaussian_sigma"], PRESET["eps"], [0, 0, 1], [0, 1, 0],
-                              coma.prob_grid_canon_human_wrt_obj, coma.prob_grid_canon_obj_wrt_human)
+                              coma.prob_grid_canon_human_wrt_obj, coma.prob_grid_canon_obj_wrt_human,
+                              bin_perm=coma._bin_perm, drop_bits=coma.orient_drop_bits, sum_order=coma.reference_sum_order)
         b.record()
         if timed:
             k3_events.append((a, b))
@@ -548,14 +549,14 @@ def main():
         hv1 = torch.from_numpy(host_block[0][:1].astype(np.float32)).to(dev)
         ov1 = torch.from_numpy(host_block[2][:1].astype(np.float32)).to(dev)
         for i in range(nsets):
-            ops.pair_accumulate(hv1, ov1, 0.05, 0.15, cs[i], ns[i])
+            ops.pair_accumulate(hv1, ov1, 0.05, 0.15, cs[i], ns[i], sum_order="cuda")
         assert _lib.last_kernel() == "pair_accumulate_stream_kernel"
         torch.cuda.synchronize()
         n_k2 = 8 * nsets
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(n_k2):   # back-to-back launches over rotating accumulator sets: average launch duration
-            ops.pair_accumulate(hv1, ov1, 0.05, 0.15, cs[i % nsets], ns[i % nsets])
+            ops.pair_accumulate(hv1, ov1, 0.05, 0.15, cs[i % nsets], ns[i % nsets], sum_order="cuda")
         b.record()
         torch.cuda.synchronize()
         k2_ms = a.elapsed_time(b) / n_k2

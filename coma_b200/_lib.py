@@ -19,7 +19,10 @@ SIGNATURES = {
     "coma_pair_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp],
     "coma_pair_accumulate_order_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _int, _vp, _vp, _vp],
     "coma_orient_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _vp, _vp],
+    "coma_orient_accumulate_cone_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _int, _int, _vp, _vp, _vp],
+    "coma_orient_bin_patches": [_c.POINTER(_c.c_double), _i64, _c.POINTER(_c.c_int32)],
     "coma_canonicalize_f32": [_vp, _i64, _vp, _i64, _f32p, _f32p, _f32, _vp, _vp],
+    "coma_canonicalize_order_f32": [_vp, _i64, _vp, _i64, _f32p, _f32p, _f32, _int, _vp, _vp],
     "coma_occupancy_accumulate": [_vp, _i64, _i64, _vp, _i64, _f64, _vp, _vp],
     "coma_normalize_contact_readout_f32": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
     "coma_significant_pairs": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp],

@@ -56,6 +56,9 @@ class ComA:
     # distance as (x2+z2)+y2, its CPU reduction as (x2+y2)+z2 (include/coma_b200.h). The reference's production runs are
     # device="cuda" (src/coma/extract_coma.py:329), hence the default; "cpu" reproduces a CPU run of the reference.
     reference_sum_order = "cuda"
+    # K3: scores below 2^-orient_drop_bits (bins far outside the Gaussian's cone) are not evaluated; each bin stays within
+    # S * 2^-32 absolute of the dense evaluation (include/coma_b200.h). 0 = dense kernel.
+    orient_drop_bits = 32
 
     def __init__(self, human_res: int, obj_res: int, normal_res: int, spatial_res: int, proximity_settings=dict(),
                  principle_vec=[0, 0, 1], sub_principle_vec=[0, 1, 0], rel_dist_method: str = "dist",
@@ -68,7 +71,10 @@ class ComA:
         self.normal_res, self.spatial_res = normal_res, spatial_res
 
         x, y, z = get_uniform_points_on_sphere(num_points=normal_res)
-        self.canon_normal_grid = torch.tensor(np.stack([x, y, z], axis=-1)).to(device)  # fp64 [N,3], :204-205
+        grid_host = np.stack([x, y, z], axis=-1)
+        self.canon_normal_grid = torch.tensor(grid_host).to(device)  # fp64 [N,3], :204-205
+        # compact 32-bin patches of the bin centres for the cone-limited K3 kernel (host-side, once per instance)
+        self._bin_perm = ops.bin_patches(grid_host, device) if 0 < normal_res <= 256 else None
 
         if self.spatial_res == 0:
             H, O, N = self._human_slice[1] - self._human_slice[0], obj_res, normal_res
@@ -176,7 +182,8 @@ class ComA:
             grid = grid.double()
         ops.orient_accumulate(human_normals, obj_normals, grid.contiguous(), self.normal_gaussian_sigma, self.eps,
                               self.principle_vec.tolist(), self.sub_principle_vec.tolist(),
-                              self.prob_grid_canon_human_wrt_obj, self.prob_grid_canon_obj_wrt_human)
+                              self.prob_grid_canon_human_wrt_obj, self.prob_grid_canon_obj_wrt_human,
+                              bin_perm=self._bin_perm, drop_bits=self.orient_drop_bits, sum_order=self.reference_sum_order)
 
     # ------------------------------------------------------------------------------------------------- read-outs
     def _contact_weights(self):

@@ -20,7 +20,11 @@
 // branch), so the canonical normals are bit-identical to torch's fp32 result.  The reference then promotes to fp64 for
 // dot/acos/exp and rounds each per-sample sum to fp32; here those run in fp32, which keeps every grid entry within
 // ~4e-5 relative of the reference for any sigma (tolerance 1e-4).
+#include <math.h>
 #include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -30,19 +34,26 @@ struct Vec3 {
     float x, y, z;
 };
 
-// v / (sqrt((x^2+y^2)+z^2) + eps)   — utils/transformations.py:14-17
-__device__ __forceinline__ Vec3 normalize_ref(Vec3 v, float eps) {
-    float n = __fadd_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z))), eps);
+// The reference's 3-term `torch.sum(., dim=-1)`: (x+y)+z on the CPU, (x+z)+y on CUDA (ord = 1; measured on B200, see pair.cu).
+// A runtime flag: the prologue runs once per (pair, sample) against hundreds of bin evaluations, two selects per sum are free.
+__device__ __forceinline__ float sum3_ref(float x, float y, float z, int ord) {
+    const float m = ord ? z : y, l = ord ? y : z;
+    return __fadd_rn(__fadd_rn(x, m), l);
+}
+
+// v / (sqrt(sum3(x^2, y^2, z^2)) + eps)   — utils/transformations.py:14-17
+__device__ __forceinline__ Vec3 normalize_ref(Vec3 v, float eps, int ord = 0) {
+    float n = __fadd_rn(__fsqrt_rn(sum3_ref(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), ord)), eps);
     return Vec3{__fdiv_rn(v.x, n), __fdiv_rn(v.y, n), __fdiv_rn(v.z, n)};
 }
 
-__device__ __forceinline__ float dot_ref(Vec3 a, Vec3 b) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+__device__ __forceinline__ float dot_ref(Vec3 a, Vec3 b, int ord = 0) {
+    return sum3_ref(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), ord);
 }
 
 // canonicalize_a_wrt_b_to_p for one (a, b) pair; a, b, p, sp already normalised — utils/coma.py:135-170
-__device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp, float eps) {
-    const float b_dot_p = dot_ref(b, p), a_dot_b = dot_ref(a, b), a_dot_p = dot_ref(a, p), a_dot_sp = dot_ref(a, sp);
+__device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp, float eps, int ord = 0) {
+    const float b_dot_p = dot_ref(b, p, ord), a_dot_b = dot_ref(a, b, ord), a_dot_p = dot_ref(a, p, ord), a_dot_sp = dot_ref(a, sp, ord);
     const float one_plus = __fadd_rn(1.0f, b_dot_p);
     const bool replace = one_plus < eps;  // :143
     // rows of the reference's "cross product matrix" (:149-155): [b0,-b2,b1], [b2,0,-b0], [-b1,0,0]
@@ -50,7 +61,7 @@ __device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp
     bxp.x = __fadd_rn(__fadd_rn(__fmul_rn(b.x, p.x), __fmul_rn(-b.z, p.y)), __fmul_rn(b.y, p.z));
     bxp.y = __fadd_rn(__fadd_rn(__fmul_rn(b.z, p.x), __fmul_rn(0.0f, p.y)), __fmul_rn(-b.x, p.z));
     bxp.z = __fadd_rn(__fadd_rn(__fmul_rn(-b.y, p.x), __fmul_rn(0.0f, p.y)), __fmul_rn(0.0f, p.z));
-    const float a_dot_bxp = dot_ref(a, bxp);  // :159
+    const float a_dot_bxp = dot_ref(a, bxp, ord);  // :159
     const float av[3] = {a.x, a.y, a.z}, bv[3] = {b.x, b.y, b.z}, pv[3] = {p.x, p.y, p.z}, sv[3] = {sp.x, sp.y, sp.z};
     const float xv[3] = {bxp.x, bxp.y, bxp.z};
     float f[3];
@@ -64,7 +75,7 @@ __device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp
         if (replace) v = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, a_dot_sp), sv[k]), av[k]);  // :145,:169
         f[k] = v;
     }
-    const float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(f[0], f[0]), __fmul_rn(f[1], f[1])), __fmul_rn(f[2], f[2])));
+    const float n = __fsqrt_rn(sum3_ref(__fmul_rn(f[0], f[0]), __fmul_rn(f[1], f[1]), __fmul_rn(f[2], f[2]), ord));
     return Vec3{__fdiv_rn(f[0], n), __fdiv_rn(f[1], n), __fdiv_rn(f[2], n)};  // :170
 }
 
@@ -103,7 +114,7 @@ constexpr int K3_WARPS = 8;
 template <int NB>
 __global__ void __launch_bounds__(K3_WARPS * 32)
     orient_accumulate_kernel(const float *__restrict__ hn, const float *__restrict__ on, int S, int H, int O,
-                             const double *__restrict__ grid, int N, int n_base, float sk, float hp_sk, float eps, Vec3 p,
+                             const double *__restrict__ grid, int N, int n_base, float sk, float hp_sk, float eps, int ord, Vec3 p,
                              Vec3 sp, float *__restrict__ PH, float *__restrict__ PO) {
     __shared__ __align__(16) float cnbuf[K3_WARPS][32][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -129,10 +140,10 @@ __global__ void __launch_bounds__(K3_WARPS * 32)
         if (lane < ns) {
             const float *ph3 = hn + ((size_t)(s0 + lane) * H + h) * 3;
             const float *po3 = on + ((size_t)(s0 + lane) * O + o) * 3;
-            const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps);
-            const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps);
-            const Vec3 ch = canonicalize_ref(a, b, p, sp, eps);  // human normal w.r.t. object normal (:295-301)
-            const Vec3 co = canonicalize_ref(b, a, p, sp, eps);  // object normal w.r.t. human normal (:302-309)
+            const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps, ord);
+            const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps, ord);
+            const Vec3 ch = canonicalize_ref(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
+            const Vec3 co = canonicalize_ref(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
             float4 *dst = reinterpret_cast<float4 *>(&cnbuf[warp][lane][0]);
             dst[0] = make_float4(ch.x, ch.y, ch.z, co.x);
             dst[1] = make_float4(co.y, co.z, 0.f, 0.f);
@@ -189,7 +200,7 @@ __device__ __forceinline__ float2 orient_score2(float2 c, float2 nsk2, float2 hp
 template <int K3_NP, int MINB>
 __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
     orient_accumulate_kernel_x2(const float *__restrict__ hn, const float *__restrict__ on, int S, int H, int O,
-                                const double *__restrict__ grid, int N, int n_base, float sk, float hp_sk, float eps, Vec3 p,
+                                const double *__restrict__ grid, int N, int n_base, float sk, float hp_sk, float eps, int ord, Vec3 p,
                                 Vec3 sp, float *__restrict__ PH, float *__restrict__ PO) {
     // per warp: 32 samples x {chx,chx,chy,chy | chz,chz,cox,cox | coy,coy,coz,coz}: broadcast LDS.128 yields (v,v) pairs
     __shared__ __align__(16) float4 cnbuf[K3_WARPS][32][3];
@@ -218,10 +229,10 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
         if (lane < ns) {
             const float *ph3 = hn + ((size_t)(s0 + lane) * H + h) * 3;
             const float *po3 = on + ((size_t)(s0 + lane) * O + o) * 3;
-            const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps);
-            const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps);
-            const Vec3 ch = canonicalize_ref(a, b, p, sp, eps);  // human normal w.r.t. object normal (:295-301)
-            const Vec3 co = canonicalize_ref(b, a, p, sp, eps);  // object normal w.r.t. human normal (:302-309)
+            const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps, ord);
+            const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps, ord);
+            const Vec3 ch = canonicalize_ref(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
+            const Vec3 co = canonicalize_ref(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
             cnbuf[warp][lane][0] = make_float4(ch.x, ch.x, ch.y, ch.y);
             cnbuf[warp][lane][1] = make_float4(ch.z, ch.z, co.x, co.x);
             cnbuf[warp][lane][2] = make_float4(co.y, co.y, co.z, co.z);
@@ -256,14 +267,178 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
     }
 }
 
+// ---- cone-limited variant (default whenever sigma is small enough) ------------------------------------------------------
+// exp(-g^2/sigma^2) with sigma = 0.25 rad is below 2^-32 for every bin further than gamma = sigma*sqrt(32 ln 2) = 1.18 rad from
+// the canonical normal: ~70 % of the 250 bins of a (pair, sample, histogram). This kernel never evaluates them:
+//   * bins are grouped into <= 8 PATCHES of <= 32 spatially compact bins (coma_orient_bin_patches, host; any partition is
+//     correct, compactness only buys speed); lane l owns bin l of every patch, so G and both accumulators stay in registers;
+//   * per chunk of 32 samples, lane l canonicalises sample l (as before) and tests its two directions against every patch's
+//     bounding cap: patch j is needed iff dir . centre_j > cos(gamma + r_j). A ballot turns that into the list of samples that
+//     need patch j, and the warp walks the list TWO SAMPLES PER STEP (packed FP32x2 math), reading the directions back as
+//     warp-broadcast LDS.128;
+//   * inside the cone acos(c)^2 is an analytic function of t = 1 - c: acos(1-t)^2 = t R(t), R a degree 3-6 minimax polynomial
+//     on [0, tmax] (tools/fit_acos2.py) — no square root: ONE MUFU (ex2) and 3 + DEG + 2 FMA-pipe ops per evaluation instead of
+//     two MUFU and ~15. t is clamped at tmax = 1 - cos(gamma), so a bin of a needed patch that lies outside the cone receives
+//     2^-drop_bits instead of its true (smaller) score.
+// Contract: every term the dense kernel would add and this one drops or clamps is < 2^-drop_bits (default 2^-32), i.e. after S
+// samples each bin is within S * 2^-32 ABSOLUTE of the dense result — < 2e-7 of the pair's largest bin in the worst case (some
+// bin of a pair always holds >= 0.002 S) — on top of the same ~5e-6 relative evaluation error as before.
+struct ConeParams {
+    float c[7];      // R's coefficients times -log2(e)/sigma^2: score = 2^(t * sum c[k] t^k)
+    float tmax;      // 1 - cos(gamma)
+    float gamma;     // cone half-angle (rad)
+    int npatch;
+};
+
+// One patch, one histogram, one chunk: `cnt` directions were compacted into `list` as sample PAIRS, component-interleaved
+// (x1,x2,y1,y2 | z1,z2,-,-), so one LDS.128 + one LDS.64 deliver the operands of three packed FFMA2 (pair x broadcast G).
+template <int DEG>
+__device__ __forceinline__ float cone_steps(int cnt, const float4 *__restrict__ list, float ngx, float ngy, float ngz, float acc,
+                                            const ConeParams &cp) {
+    const float2 c0 = f2(cp.c[0]), c1 = f2(cp.c[1]), c2 = f2(cp.c[2]), c3 = f2(cp.c[3]), c4 = f2(cp.c[DEG >= 4 ? 4 : 0]),
+                 c5 = f2(cp.c[DEG >= 5 ? 5 : 0]), c6 = f2(cp.c[DEG >= 6 ? 6 : 0]);
+    auto score2 = [&](float2 t) -> float2 {
+        t = make_float2(fminf(t.x, cp.tmax), fminf(t.y, cp.tmax));
+        float2 r = DEG == 6 ? c6 : DEG == 5 ? c5 : DEG == 4 ? c4 : c3;
+        if (DEG >= 6) r = __ffma2_rn(r, t, c5);
+        if (DEG >= 5) r = __ffma2_rn(r, t, c4);
+        if (DEG >= 4) r = __ffma2_rn(r, t, c3);
+        r = __ffma2_rn(r, t, c2);
+        r = __ffma2_rn(r, t, c1);
+        r = __ffma2_rn(r, t, c0);
+        const float2 a = __fmul2_rn(t, r);
+        return make_float2(mufu_ex2(a.x), mufu_ex2(a.y));
+    };
+    int k = 0;
+    for (; k + 1 < cnt; k += 2) {   // cnt is warp-uniform: no divergence
+        const float4 xy = list[k];                                               // pair k/2: (x1, x2, y1, y2)
+        const float2 z = *reinterpret_cast<const float2 *>(&list[k + 1]);        //           (z1, z2)
+        const float2 t = __ffma2_rn(make_float2(xy.x, xy.y), f2(ngx),
+                                    __ffma2_rn(make_float2(xy.z, xy.w), f2(ngy), __ffma2_rn(z, f2(ngz), f2(1.0f))));   // 1 - G.n
+        const float2 s = score2(t);
+        acc += s.x;
+        acc += s.y;
+    }
+    if (k < cnt) {   // odd tail: only the first half of the last pair is live
+        const float4 xy = list[k];
+        const float z = list[k + 1].x;
+        const float t = fmaf(xy.x, ngx, fmaf(xy.z, ngy, fmaf(z, ngz, 1.0f)));
+        acc += score2(make_float2(t, t)).x;
+    }
+    return acc;
+}
+
+// Compacts the directions of the lanes with `need` into the warp's pair list; returns their number (warp-uniform).
+__device__ __forceinline__ int cone_compact(bool need, Vec3 d, float *__restrict__ list, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (need) {
+        const int pos = __popc(m & ((1u << lane) - 1u));
+        float *e = list + (pos >> 1) * 8 + (pos & 1);   // two float4 per pair
+        e[0] = d.x;
+        e[2] = d.y;
+        e[4] = d.z;
+    }
+    __syncwarp();
+    return __popc(m);
+}
+
+constexpr int K3C_PATCHES = 8;
+
+template <int DEG, int MINB>
+__global__ void __launch_bounds__(K3_WARPS * 32, MINB)
+    orient_accumulate_cone_kernel(const float *__restrict__ hn, const float *__restrict__ on, int S, int H, int O,
+                                  const double *__restrict__ grid, int N, const int *__restrict__ perm, ConeParams cp, float eps, int ord,
+                                  Vec3 p, Vec3 sp, float *__restrict__ PH, float *__restrict__ PO) {
+    __shared__ float4 caps[K3C_PATCHES];                             // (centre, cos(min(gamma + radius, pi))) per patch
+    __shared__ __align__(16) float4 lists[K3_WARPS][2][32];          // per warp, per histogram: 16 sample pairs x 2 float4
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long pair = (long long)blockIdx.x * K3_WARPS + warp;
+
+    // bin owned by this lane in patch j (-1: none); re-derived where needed instead of being kept in 8 registers
+    auto bin_of = [&](int j) -> int {
+        const int slot = 32 * j + lane;
+        return j < cp.npatch ? (perm ? __ldg(perm + slot) : (slot < N ? slot : -1)) : -1;
+    };
+    float ngx[K3C_PATCHES], ngy[K3C_PATCHES], ngz[K3C_PATCHES];
+#pragma unroll
+    for (int j = 0; j < K3C_PATCHES; ++j) {
+        const int n = bin_of(j);
+        ngx[j] = n >= 0 ? -(float)grid[3 * n + 0] : 0.f;   // fp64 bin centres, rounded once; stored negated (t = 1 - G.n)
+        ngy[j] = n >= 0 ? -(float)grid[3 * n + 1] : 0.f;
+        ngz[j] = n >= 0 ? -(float)grid[3 * n + 2] : 0.f;
+    }
+    // bounding cap of every patch (all warps of the CTA own the same bins: warp w handles patch w)
+#pragma unroll
+    for (int j = 0; j < K3C_PATCHES; ++j) {
+        if (j == warp && j < cp.npatch) {
+            const bool ok = bin_of(j) >= 0;
+            float sx = warp_sum(-ngx[j]), sy = warp_sum(-ngy[j]), sz = warp_sum(-ngz[j]);
+            const float nrm = sqrtf(sx * sx + sy * sy + sz * sz);
+            if (nrm > 1e-6f) { sx /= nrm; sy /= nrm; sz /= nrm; } else { sx = 0.f; sy = 0.f; sz = 1.f; }
+            float cmin = ok ? -(ngx[j] * sx + ngy[j] * sy + ngz[j] * sz) : 1.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+            const float reach = cp.gamma + acosf(fminf(fmaxf(cmin, -1.0f), 1.0f)) + 4e-3f;   // + margin for fp32 rounding of the test
+            if (lane == 0) caps[j] = make_float4(sx, sy, sz, reach >= 3.14159f ? -2.0f : cosf(reach));
+        }
+    }
+    __syncthreads();
+    if (pair >= (long long)H * O) return;   // after the only block-wide barrier; below only __syncwarp
+    const int h = (int)(pair / O), o = (int)(pair % O);
+
+    float accH[K3C_PATCHES], accO[K3C_PATCHES];
+    float *ph = PH + (size_t)pair * N, *po = PO + (size_t)pair * N;
+#pragma unroll
+    for (int j = 0; j < K3C_PATCHES; ++j) {
+        const int n = bin_of(j);
+        accH[j] = n >= 0 ? ph[n] : 0.f;
+        accO[j] = n >= 0 ? po[n] : 0.f;
+    }
+
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int ns = min(32, S - s0);
+        Vec3 ch = {0.f, 0.f, 1.f}, co = {0.f, 0.f, 1.f};
+        if (lane < ns) {
+            const float *ph3 = hn + ((size_t)(s0 + lane) * H + h) * 3;
+            const float *po3 = on + ((size_t)(s0 + lane) * O + o) * 3;
+            const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps, ord);
+            const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps, ord);
+            ch = canonicalize_ref(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
+            co = canonicalize_ref(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
+        }
+#pragma unroll
+        for (int j = 0; j < K3C_PATCHES; ++j) {
+            if (j < cp.npatch) {
+                const float4 cap = caps[j];
+                // a NaN direction (degenerate normal) must poison its bins like in the reference: !(x <= w) keeps it "needed"
+                const bool needH = lane < ns && !(fmaf(ch.x, cap.x, fmaf(ch.y, cap.y, ch.z * cap.z)) <= cap.w);
+                const bool needO = lane < ns && !(fmaf(co.x, cap.x, fmaf(co.y, cap.y, co.z * cap.z)) <= cap.w);
+                const int cntH = cone_compact(needH, ch, reinterpret_cast<float *>(lists[warp][0]), lane);
+                const int cntO = cone_compact(needO, co, reinterpret_cast<float *>(lists[warp][1]), lane);
+                accH[j] = cone_steps<DEG>(cntH, lists[warp][0], ngx[j], ngy[j], ngz[j], accH[j], cp);
+                accO[j] = cone_steps<DEG>(cntO, lists[warp][1], ngx[j], ngy[j], ngz[j], accO[j], cp);
+                __syncwarp();   // the lists are rewritten for the next patch
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K3C_PATCHES; ++j) {
+        const int n = bin_of(j);
+        if (n >= 0) {
+            ph[n] = accH[j];
+            po[n] = accO[j];
+        }
+    }
+}
+
 __global__ void canonicalize_kernel(const float *__restrict__ a, int A, const float *__restrict__ b, int B, Vec3 p, Vec3 sp,
-                                    float eps, float *__restrict__ out) {
+                                    float eps, int ord, float *__restrict__ out) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= (long long)A * B) return;
     const int i = (int)(q / B), j = (int)(q % B);
-    const Vec3 an = normalize_ref(Vec3{a[3 * i], a[3 * i + 1], a[3 * i + 2]}, eps);
-    const Vec3 bn = normalize_ref(Vec3{b[3 * j], b[3 * j + 1], b[3 * j + 2]}, eps);
-    const Vec3 f = canonicalize_ref(an, bn, p, sp, eps);
+    const Vec3 an = normalize_ref(Vec3{a[3 * i], a[3 * i + 1], a[3 * i + 2]}, eps, ord);
+    const Vec3 bn = normalize_ref(Vec3{b[3 * j], b[3 * j + 1], b[3 * j + 2]}, eps, ord);
+    const Vec3 f = canonicalize_ref(an, bn, p, sp, eps, ord);
     out[3 * q + 0] = f.x;
     out[3 * q + 1] = f.y;
     out[3 * q + 2] = f.z;
@@ -281,20 +456,24 @@ static Vec3 normalize_host(const float *v, float eps) {
 
 }  // namespace coma
 
-extern "C" int coma_orient_accumulate_f32(const float *hn, const float *on, int64_t S, int64_t H, int64_t O,
-                                          const double *grid, int64_t N, double sigma, double eps, const float *p_host,
-                                          const float *sub_p_host, float *PH, float *PO, coma_stream_t stream) {
-    using namespace coma;
-    COMA_REQUIRE(hn && on && grid && p_host && sub_p_host && PH && PO, "null pointer");
-    COMA_REQUIRE(S >= 0 && H > 0 && O > 0 && N > 0, "bad sizes");
-    COMA_REQUIRE(sigma > 0.0, "normal_gaussian_sigma must be positive");
-    COMA_REQUIRE(H * O < (int64_t)1 << 34, "H*O out of range");
-    if (S == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const float epsf = (float)eps;
-    const Vec3 p = normalize_host(p_host, epsf), sp = normalize_host(sub_p_host, epsf);
-    const double sk = sqrt(1.4426950408889634) / sigma;
-    const float skf = (float)sk, hp = (float)(sk * 1.5707963267948966);
+namespace coma {
+// acos(1-t)^2 = t R(t): generated by tools/fit_acos2.py --emit (R minimax on [0, tmax], max |dR| listed)
+struct Acos2Fit {
+    float tmax;
+    int deg;
+    float c[7];
+};
+static const Acos2Fit kAcos2Fits[] = {
+    {0.10f, 3, {1.999999991e+00f, 3.333361032e-01f, 8.875197085e-02f, 3.071955545e-02f, 0.000000000e+00f, 0.000000000e+00f, 0.000000000e+00f}},   // |dR| <= 8.8e-09
+    {0.20f, 4, {2.000000003e+00f, 3.333325774e-01f, 8.891860234e-02f, 2.816586494e-02f, 1.237028604e-02f, 0.000000000e+00f, 0.000000000e+00f}},   // |dR| <= 3.1e-09
+    {0.32f, 4, {2.000000038e+00f, 3.333275810e-01f, 8.902846103e-02f, 2.740019559e-02f, 1.403493065e-02f, 0.000000000e+00f, 0.000000000e+00f}},   // |dR| <= 3.8e-08
+    {0.46f, 5, {1.999999985e+00f, 3.333355296e-01f, 8.883518296e-02f, 2.904723379e-02f, 8.295234272e-03f, 7.016475926e-03f, 0.000000000e+00f}},   // |dR| <= 1.5e-08
+    {0.64f, 5, {1.999999854e+00f, 3.333489836e-01f, 8.861818956e-02f, 3.026155092e-02f, 5.534580991e-03f, 9.209118341e-03f, 0.000000000e+00f}},   // |dR| <= 1.5e-07
+    {0.86f, 6, {2.000000152e+00f, 3.333169853e-01f, 8.917436458e-02f, 2.672181738e-02f, 1.573746627e-02f, -4.379195104e-03f, 6.805618570e-03f}},   // |dR| <= 1.5e-07
+};
+
+static int launch_dense(const float *hn, const float *on, int64_t S, int64_t H, int64_t O, const double *grid, int64_t N, float skf,
+                        float hp, float epsf, int ord, Vec3 p, Vec3 sp, float *PH, float *PO, cudaStream_t st) {
     static const char *const variant = getenv("COMA_B200_K3");  // experiments only (read once): "v1" selects the scalar-FP32 kernel
     const bool use_x2 = !(variant && variant[0] == 'v' && variant[1] == '1');
     // x3 (default: 8 bins/lane, 80 regs, 3 CTAs/SM) | x2 (128 regs, 2 CTAs/SM) | x4 (4 bins/lane, 4 CTAs/SM, two passes)
@@ -307,10 +486,10 @@ extern "C" int coma_orient_accumulate_f32(const float *hn, const float *on, int6
         const int nb = (int)((rem > 256 ? 256 : rem) + 31) / 32;
 #define LAUNCH(NBV)                                                                                                   \
     orient_accumulate_kernel<NBV><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N,     \
-                                                                     (int)n_base, skf, hp, epsf, p, sp, PH, PO)
+                                                                     (int)n_base, skf, hp, epsf, ord, p, sp, PH, PO)
 #define LAUNCH_X2(NP, MINB)                                                                                          \
     orient_accumulate_kernel_x2<NP, MINB><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, \
-                                                                            (int)n_base, skf, hp, epsf, p, sp, PH, PO)
+                                                                            (int)n_base, skf, hp, epsf, ord, p, sp, PH, PO)
         if (use_x2) {
             if (x2_kind == 3) LAUNCH_X2(4, 3);
             else if (x2_kind == 4) LAUNCH_X2(2, 4);
@@ -320,18 +499,146 @@ extern "C" int coma_orient_accumulate_f32(const float *hn, const float *on, int6
         else if (nb <= 4) LAUNCH(4);
         else LAUNCH(8);
 #undef LAUNCH
-        if (int e = check_launch("orient_accumulate_kernel")) return e;
+#undef LAUNCH_X2
+        if (int e = check_launch(use_x2 ? "orient_accumulate_kernel_x2" : "orient_accumulate_kernel")) return e;
+    }
+    return 0;
+}
+}  // namespace coma
+
+extern "C" int coma_orient_accumulate_cone_f32(const float *hn, const float *on, int64_t S, int64_t H, int64_t O,
+                                               const double *grid, int64_t N, double sigma, double eps, const float *p_host,
+                                               const float *sub_p_host, const int32_t *bin_perm, int drop_bits, int sum_order, float *PH,
+                                               float *PO, coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(hn && on && grid && p_host && sub_p_host && PH && PO, "null pointer");
+    COMA_REQUIRE(S >= 0 && H > 0 && O > 0 && N > 0, "bad sizes");
+    COMA_REQUIRE(sigma > 0.0, "normal_gaussian_sigma must be positive");
+    COMA_REQUIRE(H * O < (int64_t)1 << 34, "H*O out of range");
+    COMA_REQUIRE(drop_bits == 0 || (drop_bits >= 24 && drop_bits <= 120), "drop_bits must be 0 (dense) or in [24, 120]");
+    COMA_REQUIRE(sum_order == COMA_SUM_ORDER_TORCH_CPU || sum_order == COMA_SUM_ORDER_TORCH_CUDA, "sum_order must be 0 (torch CPU) or 1 (torch CUDA)");
+    const int ord = sum_order;
+    if (S == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float epsf = (float)eps;
+    const Vec3 p = normalize_host(p_host, epsf), sp = normalize_host(sub_p_host, epsf);
+    const double sk = sqrt(1.4426950408889634) / sigma;
+    // cone form: needs the whole histogram in one launch (N <= 256) and a cone inside the polynomial's domain
+    const double gamma = sigma * sqrt(drop_bits * 0.6931471805599453);
+    const double tneed = 1.0 - cos(gamma);
+    const Acos2Fit *fit = nullptr;
+    if (drop_bits > 0 && N <= 32 * K3C_PATCHES && gamma < 1.5)
+        for (const Acos2Fit &f : kAcos2Fits)
+            if (tneed <= f.tmax) {
+                fit = &f;
+                break;
+            }
+    static const bool force_dense = getenv("COMA_B200_K3_DENSE") != nullptr;   // A/B switch for benchmarks (read once)
+    if (!fit || force_dense)
+        return launch_dense(hn, on, S, H, O, grid, N, (float)sk, (float)(sk * 1.5707963267948966), epsf, ord, p, sp, PH, PO, st);
+    ConeParams cp;
+    for (int k = 0; k < 7; ++k) cp.c[k] = (float)(-sk * sk * (double)fit->c[k]);
+    cp.tmax = (float)tneed;
+    cp.gamma = (float)gamma;
+    cp.npatch = (int)((N + 31) / 32);
+    const long long pairs = (long long)H * O;
+    const unsigned blocks = (unsigned)((pairs + K3_WARPS - 1) / K3_WARPS);
+    static const bool two_ctas = getenv("COMA_B200_K3C_2CTA") != nullptr;   // A/B: 128 registers, 2 CTAs/SM (read once)
+#define LAUNCH_CONE(DEG)                                                                                                          \
+    if (two_ctas)                                                                                                                 \
+        orient_accumulate_cone_kernel<DEG, 2><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+                                                                                cp, epsf, ord, p, sp, PH, PO);                    \
+    else                                                                                                                          \
+        orient_accumulate_cone_kernel<DEG, 3><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+                                                                                cp, epsf, ord, p, sp, PH, PO)
+    switch (fit->deg) {
+        case 3: LAUNCH_CONE(3); break;
+        case 4: LAUNCH_CONE(4); break;
+        case 5: LAUNCH_CONE(5); break;
+        default: LAUNCH_CONE(6); break;
+    }
+#undef LAUNCH_CONE
+    return check_launch("orient_accumulate_cone_kernel");
+}
+
+extern "C" int coma_orient_accumulate_f32(const float *hn, const float *on, int64_t S, int64_t H, int64_t O,
+                                          const double *grid, int64_t N, double sigma, double eps, const float *p_host,
+                                          const float *sub_p_host, float *PH, float *PO, coma_stream_t stream) {
+    return coma_orient_accumulate_cone_f32(hn, on, S, H, O, grid, N, sigma, eps, p_host, sub_p_host, nullptr, 0, COMA_SUM_ORDER_TORCH_CPU,
+                                           PH, PO, stream);
+}
+
+namespace coma {
+// Recursive bisection along the principal axis of the point set: `leaves` groups of <= 32 points each, spatially contiguous.
+static void bisect_bins(const std::vector<double> &g, std::vector<int> idx, int leaves, std::vector<std::vector<int>> &out) {
+    if (leaves == 1) {
+        out.push_back(idx);
+        return;
+    }
+    const int n = (int)idx.size();
+    double c[3] = {0, 0, 0}, M[3][3] = {{0}};
+    for (int i : idx) for (int d = 0; d < 3; ++d) c[d] += g[3 * i + d] / n;
+    for (int i : idx)
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) M[a][b] += (g[3 * i + a] - c[a]) * (g[3 * i + b] - c[b]);
+    double v[3] = {0.5773, 0.5774, 0.5775};   // power iteration: dominant eigenvector of the 3x3 scatter matrix
+    for (int it = 0; it < 200; ++it) {
+        double w[3] = {0, 0, 0};
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) w[a] += M[a][b] * v[b];
+        const double nrm = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (nrm < 1e-300) break;
+        for (int a = 0; a < 3; ++a) v[a] = w[a] / nrm;
+    }
+    std::vector<std::pair<double, int>> proj;
+    for (int i : idx) proj.push_back({(g[3 * i] - c[0]) * v[0] + (g[3 * i + 1] - c[1]) * v[1] + (g[3 * i + 2] - c[2]) * v[2], i});
+    std::stable_sort(proj.begin(), proj.end());
+    const int ll = leaves / 2, lr = leaves - ll;
+    int nl = (int)llround((double)n * ll / leaves);
+    nl = std::max(nl, n - 32 * lr);   // the right part must fit its leaves
+    nl = std::min(nl, 32 * ll);       // and so must the left
+    std::vector<int> left, right;
+    for (int q = 0; q < n; ++q) (q < nl ? left : right).push_back(proj[q].second);
+    bisect_bins(g, left, ll, out);
+    bisect_bins(g, right, lr, out);
+}
+}  // namespace coma
+
+// Host-only: group the N bin centres into ceil(N/32) patches of <= 32 spatially compact bins (recursive principal-axis bisection,
+// deterministic; bounding-cap radius 0.80-0.88 rad for the 250-point Fibonacci sphere, the 8-cap covering bound being 0.84).
+// perm_host[32*j + l] = bin index of lane l in patch j, -1 where a patch has fewer than 32 bins.
+extern "C" int coma_orient_bin_patches(const double *grid_host, int64_t N, int32_t *perm_host) {
+    using namespace coma;
+    COMA_REQUIRE(grid_host && perm_host, "null pointer");
+    COMA_REQUIRE(N > 0 && N <= 32 * K3C_PATCHES, "N must be in [1, 256]");
+    const int n = (int)N, k = (n + 31) / 32;
+    std::vector<double> g(grid_host, grid_host + 3 * n);
+    std::vector<int> all(n);
+    for (int i = 0; i < n; ++i) all[i] = i;
+    std::vector<std::vector<int>> parts;
+    bisect_bins(g, all, k, parts);
+    for (int q = 0; q < 32 * k; ++q) perm_host[q] = -1;
+    for (int j = 0; j < k; ++j) {
+        std::sort(parts[j].begin(), parts[j].end());   // ascending bin index inside a patch: neighbouring lanes, neighbouring addresses
+        for (size_t l = 0; l < parts[j].size(); ++l) perm_host[32 * j + (int)l] = parts[j][l];
     }
     return 0;
 }
 
+extern "C" int coma_canonicalize_order_f32(const float *a, int64_t A, const float *b, int64_t B, const float *p_host,
+                                           const float *sub_p_host, float eps, int sum_order, float *out, coma_stream_t stream);
 extern "C" int coma_canonicalize_f32(const float *a, int64_t A, const float *b, int64_t B, const float *p_host,
                                      const float *sub_p_host, float eps, float *out, coma_stream_t stream) {
+    return coma_canonicalize_order_f32(a, A, b, B, p_host, sub_p_host, eps, COMA_SUM_ORDER_TORCH_CPU, out, stream);
+}
+
+extern "C" int coma_canonicalize_order_f32(const float *a, int64_t A, const float *b, int64_t B, const float *p_host,
+                                           const float *sub_p_host, float eps, int sum_order, float *out, coma_stream_t stream) {
     using namespace coma;
     COMA_REQUIRE(a && b && p_host && sub_p_host && out, "null pointer");
+    COMA_REQUIRE(sum_order == 0 || sum_order == 1, "sum_order must be 0 (torch CPU) or 1 (torch CUDA)");
     COMA_REQUIRE(A > 0 && B > 0 && A * B < (int64_t)1 << 38, "bad sizes");
     const Vec3 p = normalize_host(p_host, eps), sp = normalize_host(sub_p_host, eps);
     const long long q = (long long)A * B;
-    canonicalize_kernel<<<(unsigned)((q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, (int)A, b, (int)B, p, sp, eps, out);
+    canonicalize_kernel<<<(unsigned)((q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, (int)A, b, (int)B, p, sp, eps, sum_order, out);
     return check_launch("canonicalize_kernel");
 }

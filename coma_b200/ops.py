@@ -38,8 +38,24 @@ def pair_accumulate(hv, ov, thres, grid_size, count, nom, sum_order="cpu"):
              _ptr(count), _ptr(nom), _stream())
 
 
-def orient_accumulate(hn, on, grid, sigma, eps, p, sub_p, PH, PO):
-    """utils/coma.py:295-323 over S samples. hn [S,H,3], on [S,O,3] f32; grid [N,3] f64; PH, PO [H,O,N] f32 in place."""
+def bin_patches(grid_host, device=None):
+    """Host-side grouping of the bin centres [N,3] (numpy fp64, N <= 256) into compact 32-bin patches for the cone-limited K3
+    kernel -> int32 tensor [32 * ceil(N/32)] (on `device` if given), -1 = empty slot. No GPU work."""
+    import ctypes
+    import numpy as np
+    g = np.ascontiguousarray(np.asarray(grid_host, dtype=np.float64).reshape(-1, 3))
+    n = g.shape[0]
+    perm = np.empty(32 * ((n + 31) // 32), dtype=np.int32)
+    call("coma_orient_bin_patches", g.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n, perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    t = torch.from_numpy(perm)
+    return t.to(device) if device is not None else t
+
+
+def orient_accumulate(hn, on, grid, sigma, eps, p, sub_p, PH, PO, bin_perm=None, drop_bits=0, sum_order="cpu"):
+    """utils/coma.py:295-323 over S samples. hn [S,H,3], on [S,O,3] f32; grid [N,3] f64; PH, PO [H,O,N] f32 in place.
+    drop_bits = 0: dense evaluation of all N bins. drop_bits = b >= 24: cone-limited kernel — scores below 2^-b are not evaluated
+    (absolute error <= S * 2^-b per bin, include/coma_b200.h); bin_perm = `bin_patches(grid)` groups the bins into compact patches.
+    sum_order: "cpu" / "cuda" association of the reference's 3-term sums in the canonicalisation (see pair_accumulate)."""
     S, H, _ = hn.shape
     O, N = on.shape[1], grid.shape[0]
     assert on.shape[0] == S and PH.shape == (H, O, N) and PO.shape == (H, O, N)
@@ -47,17 +63,20 @@ def orient_accumulate(hn, on, grid, sigma, eps, p, sub_p, PH, PO):
         _chk(t, torch.float32, n)
     _chk(grid, torch.float64, "grid")
     with torch.cuda.device(hn.device):
-        call("coma_orient_accumulate_f32", _ptr(hn), _ptr(on), S, H, O, _ptr(grid), N, float(sigma), float(eps), _host3(p),
-             _host3(sub_p), _ptr(PH), _ptr(PO), _stream())
+        if bin_perm is not None:
+            _chk(bin_perm, torch.int32, "bin_perm")
+            assert bin_perm.numel() == 32 * ((N + 31) // 32)
+        call("coma_orient_accumulate_cone_f32", _ptr(hn), _ptr(on), S, H, O, _ptr(grid), N, float(sigma), float(eps), _host3(p),
+             _host3(sub_p), _ptr(bin_perm), int(drop_bits), SUM_ORDERS[sum_order], _ptr(PH), _ptr(PO), _stream())
 
 
-def canonicalize(a, b, p, sub_p, eps):
+def canonicalize(a, b, p, sub_p, eps, sum_order="cpu"):
     """utils/coma.py:123-172 -> [A,B,3] f32."""
     a, b = _chk(a, torch.float32, "a").contiguous(), _chk(b, torch.float32, "b").contiguous()
     out = torch.empty((a.shape[0], b.shape[0], 3), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        call("coma_canonicalize_f32", _ptr(a), a.shape[0], _ptr(b), b.shape[0], _host3(p), _host3(sub_p), float(eps), _ptr(out),
-             _stream())
+        call("coma_canonicalize_order_f32", _ptr(a), a.shape[0], _ptr(b), b.shape[0], _host3(p), _host3(sub_p), float(eps),
+             SUM_ORDERS[sum_order], _ptr(out), _stream())
     return out
 
 

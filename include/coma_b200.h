@@ -84,9 +84,29 @@ COMA_API int coma_orient_accumulate_f32(const float *hn, const float *on, int64_
                                int64_t N, double sigma, double eps, const float *p_host, const float *sub_p_host,
                                float *PH, float *PO, coma_stream_t stream);
 
+/* Same accumulation, CONE-LIMITED: scores below 2^-drop_bits (bins further than sigma*sqrt(drop_bits ln 2) from the canonical
+ * normal: ~70 % of the bins at sigma = 0.25, drop_bits = 32) are not evaluated. Every term this entry point drops or clamps is
+ * < 2^-drop_bits, so after S samples each bin is within S * 2^-drop_bits ABSOLUTE of coma_orient_accumulate_f32's result; terms
+ * inside the cone carry the same ~5e-6 relative evaluation error. drop_bits = 0 selects the dense kernel (bit-identical to
+ * coma_orient_accumulate_f32); when the cone does not fit the kernel's polynomial domain (sigma > ~0.31 at 32 bits) or N > 256
+ * the dense kernel runs as well. bin_perm: DEVICE int32 [32 * ceil(N/32)] from coma_orient_bin_patches (compact patches = fewer
+ * evaluations) or NULL (bins grouped in index order; same results, less culling). sum_order (COMA_SUM_ORDER_*): the association of
+ * the reference's 3-term torch.sum(dim=-1) inside normalisation / canonicalisation — only the last bits of the canonical normals
+ * depend on it, except next to the antipodal singularity (1 + b.p -> 0) where the reference itself differs by ~1e-3 between its
+ * CPU and CUDA runs. */
+COMA_API int coma_orient_accumulate_cone_f32(const float *hn, const float *on, int64_t S, int64_t H, int64_t O, const double *grid,
+                                             int64_t N, double sigma, double eps, const float *p_host, const float *sub_p_host,
+                                             const int32_t *bin_perm, int drop_bits, int sum_order, float *PH, float *PO,
+                                             coma_stream_t stream);
+/* HOST-only helper (no GPU work): groups the N <= 256 bin centres grid_host [N,3] f64 into ceil(N/32) patches of <= 32 compact
+ * bins; perm_host [32 * ceil(N/32)] int32 receives the bin index of each (patch, lane) slot, -1 for empty slots. */
+COMA_API int coma_orient_bin_patches(const double *grid_host, int64_t N, int32_t *perm_host);
+
 /* Canonicalised normals only (utils/coma.py:123-172): out[i,j,:] = canon(a[i] | b[j]); a [A,3], b [B,3] f32. */
 COMA_API int coma_canonicalize_f32(const float *a, int64_t A, const float *b, int64_t B, const float *p_host,
                           const float *sub_p_host, float eps, float *out, coma_stream_t stream);
+COMA_API int coma_canonicalize_order_f32(const float *a, int64_t A, const float *b, int64_t B, const float *p_host,
+                                         const float *sub_p_host, float eps, int sum_order, float *out, coma_stream_t stream);
 
 /* ---- K4: per-vertex occupancy voxel counts ----------------------------------------------------------------------
  * Replaces ComA_Occupancy.aggregate_single_sample_for_occupancy, utils/coma_occupancy.py:289-295, for S samples:

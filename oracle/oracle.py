@@ -49,6 +49,7 @@ def lib():
         L = ctypes.CDLL(build())
         L.oracle_num_threads.restype = ctypes.c_int
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+        L.oracle_set_sum_order.argtypes = [ctypes.c_int]
         L.oracle_nearest_vertex_f64.argtypes = [_f64p, _i64, _f64p, _i64, _i64p]
         L.oracle_pair_accumulate_f32.argtypes = [_f32p, _f32p, _i64, _i64, _i64, ctypes.c_float, ctypes.c_float, _f32p, _f32p]
         L.oracle_pair_accumulate_order_f32.argtypes = [_f32p, _f32p, _i64, _i64, _i64, ctypes.c_float, ctypes.c_float, ctypes.c_int, _f32p, _f32p]
@@ -147,7 +148,8 @@ def pair_accumulate(hv, ov, thres, grid_size, count=None, nom=None, sum_order="c
     return count, nom
 
 
-def canonicalize(a, b, p=(0, 0, 1), sub_p=(0, 1, 0), eps=1e-8):
+def canonicalize(a, b, p=(0, 0, 1), sub_p=(0, 1, 0), eps=1e-8, sum_order="cpu"):
+    lib().oracle_set_sum_order({"cpu": 0, "cuda": 1}[sum_order])
     a, b = to_f32(a), to_f32(b)
     p, sp = to_f32(p), to_f32(sub_p)
     out = np.empty((len(a), len(b), 3), np.float32)
@@ -156,7 +158,7 @@ def canonicalize(a, b, p=(0, 0, 1), sub_p=(0, 1, 0), eps=1e-8):
     return out
 
 
-def orient_accumulate(hn, on, grid, sigma, eps, p=(0, 0, 1), sub_p=(0, 1, 0), PH=None, PO=None):
+def orient_accumulate(hn, on, grid, sigma, eps, p=(0, 0, 1), sub_p=(0, 1, 0), PH=None, PO=None, sum_order="cpu"):
     hn, on = to_f32(hn), to_f32(on)
     grid = _c(grid, np.float64)
     S, H, _ = hn.shape
@@ -164,6 +166,7 @@ def orient_accumulate(hn, on, grid, sigma, eps, p=(0, 0, 1), sub_p=(0, 1, 0), PH
     PH = np.zeros((H, O, N), np.float32) if PH is None else PH
     PO = np.zeros((H, O, N), np.float32) if PO is None else PO
     p, sp = to_f32(p), to_f32(sub_p)
+    lib().oracle_set_sum_order({"cpu": 0, "cuda": 1}[sum_order])
     lib().oracle_orient_accumulate(_p(hn, _f32p), _p(on, _f32p), S, H, O, _p(grid, _f64p), N, float(sigma), float(eps),
                                    _p(p, _f32p), _p(sp, _f32p), _p(PH, _f32p), _p(PO, _f32p))
     return PH, PO

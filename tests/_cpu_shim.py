@@ -25,8 +25,8 @@ def install():
         count += torch.from_numpy(c)
         nom += torch.from_numpy(n)
 
-    def orient_accumulate(hn, on, grid, sigma, eps, p, sub_p, PH, PO):
-        a, b = oracle.orient_accumulate(_np(hn), _np(on), _np(grid), sigma, eps, p, sub_p)
+    def orient_accumulate(hn, on, grid, sigma, eps, p, sub_p, PH, PO, bin_perm=None, drop_bits=0, sum_order="cpu"):
+        a, b = oracle.orient_accumulate(_np(hn), _np(on), _np(grid), sigma, eps, p, sub_p, sum_order=sum_order)
         PH += torch.from_numpy(a)
         PO += torch.from_numpy(b)
 

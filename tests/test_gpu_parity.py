@@ -30,13 +30,13 @@ def _t(a, dev, dt=torch.float32):
     return torch.tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
 
 
-def _grid_close(mine, ref, rtol=RTOL):
-    """Orientation grids: pure relative tolerance down to 1e-30; below that an absolute floor of 1e-7 x the pair's
-    largest bin (such entries are < 1e-23 of the pair's mass and vanish in every read-out)."""
-    floor = 1e-30 + 1e-7 * 0  # noqa
+def _grid_close(mine, ref, rtol=RTOL, atol=0.0):
+    """Orientation grids: pure relative tolerance down to 1e-30 plus a floor of 1e-23 x the pair's largest bin (DENSE kernel).
+    `atol` = S * 2^-31 for the CONE-LIMITED kernel (ComA's default): terms below 2^-32 are dropped or clamped, S of them per bin
+    (include/coma_b200.h); such a floor is < 2e-7 of the pair's largest bin and vanishes in every read-out."""
     pair_max = ref.max(axis=-1, keepdims=True)
     err = np.abs(mine.astype(np.float64) - ref.astype(np.float64))
-    tol = rtol * np.abs(ref).astype(np.float64) + 1e-30 + 1e-23 * pair_max
+    tol = rtol * np.abs(ref).astype(np.float64) + 1e-30 + 1e-23 * pair_max + atol
     bad = err > tol
     assert not bad.any(), f"{bad.sum()} / {bad.size} entries off; worst rel {np.max(err / (np.abs(ref) + 1e-30)):.3e}"
 
@@ -231,6 +231,42 @@ def test_orient_accumulate_oracle(dev, H, O, N, S, sigma):
     _grid_close(PO.cpu().numpy(), rPO)
 
 
+@pytest.mark.parametrize("order", ["cpu", "cuda"])
+@pytest.mark.parametrize("H,O,N,S,sigma,bits", [(40, 33, 250, 70, 0.25, 32), (24, 20, 250, 33, 0.2, 32), (16, 9, 64, 5, 0.1, 32),
+                                                (31, 17, 250, 40, 0.25, 24), (12, 10, 256, 9, 0.3, 32), (9, 7, 31, 3, 0.25, 40),
+                                                (9, 7, 300, 3, 0.25, 32), (5, 4, 250, 2, 1.0, 32)])
+def test_orient_accumulate_cone_limited(dev, H, O, N, S, sigma, bits, order):
+    """The cone-limited K3 kernel (ComA's default): against the oracle at rtol 1e-4 + S * 2^-bits absolute (its contract: every
+    dropped / clamped term is < 2^-bits), and against the dense kernel; with compact patches and with index-order patches; both
+    sum associations. N = 300 and sigma = 1.0 fall back to the dense kernel (asserted through the C ABI)."""
+    from coma_b200 import _lib, ops, synth
+    from oracle import oracle
+    samples = synth.make_samples(S, H, O, seed=N + S) + synth.make_adversarial_samples(H, O, 0.03, seed=S)
+    hn = np.stack([s["human_normals"] for s in samples])
+    on = np.stack([s["obj_normals"] for s in samples])
+    St = len(samples)
+    grid = oracle.fibonacci_sphere(N)
+    rPH, rPO = oracle.orient_accumulate(hn, on, grid, sigma, 1e-10, sum_order=order)
+    gt = _t(grid, dev, torch.float64)
+    dPH, dPO = torch.zeros((H, O, N), device=dev), torch.zeros((H, O, N), device=dev)
+    ops.orient_accumulate(_t(hn, dev), _t(on, dev), gt, sigma, 1e-10, [0, 0, 1], [0, 1, 0], dPH, dPO, sum_order=order)
+    assert _lib.last_kernel() == "orient_accumulate_kernel_x2"
+    cone_applies = N <= 256 and sigma * np.sqrt(bits * np.log(2)) < 1.5 and 1 - np.cos(sigma * np.sqrt(bits * np.log(2))) <= 0.86
+    floor = St * 2.0 ** -bits
+    for perm in ((ops.bin_patches(grid, dev) if N <= 256 else None), None):
+        PH, PO = torch.zeros((H, O, N), device=dev), torch.zeros((H, O, N), device=dev)
+        k = St // 2   # two accumulating calls == one call over the concatenation
+        for sl in (slice(0, k), slice(k, St)):
+            ops.orient_accumulate(_t(hn[sl], dev), _t(on[sl], dev), gt, sigma, 1e-10, [0, 0, 1], [0, 1, 0], PH, PO, bin_perm=perm,
+                                  drop_bits=bits, sum_order=order)
+        assert _lib.last_kernel() == ("orient_accumulate_cone_kernel" if cone_applies else "orient_accumulate_kernel_x2")
+        for mine, dense, ref in ((PH, dPH, rPH), (PO, dPO, rPO)):
+            _grid_close(mine.cpu().numpy(), ref, atol=1.01 * floor if cone_applies else 0.0)
+            err = (mine - dense).abs()
+            assert bool((err <= 1.01 * floor + 3e-5 * dense).all()), float((err - 3e-5 * dense).max())
+    assert not cone_applies or float((PH - dPH).abs().max()) > 0      # it really is a different evaluation
+
+
 # --------------------------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("name", ["occupancy_small", "occupancy_s30"])
 def test_occupancy_golden(dev, golden_dir, name):
@@ -305,8 +341,9 @@ def test_coma_class_matches_reference_golden(dev, golden_dir, name, tmp_path):
     np.testing.assert_array_equal(exp["contact_dist_expectation_grid_denom"], g["denom"])
     np.testing.assert_array_equal(exp["canon_normal_grid"], g["canon_normal_grid"])
     np.testing.assert_allclose(exp["contact_dist_expectation_grid_nom"], g["nom"], rtol=RTOL)
-    _grid_close(exp["prob_grid_canon_human_wrt_obj"], g["PH"])
-    _grid_close(exp["prob_grid_canon_obj_wrt_human"], g["PO"])
+    cone_floor = S * 2.0 ** -31 if coma.orient_drop_bits else 0.0
+    _grid_close(exp["prob_grid_canon_human_wrt_obj"], g["PH"], atol=cone_floor)
+    _grid_close(exp["prob_grid_canon_obj_wrt_human"], g["PO"], atol=cone_floor)
 
     agg_h, idx_o = get_aggregated_contact(coma, "human", ratio)
     agg_o, idx_h = get_aggregated_contact(coma, "obj", ratio)
@@ -411,7 +448,9 @@ def test_cfg4_shape_orientation_and_readout_sampled_rows(dev):
     gt = _t(grid, dev, torch.float64)
     PH = torch.zeros((H, O, N), device=dev)
     PO = torch.zeros((H, O, N), device=dev)
-    ops.orient_accumulate(hn, on, gt, 0.25, 1e-10, [0, 0, 1], [0, 1, 0], PH, PO)
+    ops.orient_accumulate(hn, on, gt, 0.25, 1e-10, [0, 0, 1], [0, 1, 0], PH, PO, bin_perm=ops.bin_patches(grid, dev), drop_bits=32)
+    from coma_b200 import _lib
+    assert _lib.last_kernel() == "orient_accumulate_cone_kernel"      # the kernel bench.py reports
     rng = np.random.default_rng(5)
     hs = np.unique(np.concatenate([[0, H - 1, H - 2, 8192], rng.integers(0, H, 12)]))[:16]
     os_ = np.unique(np.concatenate([[0, O - 1, O - 2, 1024], rng.integers(0, O, 12)]))[:16]
@@ -419,8 +458,8 @@ def test_cfg4_shape_orientation_and_readout_sampled_rows(dev):
     rPH, rPO = oracle.orient_accumulate(hn_h[:, hs], on_h[:, os_], grid, 0.25, 1e-10)
     ht, ot = torch.tensor(hs, device=dev), torch.tensor(os_, device=dev)
     mPH, mPO = PH[ht][:, ot].cpu().numpy(), PO[ht][:, ot].cpu().numpy()
-    _grid_close(mPH, rPH)
-    _grid_close(mPO, rPO)
+    _grid_close(mPH, rPH, atol=S * 2.0 ** -31)
+    _grid_close(mPO, rPO, atol=S * 2.0 ** -31)
     # nothing outside [0, S] and no untouched (all-zero) pair anywhere in the 3.9e9-element grid's last rows
     assert float(PH[-1].min()) >= 0 and float(PH[-1].sum(-1).min()) > 0 and float(PO[-1].sum(-1).min()) > 0
     # K5a on the full grids, checked on the sampled pairs
@@ -434,7 +473,7 @@ def test_cfg4_shape_orientation_and_readout_sampled_rows(dev):
         rPn = oracle.normalize_normals(rP.copy(), 1e-10)
         ref = oracle.contact_map(rPn, grid, nom_s, np.full_like(nom_s, S))
         np.testing.assert_allclose(cm[ht][:, ot].cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
-        np.testing.assert_allclose(P[ht][:, ot].cpu().numpy(), rPn, rtol=RTOL, atol=1e-30 + 1e-23 * float(rPn.max()))
+        np.testing.assert_allclose(P[ht][:, ot].cpu().numpy(), rPn, rtol=RTOL, atol=S * 2.0 ** -31)
         s = P[-1].sum(-1)
         assert float((s - 1).abs().max()) < 1e-5          # every pair of the LAST row is normalised (index > 2^31)
 
