@@ -16,6 +16,8 @@ _f32p = _c.POINTER(_c.c_float)
 SIGNATURES = {
     "coma_vertex_normals_f64": [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _f64, _vp, _vp],
     "coma_nearest_vertex_f64": [_vp, _i64, _vp, _i64, _vp, _vp],
+    "coma_nearest_distance_f32": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
+    "coma_nearest_distance_backward_f32": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "coma_pair_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp],
     "coma_pair_accumulate_order_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _int, _vp, _vp, _vp],
     "coma_orient_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _vp, _vp],
@@ -45,6 +47,7 @@ SIGNATURES = {
     "coma_im2col3x3_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp, _int, _vp, _i64, _vp],
     "coma_layernorm_f16": [_vp, _i64, _i64, _i64, _vp, _vp, _f32, _vp, _i64, _vp],
     "coma_softmax_rows_f16": [_vp, _i64, _i64, _i64, _vp],
+    "coma_softmax_rows_causal_f16": [_vp, _i64, _i64, _i64, _i64, _vp],
     "coma_geglu_f16": [_vp, _i64, _i64, _i64, _vp, _i64, _vp],
     "coma_transpose_heads_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp],
     "coma_timestep_embedding_f16": [_vp, _i64, _i64, _vp, _vp],

@@ -182,13 +182,7 @@ def set_pipeline(model_dir, adaptive_mask_model_type, default_ddim_steps, defaul
 
 
 def clip_embedder(model_dir, device="cuda"):
-    """CLIP-L/14 text encoder of the checkpoint via transformers (utils/adaptive_mask_inpainting.py:405-554, single prompt)."""
-    from transformers import CLIPTextModel, CLIPTokenizer
-    tok = CLIPTokenizer.from_pretrained(os.path.join(model_dir, "tokenizer"))
-    enc = CLIPTextModel.from_pretrained(os.path.join(model_dir, "text_encoder"), torch_dtype=torch.float16).to(device).eval()
-
-    @torch.no_grad()
-    def embed(text):
-        ids = tok(text, padding="max_length", max_length=tok.model_max_length, truncation=True, return_tensors="pt").input_ids.to(device)
-        return enc(ids)[0][0]
-    return embed
+    """CLIP-L/14 text encoder of the checkpoint (utils/adaptive_mask_inpainting.py:405-554, single prompt) on the B200 kernels
+    (coma_b200/inpaint/clip.py); only the tokenizer (string processing) is transformers'."""
+    from coma_b200.inpaint.clip import make_embedder
+    return make_embedder(model_dir, device)

@@ -147,7 +147,7 @@ struct GemmEpilogue {
     int ldo;
     long long o_s1, o_s2;    // output element strides of the two batch dims
     float alpha;             // scales the accumulator (attention: 1/sqrt(d))
-    int act;                 // 0 = identity, 1 = SiLU
+    int act;                 // 0 = identity, 1 = SiLU, 2 = quick-GELU x*sigmoid(1.702x)
     int nb1;                 // extent of batch dim 1 (blockIdx.z = b2 * nb1 + b1)
     int tma;                 // 1: fp16 output (and residual) move as 32x32 boxes through shared memory + TMA (tmO / tmR)
     float *stats;            // TMA form only, or null: [M/32, N, 2] per-(32-row block, column) sum / sum of squares of the fp16
@@ -464,6 +464,9 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 if (act == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+                } else if (act == 2) {   // quick-GELU (CLIP text encoder): x * sigmoid(1.702 x)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
                 }
                 }  // !GEGLU
 #pragma unroll
@@ -569,6 +572,9 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                         if (act == 1) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+                        } else if (act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
                         }
                         if (out16) {
 #pragma unroll
@@ -592,6 +598,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                                 if (brow) x += brow[nb + j];
                                 if (residual) x += __half2float(residual[off + j]);
                                 if (act == 1) x = x / (1.0f + __expf(-x));
+                                else if (act == 2) x = x / (1.0f + __expf(-1.702f * x));
                                 if (out16) out16[off + j] = __float2half_rn(x);
                                 if (out32) out32[off + j] = x;
                             }
@@ -803,6 +810,9 @@ __global__ void splitk_finish_kernel(const float *__restrict__ ws, int ksplit, l
     if (act == 1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+    } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
     }
     if (out16) {
         uint4 w;
@@ -868,7 +878,7 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     COMA_REQUIRE((nb1 == 1 || (g->a_s1 % 8 == 0 && g->w_s1 % 8 == 0)) && (nb2 == 1 || (g->a_s2 % 8 == 0 && g->w_s2 % 8 == 0)),
                  "batch strides of A / W must be multiples of 8 elements");
     COMA_REQUIRE(((uintptr_t)g->A | (uintptr_t)g->W) % 16 == 0, "A and W must be 16-byte aligned");
-    COMA_REQUIRE(g->act == 0 || g->act == 1, "act must be 0 (identity) or 1 (SiLU)");
+    COMA_REQUIRE(g->act >= 0 && g->act <= 2, "act must be 0 (identity), 1 (SiLU) or 2 (quick-GELU)");
     COMA_REQUIRE(!g->out_f16 || (uintptr_t)g->out_f16 % 16 == 0, "out_f16 must be 16-byte aligned");
     COMA_REQUIRE(!g->out_f32 || (uintptr_t)g->out_f32 % 16 == 0, "out_f32 must be 16-byte aligned");
     COMA_REQUIRE(!g->residual || (uintptr_t)g->residual % 16 == 0, "residual must be 16-byte aligned");

@@ -493,12 +493,14 @@ __global__ void __launch_bounds__(256)
 //   L <= 1024 : one warp per row, up to 32 values per lane (cross-attention rows, L = 77, and the 16x16 / 32x32 levels)
 //   L <= 4096 and 16-byte aligned rows: one 256-thread CTA per row, 16 values per thread as two 16-byte loads
 //   otherwise : three-pass fallback
-__global__ void __launch_bounds__(256) softmax_rows_warp_kernel(__half *__restrict__ s, long long R, int L, long long ld) {
+// causal_S > 0: the rows form [causal_S x L] matrices and row q of a matrix only sees columns <= q (CLIP's causal text mask)
+__global__ void __launch_bounds__(256) softmax_rows_warp_kernel(__half *__restrict__ s, long long R, int L_full, long long ld, int causal_S) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= R) return;
+    const int L = causal_S > 0 ? min(L_full, (int)(r % causal_S) + 1) : L_full;
     __half *row = s + r * ld;
     float v[32];
     float m = -INFINITY;
@@ -823,7 +825,7 @@ extern "C" int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, 
     COMA_REQUIRE(R > 0 && L > 0 && ld >= L && R < (1LL << 31), "bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     if (ld <= 1024) {
-        launch_pdl(softmax_rows_warp_kernel, dim3((unsigned)((R + 7) / 8)), dim3(256), 0, st, (__half *)s, R, (int)L, ld);
+        launch_pdl(softmax_rows_warp_kernel, dim3((unsigned)((R + 7) / 8)), dim3(256), 0, st, (__half *)s, R, (int)L, ld, 0);
         return check_launch("softmax_rows_warp_kernel");
     }
     if (ld <= 4096 && ld % 8 == 0 && (uintptr_t)s % 16 == 0) {
@@ -832,6 +834,13 @@ extern "C" int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, 
     }
     launch_pdl(softmax_rows_kernel, dim3((unsigned)R), dim3(256), 0, st, (__half *)s, (int)L, ld);
     return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int coma_softmax_rows_causal_f16(void *s, int64_t R, int64_t S, int64_t L, int64_t ld, coma_stream_t stream) {
+    COMA_REQUIRE(s, "null pointer");
+    COMA_REQUIRE(R > 0 && S > 0 && L > 0 && ld >= L && ld <= 1024 && R % S == 0 && R < (1LL << 31), "bad sizes (causal rows: ld <= 1024)");
+    launch_pdl(softmax_rows_warp_kernel, dim3((unsigned)((R + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, (__half *)s, R, (int)L, ld, (int)S);
+    return check_launch("softmax_rows_warp_kernel");
 }
 
 extern "C" int coma_geglu_f16(const void *h, int64_t M, int64_t C, int64_t ldh, void *y, int64_t ldy, coma_stream_t stream) {

@@ -57,6 +57,19 @@ COMA_API int coma_vertex_normals_f64(const double *verts, int64_t S, int64_t V, 
 COMA_API int coma_nearest_vertex_f64(const double *pts, int64_t N, const double *verts, int64_t V, int64_t *out_idx,
                             coma_stream_t stream);
 
+/* ---- K7: nearest-neighbour distances between two point sets, forward + backward ------------------------
+ * Replaces the torch.cdist + row-min of `chamfer_distance` (src/application/optimize.py:155-165, differentiated inside the pose
+ * optimiser) and `minimum_distance` (src/generation/optimize_depth.py:29-44) without the [NA,NB] matrix:
+ *   dist[i] = min_j ||a_i - b_j||  (IEEE sqrt of the exactly accumulated (dx^2+dy^2)+dz^2),  idx[i] = the first arg-min.
+ * a [NA,3], b [NB,3] f32; dist [NA] f32, idx [NA] i32; scratch: NA uint64 (contents irrelevant). */
+COMA_API int coma_nearest_distance_f32(const float *a, int64_t NA, const float *b, int64_t NB, float *dist, int32_t *idx,
+                                       uint64_t *scratch, coma_stream_t stream);
+/* Backward of the above: grad_a[i] = grad_dist[i] * (a_i - b_idx[i]) / dist[i] (0 where dist = 0, like torch.cdist), written;
+ * grad_b[idx[i]] -= the same, ACCUMULATED with atomics into a caller-zeroed [NB,3] buffer. Either gradient may be NULL. */
+COMA_API int coma_nearest_distance_backward_f32(const float *a, int64_t NA, const float *b, int64_t NB, const int32_t *idx,
+                                                const float *dist, const float *grad_dist, float *grad_a, float *grad_b,
+                                                coma_stream_t stream);
+
 /* ---- K2: pair distance -> contact count + proximity expectation -------------------------------------------------
  * Replaces ComA.aggregate_single_sample_for_contact, utils/coma.py:284-291 (+ negative_exp :116-119), for S samples:
  *   d = sqrt(((hx-ox)^2+(hy-oy)^2)+(hz-oz)^2) (fp32, separately rounded);  count[h,o] += (d < thres);
@@ -153,7 +166,7 @@ COMA_API int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, cons
  * :680 (vae.encode), :1086,:1112 (vae.decode): linear layers, 1x1 convs, attention projections and the im2col form of
  * the 3x3 convs (diffusers UNet2DConditionModel / AutoencoderKL, not vendored in the reference).
  * A [M,K] fp16 row stride lda; W [N,K] fp16 row stride ldw (lda, ldw multiples of 8); bias [N] f32 or NULL;
- * residual [M,N] fp16 with row stride ldo or NULL; act: 0 identity, 1 SiLU; out_f16 / out_f32 [M,N] row stride ldo
+ * residual [M,N] fp16 with row stride ldo or NULL; act: 0 identity, 1 SiLU, 2 quick-GELU x*sigmoid(1.702x) (CLIP MLP); out_f16 / out_f32 [M,N] row stride ldo
  * (either may be NULL, not both). */
 /* General form: two batch dimensions (nb1 fastest) with independent element strides for A, W and the output, an
  * accumulator scale `alpha` (applied before the bias terms) and a second, per-row-group bias
@@ -251,6 +264,9 @@ COMA_API int coma_layernorm_f16(const void *x, int64_t M, int64_t C, int64_t ldx
                                 void *y, int64_t ldy, coma_stream_t stream);
 /* In-place softmax over the first L columns of each of R rows (row stride ld); columns [L, ld) are set to 0. */
 COMA_API int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, coma_stream_t stream);
+/* Same with a CAUSAL mask: the R rows form [S x L] matrices and row q of each only attends to columns <= q (the text-encoder
+ * attention of transformers' CLIPTextModel, called at utils/adaptive_mask_inpainting.py:478,534). ld <= 1024. */
+COMA_API int coma_softmax_rows_causal_f16(void *s, int64_t R, int64_t S, int64_t L, int64_t ld, coma_stream_t stream);
 /* GEGLU: y[m,c] = h[m,c] * gelu(h[m,C+c]) (exact erf GELU), h [M,2C] -> y [M,C]. */
 COMA_API int coma_geglu_f16(const void *h, int64_t M, int64_t C, int64_t ldh, void *y, int64_t ldy, coma_stream_t stream);
 /* v [B,L,heads*d] (row stride ldv) -> vt [B,heads,d,Lpad] zero padded: the K-major operand of P.V. */

@@ -15,6 +15,9 @@ Reference lines followed (relative to the reference root):
   aggregate_contact           utils/coma.py:385-438, 614-641
   entropy_score               utils/coma.py:441-476
   occupancy_field             utils/coma_occupancy.py:297-312
+  nearest_distance / chamfer_distance / minimum_distance
+                              src/application/optimize.py:155-165, src/generation/optimize_depth.py:29-44 (pinned against the
+                              reference's own torch.cdist expressions in tests/test_geometry.py)
 """
 import ctypes
 import math
@@ -183,6 +186,33 @@ def occupancy_accumulate(human_verts, obj_verts, Sg, scale_tolerance, grids=None
     lib().oracle_occupancy_accumulate(_p(hvc, _f32p), S, H, _p(centers, _f64p), Sg, float(voxel * scale_tolerance),
                                       _p(grids, _f32p))
     return grids
+
+
+# ----------------------------------------------------------------------------------------------- point-set distances (8f-3)
+def nearest_distance(a, b, block=2048):
+    """min_j ||a_i - b_j|| and the first arg-min, fp32 with separately rounded ops in the order (dx^2+dy^2)+dz^2 — the row minima of
+    torch.cdist(a, b, compute_mode="donot_use_mm_for_euclid_dist") that `chamfer_distance` (src/application/optimize.py:155-165) and
+    `minimum_distance` (src/generation/optimize_depth.py:29-44) reduce. Blocked over a to bound memory."""
+    a, b = to_f32(a), to_f32(b)
+    dist = np.empty(len(a), np.float32)
+    idx = np.empty(len(a), np.int32)
+    for i0 in range(0, len(a), block):
+        d = a[i0:i0 + block, None, :] - b[None, :, :]
+        sq = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        j = np.argmin(sq, axis=1)
+        idx[i0:i0 + block] = j
+        dist[i0:i0 + block] = np.sqrt(sq[np.arange(len(j)), j])
+    return dist, idx
+
+
+def chamfer_distance(a, b):
+    """src/application/optimize.py:155-165."""
+    return np.float32(nearest_distance(a, b)[0].mean(dtype=np.float32) + nearest_distance(b, a)[0].mean(dtype=np.float32))
+
+
+def minimum_distance(a, b, num_vertices=100):
+    """src/generation/optimize_depth.py:29-44."""
+    return np.float32(np.sort(nearest_distance(a, b)[0])[:num_vertices].mean(dtype=np.float32))
 
 
 # ----------------------------------------------------------------------------------------------- read-outs

@@ -275,3 +275,37 @@ def test_groupnorm_from_conv_epilogue_stats(dev, C, Cout, H, B, groups, res):
     torch.testing.assert_close(_nchw(y.t, B, H, H), ref, rtol=2e-3, atol=2e-3)
     again = nn.conv3x3(_nhwc(x), nn.prep_conv3x3(w, dev), b, residual=r, stats=True)
     assert torch.equal(again.stats, out.stats)                                   # deterministic
+
+
+@pytest.mark.parametrize("cfg_name", ["clip_l", "small"])
+def test_clip_text_encoder_vs_transformers(dev, cfg_name):
+    """the text encoder of `_encode_prompt` (utils/adaptive_mask_inpainting.py:478,534) is transformers' CLIPTextModel —
+    installed in this image, so it IS the reference here: same random-initialised weights (fp16-rounded), real ViT-L/14 text-tower
+    shape, causal mask, quick-GELU; last_hidden_state against the fp32 reference at the fp16-storage bound."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from coma_b200.inpaint.clip import CLIP_L_TEXT_CFG, CLIPTextEncoder
+    cfg = dict(CLIP_L_TEXT_CFG) if cfg_name == "clip_l" else dict(CLIP_L_TEXT_CFG, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                                                                   num_attention_heads=4, vocab_size=1000)
+    torch.manual_seed(0)
+    ref = CLIPTextModel(CLIPTextConfig(**cfg)).eval()
+    sd = {k: v.half().float() for k, v in ref.state_dict().items() if v.is_floating_point()}
+    ref.load_state_dict(sd, strict=False)
+    ref = ref.to(dev).float()
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, cfg["vocab_size"] - 2, (2, 77), generator=g)
+    ids[:, 0] = cfg["vocab_size"] - 2                       # BOS
+    ids[0, 9:] = cfg["vocab_size"] - 1                      # EOS + padding (pad token = EOS in CLIP)
+    ids[1, 40:] = cfg["vocab_size"] - 1
+    with torch.no_grad():
+        want = ref(input_ids=ids.to(dev)).last_hidden_state
+    enc = CLIPTextEncoder(sd, cfg, dev)
+    got = enc(ids)
+    assert got.shape == want.shape == (2, 77, cfg["hidden_size"]) and got.dtype == torch.float16
+    _close(got.float(), want, 1e-2)
+    rel_rms = ((got.float() - want).pow(2).mean().sqrt() / want.pow(2).mean().sqrt()).item()
+    assert rel_rms < 3e-3, rel_rms
+    # causality: changing a later token must not change earlier positions
+    ids2 = ids.clone()
+    ids2[:, 30] = 5
+    got2 = enc(ids2)
+    assert torch.equal(got2[:, :30], got[:, :30]) and not torch.equal(got2[:, 30:], got[:, 30:])
