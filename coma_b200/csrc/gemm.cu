@@ -463,10 +463,10 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 }
                 if (act == 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+                    for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
                 } else if (act == 2) {   // quick-GELU (CLIP text encoder): x * sigmoid(1.702 x)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
+                    for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-1.702f * f[j]));
                 }
                 }  // !GEGLU
 #pragma unroll
@@ -571,10 +571,10 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                         }
                         if (act == 1) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+                            for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
                         } else if (act == 2) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
+                            for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-1.702f * f[j]));
                         }
                         if (out16) {
 #pragma unroll
@@ -597,8 +597,8 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                                 float x = __uint_as_float(v[j]) * ep.alpha + (bias ? bias[nb + j] : 0.0f);
                                 if (brow) x += brow[nb + j];
                                 if (residual) x += __half2float(residual[off + j]);
-                                if (act == 1) x = x / (1.0f + __expf(-x));
-                                else if (act == 2) x = x / (1.0f + __expf(-1.702f * x));
+                                if (act == 1) x = __fdividef(x, 1.0f + __expf(-x));
+                                else if (act == 2) x = __fdividef(x, 1.0f + __expf(-1.702f * x));
                                 if (out16) out16[off + j] = __float2half_rn(x);
                                 if (out32) out32[off + j] = x;
                             }
@@ -809,10 +809,10 @@ __global__ void splitk_finish_kernel(const float *__restrict__ ws, int ksplit, l
     }
     if (act == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+        for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
     } else if (act == 2) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
+        for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-1.702f * f[j]));
     }
     if (out16) {
         uint4 w;

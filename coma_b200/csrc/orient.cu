@@ -290,10 +290,10 @@ struct ConeParams {
     int npatch;
 };
 
-// One patch, one histogram, one chunk: `cnt` directions were compacted into `list` as sample PAIRS, component-interleaved
-// (x1,x2,y1,y2 | z1,z2,-,-), so one LDS.128 + one LDS.64 deliver the operands of three packed FFMA2 (pair x broadcast G).
+// One patch, one histogram, one chunk: `cnt` directions were compacted into the warp's list (structure of arrays: x[32], y[32],
+// z[32], conflict-free to write), so three broadcast LDS.64 deliver a PAIR of samples as the packed operands of three FFMA2.
 template <int DEG>
-__device__ __forceinline__ float cone_steps(int cnt, const float4 *__restrict__ list, float ngx, float ngy, float ngz, float acc,
+__device__ __forceinline__ float cone_steps(int cnt, const float *__restrict__ list, float ngx, float ngy, float ngz, float acc,
                                             const ConeParams &cp) {
     const float2 c0 = f2(cp.c[0]), c1 = f2(cp.c[1]), c2 = f2(cp.c[2]), c3 = f2(cp.c[3]), c4 = f2(cp.c[DEG >= 4 ? 4 : 0]),
                  c5 = f2(cp.c[DEG >= 5 ? 5 : 0]), c6 = f2(cp.c[DEG >= 6 ? 6 : 0]);
@@ -309,34 +309,30 @@ __device__ __forceinline__ float cone_steps(int cnt, const float4 *__restrict__ 
         const float2 a = __fmul2_rn(t, r);
         return make_float2(mufu_ex2(a.x), mufu_ex2(a.y));
     };
+    const float2 *lx = reinterpret_cast<const float2 *>(list), *ly = lx + 16, *lz = lx + 32;
     int k = 0;
+#pragma unroll 2
     for (; k + 1 < cnt; k += 2) {   // cnt is warp-uniform: no divergence
-        const float4 xy = list[k];                                               // pair k/2: (x1, x2, y1, y2)
-        const float2 z = *reinterpret_cast<const float2 *>(&list[k + 1]);        //           (z1, z2)
-        const float2 t = __ffma2_rn(make_float2(xy.x, xy.y), f2(ngx),
-                                    __ffma2_rn(make_float2(xy.z, xy.w), f2(ngy), __ffma2_rn(z, f2(ngz), f2(1.0f))));   // 1 - G.n
+        const float2 t = __ffma2_rn(lx[k >> 1], f2(ngx), __ffma2_rn(ly[k >> 1], f2(ngy), __ffma2_rn(lz[k >> 1], f2(ngz), f2(1.0f))));   // 1 - G.n
         const float2 s = score2(t);
         acc += s.x;
         acc += s.y;
     }
     if (k < cnt) {   // odd tail: only the first half of the last pair is live
-        const float4 xy = list[k];
-        const float z = list[k + 1].x;
-        const float t = fmaf(xy.x, ngx, fmaf(xy.z, ngy, fmaf(z, ngz, 1.0f)));
+        const float t = fmaf(list[k], ngx, fmaf(list[32 + k], ngy, fmaf(list[64 + k], ngz, 1.0f)));
         acc += score2(make_float2(t, t)).x;
     }
     return acc;
 }
 
-// Compacts the directions of the lanes with `need` into the warp's pair list; returns their number (warp-uniform).
+// Compacts the directions of the lanes with `need` into the warp's list; returns their number (warp-uniform).
 __device__ __forceinline__ int cone_compact(bool need, Vec3 d, float *__restrict__ list, int lane) {
     const unsigned m = __ballot_sync(0xffffffffu, need);
     if (need) {
         const int pos = __popc(m & ((1u << lane) - 1u));
-        float *e = list + (pos >> 1) * 8 + (pos & 1);   // two float4 per pair
-        e[0] = d.x;
-        e[2] = d.y;
-        e[4] = d.z;
+        list[pos] = d.x;
+        list[32 + pos] = d.y;
+        list[64 + pos] = d.z;
     }
     __syncwarp();
     return __popc(m);
@@ -344,57 +340,55 @@ __device__ __forceinline__ int cone_compact(bool need, Vec3 d, float *__restrict
 
 constexpr int K3C_PATCHES = 8;
 
+// The per-patch state (the lane's bin centre, its two accumulators) lives in SHARED memory and the patch loop is ROLLED: the
+// first version kept it in registers with the loop unrolled 8x — 93 KB of SASS, `no_instruction` (instruction-cache misses) the
+// second-largest stall and 80 registers (3 CTAs/SM). Rolled: ~12 KB of code, ~40 registers, 5-6 CTAs/SM to hide the LDS -> FFMA2
+// -> MUFU chains; the price is 7 conflict-free shared-memory accesses per (patch, chunk) against ~450 instructions of work.
 template <int DEG, int MINB>
 __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
     orient_accumulate_cone_kernel(const float *__restrict__ hn, const float *__restrict__ on, int S, int H, int O,
                                   const double *__restrict__ grid, int N, const int *__restrict__ perm, ConeParams cp, float eps, int ord,
                                   Vec3 p, Vec3 sp, float *__restrict__ PH, float *__restrict__ PO) {
-    __shared__ float4 caps[K3C_PATCHES];                             // (centre, cos(min(gamma + radius, pi))) per patch
-    __shared__ __align__(16) float4 lists[K3_WARPS][2][32];          // per warp, per histogram: 16 sample pairs x 2 float4
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float4 caps[K3C_PATCHES];                               // (centre, cos(min(gamma + radius, pi))) per patch
+    __shared__ float sG[K3C_PATCHES][3][32];                           // negated bin centres: [patch][component][lane]
+    __shared__ float sAcc[K3C_PATCHES][2][K3_WARPS * 32];              // accumulators: [patch][histogram][thread]
+    __shared__ __align__(16) float lists[K3_WARPS][2][96];             // per warp, per histogram: x[32] y[32] z[32] of the needed samples
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
     const long long pair = (long long)blockIdx.x * K3_WARPS + warp;
 
-    // bin owned by this lane in patch j (-1: none); re-derived where needed instead of being kept in 8 registers
-    auto bin_of = [&](int j) -> int {
+    auto bin_of = [&](int j) -> int {   // bin owned by this lane in patch j (-1: none)
         const int slot = 32 * j + lane;
         return j < cp.npatch ? (perm ? __ldg(perm + slot) : (slot < N ? slot : -1)) : -1;
     };
-    float ngx[K3C_PATCHES], ngy[K3C_PATCHES], ngz[K3C_PATCHES];
-#pragma unroll
-    for (int j = 0; j < K3C_PATCHES; ++j) {
+    // bin centres + bounding cap of every patch (all warps of the CTA own the same bins: warp w prepares patch w)
+    for (int j = warp; j < cp.npatch; j += K3_WARPS) {
         const int n = bin_of(j);
-        ngx[j] = n >= 0 ? -(float)grid[3 * n + 0] : 0.f;   // fp64 bin centres, rounded once; stored negated (t = 1 - G.n)
-        ngy[j] = n >= 0 ? -(float)grid[3 * n + 1] : 0.f;
-        ngz[j] = n >= 0 ? -(float)grid[3 * n + 2] : 0.f;
+        const bool ok = n >= 0;
+        const float gx = ok ? (float)grid[3 * n + 0] : 0.f, gy = ok ? (float)grid[3 * n + 1] : 0.f, gz = ok ? (float)grid[3 * n + 2] : 0.f;
+        sG[j][0][lane] = -gx;   // fp64 bin centres, rounded once; stored negated (t = 1 - G.n)
+        sG[j][1][lane] = -gy;
+        sG[j][2][lane] = -gz;
+        float sx = warp_sum(gx), sy = warp_sum(gy), sz = warp_sum(gz);
+        const float nrm = sqrtf(sx * sx + sy * sy + sz * sz);
+        if (nrm > 1e-6f) { sx /= nrm; sy /= nrm; sz /= nrm; } else { sx = 0.f; sy = 0.f; sz = 1.f; }
+        float cmin = ok ? gx * sx + gy * sy + gz * sz : 1.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        const float reach = cp.gamma + acosf(fminf(fmaxf(cmin, -1.0f), 1.0f)) + 4e-3f;   // + margin for fp32 rounding of the test
+        if (lane == 0) caps[j] = make_float4(sx, sy, sz, reach >= 3.14159f ? -2.0f : cosf(reach));
     }
-    // bounding cap of every patch (all warps of the CTA own the same bins: warp w handles patch w)
-#pragma unroll
-    for (int j = 0; j < K3C_PATCHES; ++j) {
-        if (j == warp && j < cp.npatch) {
-            const bool ok = bin_of(j) >= 0;
-            float sx = warp_sum(-ngx[j]), sy = warp_sum(-ngy[j]), sz = warp_sum(-ngz[j]);
-            const float nrm = sqrtf(sx * sx + sy * sy + sz * sz);
-            if (nrm > 1e-6f) { sx /= nrm; sy /= nrm; sz /= nrm; } else { sx = 0.f; sy = 0.f; sz = 1.f; }
-            float cmin = ok ? -(ngx[j] * sx + ngy[j] * sy + ngz[j] * sz) : 1.0f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
-            const float reach = cp.gamma + acosf(fminf(fmaxf(cmin, -1.0f), 1.0f)) + 4e-3f;   // + margin for fp32 rounding of the test
-            if (lane == 0) caps[j] = make_float4(sx, sy, sz, reach >= 3.14159f ? -2.0f : cosf(reach));
-        }
+    const bool live = pair < (long long)H * O;
+    const int h = live ? (int)(pair / O) : 0, o = live ? (int)(pair % O) : 0;
+    float *ph = PH + (size_t)(live ? pair : 0) * N, *po = PO + (size_t)(live ? pair : 0) * N;
+    for (int j = 0; j < cp.npatch; ++j) {
+        const int n = live ? bin_of(j) : -1;
+        sAcc[j][0][tid] = n >= 0 ? ph[n] : 0.f;
+        sAcc[j][1][tid] = n >= 0 ? po[n] : 0.f;
     }
     __syncthreads();
-    if (pair >= (long long)H * O) return;   // after the only block-wide barrier; below only __syncwarp
-    const int h = (int)(pair / O), o = (int)(pair % O);
+    if (!live) return;   // after the only block-wide barrier; below only __syncwarp (sAcc columns are thread-private)
 
-    float accH[K3C_PATCHES], accO[K3C_PATCHES];
-    float *ph = PH + (size_t)pair * N, *po = PO + (size_t)pair * N;
-#pragma unroll
-    for (int j = 0; j < K3C_PATCHES; ++j) {
-        const int n = bin_of(j);
-        accH[j] = n >= 0 ? ph[n] : 0.f;
-        accO[j] = n >= 0 ? po[n] : 0.f;
-    }
-
+    float *listH = lists[warp][0], *listO = lists[warp][1];
     for (int s0 = 0; s0 < S; s0 += 32) {
         const int ns = min(32, S - s0);
         Vec3 ch = {0.f, 0.f, 1.f}, co = {0.f, 0.f, 1.f};
@@ -406,27 +400,25 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
             ch = canonicalize_ref(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
             co = canonicalize_ref(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
         }
-#pragma unroll
-        for (int j = 0; j < K3C_PATCHES; ++j) {
-            if (j < cp.npatch) {
-                const float4 cap = caps[j];
-                // a NaN direction (degenerate normal) must poison its bins like in the reference: !(x <= w) keeps it "needed"
-                const bool needH = lane < ns && !(fmaf(ch.x, cap.x, fmaf(ch.y, cap.y, ch.z * cap.z)) <= cap.w);
-                const bool needO = lane < ns && !(fmaf(co.x, cap.x, fmaf(co.y, cap.y, co.z * cap.z)) <= cap.w);
-                const int cntH = cone_compact(needH, ch, reinterpret_cast<float *>(lists[warp][0]), lane);
-                const int cntO = cone_compact(needO, co, reinterpret_cast<float *>(lists[warp][1]), lane);
-                accH[j] = cone_steps<DEG>(cntH, lists[warp][0], ngx[j], ngy[j], ngz[j], accH[j], cp);
-                accO[j] = cone_steps<DEG>(cntO, lists[warp][1], ngx[j], ngy[j], ngz[j], accO[j], cp);
-                __syncwarp();   // the lists are rewritten for the next patch
-            }
+#pragma unroll 1
+        for (int j = 0; j < cp.npatch; ++j) {
+            const float4 cap = caps[j];
+            // a NaN direction (degenerate normal) must poison its bins like in the reference: !(x <= w) keeps it "needed"
+            const bool needH = lane < ns && !(fmaf(ch.x, cap.x, fmaf(ch.y, cap.y, ch.z * cap.z)) <= cap.w);
+            const bool needO = lane < ns && !(fmaf(co.x, cap.x, fmaf(co.y, cap.y, co.z * cap.z)) <= cap.w);
+            const int cntH = cone_compact(needH, ch, listH, lane);
+            const int cntO = cone_compact(needO, co, listO, lane);
+            const float ngx = sG[j][0][lane], ngy = sG[j][1][lane], ngz = sG[j][2][lane];
+            sAcc[j][0][tid] = cone_steps<DEG>(cntH, listH, ngx, ngy, ngz, sAcc[j][0][tid], cp);
+            sAcc[j][1][tid] = cone_steps<DEG>(cntO, listO, ngx, ngy, ngz, sAcc[j][1][tid], cp);
+            __syncwarp();   // the lists are rewritten for the next patch
         }
     }
-#pragma unroll
-    for (int j = 0; j < K3C_PATCHES; ++j) {
+    for (int j = 0; j < cp.npatch; ++j) {
         const int n = bin_of(j);
         if (n >= 0) {
-            ph[n] = accH[j];
-            po[n] = accO[j];
+            ph[n] = sAcc[j][0][tid];
+            po[n] = sAcc[j][1][tid];
         }
     }
 }
@@ -543,13 +535,16 @@ extern "C" int coma_orient_accumulate_cone_f32(const float *hn, const float *on,
     cp.npatch = (int)((N + 31) / 32);
     const long long pairs = (long long)H * O;
     const unsigned blocks = (unsigned)((pairs + K3_WARPS - 1) / K3_WARPS);
-    static const bool two_ctas = getenv("COMA_B200_K3C_2CTA") != nullptr;   // A/B: 128 registers, 2 CTAs/SM (read once)
+    static const int ctas = getenv("COMA_B200_K3C_CTAS") ? atoi(getenv("COMA_B200_K3C_CTAS")) : 5;   // A/B: CTAs per SM (read once)
 #define LAUNCH_CONE(DEG)                                                                                                          \
-    if (two_ctas)                                                                                                                 \
-        orient_accumulate_cone_kernel<DEG, 2><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+    if (ctas == 4)                                                                                                                \
+        orient_accumulate_cone_kernel<DEG, 4><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+                                                                                cp, epsf, ord, p, sp, PH, PO);                    \
+    else if (ctas == 6)                                                                                                           \
+        orient_accumulate_cone_kernel<DEG, 6><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
                                                                                 cp, epsf, ord, p, sp, PH, PO);                    \
     else                                                                                                                          \
-        orient_accumulate_cone_kernel<DEG, 3><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+        orient_accumulate_cone_kernel<DEG, 5><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
                                                                                 cp, epsf, ord, p, sp, PH, PO)
     switch (fit->deg) {
         case 3: LAUNCH_CONE(3); break;

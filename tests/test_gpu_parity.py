@@ -268,7 +268,7 @@ def test_orient_accumulate_cone_limited(dev, H, O, N, S, sigma, bits, order):
 
 
 # --------------------------------------------------------------------------------------------- K4
-@pytest.mark.parametrize("name", ["occupancy_small", "occupancy_s30"])
+@pytest.mark.parametrize("name", ["occupancy_small", "occupancy_s30", "cuda_occupancy_small"])
 def test_occupancy_golden(dev, golden_dir, name):
     from coma_b200 import ops
     from oracle import oracle

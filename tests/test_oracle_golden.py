@@ -30,15 +30,20 @@ def test_nearest_vertex_bit_exact(golden_dir):
     assert idx[0] == 3 and idx[1] == 0  # ties resolve to the lowest index
 
 
-@pytest.mark.parametrize("name", ["contact_small", "contact_sigma02"])
+@pytest.mark.parametrize("name", ["contact_small", "contact_sigma02", "cuda_contact_small", "cuda_contact_sigma02", "cuda_contact_boundary"])
 def test_contact_accumulators(golden_dir, name):
+    """`cuda_*` fixtures were written by the reference running with device="cuda" on a B200 (tests/golden/make_golden_cuda.py):
+    they pin the oracle's sum_order="cuda" association ((x2+z2)+y2, ATen's CUDA reduction); the others its CPU association."""
+    if not os.path.exists(os.path.join(golden_dir, name + ".npz")):
+        pytest.skip(f"{name}.npz not generated yet")
     g = _load(golden_dir, name)
+    order = "cuda" if name.startswith("cuda_") else "cpu"
     size, thres, sigma, eps, ratio = g["params"]
-    count, nom = oracle.pair_accumulate(g["hv"], g["ov"], thres, size)
+    count, nom = oracle.pair_accumulate(g["hv"], g["ov"], thres, size, sum_order=order)
     np.testing.assert_array_equal(count, g["count"])                       # integer histogram: bit-exact
     np.testing.assert_allclose(nom, g["nom"], rtol=RTOL, atol=0)
     grid = oracle.fibonacci_sphere(int(g["N"]))
-    PH, PO = oracle.orient_accumulate(g["hn"], g["on"], grid, sigma, eps)
+    PH, PO = oracle.orient_accumulate(g["hn"], g["on"], grid, sigma, eps, sum_order=order)
     # pure relative tolerance down to the smallest normal fp32 (below that the fp32 store rounds to denormals/zero)
     np.testing.assert_allclose(PH, g["PH"], rtol=RTOL, atol=1e-37)
     np.testing.assert_allclose(PO, g["PO"], rtol=RTOL, atol=1e-37)
