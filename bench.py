@@ -50,8 +50,14 @@ K3_NCU_DRAM_BYTES = 31.467172e9 + 31.378264e9
 # K2 streaming kernel (one sample per launch), profiles/r01_k2_full.md: 125.9 MB read + 70.2 MB written while the capture ran (the
 # rest of the 125.7 MB of accumulator writes is still dirty in the 126 MB L2 when the single profiled launch ends)
 K2_NCU_DRAM_BYTES = 125.852928e6 + 70.227456e6
-K3_MUFU_PER_EVAL = 2.0     # MUFU.SQRT + MUFU.EX2 per bin evaluation in the K3 inner loop (cuobjdump)
+K3_MUFU_PER_EVAL = 2.0     # DENSE kernel: MUFU.SQRT + MUFU.EX2 per bin evaluation (cuobjdump)
 MUFU_CLK_PER_WARP_INSTR = 8.05  # measured on B200 with tools/ubench_pipes.cu (4 lanes/clk per SM sub-partition)
+# CONE-LIMITED kernel (the default): what binds it is the FP32 "heavy" pipe, the only one that executes the packed FFMA2 / FMUL2 /
+# FADD2 (ncu: sm__pipe_fmaheavy_cycles_active 64 % vs 36 % for the whole FMA pipe, profiles/r02_k3cone_full.md).
+K3C_EXEC_FRACTION = 0.748       # executed / algorithmic bin evaluations on this seeded workload: MUFU.EX2 warp-instructions x 32 lanes
+                                # / (2 x 250 x pair-samples) from the ncu capture of the same generator (profiles/r02_k3cone_full.md)
+K3C_PACKED_PER_STEP = 10.0      # FFMA2-class instructions per step of 64 evaluations at degree 5: 3 (dot) + 5 (Horner) + FMUL2 + FADD2
+FFMA2_CLK_PER_WARP_INSTR = 2.1  # tools/ubench_pipes.cu
 OCC = dict(Sg=128, S=4096, H_per_rank=1310, tol=3.0)   # BASELINE configs[4]
 
 
@@ -623,16 +629,25 @@ def main():
                          "peak": peak, "unit": "GB/s", "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / peak,
                          "traffic": K3_NCU_DRAM_BYTES if world == 1 else None,
                          "algorithmic_bytes": k3_bytes, "peak_source": peak_src, "ms": k3_ms,
-                         "note": "K3 is SFU (MUFU) / FP32-pipe bound once samples are fused (2 MUFU per bin evaluation): see roofline_sfu; "
-                                 "the HBM fraction is reported because the schema asks for it"},
-            "roofline_sfu": {"bound": "sfu", "kernel": f"{k3_kernel} (K3)", "achieved": evals_per_s * K3_MUFU_PER_EVAL / 1e9,
-                             "peak": 148 * 4 * 32 * sm_hz / MUFU_CLK_PER_WARP_INSTR / 1e9, "unit": "G MUFU lane-ops/s",
-                             "frac": evals_per_s * K3_MUFU_PER_EVAL / (148 * 4 * 32 * sm_hz / MUFU_CLK_PER_WARP_INSTR),
-                             "bin_evals_per_s": evals_per_s, "mufu_per_eval": K3_MUFU_PER_EVAL,
-                             "note": "ALGORITHMIC bin evaluations (2 x 250 per vertex-pair) per second; the cone-limited kernel executes only "
-                                     "the evaluations that can reach the accumulator, so this fraction can exceed what the MUFU pipe alone would allow",
-                             "peak_source": "148 SMs x 4 sub-partitions x 32 lanes / 8.05 clk per MUFU warp-instr (tools/ubench_pipes.cu) x median SM clock under load"},
+                         "note": "K3 is FP32-pipe bound once samples are fused (see roofline_pipe / roofline_sfu); the HBM fraction is reported "
+                                 "because the schema asks for it"},
         }
+        if k3_kernel == "orient_accumulate_cone_kernel":
+            steps_per_s = evals_per_s * K3C_EXEC_FRACTION / 64.0
+            peak_instr = 148 * 4 * sm_hz / FFMA2_CLK_PER_WARP_INSTR
+            line["roofline_pipe"] = {
+                "bound": "fp32-heavy pipe (packed FFMA2)", "kernel": f"{k3_kernel} (K3)", "achieved": steps_per_s * K3C_PACKED_PER_STEP / 1e9,
+                "peak": peak_instr / 1e9, "unit": "G packed-FP32 warp-instructions/s", "frac": steps_per_s * K3C_PACKED_PER_STEP / peak_instr,
+                "algorithmic_bin_evals_per_s": evals_per_s, "executed_fraction": K3C_EXEC_FRACTION, "packed_instr_per_64_evals": K3C_PACKED_PER_STEP,
+                "speedup_vs_dense_evaluation": "the dense kernel (all 2 x 250 bins, 2 MUFU each) ran this workload at 3.40e9 vertex-pairs/s (BENCH_r01)",
+                "peak_source": "148 SMs x 4 sub-partitions / 2.1 clk per FFMA2 warp-instr (tools/ubench_pipes.cu) x median SM clock under load; "
+                               "executed fraction from the ncu capture profiles/r02_k3cone_full.md"}
+        else:
+            line["roofline_sfu"] = {"bound": "sfu", "kernel": f"{k3_kernel} (K3)", "achieved": evals_per_s * K3_MUFU_PER_EVAL / 1e9,
+                                    "peak": 148 * 4 * 32 * sm_hz / MUFU_CLK_PER_WARP_INSTR / 1e9, "unit": "G MUFU lane-ops/s",
+                                    "frac": evals_per_s * K3_MUFU_PER_EVAL / (148 * 4 * 32 * sm_hz / MUFU_CLK_PER_WARP_INSTR),
+                                    "bin_evals_per_s": evals_per_s, "mufu_per_eval": K3_MUFU_PER_EVAL,
+                                    "peak_source": "148 SMs x 4 sub-partitions x 32 lanes / 8.05 clk per MUFU warp-instr (tools/ubench_pipes.cu) x median SM clock under load"}
         if k2 is not None:
             line["roofline_k2_stream"] = k2
         if occupancy is not None:

@@ -30,6 +30,7 @@ SIGNATURES = {
     "coma_significant_pairs": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp],
     "coma_masked_max_f32": [_vp, _i64, _i64, _vp, _int, _vp, _vp],
     "coma_entropy_readout_f32": [_vp, _i64, _i64, _f32, _vp, _vp],
+    "coma_entropy_readout_weighted_f32": [_vp, _i64, _i64, _f32, _vp, _f32, _vp, _vp],
     "coma_occupancy_readout_f32": [_vp, _i64, _i64, _vp, _i64, _vp, _vp],
     "coma_gemm_f16_tn": [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp, _i64, _vp],
     "coma_gemm_f16_ex": [_vp, _vp],

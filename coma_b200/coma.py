@@ -152,7 +152,9 @@ class ComA:
         if exchange:
             chunk = min(chunk, 128)                          # world x chunk samples per launch
         else:
-            chunk = min(chunk, (len(samples) + 31) // 32 * 32)
+            # <= 128 samples per launch: the host fills the next pinned chunk (fp64 -> fp32, ~0.25 ms per sample at cfg 4) while
+            # K2 / K3 of the previous one run; a K3 launch re-reads the grids, which costs ~3 % at 128 samples per launch
+            chunk = min(chunk, 128, (len(samples) + 31) // 32 * 32)
         stager = BatchStager(dict(hv=Hs, hn=Hs, ov=O, on=O), chunk, self.significant_contact_count.device)
         getters = dict(hv=lambda i: samples[i]["human_verts"][rows], hn=lambda i: samples[i]["human_normals"][rows],
                        ov=lambda i: samples[i]["obj_verts"], on=lambda i: samples[i]["obj_normals"])
@@ -267,6 +269,23 @@ class ComA:
             sh = ops.entropy_readout(self.prob_grid_canon_human_wrt_obj, n_bin)
         if nonphysical_type in ["obj", "both"]:
             so = ops.entropy_readout(self.prob_grid_canon_obj_wrt_human, n_bin)
+        out = {"human": sh, "obj": so, "n_bin": n_bin}
+        if as_numpy:
+            out = {k: (self._full_rows(v) if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+            return to_np_torch_recursive(out, use_torch=False, device="cpu")
+        return out
+
+    def compute_nonphysical_response_sphere_v2(self, n_bin: int, nonphysical_type: str, as_numpy: bool = True):
+        """utils/coma.py:529-579 (defined by the reference, used by none of its scripts): the per-bin normalised self-information
+        weighted by the bin's alignment with the principle vector."""
+        self.assert_inputs(nonphysical_type=nonphysical_type)
+        self.normalize_prob_grid_for_normals()
+        align = (self.canon_normal_grid * self.principle_vec[None]).sum(dim=-1).to(torch.float32).contiguous()   # :541
+        sh = so = None
+        if nonphysical_type in ["human", "both"]:
+            sh = ops.entropy_readout(self.prob_grid_canon_human_wrt_obj, n_bin, weights=align)
+        if nonphysical_type in ["obj", "both"]:
+            so = ops.entropy_readout(self.prob_grid_canon_obj_wrt_human, n_bin, weights=align)
         out = {"human": sh, "obj": so, "n_bin": n_bin}
         if as_numpy:
             out = {k: (self._full_rows(v) if isinstance(v, torch.Tensor) else v) for k, v in out.items()}

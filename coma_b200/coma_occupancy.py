@@ -104,24 +104,29 @@ class ComA_Occupancy:
     def aggregate_single_sample(self, **kwargs):
         self._aggregate_samples([kwargs])
 
-    def _canonical_human_verts(self, sample, all_rows=False):
-        """Host part of aggregate_single_sample_for_occupancy (:274-288): invariants + subtraction in the input dtype."""
+    def _canonical_human_verts(self, sample, all_rows=False, out=None):
+        """Host part of aggregate_single_sample_for_occupancy (:274-288): invariants + subtraction in the input dtype.
+        `out` (an fp32 row of the pinned staging buffer): the fp64 difference is rounded to fp32 on the store — the same values as
+        the reference's `(human_verts - obj_vert).astype(float32)` without the temporary."""
         human_verts, obj_verts, obj_normals = sample["human_verts"], sample["obj_verts"], sample["obj_normals"]
-        out = None
+        res = None
         for obj_idx in self.selected_obj_idxs:
             obj_vert, obj_normal = obj_verts[obj_idx], obj_normals[obj_idx]
             if self.debug_obj_vert is None:
                 self.debug_obj_vert = obj_vert
-            else:
-                assert np.allclose(self.debug_obj_vert, obj_vert)
+            else:   # bitwise-equal objects (the normal case) skip np.allclose's ~15 us
+                assert obj_vert is self.debug_obj_vert or np.array_equal(self.debug_obj_vert, obj_vert) or np.allclose(self.debug_obj_vert, obj_vert)
             if self.debug_obj_normal is None:
                 self.debug_obj_normal = obj_normal
             else:
-                assert np.allclose(self.debug_obj_normal, obj_normal)
+                assert obj_normal is self.debug_obj_normal or np.array_equal(self.debug_obj_normal, obj_normal) or np.allclose(self.debug_obj_normal, obj_normal)
             assert human_verts.shape[0] == self.human_res
             h0, h1 = (0, self.human_res) if all_rows else self._human_slice
-            out = human_verts[h0:h1] - obj_vert[None]     # only the rows this rank owns (elementwise: same values as slicing after)
-        return out
+            if out is None:
+                res = human_verts[h0:h1] - obj_vert[None]     # only the rows this rank owns (elementwise: same values as slicing after)
+            else:
+                res = np.subtract(human_verts[h0:h1], obj_vert[None], out=out, casting="same_kind")
+        return res
 
     def _aggregate_samples(self, samples, exchange=False, group=None):
         exchange = exchange and cdist.is_distributed(group)
@@ -134,7 +139,11 @@ class ComA_Occupancy:
         chunk = max(32, min(8192, (_STAGING_BYTES // (rows * 12)) // 32 * 32))
         chunk = min(chunk, 256) if exchange else min(chunk, (len(samples) + 31) // 32 * 32)
         stager = BatchStager(dict(hvc=self.human_res if exchange else h1 - h0), chunk, self.spatial_occupancy_grids.device)
-        getters = dict(hvc=lambda i: self._canonical_human_verts(samples[i], all_rows=exchange))
+        class _Getter:   # writes each sample's canonical vertices straight into its pinned fp32 row
+            @staticmethod
+            def fill(dst, i):
+                self._canonical_human_verts(samples[i], all_rows=exchange, out=dst)
+        getters = dict(hvc=_Getter)
         total = 0
         if exchange:
             for n, b in exchanged_batches(stager, getters, len(samples), group):

@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
 //     warp-broadcast LDS.128;
 //   * inside the cone acos(c)^2 is an analytic function of t = 1 - c: acos(1-t)^2 = t R(t), R a degree 3-6 minimax polynomial
 //     on [0, tmax] (tools/fit_acos2.py) — no square root: ONE MUFU (ex2) and 3 + DEG + 2 FMA-pipe ops per evaluation instead of
-//     two MUFU and ~15. t is clamped at tmax = 1 - cos(gamma), so a bin of a needed patch that lies outside the cone receives
-//     2^-drop_bits instead of its true (smaller) score.
+//     two MUFU and ~15. Beyond tmax = 1 - cos(gamma) the polynomial keeps growing, so a bin of a needed patch that lies outside
+//     the cone receives some positive value below 2^-drop_bits instead of its true (smaller) score.
 // Contract: every term the dense kernel would add and this one drops or clamps is < 2^-drop_bits (default 2^-32), i.e. after S
 // samples each bin is within S * 2^-32 ABSOLUTE of the dense result — < 2e-7 of the pair's largest bin in the worst case (some
 // bin of a pair always holds >= 0.002 S) — on top of the same ~5e-6 relative evaluation error as before.
@@ -290,15 +290,26 @@ struct ConeParams {
     int npatch;
 };
 
-// One patch, one histogram, one chunk: `cnt` directions were compacted into the warp's list (structure of arrays: x[32], y[32],
-// z[32], conflict-free to write), so three broadcast LDS.64 deliver a PAIR of samples as the packed operands of three FFMA2.
+// One patch, one histogram, one chunk: `cnt` (even) directions were compacted into the warp's list (structure of arrays x[], y[],
+// z[], conflict-free to write), so three broadcast LDS.64 deliver a PAIR of samples as the packed operands of three FFMA2.
+constexpr int K3C_LIST = 72;   // floats per component array: 64 samples of a chunk + the null entry, 16-byte multiple
+
 template <int DEG>
 __device__ __forceinline__ float cone_steps(int cnt, const float *__restrict__ list, float ngx, float ngy, float ngz, float acc,
                                             const ConeParams &cp) {
     const float2 c0 = f2(cp.c[0]), c1 = f2(cp.c[1]), c2 = f2(cp.c[2]), c3 = f2(cp.c[3]), c4 = f2(cp.c[DEG >= 4 ? 4 : 0]),
                  c5 = f2(cp.c[DEG >= 5 ? 5 : 0]), c6 = f2(cp.c[DEG >= 6 ? 6 : 0]);
-    auto score2 = [&](float2 t) -> float2 {
-        t = make_float2(fminf(t.x, cp.tmax), fminf(t.y, cp.tmax));
+    const float2 *lx = reinterpret_cast<const float2 *>(list), *ly = lx + K3C_LIST / 2, *lz = lx + K3C_LIST;
+    const float2 gx2 = f2(ngx), gy2 = f2(ngy), gz2 = f2(ngz), one2 = f2(1.0f);
+    // the pair's two samples accumulate into the two halves of one register pair (one FADD2 per step); within each half the
+    // samples are added in ascending order, the halves meet once at the end
+    float2 acc2 = make_float2(acc, 0.0f);
+    const int pairs = cnt >> 1;
+#pragma unroll 4
+    for (int k = 0; k < pairs; ++k) {   // cnt is warp-uniform: no divergence
+        const float2 t = __ffma2_rn(lx[k], gx2, __ffma2_rn(ly[k], gy2, __ffma2_rn(lz[k], gz2, one2)));   // 1 - G.n
+        // No clamp at tmax: every fitted t*R(t) keeps growing on (tmax, 2] (tools/fit_acos2.py, "monotone beyond"), so a bin of a
+        // needed patch that lies outside the cone receives a positive value BELOW 2^-drop_bits instead of its true, smaller score.
         float2 r = DEG == 6 ? c6 : DEG == 5 ? c5 : DEG == 4 ? c4 : c3;
         if (DEG >= 6) r = __ffma2_rn(r, t, c5);
         if (DEG >= 5) r = __ffma2_rn(r, t, c4);
@@ -307,43 +318,47 @@ __device__ __forceinline__ float cone_steps(int cnt, const float *__restrict__ l
         r = __ffma2_rn(r, t, c1);
         r = __ffma2_rn(r, t, c0);
         const float2 a = __fmul2_rn(t, r);
-        return make_float2(mufu_ex2(a.x), mufu_ex2(a.y));
-    };
-    const float2 *lx = reinterpret_cast<const float2 *>(list), *ly = lx + 16, *lz = lx + 32;
-    int k = 0;
-#pragma unroll 2
-    for (; k + 1 < cnt; k += 2) {   // cnt is warp-uniform: no divergence
-        const float2 t = __ffma2_rn(lx[k >> 1], f2(ngx), __ffma2_rn(ly[k >> 1], f2(ngy), __ffma2_rn(lz[k >> 1], f2(ngz), f2(1.0f))));   // 1 - G.n
-        const float2 s = score2(t);
-        acc += s.x;
-        acc += s.y;
+        acc2 = __fadd2_rn(acc2, make_float2(mufu_ex2(a.x), mufu_ex2(a.y)));
     }
-    if (k < cnt) {   // odd tail: only the first half of the last pair is live
-        const float t = fmaf(list[k], ngx, fmaf(list[32 + k], ngy, fmaf(list[64 + k], ngz, 1.0f)));
-        acc += score2(make_float2(t, t)).x;
-    }
-    return acc;
+    return acc2.x + acc2.y;
 }
 
-// Compacts the directions of the lanes with `need` into the warp's list; returns their number (warp-uniform).
-__device__ __forceinline__ int cone_compact(bool need, Vec3 d, float *__restrict__ list, int lane) {
-    const unsigned m = __ballot_sync(0xffffffffu, need);
-    if (need) {
-        const int pos = __popc(m & ((1u << lane) - 1u));
-        list[pos] = d.x;
-        list[32 + pos] = d.y;
-        list[64 + pos] = d.z;
+// Compacts the directions of the lanes' two samples (slot A: sample s0+lane, slot B: s0+32+lane) that need the patch into the
+// warp's list, A entries first, both in ascending sample order; an odd count is padded with the NULL direction (0,0,0): t = 1,
+// i.e. 90 degrees off every bin — beyond every cone this kernel accepts (gamma < 1.5), so the pad adds a term below 2^-drop_bits,
+// like any other out-of-cone evaluation. Returns the (even, warp-uniform) entry count.
+__device__ __forceinline__ int cone_compact(bool needA, Vec3 dA, bool needB, Vec3 dB, float *__restrict__ list, int lane) {
+    const unsigned mA = __ballot_sync(0xffffffffu, needA), mB = __ballot_sync(0xffffffffu, needB);
+    const unsigned lt = (1u << lane) - 1u;
+    const int nA = __popc(mA), cnt = nA + __popc(mB);
+    if (needA) {
+        const int pos = __popc(mA & lt);
+        list[pos] = dA.x;
+        list[K3C_LIST + pos] = dA.y;
+        list[2 * K3C_LIST + pos] = dA.z;
+    }
+    if (needB) {
+        const int pos = nA + __popc(mB & lt);
+        list[pos] = dB.x;
+        list[K3C_LIST + pos] = dB.y;
+        list[2 * K3C_LIST + pos] = dB.z;
+    }
+    if ((cnt & 1) && lane == 0) {
+        list[cnt] = 0.f;
+        list[K3C_LIST + cnt] = 0.f;
+        list[2 * K3C_LIST + cnt] = 0.f;
     }
     __syncwarp();
-    return __popc(m);
+    return (cnt + 1) & ~1;
 }
 
 constexpr int K3C_PATCHES = 8;
 
 // The per-patch state (the lane's bin centre, its two accumulators) lives in SHARED memory and the patch loop is ROLLED: the
 // first version kept it in registers with the loop unrolled 8x — 93 KB of SASS, `no_instruction` (instruction-cache misses) the
-// second-largest stall and 80 registers (3 CTAs/SM). Rolled: ~12 KB of code, ~40 registers, 5-6 CTAs/SM to hide the LDS -> FFMA2
-// -> MUFU chains; the price is 7 conflict-free shared-memory accesses per (patch, chunk) against ~450 instructions of work.
+// second-largest stall and 80 registers (3 CTAs/SM). Rolled: ~12 KB of code, ~50 registers; the price is 7 conflict-free
+// shared-memory accesses per (patch, chunk) against ~900 instructions of work. Chunks are 64 samples (two per lane), which
+// halves the per-(patch, histogram) bookkeeping — ballots, compaction, loop set-up and remainder — per sample.
 template <int DEG, int MINB>
 __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
     orient_accumulate_cone_kernel(const float *__restrict__ hn, const float *__restrict__ on, int S, int H, int O,
@@ -352,7 +367,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
     __shared__ float4 caps[K3C_PATCHES];                               // (centre, cos(min(gamma + radius, pi))) per patch
     __shared__ float sG[K3C_PATCHES][3][32];                           // negated bin centres: [patch][component][lane]
     __shared__ float sAcc[K3C_PATCHES][2][K3_WARPS * 32];              // accumulators: [patch][histogram][thread]
-    __shared__ __align__(16) float lists[K3_WARPS][2][96];             // per warp, per histogram: x[32] y[32] z[32] of the needed samples
+    __shared__ __align__(16) float lists[K3_WARPS][2][3 * K3C_LIST];   // per warp, per histogram: x[] y[] z[] of the needed samples
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
     const long long pair = (long long)blockIdx.x * K3_WARPS + warp;
 
@@ -389,25 +404,30 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
     if (!live) return;   // after the only block-wide barrier; below only __syncwarp (sAcc columns are thread-private)
 
     float *listH = lists[warp][0], *listO = lists[warp][1];
-    for (int s0 = 0; s0 < S; s0 += 32) {
-        const int ns = min(32, S - s0);
-        Vec3 ch = {0.f, 0.f, 1.f}, co = {0.f, 0.f, 1.f};
-        if (lane < ns) {
-            const float *ph3 = hn + ((size_t)(s0 + lane) * H + h) * 3;
-            const float *po3 = on + ((size_t)(s0 + lane) * O + o) * 3;
-            const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps, ord);
-            const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps, ord);
-            ch = canonicalize_ref(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
-            co = canonicalize_ref(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
+    for (int s0 = 0; s0 < S; s0 += 64) {
+        Vec3 ch[2], co[2];
+        bool have[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int s = s0 + 32 * u + lane;
+            have[u] = s < S;
+            ch[u] = co[u] = Vec3{0.f, 0.f, 1.f};
+            if (have[u]) {
+                const float *ph3 = hn + ((size_t)s * H + h) * 3;
+                const float *po3 = on + ((size_t)s * O + o) * 3;
+                const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps, ord);
+                const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps, ord);
+                ch[u] = canonicalize_ref(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
+                co[u] = canonicalize_ref(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
+            }
         }
 #pragma unroll 1
         for (int j = 0; j < cp.npatch; ++j) {
             const float4 cap = caps[j];
             // a NaN direction (degenerate normal) must poison its bins like in the reference: !(x <= w) keeps it "needed"
-            const bool needH = lane < ns && !(fmaf(ch.x, cap.x, fmaf(ch.y, cap.y, ch.z * cap.z)) <= cap.w);
-            const bool needO = lane < ns && !(fmaf(co.x, cap.x, fmaf(co.y, cap.y, co.z * cap.z)) <= cap.w);
-            const int cntH = cone_compact(needH, ch, listH, lane);
-            const int cntO = cone_compact(needO, co, listO, lane);
+            auto need = [&](const Vec3 &d) { return !(fmaf(d.x, cap.x, fmaf(d.y, cap.y, d.z * cap.z)) <= cap.w); };
+            const int cntH = cone_compact(have[0] && need(ch[0]), ch[0], have[1] && need(ch[1]), ch[1], listH, lane);
+            const int cntO = cone_compact(have[0] && need(co[0]), co[0], have[1] && need(co[1]), co[1], listO, lane);
             const float ngx = sG[j][0][lane], ngy = sG[j][1][lane], ngz = sG[j][2][lane];
             sAcc[j][0][tid] = cone_steps<DEG>(cntH, listH, ngx, ngy, ngz, sAcc[j][0][tid], cp);
             sAcc[j][1][tid] = cone_steps<DEG>(cntO, listO, ngx, ngy, ngz, sAcc[j][1][tid], cp);
@@ -535,7 +555,7 @@ extern "C" int coma_orient_accumulate_cone_f32(const float *hn, const float *on,
     cp.npatch = (int)((N + 31) / 32);
     const long long pairs = (long long)H * O;
     const unsigned blocks = (unsigned)((pairs + K3_WARPS - 1) / K3_WARPS);
-    static const int ctas = getenv("COMA_B200_K3C_CTAS") ? atoi(getenv("COMA_B200_K3C_CTAS")) : 5;   // A/B: CTAs per SM (read once)
+    static const int ctas = getenv("COMA_B200_K3C_CTAS") ? atoi(getenv("COMA_B200_K3C_CTAS")) : 4;   // A/B: CTAs per SM (read once; 4 = 64 registers, no spills)
 #define LAUNCH_CONE(DEG)                                                                                                          \
     if (ctas == 4)                                                                                                                \
         orient_accumulate_cone_kernel<DEG, 4><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \

@@ -124,12 +124,17 @@ def masked_max(cmap, mask, axis):
     return out
 
 
-def entropy_readout(P, n_bin):
-    """utils/coma.py:455-463 on a normalised grid. P [H,O,N] f32 -> [H,O] f32."""
+def entropy_readout(P, n_bin, weights=None):
+    """utils/coma.py:455-463 on a normalised grid (weights [N] f32: the `_v2` form, :529-579). P [H,O,N] f32 -> [H,O] f32."""
     H, O, N = P.shape
     out = torch.empty((H, O), dtype=torch.float32, device=P.device)
     with torch.cuda.device(P.device):
-        call("coma_entropy_readout_f32", _ptr(P), H * O, N, float(n_bin), _ptr(out), _stream())
+        if weights is None:
+            call("coma_entropy_readout_f32", _ptr(P), H * O, N, float(n_bin), _ptr(out), _stream())
+        else:
+            weights = _chk(weights, torch.float32, "weights").contiguous()
+            call("coma_entropy_readout_weighted_f32", _ptr(P), H * O, N, float(n_bin), _ptr(weights), float(weights.double().sum().item()),
+                 _ptr(out), _stream())
     return out
 
 

@@ -40,8 +40,13 @@ class BatchStager:
                 self.free[b].synchronize()       # kernels that read dev[b] are done -> both buffers reusable
             for k in self.specs:
                 view = self.pinned[b][k].numpy()
-                for j in range(n):
-                    np.copyto(view[j], getters[k](s0 + j), casting="same_kind")
+                g = getters[k]
+                if hasattr(g, "fill"):            # getter that writes straight into the pinned row (no temporary)
+                    for j in range(n):
+                        g.fill(view[j], s0 + j)
+                else:
+                    for j in range(n):
+                        np.copyto(view[j], g(s0 + j), casting="same_kind")
             if self.is_cuda:
                 with torch.cuda.stream(self.copy_stream):
                     for k in self.specs:

@@ -151,6 +151,10 @@ COMA_API int coma_masked_max_f32(const float *cmap, int64_t H, int64_t O, const 
 /* K5b  compute_nonphysical_response_sphere (:455-463) on an already-normalised grid:
  *      q = rint(P*n_bin)/n_bin; out[q] = 1 + sum_n (q==0 ? 0 : q*log q) / log(n_bin). P [HO,N] f32 -> out [HO] f32. */
 COMA_API int coma_entropy_readout_f32(const float *P, int64_t HO, int64_t N, float n_bin, float *out, coma_stream_t stream);
+/* `_v2` of the same read-out (utils/coma.py:529-579): every term (q ln q / ln n_bin + 1) is weighted by weights[n] (the bin's
+ * alignment G[n] . p, [N] f32 on the device); weight_sum = sum_n weights[n] (host). weights = NULL gives the unweighted form. */
+COMA_API int coma_entropy_readout_weighted_f32(const float *P, int64_t HO, int64_t N, float n_bin, const float *weights,
+                                               float weight_sum, float *out, coma_stream_t stream);
 
 /* K5c  normalize_prob_grid_for_spatials + max over vertices (utils/coma_occupancy.py:297-312):
  *      grids[h,:] /= sum(grids[h,:]) IN PLACE (NaN where a vertex never hit, as in the reference), then
