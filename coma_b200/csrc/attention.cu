@@ -145,7 +145,7 @@ template <int DKB, int DN, int STAGES, int FA_BKV, int NSB = 2, int NPB = 2>
 __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NSB))
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
-                         long long ldo, long long o_bstride) {
+                         float *__restrict__ out32, long long ldo, long long o_bstride) {
     using namespace fa;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = q0 + r;
         const float inv = 1.0f / l_run;
-        __half *dst = out + (size_t)b * o_bstride + (size_t)row * ldo + (size_t)h * d;
+        const size_t o_off = (size_t)b * o_bstride + (size_t)row * ldo + (size_t)h * d;
+        __half *dst = out + o_off;
 #pragma unroll
         for (int c0 = 0; c0 < DN; c0 += 16) {
             float t16[16];
@@ -369,6 +370,11 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
 #pragma unroll
             for (int c = 0; c < 16; c += 8) {
                 if (row < S && c0 + c < d) {  // d % 8 == 0
+                    if (out32) {   // fp32 output (parity tests: isolates the kernel's arithmetic from the fp16 store)
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) out32[o_off + c0 + c + t] = t16[c + t] * inv;
+                        continue;
+                    }
                     uint4 w;
                     __half2 *hp = reinterpret_cast<__half2 *>(&w);
 #pragma unroll
@@ -415,7 +421,7 @@ static int make_map4(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], 
 
 template <int DKB, int DN, int STAGES, int BKV, int NSB = 2, int NPB = 2>
 static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads, int S, int L, int d,
-                            float scale_log2, __half *out, long long ldo, long long o_bstride, cudaStream_t st) {
+                            float scale_log2, __half *out, float *out32, long long ldo, long long o_bstride, cudaStream_t st) {
     constexpr size_t smem = (size_t)DKB * 16384 + (size_t)STAGES * (DKB * BKV * 128 + ((DN * BKV * 2 + 1023) / 1024) * 1024) + NPB * 128 * BKV * 2 +
                             256 + 1024;
     static bool attr[16] = {false};
@@ -430,22 +436,32 @@ static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const 
         attr[dev] = true;
     }
     dim3 grid((S + FA_BQ - 1) / FA_BQ, heads, B);
-    launch_pdl(attention_fwd_kernel<DKB, DN, STAGES, BKV, NSB, NPB>, grid, dim3(FA_THREADS), smem, st, tq, tk, tv, S, L, d, scale_log2, out, ldo, o_bstride);
+    launch_pdl(attention_fwd_kernel<DKB, DN, STAGES, BKV, NSB, NPB>, grid, dim3(FA_THREADS), smem, st, tq, tk, tv, S, L, d, scale_log2, out, out32, ldo, o_bstride);
     return check_launch("attention_fwd_kernel");
 }
 
 }  // namespace coma
 
+extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                         int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32, int64_t ldo,
+                                         coma_stream_t stream);
 extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
                                       int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, int64_t ldo,
                                       coma_stream_t stream) {
+    COMA_REQUIRE(out, "null pointer");
+    return coma_attention_fwd_ex_f16(q, k, vt, B, heads, S, L, d, ldq, ldk, Lp, scale, out, nullptr, ldo, stream);
+}
+
+extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                         int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32, int64_t ldo,
+                                         coma_stream_t stream) {
     using namespace coma;
-    COMA_REQUIRE(q && k && vt && out, "null pointer");
+    COMA_REQUIRE(q && k && vt && (out || out_f32), "null pointer");
     COMA_REQUIRE(B > 0 && heads > 0 && S > 0 && L > 0 && d > 0 && B <= 65535 && heads <= 65535, "bad sizes");
     COMA_REQUIRE(d % 8 == 0 && d <= 192, "head dim must be a multiple of 8 and <= 192");
     COMA_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && Lp % 8 == 0 && Lp >= L && ldo % 8 == 0, "strides must be multiples of 8 elements");
     COMA_REQUIRE(ldq >= heads * d && ldk >= heads * d && ldo >= heads * d, "row strides smaller than heads*d");
-    COMA_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out) % 16 == 0, "pointers must be 16-byte aligned");
+    COMA_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out | (uintptr_t)out_f32) % 16 == 0, "pointers must be 16-byte aligned");
     // DN = accumulator width of the kernel instantiation that will run; the V^T TMA box must have exactly DN rows
     // (rows >= d are zero-filled) or the producer's expect_tx byte count never completes.
     const int d16 = (int)((d + 15) / 16 * 16);
@@ -478,7 +494,7 @@ extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *
     cudaStream_t st = (cudaStream_t)stream;
     __half *o = (__half *)out;
     const long long obs = (long long)S * ldo;
-#define COMA_FA_ARGS tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, ldo, obs, st
+#define COMA_FA_ARGS tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, out_f32, ldo, obs, st
     if (d <= 64) {
         if (BKV == 32) {
             if (DN == 48) return launch_attention<1, 48, 3, 32>(COMA_FA_ARGS);

@@ -238,6 +238,11 @@ COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t
 COMA_API int coma_attention_fwd_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
                                     int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, int64_t ldo,
                                     coma_stream_t stream);
+/* Same with an optional fp32 output: out_f32 [B,S,heads*d] f32 (row stride ldo, in elements) is written INSTEAD of the fp16 `out`
+ * when non-NULL — the normalised TMEM accumulator without the final fp16 rounding (parity tests). */
+COMA_API int coma_attention_fwd_ex_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                       int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32,
+                                       int64_t ldo, coma_stream_t stream);
 
 /* ---- U*: the non-contraction layers of the UNet / VAE, NHWC fp16 activations ([B, H*W, C], row stride ld*) -------------
  * (diffusers UNet2DConditionModel / AutoencoderKL layers reached from utils/adaptive_mask_inpainting.py:1001, :680, :1086) */

@@ -309,3 +309,30 @@ def test_clip_text_encoder_vs_transformers(dev, cfg_name):
     ids2[:, 30] = 5
     got2 = enc(ids2)
     assert torch.equal(got2[:, :30], got[:, :30]) and not torch.equal(got2[:, 30:], got[:, 30:])
+
+
+@pytest.mark.parametrize("S,L,heads,d", [(4096, 4096, 8, 40), (1024, 1024, 8, 80), (256, 256, 8, 160), (4096, 77, 8, 40), (200, 300, 2, 64)])
+def test_attention_kernel_fp32_output(dev, S, L, heads, d):
+    """The fused attention kernel alone (no projections), fp32 output (`coma_attention_fwd_ex_f16`), against fp32 torch on the same
+    fp16 Q / K / V at the UNet's three head sizes. What remains is the kernel's own arithmetic: fp32 accumulation order, ex2.approx,
+    and the one rounding it cannot avoid — P is an fp16 tensor-core operand (2^-11 relative per probability, averaged down by the
+    keys it is summed over). Bars: 1e-4 of the output scale in RMS (the north-star figure), 3e-4 for the worst single element."""
+    from coma_b200._lib import _stream, call
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(S + d)
+    B, C, Lp = 2, heads * d, nn.rup(L)
+    q = torch.randn((B, S, C), device=dev, generator=g).half()
+    k = torch.randn((B, L, C), device=dev, generator=g).half()
+    v = torch.randn((B, L, C), device=dev, generator=g).half()
+    vt = torch.zeros((B, heads, d, Lp), dtype=torch.float16, device=dev)
+    vt[..., :L] = v.view(B, L, heads, d).permute(0, 2, 3, 1)
+    out = torch.zeros((B, S, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("coma_attention_fwd_ex_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, C, C, Lp, float(d ** -0.5), None,
+             out.data_ptr(), C, _stream())
+    qf, kf, vf = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, -1) @ vf).transpose(1, 2).reshape(B, S, C)
+    scale = ref.abs().max().item()
+    err = (out - ref).abs()
+    assert err.pow(2).mean().sqrt().item() <= 1e-4 * scale, err.pow(2).mean().sqrt().item() / scale
+    assert err.max().item() <= 3e-4 * scale, err.max().item() / scale

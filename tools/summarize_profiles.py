@@ -17,7 +17,8 @@ KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum ", "dram__bytes_write.su
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor", "lts__throughput.avg.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size",
         "launch__block_size", "smsp__average_warp", "smsp__warp_issue_stalled", "sm__cycles_elapsed.avg ", "launch__shared_mem_per_block",
-        "smsp__inst_executed.sum ", "lts__t_sectors_op_atom", "lts__t_sectors_op_red", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum ")
+        "smsp__inst_executed.sum ", "lts__t_sectors_op_atom", "lts__t_sectors_op_red", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum ",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct", "sm__pipe_fmalite_cycles_active.avg.pct", "smsp__issue_active.avg.pct", "smsp__average_warps_issue_stalled")
 
 
 def raw(rep):
