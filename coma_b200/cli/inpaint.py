@@ -132,6 +132,28 @@ def load_state_dict(path):
     return torch.load(os.path.join(path, "diffusion_pytorch_model.bin"), map_location="cpu")
 
 
+def read_diffusers_config(model_dir, sub):
+    """<model_dir>/<sub>/config.json (diffusers layout) -> the cfg dict of coma_b200.inpaint.{unet.UNet, vae.VAE}, or None when the
+    file is absent (the SD-1.5-inpainting / SD VAE defaults then apply). diffusers quirk kept: `attention_head_dim` of the SD-1.x UNet
+    config is the NUMBER of heads (8)."""
+    import json
+    pth = os.path.join(model_dir, sub, "config.json")
+    if not os.path.exists(pth):
+        return None
+    with open(pth) as fh:
+        c = json.load(fh)
+    if sub == "unet":
+        down = c.get("down_block_types", ["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"])
+        heads = c.get("attention_head_dim", 8)
+        return dict(in_channels=c.get("in_channels", 9), out_channels=c.get("out_channels", 4),
+                    block_out_channels=tuple(c.get("block_out_channels", (320, 640, 1280, 1280))), layers_per_block=c.get("layers_per_block", 2),
+                    heads=heads[0] if isinstance(heads, (list, tuple)) else heads, cross_attention_dim=c.get("cross_attention_dim", 768),
+                    groups=c.get("norm_num_groups", 32), attn_levels=tuple("CrossAttn" in t for t in down))
+    return dict(in_channels=c.get("in_channels", 3), latent_channels=c.get("latent_channels", 4),
+                block_out_channels=tuple(c.get("block_out_channels", (128, 256, 512, 512))), layers_per_block=c.get("layers_per_block", 2),
+                groups=c.get("norm_num_groups", 32), scaling_factor=c.get("scaling_factor", 0.18215))
+
+
 def build_segmenter(adaptive_mask_model_type, segmenter=None, default_pointrend_threshold=0.2):
     """The in-loop human segmenter (src/generation/inpaint.py:66-110) is a PLUG-IN here: detectron2 PointRend / SAM and their
     weights live outside this repository.
@@ -165,10 +187,11 @@ def set_pipeline(model_dir, adaptive_mask_model_type, default_ddim_steps, defaul
     from coma_b200.inpaint.pipeline import (AdaptiveMaskInpaintPipeline, AdaptiveMaskSettings, MaskDilateScheduler, ProvokeScheduler,
                                             default_adaptive_mask_settings)
     seg_model = build_segmenter(adaptive_mask_model_type, segmenter, default_pointrend_threshold)   # fails fast, before the weights
-    from coma_b200.inpaint.unet import UNet
-    from coma_b200.inpaint.vae import VAE
-    pipe = AdaptiveMaskInpaintPipeline(UNet(load_state_dict(os.path.join(model_dir, "unet")), device=device),
-                                       VAE(load_state_dict(os.path.join(model_dir, "vae")), device=device))
+    from coma_b200.inpaint.unet import SD15_INPAINT, UNet
+    from coma_b200.inpaint.vae import SD_VAE, VAE
+    ucfg, vcfg = read_diffusers_config(model_dir, "unet") or SD15_INPAINT, read_diffusers_config(model_dir, "vae") or SD_VAE
+    pipe = AdaptiveMaskInpaintPipeline(UNet(load_state_dict(os.path.join(model_dir, "unet")), ucfg, device=device),
+                                       VAE(load_state_dict(os.path.join(model_dir, "vae")), vcfg, device=device))
     pipe.register_adaptive_mask_model(seg_model)
     n = int(default_ddim_steps * 0.1)
     if adaptive_mask_model_type in ("p", "stub"):

@@ -307,7 +307,12 @@ __device__ __forceinline__ float cone_steps(int cnt, const float *__restrict__ l
     const int pairs = cnt >> 1;
 #pragma unroll 4
     for (int k = 0; k < pairs; ++k) {   // cnt is warp-uniform: no divergence
+#ifdef K3C_SCALAR_DOT   // A/B (measured 2 % SLOWER: 692 vs 678 ms at cfg 4, S = 256): scalar FFMAs (lite-pipe eligible) for the dot product
+        const float2 ax = lx[k], ay = ly[k], az = lz[k];
+        const float2 t = make_float2(fmaf(ax.x, ngx, fmaf(ay.x, ngy, fmaf(az.x, ngz, 1.0f))), fmaf(ax.y, ngx, fmaf(ay.y, ngy, fmaf(az.y, ngz, 1.0f))));
+#else
         const float2 t = __ffma2_rn(lx[k], gx2, __ffma2_rn(ly[k], gy2, __ffma2_rn(lz[k], gz2, one2)));   // 1 - G.n
+#endif
         // No clamp at tmax: every fitted t*R(t) keeps growing on (tmax, 2] (tools/fit_acos2.py, "monotone beyond"), so a bin of a
         // needed patch that lies outside the cone receives a positive value BELOW 2^-drop_bits instead of its true, smaller score.
         float2 r = DEG == 6 ? c6 : DEG == 5 ? c5 : DEG == 4 ? c4 : c3;
