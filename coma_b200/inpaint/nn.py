@@ -102,6 +102,7 @@ def gemm_batched(A, lda, a_s1, a_s2, W, ldw, w_s1, w_s2, out, ldo, o_s1, o_s2, M
     return out
 
 
+SMALL_N_CONV = True     # conv_out layers (Cout <= 4) on the direct fused kernel C1 (A/B switch for tests and tuning)
 _GN_COUNTERS = {}
 FUSED_GN_STATS = True   # convolutions leave GroupNorm partial sums for their consumer (A/B switch for tests and tuning)
 
@@ -166,6 +167,16 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
     stride 1, Cin % 64 == 0: implicit GEMM (shifted TMA tiles, no im2col matrix) on the pre-activated tensor;
     otherwise (stride 2, tiny Cin): im2col with the GroupNorm affine + SiLU applied while gathering, then GEMM."""
     Ho, Wo = conv_out_hw(x.H, x.W, stride, pad, up)
+    if SMALL_N_CONV and w.shape[0] <= 4 and stride == 1 and pad == 1 and not up and x.C % 8 == 0 and residual is None and bias_rows is None:
+        # C1: a handful of output channels (VAE / UNet conv_out): direct halo-tiled kernel with the GroupNorm affine + SiLU of the
+        # input fused in — no normalised intermediate tensor, no 64-wide tensor-core tile for 3 columns
+        scale, shift = gn if gn is not None else (None, None)
+        out = new_act(x.B, Ho, Wo, w.shape[0], x.t.device, out_dtype)
+        with torch.cuda.device(x.t.device):
+            call("coma_conv3x3_small_n_f16", x.t.data_ptr(), x.B, x.H, x.W, x.C, x.ld, _ptr(scale), _ptr(shift), act if gn is not None else 0,
+                 w.data_ptr(), w.stride(0), w.shape[0], _ptr(bias), out.t.data_ptr() if out_dtype == F32 else None,
+                 out.t.data_ptr() if out_dtype == F16 else None, out.t.stride(0), _stream())
+        return out
     strided_ok = stride == 2 and not up and gn is None and Ho * Wo >= 128   # element-strided TMA tiles
     if IMPLICIT_CONV and ((stride == 1 and pad == 1) or strided_ok) and x.C % 64 == 0 and _tiles_128(Ho, Wo):
         scale, shift = gn if gn is not None else (None, None)

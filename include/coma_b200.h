@@ -230,6 +230,16 @@ COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
                               coma_stream_t stream);
 
+/* ---- C1: 3x3 convolution (stride 1, zero padding 1) with 1..4 output channels, fused with the GroupNorm affine + SiLU of its
+ * input: out[b,y,x,n] = bias[n] + sum_{ky,kx,c} W[n,(ky,kx,c)] * act(x[b,y+ky-1,x+kx-1,c]*scale[b,c] + shift[b,c]) (zero outside the image).
+ * Replaces decoder.conv_norm_out -> SiLU -> conv_out (128 -> 3) of AutoencoderKL.decode and conv_norm_out -> SiLU -> conv_out (320 -> 4) of
+ * the UNet (utils/adaptive_mask_inpainting.py:1086,:1112,:1001) without the normalised intermediate tensor. CUDA cores, halo tiles in shared
+ * memory. x [B,H,W,C] NHWC f16 (row stride ldx), C % 8 == 0; scale / shift [B,C] f32 or both NULL; Wt [Cout, ldw >= 9C] f16, K order
+ * (ky,kx,c); out_f32 / out_f16 [B*H*W, ldo] (either may be NULL). */
+COMA_API int coma_conv3x3_small_n_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const float *scale,
+                                      const float *shift, int act, const void *Wt, int64_t ldw, int64_t Cout, const float *bias,
+                                      float *out_f32, void *out_f16, int64_t ldo, coma_stream_t stream);
+
 /* ---- A1: fused multi-head attention forward (tcgen05: S = Q K^T and O = P V on the tensor cores, online softmax between
  * them, scores never leave the SM). out[b,s,h*d:(h+1)*d] = softmax(Q_h K_h^T * scale) V_h.
  * q [B,S,heads*d] (row stride ldq), k [B,L,heads*d] (ldk), vt = V^T [B,heads,d,Lp] (coma_transpose_heads_f16), all f16;

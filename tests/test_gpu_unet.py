@@ -337,3 +337,32 @@ def test_attention_kernel_fp32_output(dev, S, L, heads, d):
     err = (out - ref).abs()
     assert err.pow(2).mean().sqrt().item() <= 1e-4 * scale, err.pow(2).mean().sqrt().item() / scale
     assert err.max().item() <= 5e-4 * scale, err.max().item() / scale
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout,gn,out32", [(2, 64, 64, 128, 3, True, True), (1, 40, 72, 320, 4, True, False), (3, 17, 33, 64, 1, False, True),
+                                                  (1, 512, 512, 128, 3, True, True), (2, 16, 16, 72, 2, True, True)])
+def test_conv3x3_small_n_fused(dev, B, H, W, C, Cout, gn, out32):
+    """C1: the conv_out layers (Cout <= 4) as a direct halo-tiled kernel with the GroupNorm affine + SiLU of the input fused in,
+    against fp32 torch on the same fp16 operands (the activated input is rounded to fp16 in shared memory like the tensor it replaces)."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(C + H)
+    x = torch.randn((B, C, H, W), device=dev, generator=g).half().float()
+    w = (torch.randn((Cout, C, 3, 3), device=dev, generator=g) * (9 * C) ** -0.5).half().float()
+    b = torch.randn(Cout, device=dev, generator=g)
+    xa = _nhwc(x)
+    gnp, xin = None, x
+    if gn:
+        gamma, beta = 1 + 0.1 * torch.randn(C, device=dev, generator=g), 0.1 * torch.randn(C, device=dev, generator=g)
+        gnp = nn.gn_affine(xa, gamma, beta, 8, 1e-6)
+        xin = F.silu(F.group_norm(x, 8, gamma, beta, 1e-6)).half().float()
+    out = nn.conv3x3(xa, nn.prep_conv3x3(w, dev), b, gn=gnp, act=1, out_dtype=torch.float32 if out32 else torch.float16)
+    from coma_b200 import _lib
+    assert _lib.last_kernel() == "conv3x3_small_n_kernel"
+    ref = F.conv2d(xin, w, b, padding=1)
+    _close(_nchw(out.t[:, :Cout], B, H, W), ref, 2e-3 if gn else (1e-4 if out32 else 1e-3))
+    nn.SMALL_N_CONV = False     # the tensor-core path computes the same thing
+    try:
+        old = nn.conv3x3(xa, nn.prep_conv3x3(w, dev), b, gn=gnp, act=1, out_dtype=torch.float32 if out32 else torch.float16)
+    finally:
+        nn.SMALL_N_CONV = True
+    _close(_nchw(out.t[:, :Cout], B, H, W), _nchw(old.t[:, :Cout], B, H, W), 2e-3)
