@@ -88,7 +88,7 @@ def _cli(root, ckpt, *extra, env=None):
     cmd = [sys.executable, os.path.join(ROOT, "src", "generation", "inpaint.py"), "--supercategories", "BEHAVE", "--categories", "backpack",
            "--asset_render_dir", f"{root}/asset_renders", "--asset_mask_dir", f"{root}/asset_masks", "--asset_seg_dir", f"{root}/asset_segs",
            "--prompts_dir", f"{root}/prompts", "--save_dir", f"{root}/inpaintings", "--model_dir", ckpt, "--num_img_per_combination", "3",
-           "--default_ddim_steps", "50", "--batch_size", "3"]   # the provoke schedule is hard-coded up to step 45 (reference :125-129) + list(extra)
+           "--default_ddim_steps", "50", "--batch_size", "3"] + list(extra)   # 50 steps: the provoke schedule is hard-coded up to step 45 (:125-129)
     return subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, **(env or {})), timeout=900)
 
 
