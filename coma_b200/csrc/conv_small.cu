@@ -4,7 +4,7 @@
 //
 // On the tensor-core implicit GEMM this layer pads N = 3 to a 64-wide tile (13 TFLOP/s, 0.54 ms per B = 4 decode at 512^2) and
 // needs a separate pass that writes the normalised + activated 268 MB tensor first (0.17 ms). Here a CTA owns a 32 x 16 pixel tile:
-// it stages the 34 x 18 halo in shared memory 64 channels at a time, applying x*scale[b,c] + shift[b,c] -> SiLU on the way in
+// it stages the 34 x 18 halo in shared memory 32 channels at a time, applying x*scale[b,c] + shift[b,c] -> SiLU on the way in
 // (fp16 in smem, zero outside the image = the convolution's zero padding of the ACTIVATED tensor), and every thread accumulates two
 // pixels x Cout outputs in fp32 on the CUDA cores; weights sit in shared memory as fp32 and are read as broadcast LDS.128.
 // HBM traffic: the input once (x 1.2 for the halo, mostly L2 hits) + a 3-channel output; no intermediate tensor.
@@ -14,7 +14,7 @@
 
 namespace coma {
 
-constexpr int CS_TW = 32, CS_TH = 16, CS_CC = 64;            // tile width / height (pixels), channels per smem chunk
+constexpr int CS_TW = 32, CS_TH = 16, CS_CC = 32;            // tile width / height (pixels), channels per smem chunk (54 KB: 4 CTAs/SM)
 constexpr int CS_HW = CS_TW + 2, CS_HH = CS_TH + 2;          // halo tile
 constexpr int CS_PIX_STRIDE = CS_CC + 8;                     // halves per staged pixel (+16 B: conflict-free LDS.128 across x)
 constexpr int CS_NOUT = 4;                                   // accumulators per pixel (Cout <= 4)
@@ -32,11 +32,9 @@ __global__ void __launch_bounds__(256)
     const int tiles_x = (W + CS_TW - 1) / CS_TW;
     const int b = blockIdx.y, ty0 = (blockIdx.x / tiles_x) * CS_TH, tx0 = (blockIdx.x % tiles_x) * CS_TW;
     const int tid = threadIdx.x, px = tid & 15, py = tid >> 4;   // thread -> pixels (px, py) and (px + 16, py) of the tile
-    float acc[2][CS_NOUT];
+    float2 acc[2][2];   // [pixel][output pair (n0,n1) / (n2,n3)]: packed FP32x2 accumulation, the input value broadcast
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int n = 0; n < CS_NOUT; ++n) acc[q][n] = 0.f;
+    for (int q = 0; q < 2; ++q) acc[q][0] = acc[q][1] = make_float2(0.f, 0.f);
 
     for (int c0 = 0; c0 < C; c0 += CS_CC) {
         __syncthreads();   // previous chunk fully consumed
@@ -90,14 +88,15 @@ __global__ void __launch_bounds__(256)
                 for (int t = 0; t < 4; ++t) {
                     const float2 av = __half22float2(ah[t]), bv = __half22float2(bh[t]);
                     const float4 w0 = wp[c8 * 8 + 2 * t], w1 = wp[c8 * 8 + 2 * t + 1];   // weights of channels 2t, 2t+1: (n0..n3)
-                    acc[0][0] = fmaf(av.x, w0.x, acc[0][0]); acc[0][1] = fmaf(av.x, w0.y, acc[0][1]);
-                    acc[0][2] = fmaf(av.x, w0.z, acc[0][2]); acc[0][3] = fmaf(av.x, w0.w, acc[0][3]);
-                    acc[0][0] = fmaf(av.y, w1.x, acc[0][0]); acc[0][1] = fmaf(av.y, w1.y, acc[0][1]);
-                    acc[0][2] = fmaf(av.y, w1.z, acc[0][2]); acc[0][3] = fmaf(av.y, w1.w, acc[0][3]);
-                    acc[1][0] = fmaf(bv.x, w0.x, acc[1][0]); acc[1][1] = fmaf(bv.x, w0.y, acc[1][1]);
-                    acc[1][2] = fmaf(bv.x, w0.z, acc[1][2]); acc[1][3] = fmaf(bv.x, w0.w, acc[1][3]);
-                    acc[1][0] = fmaf(bv.y, w1.x, acc[1][0]); acc[1][1] = fmaf(bv.y, w1.y, acc[1][1]);
-                    acc[1][2] = fmaf(bv.y, w1.z, acc[1][2]); acc[1][3] = fmaf(bv.y, w1.w, acc[1][3]);
+                    const float2 w0a = make_float2(w0.x, w0.y), w0b = make_float2(w0.z, w0.w), w1a = make_float2(w1.x, w1.y), w1b = make_float2(w1.z, w1.w);
+                    acc[0][0] = __ffma2_rn(make_float2(av.x, av.x), w0a, acc[0][0]);
+                    acc[0][1] = __ffma2_rn(make_float2(av.x, av.x), w0b, acc[0][1]);
+                    acc[0][0] = __ffma2_rn(make_float2(av.y, av.y), w1a, acc[0][0]);
+                    acc[0][1] = __ffma2_rn(make_float2(av.y, av.y), w1b, acc[0][1]);
+                    acc[1][0] = __ffma2_rn(make_float2(bv.x, bv.x), w0a, acc[1][0]);
+                    acc[1][1] = __ffma2_rn(make_float2(bv.x, bv.x), w0b, acc[1][1]);
+                    acc[1][0] = __ffma2_rn(make_float2(bv.y, bv.y), w1a, acc[1][0]);
+                    acc[1][1] = __ffma2_rn(make_float2(bv.y, bv.y), w1b, acc[1][1]);
                 }
             }
         }
@@ -108,8 +107,9 @@ __global__ void __launch_bounds__(256)
         const int gx = tx0 + px + 16 * q;
         if (gy < H && gx < W) {
             const long long row = ((long long)(b * H + gy) * W + gx) * ldo;
+            const float a4[4] = {acc[q][0].x, acc[q][0].y, acc[q][1].x, acc[q][1].y};
             for (int n = 0; n < Cout; ++n) {
-                const float v = acc[q][n] + (bias ? bias[n] : 0.f);
+                const float v = a4[n] + (bias ? bias[n] : 0.f);
                 if (out32) out32[row + n] = v;
                 if (out16) out16[row + n] = __float2half_rn(v);
             }
