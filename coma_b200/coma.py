@@ -395,6 +395,25 @@ def get_nonphysical_score(coma: ComA, nonphysical_type: str):
     return coma.compute_nonphysical_response_sphere(n_bin=1e6, nonphysical_type=nonphysical_type, as_numpy=True)[nonphysical_type]
 
 
+def simplify_mesh_and_get_indices(mesh, number_of_points: int, simplify_method="poisson_disk", mesh_index_find_method="distance-based",
+                                  debug=False, device="cuda"):
+    """utils/coma.py:29-98. `mesh` is whatever the caller samples from — an open3d TriangleMesh in the reference's scripts
+    (src/coma/downsample_human.py, downsample_objects.py), or any object with `.vertices` and the two sampling methods
+    `sample_points_poisson_disk(number_of_points=)` / `sample_points_uniformly(number_of_points=)` returning an object with `.points`
+    (open3d itself is not a dependency of this package: the SAMPLING is the caller's, the O(V*N) index search is K1 on the GPU,
+    fp64-exact with np.argmin's first-minimum rule). Only the distance-based index finder works in the reference (its ray-tracing
+    branch drops into an IPython shell, :60-68) and only that one exists here. Returns (list of int vertex indices, the sampled pcd)."""
+    if simplify_method == "poisson_disk":
+        pcd = mesh.sample_points_poisson_disk(number_of_points=number_of_points)
+    elif simplify_method == "uniform":
+        pcd = mesh.sample_points_uniformly(number_of_points=number_of_points)
+    else:
+        raise NotImplementedError
+    if mesh_index_find_method != "distance-based":
+        raise NotImplementedError
+    return nearest_vertex_indices(np.asarray(pcd.points), np.asarray(mesh.vertices), device=device), pcd
+
+
 def nearest_vertex_indices(points, mesh_verts, device="cuda"):
     """The distance-based index finder of simplify_mesh_and_get_indices (utils/coma.py:87-91, :96):
     points [N,3], mesh_verts [V,3] (any float dtype, host) -> list of int vertex indices (fp64-exact argmin)."""

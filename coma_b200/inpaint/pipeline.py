@@ -8,6 +8,7 @@ Differences from the reference, all output-preserving:
   * mask logic (area test, dilation, AND, binarise, masked image, /8 mask) is one GPU call instead of cv2 on the host;
   * CFG + DDIM run as one fused fp32 kernel; latents are kept in fp32 between steps.
 """
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -282,11 +283,27 @@ class AdaptiveMaskInpaintPipeline:
                     mask_u8, masked_img, mask64, _ = self._mask_update(seg, default_u8, image_f32, B, H, W,
                                                                        settings.dilate_scheduler(i), area_thres, use_default)
                     masked_latents = self._encode_sample(masked_img, gens)
+                    if visualization_save_dir is not None and getattr(self.adaptive_mask_model, "use_visualizer", False):
+                        self._dump_step(visualization_save_dir, i, mask_u8, pred)
             if trace is not None:
                 trace.append(dict(t=t, latents=latents.clone(), x0=x0.clone(), mask64=mask64.clone()))
 
         final = self.decode_to_uint8_final(latents, B, h, w, output_type)
         return PipelineOutput(images=final, masks=mask_u8, trace=trace)
+
+    def _dump_step(self, save_dir, i, mask_u8, pred_u8):
+        """Per-provoke-step dump of the adapted mask and the decoded x0 (utils/adaptive_mask_inpainting.py:1051-1060: `masks/<i:05>.png`
+        with the reference's grey ramp clip(0.6 + (1 - mask), 0, 1), `images/<i:05>.png`); batch element b > 0 goes to `<save_dir>/<b>/`.
+        A debugging aid: it synchronises and copies to the host, exactly like the reference's visualiser."""
+        from PIL import Image
+        masks, imgs = mask_u8.cpu().numpy(), pred_u8.cpu().numpy()
+        for b in range(masks.shape[0]):
+            root = save_dir if b == 0 else os.path.join(save_dir, str(b))
+            os.makedirs(os.path.join(root, "masks"), exist_ok=True)
+            os.makedirs(os.path.join(root, "images"), exist_ok=True)
+            m = (masks[b] > 0).astype(np.float32)
+            Image.fromarray((np.clip(0.6 + (1.0 - m), 0.0, 1.0) * 255).astype(np.uint8)).convert("L").save(os.path.join(root, "masks", f"{i:05}.png"))
+            Image.fromarray(imgs[b]).save(os.path.join(root, "images", f"{i:05}.png"))
 
     def _segment(self, pred_u8):
         m = self.adaptive_mask_model

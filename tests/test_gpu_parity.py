@@ -61,6 +61,26 @@ def test_nearest_vertex_oracle_large(dev):
     assert idx[-1] == 17 and idx[-2] == 17
 
 
+def test_simplify_mesh_and_get_indices_wrapper(dev):
+    """utils/coma.py:29-98 with a caller-supplied sampler (open3d's TriangleMesh in the reference's scripts): the index search is K1."""
+    from types import SimpleNamespace
+    from utils.coma import simplify_mesh_and_get_indices
+    rng = np.random.default_rng(3)
+    verts = rng.standard_normal((2000, 3))
+
+    class Mesh:
+        vertices = verts
+
+        def sample_points_poisson_disk(self, number_of_points):
+            return SimpleNamespace(points=verts[rng.integers(0, 2000, number_of_points)] + 1e-4 * rng.standard_normal((number_of_points, 3)))
+    idx, pcd = simplify_mesh_and_get_indices(Mesh(), 300)
+    pts = np.asarray(pcd.points)
+    want = np.argmin(np.sum(np.square(pts[None, :, :] - verts[:, None, :]), axis=-1), axis=0)      # the reference's two lines (:90-91)
+    assert isinstance(idx, list) and len(idx) == 300 and np.array_equal(np.asarray(idx), want)
+    with pytest.raises(NotImplementedError):
+        simplify_mesh_and_get_indices(Mesh(), 10, mesh_index_find_method="raytracing-based")
+
+
 # --------------------------------------------------------------------------------------------- K2
 @pytest.mark.parametrize("name", ["contact_small", "contact_sigma02"])
 def test_pair_accumulate_golden(dev, golden_dir, name):

@@ -136,3 +136,36 @@ def test_adaptive_mask_loop_tiny_models(dev):
             assert err <= 3e-2 * scale, (i, err / scale)
         err = (out.images[b].permute(2, 0, 1) - final[0]).abs().max().item()
         assert err <= 5e-2, err
+
+
+def test_visualization_dumps(dev, tmp_path):
+    """`visualization_save_dir` + a segmenter with `use_visualizer = True` (utils/adaptive_mask_inpainting.py:1051-1060): one mask PNG
+    (the reference's grey ramp) and one decoded-x0 PNG per provoke step, per batch element."""
+    from PIL import Image
+    from coma_b200.inpaint.pipeline import AdaptiveMaskInpaintPipeline, AdaptiveMaskSettings, MaskDilateScheduler, ProvokeScheduler
+    from coma_b200.inpaint.segmenter import LuminanceSegmenter
+    from coma_b200.inpaint.unet import UNet
+    from coma_b200.inpaint.vae import VAE
+    from oracle import sd_oracle as so
+    ucfg, vcfg = so.tiny_unet_cfg(), so.tiny_vae_cfg()
+    pipe = AdaptiveMaskInpaintPipeline(UNet(so.make_unet_state_dict(0, ucfg), ucfg, dev), VAE(so.make_vae_state_dict(1, vcfg), vcfg, dev))
+    seg = LuminanceSegmenter(128)
+    seg.use_visualizer = True
+    pipe.register_adaptive_mask_model(seg)
+    pipe.register_adaptive_mask_settings(AdaptiveMaskSettings(MaskDilateScheduler(20, 6, [2, 2, 1, 1, 0, 0]), ProvokeScheduler(6, [2, 4], False)))
+    rng = np.random.default_rng(1)
+    image = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    default = np.zeros((64, 64), np.uint8)
+    default[8:56, 16:48] = 255
+    g = torch.Generator().manual_seed(5)
+    pe = (torch.randn((77, ucfg["cross_attention_dim"]), generator=g) * 0.5).half()
+    out_dir = str(tmp_path / "vis")
+    pipe(image=image, default_mask_image=default, prompt_embeds=pe, negative_prompt_embeds=torch.zeros_like(pe), guidance_scale=7.0, strength=1.0,
+         num_inference_steps=6, generator=[torch.Generator(device=dev).manual_seed(b) for b in range(2)], enforce_full_mask_ratio=0.0,
+         human_detection_thres=0.0002, batch_size=2, visualization_save_dir=out_dir, output_type="np")
+    for root in (out_dir, os.path.join(out_dir, "1")):
+        assert sorted(os.listdir(os.path.join(root, "masks"))) == ["00001.png", "00003.png"]      # provoke steps 2 and 4, 0-indexed loop counter
+        assert sorted(os.listdir(os.path.join(root, "images"))) == ["00001.png", "00003.png"]
+        m = np.asarray(Image.open(os.path.join(root, "masks", "00001.png")))
+        assert m.shape == (64, 64) and set(np.unique(m)) <= {153, 255}                           # clip(0.6 + (1 - mask)) * 255
+        assert np.asarray(Image.open(os.path.join(root, "images", "00003.png"))).shape == (64, 64, 3)
