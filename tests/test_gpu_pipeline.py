@@ -1,5 +1,7 @@
 """HP-A loop parity on the GPU: mask logic (bit-exact vs cv2), CFG+DDIM step, and the whole adaptive-mask loop with toy-width
 models against the torch+cv2 restatement (oracle/inpaint_loop_oracle.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
