@@ -128,6 +128,14 @@ __device__ __forceinline__ float ex2(float x) {
 // MMA-issuer / softmax barrier skeleton (that skeleton, not the arithmetic, bounds this kernel).
 #define FA_EXP 0
 #endif
+#ifdef FA_TRACE
+// Timeline instrumentation (tools/fa_trace.py): CTA (0,0,0) records clock64() at fixed points of every key step —
+// slots 0-7: softmax warp 2 lane 0, slots 8-15: the MMA-issuing thread. Timing builds only (-DFA_TRACE).
+__device__ long long fa_trace_buf[128 * 16];
+#define FA_T(slot, j) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 128) fa_trace_buf[(j) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define FA_T(slot, j) do { } while (0)
+#endif
 constexpr int FA_BQ = 128, FA_THREADS = 192;
 constexpr float FA_LAZY = 8.0f;  // log2 headroom before the running maximum (and O, l) is moved: P <= 2^8 stays exact enough in fp16
 
@@ -247,11 +255,14 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
             mbar_wait(q_full, 0);
             issue_qk(0);
             for (int j = 0; j < n_kv; ++j) {
+                FA_T(8, j);
                 if (j + 1 < n_kv) issue_qk(j + 1);  // the next scores are produced while the softmax warps work on S_j
+                FA_T(9, j);
                 // ---- O (+)= P_j V_j, accumulated in TMEM
                 const int s = j % STAGES;
                 mbar_wait(v_full + s, (j / STAGES) & 1);
                 mbar_wait(p_full + (j % NPB), (j / NPB) & 1);  // P_j is in shared memory (and any rescale of O has been stored)
+                FA_T(10, j);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < ((FA_EXP & 32) ? 0 : FA_BKV / 16); ++k) {
@@ -261,6 +272,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
                 }
                 umma_commit(v_empty + s);
                 umma_commit(p_empty + (j % NPB));  // P_j consumed; O includes tile j
+                FA_T(11, j);
             }
         }
     } else {
@@ -275,7 +287,9 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
         const float2 scale2 = make_float2(scale_log2, scale_log2);
         for (int j = 0; j < n_kv; ++j) {
             const int bsel = j % NSB, psel = j % NPB;
+            if (warp == 2 && lane == 0) FA_T(0, j);
             mbar_wait(s_full + bsel, (j / NSB) & 1);
+            if (warp == 2 && lane == 0) FA_T(1, j);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tS = tmem_S + lane_addr + (uint32_t)(bsel * FA_BKV);
             const int valid = min(FA_BKV, L - j * FA_BKV);  // keys beyond L are masked out (last tile only)
@@ -296,6 +310,7 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
             }
             float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             mx *= scale_log2;  // scale > 0: the max commutes with the scaling
+            if (warp == 2 && lane == 0) FA_T(2, j);
             if (j == 0) {
                 m_used = mx;
             } else if (__any_sync(0xffffffffu, mx > m_used + FA_LAZY)) {
@@ -316,7 +331,9 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
                 }
                 tmem_wait_st();
             }
+            if (warp == 2 && lane == 0) FA_T(3, j);
             if (j >= NPB) mbar_wait(p_empty + psel, ((j / NPB) & 1) ^ 1);  // P_{j-NPB} has been consumed: its buffer is free
+            if (warp == 2 && lane == 0) FA_T(4, j);
             const float2 negm2 = make_float2(-m_used, -m_used);
             float2 rs2 = make_float2(0.f, 0.f), rs2b = make_float2(0.f, 0.f);  // two row-sum chains
             uint8_t *p_row = p_row0 + psel * P_BYTES;
@@ -350,11 +367,13 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
                     if (!(FA_EXP & 2) || w.x == 0x12345678u) *reinterpret_cast<uint4 *>(p_row + ((chunk ^ xr) << 4)) = w;
                 }
             }
+            if (warp == 2 && lane == 0) FA_T(5, j);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(s_empty + bsel);  // this score buffer may be overwritten by Q K_{j+2}^T
             l_run += (rs2.x + rs2.y) + (rs2b.x + rs2b.y);
             if (!(FA_EXP & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
             mbar_arrive(p_full + psel);
+            if (warp == 2 && lane == 0) FA_T(6, j);
         }
         // ---- O / l
         mbar_wait(p_empty + ((n_kv - 1) % NPB), ((n_kv - 1) / NPB) & 1);
@@ -371,6 +390,272 @@ __global__ void __launch_bounds__(FA_THREADS, fa_ctas_per_sm(DKB, DN, FA_BKV, NS
             for (int c = 0; c < 16; c += 8) {
                 if (row < S && c0 + c < d) {  // d % 8 == 0
                     if (out32) {   // fp32 output (parity tests: isolates the kernel's arithmetic from the fp16 store)
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) out32[o_off + c0 + c + t] = t16[c + t] * inv;
+                        continue;
+                    }
+                    uint4 w;
+                    __half2 *hp = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) hp[t] = __floats2half2_rn(t16[c + 2 * t] * inv, t16[c + 2 * t + 1] * inv);
+                    *reinterpret_cast<uint4 *>(dst + c0 + c) = w;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- v3 ("TS"): Q and P live in TENSOR MEMORY -------------------------------------------------------------------------------------
+// The clock64 timeline of the kernel above (tools/fa_trace.py, S = 4096, d = 40, two CTAs per SM) shows what bounds it: the MMA thread
+// needs ~700 cycles to issue the three Q K^T MMAs and ~480 for the four P V ones — 120-170 cycles per tcgen05.mma whose tensor-pipe
+// floor is 24-32 — because in the SS form every K = 16 step re-reads its A operand from shared memory (Q: 4 KB, P: 4 KB per step,
+// 128 B/clk/SM) next to 16 KB of P stores and the TMA traffic: the shared-memory pipe, not the tensor pipe or the MUFU, is saturated.
+// Here the A operands come from TMEM (tcgen05.mma [d], [a], b-desc):
+//   * Q: each softmax thread loads its query row from global memory once, packs it and tcgen05.st's it (fp16 pairs per 32-bit
+//     column, 8 columns per K = 16 step) — no Q tile in shared memory, no TMA for Q;
+//   * P_j: written with tcgen05.st over the first 32 columns of the score buffer S_j it was computed from (fp16 pairs; S_j has been
+//     read into registers by then) — no P buffers in shared memory, no generic->async proxy fence, and the score buffer is recycled
+//     by the commit of P_j V_j instead of 128 thread arrivals.
+// Shared memory holds only the K / V^T ring (42 KB at d = 40); per key step the MMAs read 3 x 2 KB (K) + 4 x 1.5 KB (V^T) instead of
+// 34 KB, and the softmax warps lose eight STS.128 + a fence per step. Everything else (lazy running maximum, O in TMEM, TMA
+// producer, PDL) is unchanged. TMEM columns: S0 [0,64) S1 [64,128) O [128,128+DN) Q [128+DN, +8*ceil(d/16)).
+namespace fa {
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *u) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]),
+        "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]), "r"(u[18]), "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]),
+        "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *u) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]),
+                 "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                 : "memory");
+}
+}  // namespace fa
+
+__host__ __device__ constexpr int fa_ts_tmem_cols(int DKB, int DN) {
+    return (128 + DN + DKB * 32 <= 256) ? 256 : 512;
+}
+
+template <int DKB, int DN, int STAGES>
+__global__ void __launch_bounds__(FA_THREADS, (DKB == 1 && DN <= 64) ? 2 : 1)
+    attention_fwd_ts_kernel(const __half *__restrict__ qg, long long ldq, long long q_bstride, const __grid_constant__ CUtensorMap tmK,
+                            const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
+                            float *__restrict__ out32, long long ldo, long long o_bstride) {
+    using namespace fa;
+    constexpr int FA_BKV = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int K_BLOCK = FA_BKV * 64 * 2, K_BYTES = DKB * K_BLOCK;
+    constexpr int PV_ROW = FA_BKV * 2;
+    constexpr int VT_BYTES = ((DN * PV_ROW + 1023) / 1024) * 1024;
+    uint8_t *sK = smem;
+    uint8_t *sVt = sK + STAGES * K_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sVt + STAGES * VT_BYTES);
+    uint64_t *q_full = bar, *k_full = bar + 1, *k_empty = k_full + STAGES, *v_full = k_empty + STAGES, *v_empty = v_full + STAGES;
+    uint64_t *s_full = v_empty + STAGES, *p_full = s_full + 2, *p_empty = p_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * FA_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int n_kv = (L + FA_BKV - 1) / FA_BKV;
+    constexpr uint32_t TMEM_COLS = fa_ts_tmem_cols(DKB, DN);
+    const int ksteps = (d + 15) / 16;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVt) : "memory");
+        mbar_init(q_full, 128);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(k_full + i, 1);
+            mbar_init(k_empty + i, 1);
+            mbar_init(v_full + i, 1);
+            mbar_init(v_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(s_full + i, 1);
+            mbar_init(p_full + i, 128);
+            mbar_init(p_empty + i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * FA_BKV, tmem_Q = tmem_O + DN;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int j = 0; j < n_kv; ++j) {
+                const int s = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                mbar_wait(k_empty + s, ph ^ 1);
+                mbar_expect_tx(k_full + s, K_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sK + s * K_BYTES + kb * K_BLOCK, &tmK, k_full + s, kb * 64, j * FA_BKV, h, b);
+                mbar_wait(v_empty + s, ph ^ 1);
+                mbar_expect_tx(v_full + s, DN * PV_ROW);
+                tma_load_4d(sVt + s * VT_BYTES, &tmVt, v_full + s, j * FA_BKV, 0, h, b);
+            }
+            pdl_trigger();
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(FA_BKV >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+            constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+            auto issue_qk = [&](int j) {       // S_j = Q K_j^T into score buffer j & 1, A = Q from TMEM
+                const int s = j % STAGES;
+                mbar_wait(k_full + s, (j / STAGES) & 1);
+                if (j >= 2) mbar_wait(p_empty + (j & 1), (((j - 2) >> 1) & 1));   // P_{j-2} V_{j-2} done: S buffer (and its P alias) is free
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ts = tmem_S + (uint32_t)((j & 1) * FA_BKV);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t offk = (uint32_t)(k / 4) * K_BLOCK + (uint32_t)(k % 4) * 32;
+                    umma_f16_ts(ts, tmem_Q + (uint32_t)k * 8, umma_desc_sw128(smem_u32(sK + s * K_BYTES) + offk), idesc_s, k != 0);
+                }
+                umma_commit(k_empty + s);
+                umma_commit(s_full + (j & 1));
+            };
+            mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_qk(j + 1);
+                const int s = j % STAGES;
+                mbar_wait(v_full + s, (j / STAGES) & 1);
+                mbar_wait(p_full + (j & 1), (j >> 1) & 1);   // P_j is in TMEM (and any rescale of O has been stored)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tp = tmem_S + (uint32_t)((j & 1) * FA_BKV);
+#pragma unroll
+                for (int k = 0; k < FA_BKV / 16; ++k) {
+                    const uint32_t va = smem_u32(sVt + s * VT_BYTES) + (uint32_t)k * 32;
+                    umma_f16_ts(tmem_O, tp + (uint32_t)k * 8, umma_desc_sw128(va), idesc_o, (j | k) != 0);
+                }
+                umma_commit(v_empty + s);
+                umma_commit(p_empty + (j & 1));  // P_j consumed; O includes tile j; score buffer j & 1 may be overwritten
+            }
+        }
+    } else {
+        // ---- softmax: thread owns query row r of the tile
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int row = q0 + r;
+        // Q row -> TMEM: fp16 pairs per column, 8 columns per K = 16 step; rows beyond S and columns beyond d are zero
+        {
+            const __half *qrow = qg + (size_t)b * q_bstride + (size_t)row * ldq + (size_t)h * d;
+            for (int k = 0; k < ksteps; ++k) {
+                uint32_t u[8];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (row < S && k * 16 + c * 8 < d) v = *reinterpret_cast<const uint4 *>(qrow + k * 16 + c * 8);
+                    u[4 * c + 0] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
+                }
+                tmem_st8(tmem_Q + lane_addr + (uint32_t)k * 8, u);
+            }
+            tmem_wait_st();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(q_full);
+        }
+        float m_used = -INFINITY, l_run = 0.f;
+        const float2 scale2 = make_float2(scale_log2, scale_log2);
+        for (int j = 0; j < n_kv; ++j) {
+            const int bsel = j & 1;
+            mbar_wait(s_full + bsel, (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tS = tmem_S + lane_addr + (uint32_t)(bsel * FA_BKV);
+            const int valid = min(FA_BKV, L - j * FA_BKV);
+            const bool full_tile = valid == FA_BKV;
+            float sv[FA_BKV];   // the whole score row stays in registers: one TMEM round trip per step
+            tmem_ld32(tS, sv);
+            tmem_ld32(tS + 32, sv + 32);
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (full_tile) {
+#pragma unroll
+                for (int c = 0; c < FA_BKV; c += 2) mx4[(c >> 1) & 3] = fmaxf(mx4[(c >> 1) & 3], fmaxf(sv[c], sv[c + 1]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < FA_BKV; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], (c < valid) ? sv[c] : -INFINITY);
+            }
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            mx *= scale_log2;
+            if (j == 0) {
+                m_used = mx;
+            } else if (__any_sync(0xffffffffu, mx > m_used + FA_LAZY)) {
+                const float m_new = (mx > m_used + FA_LAZY) ? mx : m_used;
+                const float alpha = ex2(m_used - m_new);
+                m_used = m_new;
+                l_run *= alpha;
+                mbar_wait(p_empty + ((j - 1) & 1), ((j - 1) >> 1) & 1);  // every P V product issued so far has landed in O
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < DN; c0 += 16) {
+                    float t16[16];
+                    tmem_ld16(tmem_O + lane_addr + c0, t16);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) t16[c] *= alpha;
+                    tmem_st16(tmem_O + lane_addr + c0, t16);
+                }
+                tmem_wait_st();
+            }
+            const float2 negm2 = make_float2(-m_used, -m_used);
+            float2 rs2 = make_float2(0.f, 0.f), rs2b = make_float2(0.f, 0.f);
+            uint32_t pk[FA_BKV / 2];
+#pragma unroll
+            for (int c = 0; c < FA_BKV; c += 2) {
+                const float2 x = __ffma2_rn(make_float2(sv[c], sv[c + 1]), scale2, negm2);
+                float2 pr = make_float2(ex2(x.x), ex2(x.y));
+                if (!full_tile) {
+                    pr.x = (c < valid) ? pr.x : 0.f;
+                    pr.y = (c + 1 < valid) ? pr.y : 0.f;
+                }
+                const __half2 hh = __floats2half2_rn(pr.x, pr.y);
+                pk[c >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+                if (c & 2) rs2b = __fadd2_rn(rs2b, pr);
+                else rs2 = __fadd2_rn(rs2, pr);
+            }
+            tmem_st32(tS, pk);   // P_j over the first 32 columns of S_j
+            l_run += (rs2.x + rs2.y) + (rs2b.x + rs2b.y);
+            tmem_wait_st();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(p_full + bsel);
+        }
+        // ---- O / l
+        mbar_wait(p_empty + ((n_kv - 1) & 1), ((n_kv - 1) >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float inv = 1.0f / l_run;
+        const size_t o_off = (size_t)b * o_bstride + (size_t)row * ldo + (size_t)h * d;
+        __half *dst = out + o_off;
+#pragma unroll
+        for (int c0 = 0; c0 < DN; c0 += 16) {
+            float t16[16];
+            tmem_ld16(tmem_O + lane_addr + c0, t16);
+#pragma unroll
+            for (int c = 0; c < 16; c += 8) {
+                if (row < S && c0 + c < d) {
+                    if (out32) {
 #pragma unroll
                         for (int t = 0; t < 8; ++t) out32[o_off + c0 + c + t] = t16[c + t] * inv;
                         continue;
@@ -440,7 +725,35 @@ static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const 
     return check_launch("attention_fwd_kernel");
 }
 
+template <int DKB, int DN, int STAGES>
+static int launch_attention_ts(const __half *q, long long ldq, long long q_bstride, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads,
+                               int S, int L, int d, float scale_log2, __half *out, float *out32, long long ldo, long long o_bstride,
+                               cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (DKB * 64 * 128 + ((DN * 64 * 2 + 1023) / 1024) * 1024) + 256 + 1024;
+    static bool attr[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !attr[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_ts_kernel<DKB, DN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attention ts): %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr[dev] = true;
+    }
+    dim3 grid((S + FA_BQ - 1) / FA_BQ, heads, B);
+    launch_pdl(attention_fwd_ts_kernel<DKB, DN, STAGES>, grid, dim3(FA_THREADS), smem, st, q, ldq, q_bstride, tk, tv, S, L, d, scale_log2, out,
+               out32, ldo, o_bstride);
+    return check_launch("attention_fwd_ts_kernel");
+}
+
 }  // namespace coma
+
+#ifdef FA_TRACE
+extern "C" __attribute__((visibility("default"))) int coma_attention_trace(long long *host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, coma::fa_trace_buf, sizeof(long long) * 128 * 16);
+}
+#endif
 
 extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
                                          int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32, int64_t ldo,
@@ -495,6 +808,23 @@ extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const voi
     __half *o = (__half *)out;
     const long long obs = (long long)S * ldo;
 #define COMA_FA_ARGS tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, out_f32, ldo, obs, st
+    static const bool force_ss = getenv("COMA_ATTN_SS") != nullptr;   // A/B: the round-1 kernel (Q / P operands from shared memory)
+    if (BKV == 64 && !force_ss) {
+        // v3: Q and P as TMEM operands (see attention_fwd_ts_kernel)
+#define COMA_FA_TS_ARGS (const __half *)q, (long long)ldq, (long long)S * ldq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, out_f32, ldo, obs, st
+        if (d <= 64) {
+            if (DN == 48) return launch_attention_ts<1, 48, 3>(COMA_FA_TS_ARGS);
+            if (DN == 32) return launch_attention_ts<1, 32, 3>(COMA_FA_TS_ARGS);
+            return launch_attention_ts<1, 64, 3>(COMA_FA_TS_ARGS);
+        }
+        if (d <= 128) {
+            if (DN == 80) return launch_attention_ts<2, 80, 3>(COMA_FA_TS_ARGS);
+            return launch_attention_ts<2, 128, 3>(COMA_FA_TS_ARGS);
+        }
+        if (DN == 160) return launch_attention_ts<3, 160, 3>(COMA_FA_TS_ARGS);
+        return launch_attention_ts<3, 192, 3>(COMA_FA_TS_ARGS);
+#undef COMA_FA_TS_ARGS
+    }
     if (d <= 64) {
         if (BKV == 32) {
             if (DN == 48) return launch_attention<1, 48, 3, 32>(COMA_FA_ARGS);
