@@ -433,6 +433,11 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *u) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
@@ -449,17 +454,43 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *u) {
 }
 }  // namespace fa
 
-__host__ __device__ constexpr int fa_ts_tmem_cols(int DKB, int DN) {
-    return (128 + DN + DKB * 32 <= 256) ? 256 : 512;
+// exp2 on the FP32 pipes (FA-4's trick): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-4 minimax polynomial for 2^f (max relative
+// error 2.7e-6 in fp32, far below the fp16 rounding of P), exponent inserted with one integer add. Costs ~8 FMA-pipe cycles per
+// element pair against 17 XU cycles for two MUFU.EX2 — a fraction of the pairs goes here so that both pipes are busy
+// (tools/ubench_softmax.cu: 3 pairs of 8 is the measured optimum, 546 -> 450 clk per 128 x 64 tile).
+__device__ __forceinline__ float2 fa_poly_exp2(float2 x) {
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));     // low mantissa bits = round(x)
+    const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+    float2 p = __ffma2_rn(make_float2(9.570099413e-03f, 9.570099413e-03f), f, make_float2(5.591785908e-02f, 5.591785908e-02f));
+    p = __ffma2_rn(p, f, make_float2(2.402474433e-01f, 2.402474433e-01f));
+    p = __ffma2_rn(p, f, make_float2(6.931217909e-01f, 6.931217909e-01f));
+    p = __ffma2_rn(p, f, make_float2(9.999992847e-01f, 9.999992847e-01f));
+    float2 r;
+    r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+    return r;
 }
 
-template <int DKB, int DN, int STAGES>
-__global__ void __launch_bounds__(FA_THREADS, (DKB == 1 && DN <= 64) ? 2 : 1)
+// SPLIT = number of softmax threads per query row. With SPLIT = 2 a row's 64 scores of a key step are handled by two threads (warps w
+// and w + 4 own the same TMEM lane quadrant) as two INDEPENDENT online softmaxes over the even / odd 32-key halves of every step: own
+// running maximum, own row sum and own output accumulator O_h in TMEM (P_h V_h is an M128 x DN x K32 product), merged once in the
+// epilogue like a split-K attention. No per-step exchange between the two threads, and 16 softmax warps per SM (4 per scheduler)
+// instead of 8 — the MUFU pipe needs >= 3 warps per scheduler to stay busy (tools/ubench_softmax.cu: 591 -> 548 clk per tile).
+__host__ __device__ constexpr int fa_ts_tmem_need(int DN, int SPLIT) { return 128 + SPLIT * DN + DN / 2; }
+__host__ __device__ constexpr int fa_ts_tmem_cols(int DN, int SPLIT) { return fa_ts_tmem_need(DN, SPLIT) <= 256 ? 256 : 512; }
+__host__ __device__ constexpr int fa_ts_threads(int SPLIT) { return 64 + 128 * SPLIT; }
+
+template <int DKB, int DN, int STAGES, int SPLIT, int POLY>
+__global__ void __launch_bounds__(fa_ts_threads(SPLIT), fa_ts_tmem_cols(DN, SPLIT) == 256 ? 2 : 1)
     attention_fwd_ts_kernel(const __half *__restrict__ qg, long long ldq, long long q_bstride, const __grid_constant__ CUtensorMap tmK,
                             const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
                             float *__restrict__ out32, long long ldo, long long o_bstride) {
     using namespace fa;
-    constexpr int FA_BKV = 64;
+    static_assert(fa_ts_tmem_need(DN, SPLIT) <= 512, "TMEM budget");
+    constexpr int FA_BKV = 64, CW = FA_BKV / SPLIT, NSOFT = 128 * SPLIT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int K_BLOCK = FA_BKV * 64 * 2, K_BYTES = DKB * K_BLOCK;
@@ -471,12 +502,13 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 && DN <= 64) ? 2 : 1)
     uint64_t *q_full = bar, *k_full = bar + 1, *k_empty = k_full + STAGES, *v_full = k_empty + STAGES, *v_empty = v_full + STAGES;
     uint64_t *s_full = v_empty + STAGES, *p_full = s_full + 2, *p_empty = p_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p_empty + 2);
+    float2 *ml_x = reinterpret_cast<float2 *>(tmem_slot + 2);   // [SPLIT][128] (m, l) of every softmax thread, for the epilogue merge
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ, h = blockIdx.y, b = blockIdx.z;
     const int n_kv = (L + FA_BKV - 1) / FA_BKV;
-    constexpr uint32_t TMEM_COLS = fa_ts_tmem_cols(DKB, DN);
-    const int ksteps = (d + 15) / 16;
+    constexpr uint32_t TMEM_COLS = fa_ts_tmem_cols(DN, SPLIT);
+    constexpr int ksteps = DN / 16;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
@@ -490,7 +522,7 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 && DN <= 64) ? 2 : 1)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(s_full + i, 1);
-            mbar_init(p_full + i, 128);
+            mbar_init(p_full + i, NSOFT);
             mbar_init(p_empty + i, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -504,7 +536,8 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 && DN <= 64) ? 2 : 1)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * FA_BKV, tmem_Q = tmem_O + DN;
+    // columns: S0 [0,64) S1 [64,128) O_0 .. O_{SPLIT-1} [128 + h DN, +DN)  Q [128 + SPLIT DN, +DN/2)
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * FA_BKV, tmem_Q = tmem_O + SPLIT * DN;
     pdl_wait();
 
     if (warp == 0) {
@@ -523,48 +556,70 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 && DN <= 64) ? 2 : 1)
             pdl_trigger();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(FA_BKV >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
-            constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
-            auto issue_qk = [&](int j) {       // S_j = Q K_j^T into score buffer j & 1, A = Q from TMEM
-                const int s = j % STAGES;
-                mbar_wait(k_full + s, (j / STAGES) & 1);
-                if (j >= 2) mbar_wait(p_empty + (j & 1), (((j - 2) >> 1) & 1));   // P_{j-2} V_{j-2} done: S buffer (and its P alias) is free
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // MMA issuer. The warp stays CONVERGED (every lane runs the barrier waits) and one elected lane issues: inside an
+        // `if (lane == 0)` region ptxas wraps every UTCHMMA in an ELECT retry loop and rebuilds each shared-memory descriptor with a
+        // ~8-deep chain of uniform-datapath instructions — measured 110-240 clk per tcgen05.mma (tools/fa_trace.py), against the
+        // 45 clk dispatch floor of an M128 x N<=90 x K16 instruction (tools/ubench_umma.cu). That made this warp the critical path of
+        // the whole kernel. Here every descriptor is (stage base) + compile-time constant.
+        constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(FA_BKV >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+        constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+        const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK)), vdesc0 = umma_desc_sw128(smem_u32(sVt));
+        int sq = 0, sv = 0;               // ring stage of the next Q K^T / P V
+        uint32_t phq = 0, phv = 0;
+        auto issue_qk = [&](int j) {      // S_j = Q K_j^T into score buffer j & 1, A = Q from TMEM
+            mbar_wait(k_full + sq, phq);
+#ifndef FA_INORDER
+            if (j >= 2) mbar_wait(p_empty + (j & 1), (((j - 2) >> 1) & 1));   // P_{j-2} V_{j-2} done: S buffer (and its P alias) is free
+#endif
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
                 const uint32_t ts = tmem_S + (uint32_t)((j & 1) * FA_BKV);
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t offk = (uint32_t)(k / 4) * K_BLOCK + (uint32_t)(k % 4) * 32;
-                    umma_f16_ts(ts, tmem_Q + (uint32_t)k * 8, umma_desc_sw128(smem_u32(sK + s * K_BYTES) + offk), idesc_s, k != 0);
-                }
-                umma_commit(k_empty + s);
-                umma_commit(s_full + (j & 1));
-            };
-            mbar_wait(q_full, 0);
-            issue_qk(0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) issue_qk(j + 1);
-                const int s = j % STAGES;
-                mbar_wait(v_full + s, (j / STAGES) & 1);
-                mbar_wait(p_full + (j & 1), (j >> 1) & 1);   // P_j is in TMEM (and any rescale of O has been stored)
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tp = tmem_S + (uint32_t)((j & 1) * FA_BKV);
+                const uint64_t kd = kdesc0 + (uint64_t)(sq * (K_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < FA_BKV / 16; ++k) {
-                    const uint32_t va = smem_u32(sVt + s * VT_BYTES) + (uint32_t)k * 32;
-                    umma_f16_ts(tmem_O, tp + (uint32_t)k * 8, umma_desc_sw128(va), idesc_o, (j | k) != 0);
-                }
-                umma_commit(v_empty + s);
+                for (int k = 0; k < ksteps; ++k)
+                    umma_f16_ts(ts, tmem_Q + (uint32_t)k * 8, kd + (uint64_t)(((k / 4) * K_BLOCK + (k % 4) * 32) >> 4), idesc_s, k != 0);
+                umma_commit(k_empty + sq);
+                umma_commit(s_full + (j & 1));
+            }
+            __syncwarp();
+            if (++sq == STAGES) { sq = 0; phq ^= 1; }
+        };
+        mbar_wait(q_full, 0);
+        issue_qk(0);
+        for (int j = 0; j < n_kv; ++j) {
+            if (lane == 0) FA_T(8, j);
+            if (j + 1 < n_kv) issue_qk(j + 1);
+            if (lane == 0) FA_T(9, j);
+            mbar_wait(v_full + sv, phv);
+            mbar_wait(p_full + (j & 1), (j >> 1) & 1);   // P_j is in TMEM (and any rescale of O has been stored)
+            if (lane == 0) FA_T(10, j);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t tp = tmem_S + (uint32_t)((j & 1) * FA_BKV);
+                const uint64_t vd = vdesc0 + (uint64_t)(sv * (VT_BYTES >> 4));
+#pragma unroll
+                for (int hh = 0; hh < SPLIT; ++hh)
+#pragma unroll
+                    for (int k = 0; k < CW / 16; ++k)   // O_hh += P_hh V_hh: P_hh sits in the first CW/2 columns of its half of S_j
+                        umma_f16_ts(tmem_O + (uint32_t)(hh * DN), tp + (uint32_t)(hh * CW + k * 8), vd + (uint64_t)((hh * (CW / 16) + k) * 2), idesc_o,
+                                    (j | k) != 0);
+                umma_commit(v_empty + sv);
                 umma_commit(p_empty + (j & 1));  // P_j consumed; O includes tile j; score buffer j & 1 may be overwritten
             }
+            __syncwarp();
+            if (++sv == STAGES) { sv = 0; phv ^= 1; }
+            if (lane == 0) FA_T(11, j);
         }
     } else {
-        // ---- softmax: thread owns query row r of the tile
-        const int q = warp & 3, r = q * 32 + lane;
+        // ---- softmax: thread owns columns [hh CW, (hh+1) CW) of query row r of every score tile
+        const int q = warp & 3, r = q * 32 + lane, hh = (warp - 2) >> 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int row = q0 + r;
-        // Q row -> TMEM: fp16 pairs per column, 8 columns per K = 16 step; rows beyond S and columns beyond d are zero
-        {
+        const bool tracer = (warp == 2 && lane == 0);
+        // Q row -> TMEM (threads of half 0): fp16 pairs per column, 8 columns per K = 16 step; rows beyond S and columns beyond d are zero
+        if (hh == 0) {
             const __half *qrow = qg + (size_t)b * q_bstride + (size_t)row * ldq + (size_t)h * d;
+#pragma unroll
             for (int k = 0; k < ksteps; ++k) {
                 uint32_t u[8];
 #pragma unroll
@@ -579,30 +634,33 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 && DN <= 64) ? 2 : 1)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(q_full);
         }
+        const uint32_t tO = tmem_O + lane_addr + (uint32_t)(hh * DN);
         float m_used = -INFINITY, l_run = 0.f;
         const float2 scale2 = make_float2(scale_log2, scale_log2);
         for (int j = 0; j < n_kv; ++j) {
             const int bsel = j & 1;
+            if (tracer) FA_T(0, j);
             mbar_wait(s_full + bsel, (j >> 1) & 1);
+            if (tracer) FA_T(1, j);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tS = tmem_S + lane_addr + (uint32_t)(bsel * FA_BKV);
-            const int valid = min(FA_BKV, L - j * FA_BKV);
-            const bool full_tile = valid == FA_BKV;
-            float sv[FA_BKV];   // the whole score row stays in registers: one TMEM round trip per step
-            tmem_ld32(tS, sv);
-            tmem_ld32(tS + 32, sv + 32);
-            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            if (full_tile) {
+            const uint32_t tS = tmem_S + lane_addr + (uint32_t)(bsel * FA_BKV + hh * CW);
+            const int valid = min(CW, L - j * FA_BKV - hh * CW);   // may be <= 0 (last tile only)
+            const bool full_tile = valid == CW;
+            float sv[CW];   // this thread's scores stay in registers: one TMEM round trip per step
 #pragma unroll
-                for (int c = 0; c < FA_BKV; c += 2) mx4[(c >> 1) & 3] = fmaxf(mx4[(c >> 1) & 3], fmaxf(sv[c], sv[c + 1]));
-            } else {
+            for (int c0 = 0; c0 < CW; c0 += 32) tmem_ld32(tS + c0, sv + c0);
+            if (!full_tile) {   // last tile only (warp-uniform): keys beyond L score -inf -> probability exactly 0 on both exp2 paths
 #pragma unroll
-                for (int c = 0; c < FA_BKV; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], (c < valid) ? sv[c] : -INFINITY);
+                for (int c = 0; c < CW; ++c) sv[c] = (c < valid) ? sv[c] : -INFINITY;
             }
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < CW; c += 2) mx4[(c >> 1) & 3] = fmaxf(mx4[(c >> 1) & 3], fmaxf(sv[c], sv[c + 1]));
             float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             mx *= scale_log2;
+            if (tracer) FA_T(2, j);
             if (j == 0) {
-                m_used = mx;
+                m_used = (valid > 0) ? mx : 0.f;   // a half without any key (L <= CW): finite placeholder, l stays 0
             } else if (__any_sync(0xffffffffu, mx > m_used + FA_LAZY)) {
                 const float m_new = (mx > m_used + FA_LAZY) ? mx : m_used;
                 const float alpha = ex2(m_used - m_new);
@@ -613,57 +671,91 @@ __global__ void __launch_bounds__(FA_THREADS, (DKB == 1 && DN <= 64) ? 2 : 1)
 #pragma unroll
                 for (int c0 = 0; c0 < DN; c0 += 16) {
                     float t16[16];
-                    tmem_ld16(tmem_O + lane_addr + c0, t16);
+                    tmem_ld16(tO + c0, t16);
 #pragma unroll
                     for (int c = 0; c < 16; ++c) t16[c] *= alpha;
-                    tmem_st16(tmem_O + lane_addr + c0, t16);
+                    tmem_st16(tO + c0, t16);
                 }
                 tmem_wait_st();
             }
+            if (tracer) { FA_T(3, j); FA_T(4, j); }
             const float2 negm2 = make_float2(-m_used, -m_used);
             float2 rs2 = make_float2(0.f, 0.f), rs2b = make_float2(0.f, 0.f);
-            uint32_t pk[FA_BKV / 2];
+            uint32_t pk[CW / 2];
 #pragma unroll
-            for (int c = 0; c < FA_BKV; c += 2) {
+            for (int c = 0; c < CW; c += 2) {
                 const float2 x = __ffma2_rn(make_float2(sv[c], sv[c + 1]), scale2, negm2);
-                float2 pr = make_float2(ex2(x.x), ex2(x.y));
-                if (!full_tile) {
-                    pr.x = (c < valid) ? pr.x : 0.f;
-                    pr.y = (c + 1 < valid) ? pr.y : 0.f;
-                }
-                const __half2 hh = __floats2half2_rn(pr.x, pr.y);
-                pk[c >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+                float2 pr;
+                if (((c >> 1) & 7) < POLY) pr = fa_poly_exp2(x);
+                else pr = make_float2(ex2(x.x), ex2(x.y));
+                const __half2 hv = __floats2half2_rn(pr.x, pr.y);
+                pk[c >> 1] = *reinterpret_cast<const uint32_t *>(&hv);
                 if (c & 2) rs2b = __fadd2_rn(rs2b, pr);
                 else rs2 = __fadd2_rn(rs2, pr);
             }
-            tmem_st32(tS, pk);   // P_j over the first 32 columns of S_j
+            if (tracer) FA_T(5, j);
+            // P_j (this thread's half) over the first CW/2 columns of the scores it was computed from
+            if (CW == 64) tmem_st32(tS, pk);
+            else tmem_st16(tS, reinterpret_cast<const float *>(pk));
             l_run += (rs2.x + rs2.y) + (rs2b.x + rs2b.y);
             tmem_wait_st();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(p_full + bsel);
+            if (tracer) FA_T(6, j);
         }
-        // ---- O / l
+        // ---- merge the SPLIT partial softmaxes of the row (split-K style), O / l
+        float wgt[SPLIT];   // weight of partial accumulator t: 2^(m_t - m_row) / l_row
+        if (SPLIT > 1) {
+            ml_x[hh * 128 + r] = make_float2(l_run > 0.f ? m_used : -INFINITY, l_run);
+            asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
+            float2 v[SPLIT];
+            float m_all = -INFINITY, l_all = 0.f;
+#pragma unroll
+            for (int t = 0; t < SPLIT; ++t) {
+                v[t] = ml_x[t * 128 + r];
+                m_all = fmaxf(m_all, v[t].x);
+            }
+#pragma unroll
+            for (int t = 0; t < SPLIT; ++t) {
+                wgt[t] = (v[t].y > 0.f) ? ex2(v[t].x - m_all) : 0.f;
+                l_all = fmaf(v[t].y, wgt[t], l_all);
+            }
+            const float inv = 1.0f / l_all;
+#pragma unroll
+            for (int t = 0; t < SPLIT; ++t) wgt[t] *= inv;
+        } else {
+            wgt[0] = 1.0f / l_run;
+        }
         mbar_wait(p_empty + ((n_kv - 1) & 1), ((n_kv - 1) >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float inv = 1.0f / l_run;
         const size_t o_off = (size_t)b * o_bstride + (size_t)row * ldo + (size_t)h * d;
         __half *dst = out + o_off;
 #pragma unroll
         for (int c0 = 0; c0 < DN; c0 += 16) {
+            if (((c0 >> 4) % SPLIT) != hh) continue;   // 16-column chunks are dealt round-robin to the row's threads (warp-uniform)
             float t16[16];
             tmem_ld16(tmem_O + lane_addr + c0, t16);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) t16[c] *= wgt[0];
+#pragma unroll
+            for (int t = 1; t < SPLIT; ++t) {
+                float u16[16];
+                tmem_ld16(tmem_O + lane_addr + (uint32_t)(t * DN + c0), u16);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) t16[c] = fmaf(u16[c], wgt[t], t16[c]);
+            }
 #pragma unroll
             for (int c = 0; c < 16; c += 8) {
                 if (row < S && c0 + c < d) {
                     if (out32) {
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) out32[o_off + c0 + c + t] = t16[c + t] * inv;
+                        for (int t = 0; t < 8; ++t) out32[o_off + c0 + c + t] = t16[c + t];
                         continue;
                     }
                     uint4 w;
                     __half2 *hp = reinterpret_cast<__half2 *>(&w);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) hp[t] = __floats2half2_rn(t16[c + 2 * t] * inv, t16[c + 2 * t + 1] * inv);
+                    for (int t = 0; t < 4; ++t) hp[t] = __floats2half2_rn(t16[c + 2 * t], t16[c + 2 * t + 1]);
                     *reinterpret_cast<uint4 *>(dst + c0 + c) = w;
                 }
             }
@@ -725,16 +817,16 @@ static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const 
     return check_launch("attention_fwd_kernel");
 }
 
-template <int DKB, int DN, int STAGES>
+template <int DKB, int DN, int STAGES, int SPLIT, int POLY>
 static int launch_attention_ts(const __half *q, long long ldq, long long q_bstride, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads,
                                int S, int L, int d, float scale_log2, __half *out, float *out32, long long ldo, long long o_bstride,
                                cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (DKB * 64 * 128 + ((DN * 64 * 2 + 1023) / 1024) * 1024) + 256 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (DKB * 64 * 128 + ((DN * 64 * 2 + 1023) / 1024) * 1024) + 256 + SPLIT * 128 * 8 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attention_fwd_ts_kernel<DKB, DN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_ts_kernel<DKB, DN, STAGES, SPLIT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(attention ts): %s", cudaGetErrorString(e));
             return (int)e;
@@ -742,8 +834,8 @@ static int launch_attention_ts(const __half *q, long long ldq, long long q_bstri
         attr[dev] = true;
     }
     dim3 grid((S + FA_BQ - 1) / FA_BQ, heads, B);
-    launch_pdl(attention_fwd_ts_kernel<DKB, DN, STAGES>, grid, dim3(FA_THREADS), smem, st, q, ldq, q_bstride, tk, tv, S, L, d, scale_log2, out,
-               out32, ldo, o_bstride);
+    launch_pdl(attention_fwd_ts_kernel<DKB, DN, STAGES, SPLIT, POLY>, grid, dim3(fa_ts_threads(SPLIT)), smem, st, q, ldq, q_bstride, tk, tv, S, L, d,
+               scale_log2, out, out32, ldo, o_bstride);
     return check_launch("attention_fwd_ts_kernel");
 }
 
@@ -810,19 +902,31 @@ extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const voi
 #define COMA_FA_ARGS tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, out_f32, ldo, obs, st
     static const bool force_ss = getenv("COMA_ATTN_SS") != nullptr;   // A/B: the round-1 kernel (Q / P operands from shared memory)
     if (BKV == 64 && !force_ss) {
-        // v3: Q and P as TMEM operands (see attention_fwd_ts_kernel)
+        // v3: Q and P as TMEM operands (see attention_fwd_ts_kernel). Two threads per query row where that keeps two CTAs per SM
+        // (DN <= 48: 16 softmax warps per SM; measured 0.345 -> 0.321 ms at S = L = 4096, d = 40, and slower than one thread per row
+        // wherever the second accumulator costs the second CTA: d = 80, 0.035 -> 0.046 ms). The polynomial exp2 pays only with one
+        // thread per row (d = 40: 0.345 -> 0.331 ms, d = 80 / 160: 1-5 %): with two the kernel sits on the TMEM read rate
+        // (tools/ubench_tmem.cu: 54.6 B/clk/SM = 600 clk per 128 x 64 fp32 score tile), not on the MUFU. COMA_ATTN_SPLIT=1: A/B.
+        static const bool no_split = getenv("COMA_ATTN_SPLIT") && atoi(getenv("COMA_ATTN_SPLIT")) == 1;
 #define COMA_FA_TS_ARGS (const __half *)q, (long long)ldq, (long long)S * ldq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, out_f32, ldo, obs, st
+#define COMA_FA_TS(DKB_, DN_)                                                                                      \
+    do {                                                                                                           \
+        if (fa_ts_tmem_need(DN_, 2) <= 256 && !no_split)                                                           \
+            return launch_attention_ts<DKB_, DN_, 3, (fa_ts_tmem_need(DN_, 2) <= 256 ? 2 : 1), 0>(COMA_FA_TS_ARGS); \
+        return launch_attention_ts<DKB_, DN_, 3, 1, 3>(COMA_FA_TS_ARGS);                                           \
+    } while (0)
         if (d <= 64) {
-            if (DN == 48) return launch_attention_ts<1, 48, 3>(COMA_FA_TS_ARGS);
-            if (DN == 32) return launch_attention_ts<1, 32, 3>(COMA_FA_TS_ARGS);
-            return launch_attention_ts<1, 64, 3>(COMA_FA_TS_ARGS);
+            if (DN == 48) COMA_FA_TS(1, 48);
+            if (DN == 32) COMA_FA_TS(1, 32);
+            COMA_FA_TS(1, 64);
         }
         if (d <= 128) {
-            if (DN == 80) return launch_attention_ts<2, 80, 3>(COMA_FA_TS_ARGS);
-            return launch_attention_ts<2, 128, 3>(COMA_FA_TS_ARGS);
+            if (DN == 80) COMA_FA_TS(2, 80);
+            COMA_FA_TS(2, 128);
         }
-        if (DN == 160) return launch_attention_ts<3, 160, 3>(COMA_FA_TS_ARGS);
-        return launch_attention_ts<3, 192, 3>(COMA_FA_TS_ARGS);
+        if (DN == 160) COMA_FA_TS(3, 160);
+        COMA_FA_TS(3, 192);
+#undef COMA_FA_TS
 #undef COMA_FA_TS_ARGS
     }
     if (d <= 64) {

@@ -2,14 +2,15 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from coma_b200.inpaint import nn
-dev = torch.device("cuda:0"); B, S, heads, d = 8, int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 8, 40; C = heads * d
+dev = torch.device("cuda:0"); B, S, heads, d = 8, int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 8, int(os.environ.get("D", 40)); C = heads * d
 L = int(sys.argv[2]) if len(sys.argv) > 2 else S
 g = torch.Generator(device=dev).manual_seed(0)
 q = torch.randn((B * S, C), device=dev, generator=g).half()
 k, v = (torch.randn((B * L, C), device=dev, generator=g).half() for _ in range(2))
-vt = torch.empty((B, heads, d, L), dtype=torch.float16, device=dev); o = torch.empty((B * S, C), dtype=torch.float16, device=dev)
-nn.call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, C, vt.data_ptr(), L, nn._stream())
-f = lambda: nn.call("coma_attention_fwd_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, C, C, L, float(d ** -0.5), o.data_ptr(), C, nn._stream())
+Lp = (L + 7) // 8 * 8
+vt = torch.zeros((B, heads, d, Lp), dtype=torch.float16, device=dev); o = torch.empty((B * S, C), dtype=torch.float16, device=dev)
+nn.call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, C, vt.data_ptr(), Lp, nn._stream())
+f = lambda: nn.call("coma_attention_fwd_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, C, C, Lp, float(d ** -0.5), o.data_ptr(), C, nn._stream())
 for _ in range(3): f()
 torch.cuda.synchronize(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
