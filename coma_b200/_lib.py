@@ -43,6 +43,7 @@ SIGNATURES = {
     "coma_conv3x3_small_n_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp],
     "coma_attention_fwd_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
     "coma_attention_fwd_ex_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _i64, _vp],
+    "coma_attention_fwd_nt_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _i64, _vp],
     "coma_groupnorm_workspace_doubles": [_i64, _int],
     "coma_groupnorm_affine_f16": [_vp, _i64, _i64, _i64, _i64, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "coma_affine_act_f16": [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _vp],

@@ -62,6 +62,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// MN-major operand, 128B swizzle: a K row is 128 B = 64 contiguous MN elements, 8 K rows per 1024-byte atom (SBO), 64-wide MN
+// blocks lbo_bytes apart (LBO)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // K-major operand with 64-byte rows (32 fp16 of K per row), 64B swizzle: 8-row atoms of 512 B
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -483,7 +494,10 @@ __host__ __device__ constexpr int fa_ts_tmem_need(int DN, int SPLIT) { return 12
 __host__ __device__ constexpr int fa_ts_tmem_cols(int DN, int SPLIT) { return fa_ts_tmem_need(DN, SPLIT) <= 256 ? 256 : 512; }
 __host__ __device__ constexpr int fa_ts_threads(int SPLIT) { return 64 + 128 * SPLIT; }
 
-template <int DKB, int DN, int STAGES, int SPLIT, int POLY>
+// VMN: V arrives UNtransposed — tmVt is then a map over V [B, L, heads*d] of the same form as K's, a stage holds the [64 keys x 64 d]
+// blocks exactly like a K tile, and P V reads it as an MN-major B operand (instruction-descriptor bit 16; descriptor LBO = stride
+// between 64-wide d blocks, SBO = 8 key rows): no V^T tensor, no transpose kernel in front of the attention.
+template <int DKB, int DN, int STAGES, int SPLIT, int POLY, bool VMN>
 __global__ void __launch_bounds__(fa_ts_threads(SPLIT), fa_ts_tmem_cols(DN, SPLIT) == 256 ? 2 : 1)
     attention_fwd_ts_kernel(const __half *__restrict__ qg, long long ldq, long long q_bstride, const __grid_constant__ CUtensorMap tmK,
                             const __grid_constant__ CUtensorMap tmVt, int S, int L, int d, float scale_log2, __half *__restrict__ out,
@@ -495,7 +509,7 @@ __global__ void __launch_bounds__(fa_ts_threads(SPLIT), fa_ts_tmem_cols(DN, SPLI
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int K_BLOCK = FA_BKV * 64 * 2, K_BYTES = DKB * K_BLOCK;
     constexpr int PV_ROW = FA_BKV * 2;
-    constexpr int VT_BYTES = ((DN * PV_ROW + 1023) / 1024) * 1024;
+    constexpr int VT_BYTES = VMN ? K_BYTES : ((DN * PV_ROW + 1023) / 1024) * 1024;
     uint8_t *sK = smem;
     uint8_t *sVt = sK + STAGES * K_BYTES;
     uint64_t *bar = reinterpret_cast<uint64_t *>(sVt + STAGES * VT_BYTES);
@@ -550,8 +564,14 @@ __global__ void __launch_bounds__(fa_ts_threads(SPLIT), fa_ts_tmem_cols(DN, SPLI
 #pragma unroll
                 for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sK + s * K_BYTES + kb * K_BLOCK, &tmK, k_full + s, kb * 64, j * FA_BKV, h, b);
                 mbar_wait(v_empty + s, ph ^ 1);
-                mbar_expect_tx(v_full + s, DN * PV_ROW);
-                tma_load_4d(sVt + s * VT_BYTES, &tmVt, v_full + s, j * FA_BKV, 0, h, b);
+                if (VMN) {
+                    mbar_expect_tx(v_full + s, K_BYTES);
+#pragma unroll
+                    for (int kb = 0; kb < DKB; ++kb) tma_load_4d(sVt + s * VT_BYTES + kb * K_BLOCK, &tmVt, v_full + s, kb * 64, j * FA_BKV, h, b);
+                } else {
+                    mbar_expect_tx(v_full + s, DN * PV_ROW);
+                    tma_load_4d(sVt + s * VT_BYTES, &tmVt, v_full + s, j * FA_BKV, 0, h, b);
+                }
             }
             pdl_trigger();
         }
@@ -562,8 +582,9 @@ __global__ void __launch_bounds__(fa_ts_threads(SPLIT), fa_ts_tmem_cols(DN, SPLI
         // 45 clk dispatch floor of an M128 x N<=90 x K16 instruction (tools/ubench_umma.cu). That made this warp the critical path of
         // the whole kernel. Here every descriptor is (stage base) + compile-time constant.
         constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(FA_BKV >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
-        constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
-        const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK)), vdesc0 = umma_desc_sw128(smem_u32(sVt));
+        constexpr uint32_t idesc_o = (1u << 4) | (VMN ? (1u << 16) : 0u) | ((uint32_t)(DN >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+        const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK));
+        const uint64_t vdesc0 = VMN ? umma_desc_sw128_mn(smem_u32(sVt), K_BLOCK) : umma_desc_sw128(smem_u32(sVt));
         int sq = 0, sv = 0;               // ring stage of the next Q K^T / P V
         uint32_t phq = 0, phv = 0;
         auto issue_qk = [&](int j) {      // S_j = Q K_j^T into score buffer j & 1, A = Q from TMEM
@@ -601,8 +622,8 @@ __global__ void __launch_bounds__(fa_ts_threads(SPLIT), fa_ts_tmem_cols(DN, SPLI
                 for (int hh = 0; hh < SPLIT; ++hh)
 #pragma unroll
                     for (int k = 0; k < CW / 16; ++k)   // O_hh += P_hh V_hh: P_hh sits in the first CW/2 columns of its half of S_j
-                        umma_f16_ts(tmem_O + (uint32_t)(hh * DN), tp + (uint32_t)(hh * CW + k * 8), vd + (uint64_t)((hh * (CW / 16) + k) * 2), idesc_o,
-                                    (j | k) != 0);
+                        umma_f16_ts(tmem_O + (uint32_t)(hh * DN), tp + (uint32_t)(hh * CW + k * 8),
+                                    vd + (uint64_t)(VMN ? (hh * CW + k * 16) * 8 : (hh * (CW / 16) + k) * 2), idesc_o, (j | k) != 0);   // key row = 128 B
                 umma_commit(v_empty + sv);
                 umma_commit(p_empty + (j & 1));  // P_j consumed; O includes tile j; score buffer j & 1 may be overwritten
             }
@@ -817,16 +838,16 @@ static int launch_attention(const CUtensorMap &tq, const CUtensorMap &tk, const 
     return check_launch("attention_fwd_kernel");
 }
 
-template <int DKB, int DN, int STAGES, int SPLIT, int POLY>
+template <int DKB, int DN, int STAGES, int SPLIT, int POLY, bool VMN>
 static int launch_attention_ts(const __half *q, long long ldq, long long q_bstride, const CUtensorMap &tk, const CUtensorMap &tv, int B, int heads,
                                int S, int L, int d, float scale_log2, __half *out, float *out32, long long ldo, long long o_bstride,
                                cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (DKB * 64 * 128 + ((DN * 64 * 2 + 1023) / 1024) * 1024) + 256 + SPLIT * 128 * 8 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (DKB * 64 * 128 + (VMN ? DKB * 64 * 128 : ((DN * 64 * 2 + 1023) / 1024) * 1024)) + 256 + SPLIT * 128 * 8 + 1024;
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attention_fwd_ts_kernel<DKB, DN, STAGES, SPLIT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_ts_kernel<DKB, DN, STAGES, SPLIT, POLY, VMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(attention ts): %s", cudaGetErrorString(e));
             return (int)e;
@@ -834,7 +855,7 @@ static int launch_attention_ts(const __half *q, long long ldq, long long q_bstri
         attr[dev] = true;
     }
     dim3 grid((S + FA_BQ - 1) / FA_BQ, heads, B);
-    launch_pdl(attention_fwd_ts_kernel<DKB, DN, STAGES, SPLIT, POLY>, grid, dim3(fa_ts_threads(SPLIT)), smem, st, q, ldq, q_bstride, tk, tv, S, L, d,
+    launch_pdl(attention_fwd_ts_kernel<DKB, DN, STAGES, SPLIT, POLY, VMN>, grid, dim3(fa_ts_threads(SPLIT)), smem, st, q, ldq, q_bstride, tk, tv, S, L, d,
                scale_log2, out, out32, ldo, o_bstride);
     return check_launch("attention_fwd_ts_kernel");
 }
@@ -847,35 +868,26 @@ extern "C" __attribute__((visibility("default"))) int coma_attention_trace(long 
 }
 #endif
 
-extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
-                                         int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32, int64_t ldo,
-                                         coma_stream_t stream);
-extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
-                                      int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, int64_t ldo,
-                                      coma_stream_t stream) {
-    COMA_REQUIRE(out, "null pointer");
-    return coma_attention_fwd_ex_f16(q, k, vt, B, heads, S, L, d, ldq, ldk, Lp, scale, out, nullptr, ldo, stream);
-}
-
-extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
-                                         int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32, int64_t ldo,
-                                         coma_stream_t stream) {
-    using namespace coma;
-    COMA_REQUIRE(q && k && vt && (out || out_f32), "null pointer");
+namespace coma {
+// Shared body of the three entry points. v_rows = false: `v` is V^T [B, heads, d, Lp]; true: `v` is V [B, L, heads*d] (row stride ldv = Lp).
+static int attention_dispatch(const void *q, const void *k, const void *v, bool v_rows, int64_t B, int64_t heads, int64_t S, int64_t L, int64_t d,
+                              int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32, int64_t ldo, cudaStream_t st) {
+    COMA_REQUIRE(q && k && v && (out || out_f32), "null pointer");
     COMA_REQUIRE(B > 0 && heads > 0 && S > 0 && L > 0 && d > 0 && B <= 65535 && heads <= 65535, "bad sizes");
     COMA_REQUIRE(d % 8 == 0 && d <= 192, "head dim must be a multiple of 8 and <= 192");
-    COMA_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && Lp % 8 == 0 && Lp >= L && ldo % 8 == 0, "strides must be multiples of 8 elements");
+    COMA_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && Lp % 8 == 0 && ldo % 8 == 0, "strides must be multiples of 8 elements");
+    COMA_REQUIRE(v_rows ? Lp >= heads * d : Lp >= L, "V stride too small");
     COMA_REQUIRE(ldq >= heads * d && ldk >= heads * d && ldo >= heads * d, "row strides smaller than heads*d");
-    COMA_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out | (uintptr_t)out_f32) % 16 == 0, "pointers must be 16-byte aligned");
+    COMA_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)out_f32) % 16 == 0, "pointers must be 16-byte aligned");
     // DN = accumulator width of the kernel instantiation that will run; the V^T TMA box must have exactly DN rows
     // (rows >= d are zero-filled) or the producer's expect_tx byte count never completes.
     const int d16 = (int)((d + 15) / 16 * 16);
     const int DN = d <= 64 ? (d16 == 48 ? 48 : (d16 <= 32 ? 32 : 64)) : (d <= 128 ? (d16 == 80 ? 80 : 128) : (d16 == 160 ? 160 : 192));
     // keys per step: 32 for small heads with SHORT key sequences (cross-attention over 77 tokens: four CTAs per SM and no
     // half-empty 64-key step), 64 otherwise (measured: 2.23 vs 2.46 ms over the five 4096-token self-attention layers);
-    // COMA_ATTN_BKV = 32 | 64 forces one of them (tuning)
+    // COMA_ATTN_BKV = 32 | 64 forces one of them (tuning). Untransposed V exists in the 64-key kernel only.
     static const int forced_bkv = getenv("COMA_ATTN_BKV") ? atoi(getenv("COMA_ATTN_BKV")) : 0;
-    const int BKV = (d <= 64 && (forced_bkv ? forced_bkv == 32 : L <= 128)) ? 32 : 64;
+    const int BKV = (!v_rows && d <= 64 && (forced_bkv ? forced_bkv == 32 : L <= 128)) ? 32 : 64;
     CUtensorMap tq, tk, tv;
     {
         cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)S, (cuuint64_t)heads, (cuuint64_t)B};
@@ -889,19 +901,23 @@ extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const voi
         cuuint32_t box[4] = {64, (cuuint32_t)BKV, 1, 1};
         if (int e = make_map4(&tk, k, dims, str, box)) return e;
     }
-    {
+    if (v_rows) {   // V like K: [64 keys x 64 d] boxes, rows beyond L and columns beyond d zero-filled
+        cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)L, (cuuint64_t)heads, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Lp * 2, (cuuint64_t)d * 2, (cuuint64_t)(L * Lp) * 2};
+        cuuint32_t box[4] = {64, 64, 1, 1};
+        if (int e = make_map4(&tv, v, dims, str, box)) return e;
+    } else {
         cuuint64_t dims[4] = {(cuuint64_t)Lp, (cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)Lp * 2, (cuuint64_t)(d * Lp) * 2, (cuuint64_t)(heads * d * Lp) * 2};
         cuuint32_t box[4] = {(cuuint32_t)BKV, (cuuint32_t)DN, 1, 1};
-        if (int e = make_map4(&tv, vt, dims, str, box, BKV == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+        if (int e = make_map4(&tv, v, dims, str, box, BKV == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     }
     const float scale_log2 = scale * 1.4426950408889634f;
-    cudaStream_t st = (cudaStream_t)stream;
     __half *o = (__half *)out;
     const long long obs = (long long)S * ldo;
 #define COMA_FA_ARGS tq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, out_f32, ldo, obs, st
     static const bool force_ss = getenv("COMA_ATTN_SS") != nullptr;   // A/B: the round-1 kernel (Q / P operands from shared memory)
-    if (BKV == 64 && !force_ss) {
+    if (BKV == 64 && (!force_ss || v_rows)) {
         // v3: Q and P as TMEM operands (see attention_fwd_ts_kernel). Two threads per query row where that keeps two CTAs per SM
         // (DN <= 48: 16 softmax warps per SM; measured 0.345 -> 0.321 ms at S = L = 4096, d = 40, and slower than one thread per row
         // wherever the second accumulator costs the second CTA: d = 80, 0.035 -> 0.046 ms). The polynomial exp2 pays only with one
@@ -909,11 +925,16 @@ extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const voi
         // (tools/ubench_tmem.cu: 54.6 B/clk/SM = 600 clk per 128 x 64 fp32 score tile), not on the MUFU. COMA_ATTN_SPLIT=1: A/B.
         static const bool no_split = getenv("COMA_ATTN_SPLIT") && atoi(getenv("COMA_ATTN_SPLIT")) == 1;
 #define COMA_FA_TS_ARGS (const __half *)q, (long long)ldq, (long long)S * ldq, tk, tv, (int)B, (int)heads, (int)S, (int)L, (int)d, scale_log2, o, out_f32, ldo, obs, st
-#define COMA_FA_TS(DKB_, DN_)                                                                                      \
-    do {                                                                                                           \
-        if (fa_ts_tmem_need(DN_, 2) <= 256 && !no_split)                                                           \
-            return launch_attention_ts<DKB_, DN_, 3, (fa_ts_tmem_need(DN_, 2) <= 256 ? 2 : 1), 0>(COMA_FA_TS_ARGS); \
-        return launch_attention_ts<DKB_, DN_, 3, 1, 3>(COMA_FA_TS_ARGS);                                           \
+#define COMA_FA_TS2(DKB_, DN_, VMN_)                                                                                     \
+    do {                                                                                                                 \
+        if (fa_ts_tmem_need(DN_, 2) <= 256 && !no_split)                                                                 \
+            return launch_attention_ts<DKB_, DN_, 3, (fa_ts_tmem_need(DN_, 2) <= 256 ? 2 : 1), 0, VMN_>(COMA_FA_TS_ARGS); \
+        return launch_attention_ts<DKB_, DN_, 3, 1, 3, VMN_>(COMA_FA_TS_ARGS);                                           \
+    } while (0)
+#define COMA_FA_TS(DKB_, DN_)                        \
+    do {                                             \
+        if (v_rows) COMA_FA_TS2(DKB_, DN_, true);    \
+        COMA_FA_TS2(DKB_, DN_, false);               \
     } while (0)
         if (d <= 64) {
             if (DN == 48) COMA_FA_TS(1, 48);
@@ -927,6 +948,7 @@ extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const voi
         if (DN == 160) COMA_FA_TS(3, 160);
         COMA_FA_TS(3, 192);
 #undef COMA_FA_TS
+#undef COMA_FA_TS2
 #undef COMA_FA_TS_ARGS
     }
     if (d <= 64) {
@@ -948,4 +970,22 @@ extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const voi
     if (DN == 160) return launch_attention<3, 160, 2, 64>(COMA_FA_ARGS);
     return launch_attention<3, 192, 2, 64>(COMA_FA_ARGS);
 #undef COMA_FA_ARGS
+}
+}  // namespace coma
+
+extern "C" int coma_attention_fwd_ex_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                         int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32, int64_t ldo,
+                                         coma_stream_t stream) {
+    return coma::attention_dispatch(q, k, vt, false, B, heads, S, L, d, ldq, ldk, Lp, scale, out, out_f32, ldo, (cudaStream_t)stream);
+}
+extern "C" int coma_attention_fwd_f16(const void *q, const void *k, const void *vt, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                      int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, int64_t ldo,
+                                      coma_stream_t stream) {
+    COMA_REQUIRE(out, "null pointer");
+    return coma::attention_dispatch(q, k, vt, false, B, heads, S, L, d, ldq, ldk, Lp, scale, out, nullptr, ldo, (cudaStream_t)stream);
+}
+extern "C" int coma_attention_fwd_nt_f16(const void *q, const void *k, const void *v, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                         int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, float scale, void *out, float *out_f32, int64_t ldo,
+                                         coma_stream_t stream) {
+    return coma::attention_dispatch(q, k, v, true, B, heads, S, L, d, ldq, ldk, ldv, scale, out, out_f32, ldo, (cudaStream_t)stream);
 }

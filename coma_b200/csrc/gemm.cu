@@ -87,6 +87,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp; the same lane every time for a full mask
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -269,54 +274,75 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
         }
     };
 
+    // Producer and MMA issuer run as CONVERGED warps with one elected lane per issue group. Inside an `if (lane == 0)` region ptxas
+    // wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT retry loop and rebuilds the shared-memory descriptors per slab on the
+    // uniform datapath; with elect.sync the issue sequence is straight-line code (attention.cu measured 110-240 -> ~50 clk per MMA).
+    // Ring stage / phase and the convolution's (tap, channel block) are carried incrementally: no division per K-slab.
     if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
-                int m0, n0, b1, b2, cx0, cy0, cb0;
-                decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
-                const int kb0 = (t % ts.ksplit) * ts.kb_per, kb1 = min(num_k, kb0 + ts.kb_per);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(empty + s, ph ^ 1);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+            int m0, n0, b1, b2, cx0, cy0, cb0;
+            decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
+            const int kb0 = (t % ts.ksplit) * ts.kb_per, kb1 = min(num_k, kb0 + ts.kb_per);
+            int tap = 0, cb = 0;
+            if (CONV) {
+                tap = kb0 / cg.cblocks;
+                cb = kb0 - tap * cg.cblocks;
+            }
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty + s, ph ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(full + s, A_BYTES + B_BYTES);
                     if (CONV) {
-                        const int tap = kb / cg.cblocks, cb = kb % cg.cblocks;
-                        tma_load_4d(sA + s * A_BYTES, &tmA, full + s, cb * G_BK, cx0 * cg.stride + tap % 3 - cg.pad,
-                                    cy0 * cg.stride + tap / 3 - cg.pad, cb0);
+                        const int ty = (tap * 11) >> 5;   // tap / 3 for tap in [0, 9)
+                        tma_load_4d(sA + s * A_BYTES, &tmA, full + s, cb * G_BK, cx0 * cg.stride + (tap - 3 * ty) - cg.pad,
+                                    cy0 * cg.stride + ty - cg.pad, cb0);
                     } else {
                         tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
                     }
                     tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0, b1, b2);
                 }
+                __syncwarp();
+                if (CONV && ++cb == cg.cblocks) {
+                    cb = 0;
+                    ++tap;
+                }
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
-            pdl_trigger();  // all of this CTA's operands are on their way: dependents may start launching
         }
+        if (lane == 0) pdl_trigger();  // all of this CTA's operands are on their way: dependents may start launching
     } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N>>3, M>>4
-            constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
-            int it = 0, i = 0;
-            for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
-                const int acc = i & 1;
-                mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N>>3, M>>4
+        constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
+        const uint64_t da0 = umma_desc_sw128(smem_u32(sA)), db0 = umma_desc_sw128(smem_u32(sB));
+        int s = 0, i = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+            const int acc = i & 1;
+            mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            const int kb0 = (t % ts.ksplit) * ts.kb_per, kb1 = min(num_k, kb0 + ts.kb_per);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(full + s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                const int kb0 = (t % ts.ksplit) * ts.kb_per, kb1 = min(num_k, kb0 + ts.kb_per);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(full + s, ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t da = umma_desc_sw128(smem_u32(sA + s * A_BYTES));
-                    const uint64_t db = umma_desc_sw128(smem_u32(sB + s * B_BYTES));
+                if (elect_one()) {
+                    const uint64_t da = da0 + (uint64_t)(s * (A_BYTES >> 4)), db = db0 + (uint64_t)(s * (B_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < G_BK / 16; ++k)  // advance 32 B (16 fp16) inside the 128 B swizzle atom: +2 in 16-B units
                         umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
                     umma_commit(empty + s);  // frees the slab once the MMAs that read it have retired
+                    if (kb + 1 == kb1) umma_commit(tmem_full + acc);
                 }
-                umma_commit(tmem_full + acc);
+                __syncwarp();
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
     } else if (ep.tma) {

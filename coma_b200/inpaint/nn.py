@@ -299,27 +299,36 @@ def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual, wqkv=None, 
     d = C // heads
     Lp = rup(L)
     if FUSED_ATTENTION and d % 8 == 0 and d <= 192:
+        # Short key sequences with small heads (the 77-token context at d = 40) run the 32-key-step kernel, which takes V^T; every
+        # other shape reads V in place ([B*L, C] slice of the projection output) as an MN-major tensor-core operand.
+        in_place_v = not (L <= 128 and d <= 64)
+        v = vt = None
         if kv is not None:
             q = gemm(xq, wq)
             k, vt = kv
         elif wqkv is not None:
             qkv = gemm(xq, wqkv)
             q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
-            vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)
-            with torch.cuda.device(dev):
-                call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
         else:
             q = gemm(xq, wq)
-            k, vt = project_kv(xkv, B, L, wkv, heads) if wkv is not None else (gemm(xkv, wk), None)
-            if vt is None:
-                v = gemm(xkv, wv)
-                vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)
-                with torch.cuda.device(dev):
-                    call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
+            if wkv is not None and in_place_v:
+                kvp = gemm(xkv, wkv)
+                k, v = kvp[:, :C], kvp[:, C:]
+            elif wkv is not None:
+                k, vt = project_kv(xkv, B, L, wkv, heads)
+            else:
+                k, v = gemm(xkv, wk), gemm(xkv, wv)
         o = torch.empty((B * S, C), dtype=F16, device=dev)
         with torch.cuda.device(dev):
-            call("coma_attention_fwd_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, q.stride(0), k.stride(0), Lp,
-                 float(d ** -0.5), o.data_ptr(), o.stride(0), _stream())
+            if vt is None and in_place_v:
+                call("coma_attention_fwd_nt_f16", q.data_ptr(), k.data_ptr(), v.data_ptr(), B, heads, S, L, d, q.stride(0), k.stride(0), v.stride(0),
+                     float(d ** -0.5), o.data_ptr(), None, o.stride(0), _stream())
+            else:
+                if vt is None:
+                    vt = torch.empty((B, heads, d, Lp), dtype=F16, device=dev)
+                    call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
+                call("coma_attention_fwd_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, q.stride(0), k.stride(0), Lp,
+                     float(d ** -0.5), o.data_ptr(), o.stride(0), _stream())
         return gemm(o, wo, bo, residual)
     if wq is None:
         wq, wk, wv = wqkv[:C], wqkv[C:2 * C], wqkv[2 * C:]

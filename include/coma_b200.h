@@ -254,6 +254,13 @@ COMA_API int coma_attention_fwd_ex_f16(const void *q, const void *k, const void 
                                        int64_t d, int64_t ldq, int64_t ldk, int64_t Lp, float scale, void *out, float *out_f32,
                                        int64_t ldo, coma_stream_t stream);
 
+/* Same with V UNtransposed: v [B,L,heads*d] f16 (row stride ldv), e.g. a column slice of the fused q|k|v projection — the P V
+ * product reads the [keys x d] tile as an MN-major tensor-core operand, so no V^T tensor and no coma_transpose_heads_f16 launch in
+ * front of the attention. 64-key steps for every shape; out / out_f32 as in coma_attention_fwd_ex_f16. */
+COMA_API int coma_attention_fwd_nt_f16(const void *q, const void *k, const void *v, int64_t B, int64_t heads, int64_t S, int64_t L,
+                                       int64_t d, int64_t ldq, int64_t ldk, int64_t ldv, float scale, void *out, float *out_f32,
+                                       int64_t ldo, coma_stream_t stream);
+
 /* ---- U*: the non-contraction layers of the UNet / VAE, NHWC fp16 activations ([B, H*W, C], row stride ld*) -------------
  * (diffusers UNet2DConditionModel / AutoencoderKL layers reached from utils/adaptive_mask_inpainting.py:1001, :680, :1086) */
 

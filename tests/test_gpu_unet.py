@@ -339,6 +339,38 @@ def test_attention_kernel_fp32_output(dev, S, L, heads, d):
     assert err.max().item() <= 5e-4 * scale, err.max().item() / scale
 
 
+@pytest.mark.parametrize("S,L,heads,d", [(4096, 4096, 8, 40), (1024, 1024, 8, 80), (256, 256, 8, 160), (4096, 77, 8, 40), (200, 300, 2, 64), (130, 50, 3, 24),
+                                        (128, 100, 1, 128), (300, 1000, 2, 192)])
+def test_attention_kernel_untransposed_v(dev, S, L, heads, d):
+    """`coma_attention_fwd_nt_f16`: V stays [B, L, heads*d] — here a column slice of a fused q|k|v buffer, as in the UNet — and P V reads it as
+    an MN-major tensor-core operand. Same bars as the transposed form, and bit-identical to it (same products, same order)."""
+    from coma_b200._lib import _stream, call
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(S + d)
+    B, C, Lp = 2, heads * d, nn.rup(L)
+    q = torch.randn((B, S, C), device=dev, generator=g).half()
+    kv = torch.randn((B, L, 2 * C), device=dev, generator=g).half()
+    k, v = kv[..., :C], kv[..., C:]
+    out = torch.zeros((B, S, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("coma_attention_fwd_nt_f16", q.data_ptr(), k.data_ptr(), v.data_ptr(), B, heads, S, L, d, C, 2 * C, 2 * C, float(d ** -0.5), None,
+             out.data_ptr(), C, _stream())
+    qf, kf, vf = (t.float().reshape(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, -1) @ vf).transpose(1, 2).reshape(B, S, C)
+    scale = ref.abs().max().item()
+    err = (out - ref).abs()
+    assert err.pow(2).mean().sqrt().item() <= 1e-4 * scale, err.pow(2).mean().sqrt().item() / scale
+    assert err.max().item() <= 5e-4 * scale, err.max().item() / scale
+    if L > 128 or d > 64:   # the transposed entry runs the same 64-key kernel: identical arithmetic
+        vt = torch.zeros((B, heads, d, Lp), dtype=torch.float16, device=dev)
+        vt[..., :L] = v.reshape(B, L, heads, d).permute(0, 2, 3, 1)
+        out2 = torch.zeros_like(out)
+        with torch.cuda.device(dev):
+            call("coma_attention_fwd_ex_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, C, 2 * C, Lp, float(d ** -0.5), None,
+                 out2.data_ptr(), C, _stream())
+        assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("B,H,W,C,Cout,gn,out32", [(2, 64, 64, 128, 3, True, True), (1, 40, 72, 320, 4, True, False), (3, 17, 33, 64, 1, False, True),
                                                   (1, 512, 512, 128, 3, True, True), (2, 16, 16, 72, 2, True, True)])
 def test_conv3x3_small_n_fused(dev, B, H, W, C, Cout, gn, out32):
