@@ -278,7 +278,7 @@ def hoi_leg(args, dev, rank, world, barrier):
     from coma_b200.inpaint.segmenter import LuminanceSegmenter
     from coma_b200.inpaint.unet import UNet
     from coma_b200.inpaint.vae import VAE
-    from oracle import sd_oracle as so   # weight generator only (seeded random state dicts with diffusers key names)
+    from coma_b200.inpaint import synthetic as so   # seeded random state dicts with diffusers key names (no checkpoints offline)
     cfg3 = world == 8 and not args.hoi_cfg2
     B = 8 if cfg3 else args.hoi_batch
     n_views = 36 if cfg3 else world

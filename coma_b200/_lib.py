@@ -14,6 +14,8 @@ _f32p = _c.POINTER(_c.c_float)
 
 # name -> argtypes, exactly the prototypes of include/coma_b200.h (device pointers travel as void*)
 SIGNATURES = {
+    "coma_host_stage_rows_f64_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp],
+    "coma_host_rows_equal_f64": [_vp, _i64, _vp, _i64, _vp],
     "coma_vertex_normals_f64": [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _f64, _vp, _vp],
     "coma_nearest_vertex_f64": [_vp, _i64, _vp, _i64, _vp, _vp],
     "coma_nearest_distance_f32": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],

@@ -128,6 +128,35 @@ class ComA_Occupancy:
                 res = np.subtract(human_verts[h0:h1], obj_vert[None], out=out, casting="same_kind")
         return res
 
+    def _stage_chunk(self, chunk, view, all_rows):
+        """Fast path of `_canonical_human_verts` over a chunk of samples. False -> nothing is assumed written, use the numpy path."""
+        from .staging import rows_equal_f64, stage_rows_f64
+        if len(self.selected_obj_idxs) != 1 or not chunk:
+            return False
+        oi = self.selected_obj_idxs[0]
+        try:
+            hv = [s["human_verts"] for s in chunk]
+            ov = [s["obj_verts"] for s in chunk]
+            on = [s["obj_normals"] for s in chunk]
+        except (KeyError, TypeError):
+            return False
+        if not all(isinstance(a, np.ndarray) for a in hv + ov + on) or any(a.shape[0] != self.human_res for a in hv):
+            return False
+        if any(a.ndim != 2 or a.shape[1] != 3 or a.shape[0] <= oi for a in ov + on):
+            return False
+        if self.debug_obj_vert is None:
+            self.debug_obj_vert = ov[0][oi]
+        if self.debug_obj_normal is None:
+            self.debug_obj_normal = on[0][oi]
+        # the reference's invariant (:277-284) on the normals: equal values is the normal case, anything else goes to np.allclose
+        onr = on if oi == 0 else [a[oi:] for a in on]
+        if not rows_equal_f64(onr, np.asarray(self.debug_obj_normal, dtype=np.float64)):
+            return False
+        h0, h1 = (0, self.human_res) if all_rows else self._human_slice
+        ovr = ov if oi == 0 else [a[oi:] for a in ov]
+        mism = stage_rows_f64(hv, view[:len(chunk)], row0=h0, sub=ovr, equal_to=np.asarray(self.debug_obj_vert, dtype=np.float64))
+        return mism is not None and mism < 0
+
     def _aggregate_samples(self, samples, exchange=False, group=None):
         exchange = exchange and cdist.is_distributed(group)
         if not samples and not exchange:
@@ -139,10 +168,20 @@ class ComA_Occupancy:
         chunk = max(32, min(8192, (_STAGING_BYTES // (rows * 12)) // 32 * 32))
         chunk = min(chunk, 256) if exchange else min(chunk, (len(samples) + 31) // 32 * 32)
         stager = BatchStager(dict(hvc=self.human_res if exchange else h1 - h0), chunk, self.spatial_occupancy_grids.device)
-        class _Getter:   # writes each sample's canonical vertices straight into its pinned fp32 row
+        outer = self
+
+        class _Getter:   # writes the samples' canonical vertices straight into their pinned fp32 rows
             @staticmethod
             def fill(dst, i):
-                self._canonical_human_verts(samples[i], all_rows=exchange, out=dst)
+                outer._canonical_human_verts(samples[i], all_rows=exchange, out=dst)
+
+            @staticmethod
+            def fill_many(view, s0, n):
+                """One library call per chunk (fp64 subtraction, fp32 store, same-object check) when every sample is a plain float64
+                array; otherwise — or when the object differs bitwise from the first sample's — the per-sample numpy path decides."""
+                if not outer._stage_chunk(samples[s0:s0 + n], view, all_rows=exchange):
+                    for j in range(n):
+                        outer._canonical_human_verts(samples[s0 + j], all_rows=exchange, out=view[j])
         getters = dict(hvc=_Getter)
         total = 0
         if exchange:

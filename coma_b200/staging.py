@@ -1,7 +1,50 @@
 """Host->device staging of sample batches: pinned double buffers, copies on a side stream, fp64->fp32 rounding on the
 host exactly as the reference's `to_np_torch_recursive` does (utils/misc.py:47-54)."""
+import ctypes
+
 import numpy as np
 import torch
+
+
+def stage_rows_f64(arrays, out, row0=0, sub=None, equal_to=None):
+    """out[i] = fp32(arrays[i][row0:row0+rows] - sub[i]) for a list of C-contiguous float64 [*, 3] arrays, through the library's host
+    helper `coma_host_stage_rows_f64_f32` (one call for the whole list instead of one numpy call per sample). `out`: writable fp32
+    numpy view [>= n, rows, 3] (the pinned staging buffer). Returns the first index whose `sub` row differs bitwise from `equal_to`
+    (-1 if none / not requested), or None if some array does not qualify (the caller falls back to numpy)."""
+    from . import _lib
+    n = len(arrays)
+    rows = out.shape[1]
+    f64 = np.float64
+    for a in arrays:
+        if a.dtype != f64 or not a.flags.c_contiguous or a.ndim != 2 or a.shape[1] != 3 or a.shape[0] < row0 + rows:
+            return None
+    src = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    subp = None
+    if sub is not None:
+        for a in sub:
+            if a.dtype != f64 or not a.flags.c_contiguous or a.size < 3:
+                return None
+        subp = (ctypes.c_void_p * n)(*[a.ctypes.data for a in sub])
+    eq = None if equal_to is None else np.ascontiguousarray(equal_to, dtype=f64)
+    mism = ctypes.c_int64(-1)
+    _lib.call("coma_host_stage_rows_f64_f32", src, subp, n, row0, rows, out.ctypes.data, None if eq is None else eq.ctypes.data,
+              ctypes.addressof(mism))
+    return int(mism.value)
+
+
+def rows_equal_f64(arrays, ref):
+    """True iff every C-contiguous float64 array in `arrays` starts with the values of `ref` (one library call); None if an array
+    does not qualify."""
+    from . import _lib
+    ref = np.ascontiguousarray(ref, dtype=np.float64).reshape(-1)
+    for a in arrays:
+        if a.dtype != np.float64 or not a.flags.c_contiguous or a.size < ref.size:
+            return None
+    n = len(arrays)
+    ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    mism = ctypes.c_int64(-1)
+    _lib.call("coma_host_rows_equal_f64", ptrs, n, ref.ctypes.data, ref.size, ctypes.addressof(mism))
+    return mism.value < 0
 
 
 class BatchStager:
@@ -41,7 +84,10 @@ class BatchStager:
             for k in self.specs:
                 view = self.pinned[b][k].numpy()
                 g = getters[k]
-                if hasattr(g, "fill"):            # getter that writes straight into the pinned row (no temporary)
+                if hasattr(g, "fill_many"):       # getter that fills rows [0, n) of the pinned buffer in one call (host helper in the library)
+                    if n:
+                        g.fill_many(view, s0, n)
+                elif hasattr(g, "fill"):          # getter that writes straight into the pinned row (no temporary)
                     for j in range(n):
                         g.fill(view[j], s0 + j)
                 else:

@@ -36,6 +36,15 @@ COMA_API int coma_b200_version(void);
 COMA_API const char *coma_b200_last_error(void);
 /* Number of kernel launches enqueued by this library in the calling process (bench.py's `gpu_launches`). */
 COMA_API int64_t coma_b200_launch_count(void);
+
+/* Host-side staging helper (no device work, callable without a GPU): dst[i,r,c] = (float)(src[i][(row0+r)*3+c] - (sub ? sub[i][c] : 0))
+ * for n samples x `rows` rows of 3 doubles — the fp64 -> fp32 rounding of the reference's to_np_torch_recursive (utils/misc.py:47-54)
+ * and the fp64 subtraction of utils/coma_occupancy.py:287, written straight into a (pinned) fp32 staging buffer in one call per chunk.
+ * equal_to (or NULL): 3 doubles every sub[i] is compared with (the reference's "same object in every sample" invariant,
+ * utils/coma_occupancy.py:277-284); *first_mismatch = first differing sample or -1. */
+COMA_API int coma_host_rows_equal_f64(const double *const *rows, int64_t n, const double *ref, int64_t count, int64_t *first_mismatch);
+COMA_API int coma_host_stage_rows_f64_f32(const double *const *src, const double *const *sub, int64_t n, int64_t row0, int64_t rows,
+                                          float *dst, const double *equal_to, int64_t *first_mismatch);
 /* Name of the kernel (variant) the calling thread's most recent successful entry point enqueued — lets the parity tests
  * assert WHICH kernel a shape was routed to (e.g. the S <= 4 streaming form of K2). Static storage, never NULL. */
 COMA_API const char *coma_b200_last_kernel(void);

@@ -230,3 +230,52 @@ def test_ingest_corner_list_reproduces_numpy_accumulation_order():
     assert np.array_equal(mine, ref)
     # every corner appears exactly once
     assert sorted(cf.tolist()) == sorted(np.repeat(np.arange(F), 3).tolist())
+
+
+def test_host_stage_rows_helper():
+    """`coma_host_stage_rows_f64_f32` / `coma_host_rows_equal_f64` (host code of the library, no GPU): same values as the reference's
+    `(human_verts - obj_verts[0]).astype(float32)` (utils/coma_occupancy.py:287-288) and `to_np_torch_recursive`'s fp64 -> fp32 rounding
+    (utils/misc.py:47-54); first-mismatch reporting; None (= numpy fallback) for arrays that are not plain float64."""
+    from coma_b200.staging import rows_equal_f64, stage_rows_f64
+    rng = np.random.default_rng(5)
+    H, n = 257, 9
+    hv = [rng.normal(size=(H, 3)) * 10.0 ** rng.integers(-3, 3) for _ in range(n)]
+    ov = [rng.normal(size=(4, 3)) for _ in range(n)]
+    out = np.full((n + 2, 100, 3), -7.0, np.float32)
+    assert stage_rows_f64(hv, out[:n], row0=50, sub=ov, equal_to=ov[0][0]) == 1          # sample 1 has another object
+    want = np.stack([(h[50:150] - o[0][None]).astype(np.float32) for h, o in zip(hv, ov)])
+    assert np.array_equal(out[:n], want) and (out[n:] == -7.0).all()
+    same = [ov[0]] * n
+    assert stage_rows_f64(hv, out[:n], row0=0, sub=same, equal_to=ov[0][0]) == -1
+    assert stage_rows_f64(hv, out[:n], row0=157, sub=None) == -1
+    assert np.array_equal(out[:n], np.stack([h[157:].astype(np.float32) for h in hv]))
+    assert stage_rows_f64(hv, out[:n], row0=200) is None                                  # not enough rows
+    assert stage_rows_f64([h.astype(np.float32) for h in hv], out[:n]) is None            # wrong dtype -> caller falls back to numpy
+    assert stage_rows_f64([h[:, ::-1] for h in hv], out[:n]) is None                      # not contiguous
+    assert rows_equal_f64(same, ov[0][0]) is True and rows_equal_f64(ov, ov[0][0]) is False
+    assert rows_equal_f64([o.astype(np.float32) for o in ov], ov[0][0]) is None
+
+
+def test_occupancy_chunk_staging_matches_numpy_path():
+    """ComA_Occupancy._stage_chunk (one library call per chunk) writes exactly what the per-sample numpy path writes, and declines
+    (-> numpy path, which asserts / np.allclose's like the reference) when the object moves or an input is not float64."""
+    from coma_b200.coma_occupancy import ComA_Occupancy
+    rng = np.random.default_rng(11)
+    H, O, n = 64, 5, 6
+    ov, on = rng.normal(size=(O, 3)), rng.normal(size=(O, 3))
+    samples = [dict(human_verts=rng.normal(size=(H, 3)), human_normals=rng.normal(size=(H, 3)), obj_verts=ov.copy(), obj_normals=on.copy()) for _ in range(n)]
+    occ = ComA_Occupancy.__new__(ComA_Occupancy)
+    occ.human_res, occ._human_slice, occ.debug_obj_vert, occ.debug_obj_normal = H, (8, 40), None, None
+    fast = np.zeros((n, 32, 3), np.float32)
+    assert occ._stage_chunk(samples, fast, all_rows=False)
+    slow = np.zeros_like(fast)
+    for j, s in enumerate(samples):
+        occ._canonical_human_verts(s, out=slow[j])
+    assert np.array_equal(fast, slow)
+    full = np.zeros((n, H, 3), np.float32)
+    assert occ._stage_chunk(samples, full, all_rows=True) and np.array_equal(full[:, 8:40], slow)
+    moved = [dict(s) for s in samples]
+    moved[3]["obj_verts"] = ov + 1e-12
+    assert not occ._stage_chunk(moved, fast, all_rows=False)
+    f32 = [dict(s, human_verts=s["human_verts"].astype(np.float32)) for s in samples]
+    assert not occ._stage_chunk(f32, fast, all_rows=False)

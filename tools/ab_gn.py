@@ -2,7 +2,7 @@ import os, sys, torch
 sys.path.insert(0, "/root/repo")
 from coma_b200.inpaint import nn
 from coma_b200.inpaint.vae import VAE
-from oracle import sd_oracle as so
+from coma_b200.inpaint import synthetic as so  # noqa: E402  (seeded random state dicts)
 dev = torch.device("cuda:0"); B = 4
 vae = VAE(so.make_vae_state_dict(1), device=dev)
 g = torch.Generator(device=dev).manual_seed(0)

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from coma_b200.inpaint import nn
 from coma_b200.inpaint.unet import UNet
 from coma_b200.inpaint.vae import VAE
-from oracle import sd_oracle as so
+from coma_b200.inpaint import synthetic as so  # noqa: E402  (seeded random state dicts)
 dev = torch.device("cuda:0"); B = 4
 net = UNet(so.make_unet_state_dict(0), device=dev); vae = VAE(so.make_vae_state_dict(1), device=dev)
 g = torch.Generator(device=dev).manual_seed(0)

@@ -15,7 +15,7 @@ from coma_b200.inpaint.pipeline import AdaptiveMaskInpaintPipeline, default_adap
 from coma_b200.inpaint.segmenter import LuminanceSegmenter  # noqa: E402
 from coma_b200.inpaint.unet import UNet  # noqa: E402
 from coma_b200.inpaint.vae import VAE  # noqa: E402
-from oracle import sd_oracle as so  # noqa: E402  (weights generator only)
+from coma_b200.inpaint import synthetic as so  # noqa: E402  (seeded random state dicts)
 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", 4))

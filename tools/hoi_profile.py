@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from coma_b200.inpaint import nn  # noqa: E402
 from coma_b200.inpaint.unet import UNet  # noqa: E402
 from coma_b200.inpaint.vae import VAE  # noqa: E402
-from oracle import sd_oracle as so  # noqa: E402
+from coma_b200.inpaint import synthetic as so  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = 4

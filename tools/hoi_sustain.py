@@ -9,7 +9,7 @@ from coma_b200.inpaint.pipeline import AdaptiveMaskInpaintPipeline, default_adap
 from coma_b200.inpaint.segmenter import LuminanceSegmenter
 from coma_b200.inpaint.unet import UNet
 from coma_b200.inpaint.vae import VAE
-from oracle import sd_oracle as so
+from coma_b200.inpaint import synthetic as so  # noqa: E402  (seeded random state dicts)
 
 dev = torch.device("cuda:0"); B = 4
 clk = []; stop = threading.Event()

@@ -19,7 +19,7 @@ from coma_b200._lib import GemmArgs  # noqa: E402
 from coma_b200.inpaint import nn  # noqa: E402
 from coma_b200.inpaint.unet import UNet  # noqa: E402
 from coma_b200.inpaint.vae import VAE  # noqa: E402
-from oracle import sd_oracle as so  # noqa: E402  (weight generator only)
+from coma_b200.inpaint import synthetic as so  # noqa: E402  (seeded random state dicts)
 
 dev = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "unet"
