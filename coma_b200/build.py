@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("COMA_B200_LIB") or os.path.join(HERE, "libcoma_b200.so")   # override: A/B builds for tuning runs
-SOURCES = ["capi.cu", "pair.cu", "orient.cu", "occupancy.cu", "nearest.cu", "nearest_dist.cu", "normals.cu", "readout.cu", "gemm.cu", "unet_ops.cu", "pipeline_ops.cu", "attention.cu", "conv_small.cu"]
+SOURCES = ["capi.cu", "pair.cu", "orient.cu", "occupancy.cu", "nearest.cu", "nearest_dist.cu", "normals.cu", "readout.cu", "gemm.cu", "unet_ops.cu", "pipeline_ops.cu", "attention.cu", "conv_small.cu", "conv_halo.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

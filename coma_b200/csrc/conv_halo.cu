@@ -1,0 +1,533 @@
+// C2 — 3x3 convolution (stride 1, pad 1, NHWC fp16) on tcgen05 from ACTIVATION HALO TILES, with the GroupNorm affine + SiLU of the
+// input applied in shared memory: the `norm -> SiLU -> conv` of every diffusers ResnetBlock2D / conv_norm_out reached from
+// utils/adaptive_mask_inpainting.py:1001 (UNet) and :680 / :1086 / :1112 (VAE), in ONE kernel.
+//
+// The implicit-GEMM kernel (gemm.cu, CONV) fetches the A operand of every (tap, 64-channel block) K-slab with its own TMA load — each
+// input pixel crosses L2 -> SMEM nine times — and needs the normalised + activated tensor materialised in HBM by a separate pass
+// (affine_act_kernel: 12-20 % of a VAE decode). Here:
+//   * an output tile is 16 rows x 8 columns of pixels; per 64-channel block ONE TMA load brings the 18 x 10 pixel halo
+//     (zero-filled outside the image = the convolution's padding), 23 KB instead of 9 x 16 KB;
+//   * the A operand of tap (ky, kx) is a SHIFTED VIEW of that halo tile: start address + (ky * 10 + kx) * 128 B, 8-row groups
+//     1280 B apart (SBO). The tensor core applies the 128B swizzle to absolute shared-memory address bits, so any 128-byte
+//     aligned start and any SBO address the tile TMA wrote (tools/ubench_umma_layout.cu: every shift, pitch 10 / 12 / 16: exact);
+//   * eight transform warps turn the raw halo into act(x * scale[b, c] + shift[b, c]) in place (fp16, the same roundings as the
+//     tensor the unfused path stores) while the tensor core works on the previous block; pixels outside the image stay zero;
+//   * weights stream through their own ring ([BN x 64] slabs, K order (ky, kx, cin) as in prep_conv3x3);
+//   * epilogue as in gemm.cu: TMEM -> registers -> bias / per-sample bias row (time embedding) / residual / SiLU -> 64B-swizzled
+//     32 x 32 panels -> TMA store (box 32 channels x 8 px x 4 rows), GroupNorm partial sums of the rounded output for the next norm.
+// Warps: 0 TMA producer, 1 MMA issuer (both converged, one elected lane), 2-5 epilogue, 6-13 transform.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace coma {
+namespace ch {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z, int w) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int x, int y, int z, int w) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+                 "r"(x), "r"(y), "r"(z), "r"(w)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// K-major operand, 128-byte rows, 128B swizzle; sbo_bytes = distance between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }   // as affine_act_kernel (unet_ops.cu)
+}  // namespace ch
+
+constexpr int CH_TW = 8, CH_TH = 16;                       // output tile: 16 rows x 8 columns = 128 pixels (TMEM lane = py * 8 + px)
+constexpr int CH_HW = CH_TW + 2, CH_HH = CH_TH + 2;        // halo: 18 rows x 10 columns
+constexpr int CH_HPIX = CH_HW * CH_HH;                     // 180 pixels x 128 B per 64-channel block
+constexpr int CH_HALO_BYTES = CH_HPIX * 128;               // 23040
+constexpr int CH_HALO_STRIDE = (CH_HALO_BYTES + 1023) / 1024 * 1024;
+constexpr int CH_NH = 3;                                   // halo ring: one block under the MMAs, one in the transform, one in flight
+constexpr int CH_PANEL_BYTES = 32 * 32 * 2;
+__host__ __device__ constexpr int ch_epi_warps(int BN) { return 4; }   // K >= 576: the epilogue (TMEM read rate bound) hides behind the next tile's main loop even at BN = 256
+constexpr int CH_TWARPS = 8;                               // transform warps: two per scheduler hide each other's MUFU / LDS latencies
+__host__ __device__ constexpr int ch_threads(int BN) { return 64 + 32 * ch_epi_warps(BN) + 32 * CH_TWARPS; }
+__host__ __device__ constexpr int ch_b_stages(int BN) { return BN <= 128 ? 8 : (BN <= 160 ? 6 : 4); }   // 64-128 KB of weight slabs in flight (TMA latency ~2000 clk)
+__host__ __device__ constexpr size_t ch_smem(int BN) {
+    return (size_t)CH_NH * CH_HALO_STRIDE + (size_t)ch_b_stages(BN) * BN * 128 + (size_t)ch_epi_warps(BN) * 2 * CH_PANEL_BYTES + 256 + 1024;
+}
+
+struct HaloArgs {
+    int B, H, W, C, N;
+    int cblocks, tiles_x, per_img, n_tiles, total;   // total = m_tiles * n_tiles work items; id = mt * n_tiles + nt (N fastest)
+    const float *scale, *shift;                       // [B, C] or null: the input is used as stored
+    int act_in;                                       // 1: SiLU after the affine
+    const float *bias, *bias_rows;                    // [N]; [B, bias_rows_ld] per-sample rows (time embedding) or null
+    long long bias_rows_ld;
+    const __half *residual;                           // [B*H*W, ldo] or null
+    long long ldo;
+    int act_out;
+    float *stats;                                     // [B*H*W/32, N, 2] or null
+};
+
+template <int BN>
+__global__ void __launch_bounds__(ch_threads(BN), 1)
+    conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
+                     const HaloArgs a) {
+    using namespace ch;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int EPI = ch_epi_warps(BN), PW = EPI / 4, NB = ch_b_stages(BN), B_BYTES = BN * 128;
+    uint8_t *sH = smem;
+    uint8_t *sB = sH + CH_NH * CH_HALO_STRIDE;
+    uint8_t *sE = sB + NB * B_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sE + EPI * 2 * CH_PANEL_BYTES);
+    uint64_t *halo_full = bar, *halo_ready = halo_full + CH_NH, *halo_empty = halo_ready + CH_NH;
+    uint64_t *b_full = halo_empty + CH_NH, *b_empty = b_full + NB;
+    uint64_t *tmem_full = b_empty + NB, *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+        for (int i = 0; i < CH_NH; ++i) {
+            mbar_init(halo_full + i, 1);
+            mbar_init(halo_ready + i, 32 * CH_TWARPS);
+            mbar_init(halo_empty + i, 1);
+        }
+        for (int i = 0; i < NB; ++i) {
+            mbar_init(b_full + i, 1);
+            mbar_init(b_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tmem_full + i, 1);
+            mbar_init(tmem_empty + i, 32 * EPI);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    // work item -> output-channel offset, image, tile origin
+    auto coords = [&](int t, int &n0, int &img, int &x0, int &y0) {
+        const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+        n0 = nt * BN;
+        img = mt / a.per_img;
+        const int rem = mt - img * a.per_img;
+        const int ty = rem / a.tiles_x;
+        y0 = ty * CH_TH;
+        x0 = (rem - ty * a.tiles_x) * CH_TW;
+    };
+
+    if (warp == 0) {
+        // ---- producer: halo blocks two ahead of the weight slabs of the block the tensor core is on
+        int hs = 0, bs = 0;
+        uint32_t hph = 0, bph = 0;
+        int ct = blockIdx.x, ccb = 0;   // cursor of the next halo block to issue
+        auto issue_halo = [&]() {
+            if (ct >= a.total) return;
+            int n0, img, x0, y0;
+            coords(ct, n0, img, x0, y0);
+            mbar_wait(halo_empty + hs, hph ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(halo_full + hs, CH_HALO_BYTES);
+                tma_load_4d(sH + hs * CH_HALO_STRIDE, &tmX, halo_full + hs, ccb * 64, x0 - 1, y0 - 1, img);
+            }
+            __syncwarp();
+            if (++hs == CH_NH) { hs = 0; hph ^= 1; }
+            if (++ccb == a.cblocks) { ccb = 0; ct += gridDim.x; }
+        };
+        issue_halo();
+        issue_halo();
+        for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+            int n0, img, x0, y0;
+            coords(t, n0, img, x0, y0);
+            for (int cb = 0; cb < a.cblocks; ++cb) {
+                issue_halo();
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(b_empty + bs, bph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(b_full + bs, B_BYTES);
+                        tma_load_4d(sB + bs * B_BYTES, &tmW, b_full + bs, (tap * a.cblocks + cb) * 64, n0, 0, 0);
+                    }
+                    __syncwarp();
+                    if (++bs == NB) { bs = 0; bph ^= 1; }
+                }
+            }
+        }
+        if (lane == 0) pdl_trigger();
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t hdesc0 = umma_desc_sw128(smem_u32(sH), CH_HW * 128), bdesc0 = umma_desc_sw128(smem_u32(sB), 1024);
+        int hs = 0, bs = 0, i = 0;
+        uint32_t hph = 0, bph = 0;
+        for (int t = blockIdx.x; t < a.total; t += gridDim.x, ++i) {
+            const int acc = i & 1;
+            mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            for (int cb = 0; cb < a.cblocks; ++cb) {
+                mbar_wait(halo_ready + hs, hph);
+                const uint64_t hd = hdesc0 + (uint64_t)(hs * (CH_HALO_STRIDE >> 4));
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(b_full + bs, bph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const int ky = (tap * 11) >> 5, kx = tap - 3 * ky;
+                        const uint64_t da = hd + (uint64_t)((ky * CH_HW + kx) * 8);      // (ky * 10 + kx) pixel rows of 128 B, in 16-byte units
+                        const uint64_t db = bdesc0 + (uint64_t)(bs * (B_BYTES >> 4));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+                        umma_commit(b_empty + bs);
+                        if (tap == 8) {
+                            umma_commit(halo_empty + hs);
+                            if (cb == a.cblocks - 1) umma_commit(tmem_full + acc);
+                        }
+                    }
+                    __syncwarp();
+                    if (++bs == NB) { bs = 0; bph ^= 1; }
+                }
+                if (++hs == CH_NH) { hs = 0; hph ^= 1; }
+            }
+        }
+    } else if (warp >= 2 + EPI) {
+        // ---- transform: raw halo -> act(x * scale + shift) in place; 16-byte chunk c8 of pixels prow, prow + 4 * CH_TWARPS, ...
+        const int tt = threadIdx.x - (2 + EPI) * 32, c8 = tt & 7, prow = tt >> 3;
+        int hs = 0;
+        uint32_t hph = 0;
+        for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+            int n0, img, x0, y0;
+            coords(t, n0, img, x0, y0);
+            for (int cb = 0; cb < a.cblocks; ++cb) {
+                mbar_wait(halo_full + hs, hph);
+                if (a.scale) {
+                    const size_t co = (size_t)img * a.C + cb * 64 + c8 * 8;
+                    const float4 s0 = __ldg(reinterpret_cast<const float4 *>(a.scale + co)), s1 = __ldg(reinterpret_cast<const float4 *>(a.scale + co + 4));
+                    const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.shift + co)), t1 = __ldg(reinterpret_cast<const float4 *>(a.shift + co + 4));
+                    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                    uint8_t *buf = sH + hs * CH_HALO_STRIDE;
+#pragma unroll 4
+                    for (int pix = prow; pix < CH_HPIX; pix += 4 * CH_TWARPS) {
+                        const int hy = pix / CH_HW, hx = pix - hy * CH_HW;
+                        const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                        if ((unsigned)gy >= (unsigned)a.H || (unsigned)gx >= (unsigned)a.W) continue;   // padding stays zero
+                        uint4 *p = reinterpret_cast<uint4 *>(buf + pix * 128 + ((c8 ^ (pix & 7)) << 4));
+                        uint4 raw = *p;
+                        __half2 *h = reinterpret_cast<__half2 *>(&raw);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float2 v = __half22float2(h[u]);
+                            v.x = fmaf(v.x, sc[2 * u], sh[2 * u]);
+                            v.y = fmaf(v.y, sc[2 * u + 1], sh[2 * u + 1]);
+                            if (a.act_in == 1) {
+                                v.x = silu_f(v.x);
+                                v.y = silu_f(v.y);
+                            }
+                            h[u] = __floats2half2_rn(v.x, v.y);
+                        }
+                        *p = raw;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                }
+                mbar_arrive(halo_ready + hs);
+                if (++hs == CH_NH) { hs = 0; hph ^= 1; }
+            }
+        }
+    } else {
+        // ---- epilogue: warp owns TMEM lanes [32q, 32q + 32) = tile rows 4q .. 4q+3 (8 pixels each); panels of 32 output channels
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        uint8_t *ebuf = sE + (warp - 2) * (2 * CH_PANEL_BYTES);
+        uint8_t *my_row = ebuf + lane * 64;
+        const int sw = (lane >> 1) & 3;   // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
+        const int py = q * 4 + (lane >> 3), px = lane & 7;
+        uint32_t g = 0;
+        int i = 0;
+        for (int t = blockIdx.x; t < a.total; t += gridDim.x, ++i) {
+            int n0, img, x0, y0;
+            coords(t, n0, img, x0, y0);
+            const int P = (min(BN, a.N - n0) + 31) >> 5;
+            const size_t pixel = ((size_t)img * a.H + (y0 + py)) * a.W + (x0 + px);
+            const bool pix_ok = (y0 + py) < a.H && (x0 + px) < a.W;
+            const float *brow = a.bias_rows ? a.bias_rows + (size_t)img * a.bias_rows_ld : nullptr;
+            const int acc = i & 1;
+            mbar_wait(tmem_full + acc, (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int p = half; p < P; p += PW, ++g) {
+                const uint32_t buf = g & 1;
+                uint8_t *prow = my_row + buf * CH_PANEL_BYTES;
+                uint32_t v[32];
+                tmem_ld32(tmem_d + (uint32_t)(p * 32), v);
+                const int nb = n0 + p * 32;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4 *>(a.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    f[j] = __uint_as_float(v[j]) + b4.x;
+                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                }
+                if (brow) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(brow + nb + j));
+                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    }
+                }
+                if (a.residual && pix_ok) {
+                    const uint4 *rp = reinterpret_cast<const uint4 *>(a.residual + pixel * a.ldo + nb);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 r = __ldg(rp + c);
+                        const __half2 *h = reinterpret_cast<const __half2 *>(&r);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float2 x = __half22float2(h[u]);
+                            f[c * 8 + 2 * u] += x.x;
+                            f[c * 8 + 2 * u + 1] += x.y;
+                        }
+                    }
+                }
+                if (a.act_out == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+                }
+                if (lane == 0) bulk_wait_read<1>();   // the store that last read this staging buffer has drained it
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 w;
+                    __half2 *h = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(f[c * 8 + 2 * u], f[c * 8 + 2 * u + 1]);
+                    *reinterpret_cast<uint4 *>(prow + ((c ^ sw) << 4)) = w;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&tmO, ebuf + buf * CH_PANEL_BYTES, nb, x0, y0 + q * 4, img);   // clips rows / columns outside the tensor
+                    bulk_commit();
+                }
+                if (a.stats) {
+                    // GroupNorm partial sums of the ROUNDED fp16 panel (see gemm.cu): lane (cp, par) adds the 16 rows of parity par of
+                    // column pair cp, parities combined in a fixed order; block id = (pixel tile, quarter) -> 32 pixels of one image
+                    const int cp = lane & 15, par = lane >> 4;
+                    const uint8_t *pan = ebuf + buf * CH_PANEL_BYTES;
+                    float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int r16 = 0; r16 < 16; ++r16) {
+                        const int r = 2 * r16 + par;
+                        const __half2 hv = *reinterpret_cast<const __half2 *>(pan + r * 64 + ((((cp >> 2) ^ ((r >> 1) & 3))) << 4) + (cp & 3) * 4);
+                        const float2 x = __half22float2(hv);
+                        s2 = __fadd2_rn(s2, x);
+                        q2 = __ffma2_rn(x, x, q2);
+                    }
+                    s2.x += __shfl_down_sync(0xffffffffu, s2.x, 16);
+                    s2.y += __shfl_down_sync(0xffffffffu, s2.y, 16);
+                    q2.x += __shfl_down_sync(0xffffffffu, q2.x, 16);
+                    q2.y += __shfl_down_sync(0xffffffffu, q2.y, 16);
+                    const int col = nb + 2 * cp;
+                    if (par == 0 && col < a.N) {
+                        const size_t blk = (size_t)(t / a.n_tiles) * 4 + q;
+                        *reinterpret_cast<float4 *>(a.stats + (blk * a.N + col) * 2) = make_float4(s2.x, q2.x, s2.y, q2.y);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty + acc);
+        }
+        if (lane == 0) bulk_wait_read<0>();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFnH)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnH halo_encode_fn() {
+    static EncodeTiledFnH fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFnH>(p);
+    }
+    return fn;
+}
+static int halo_map(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], const cuuint64_t strides[3], const cuuint32_t box[4],
+                    CUtensorMapSwizzle swz, const char *what) {
+    EncodeTiledFnH fn = halo_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return COMA_E_NODEVICE;
+    }
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (%s) failed with CUresult %d", what, (int)r);
+        return COMA_E_BADARG;
+    }
+    return 0;
+}
+
+template <int BN>
+static int launch_halo(const CUtensorMap &tx, const CUtensorMap &tw, const CUtensorMap &to, const HaloArgs &a, cudaStream_t st) {
+    constexpr size_t smem = ch_smem(BN);
+    static bool attr[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !attr[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr[dev] = true;
+    }
+    const unsigned grid = (unsigned)(a.total < kNumSM ? a.total : kNumSM);
+    launch_pdl(conv_halo_kernel<BN>, dim3(grid), dim3(ch_threads(BN)), smem, st, tx, tw, to, a);
+    return check_launch("conv_halo_kernel");
+}
+}  // namespace coma
+
+extern "C" int coma_conv3x3_halo_supported(int64_t B, int64_t H, int64_t W, int64_t C, int64_t N) {
+    return (B > 0 && H % coma::CH_TH == 0 && W % coma::CH_TW == 0 && C % 64 == 0 && N % 64 == 0 && N >= 64 &&
+            B * (H / coma::CH_TH) * (W / coma::CH_TW) >= 2 * coma::kNumSM) ? 1 : 0;
+}
+
+extern "C" int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const float *scale,
+                                     const float *shift, int act_in, const void *Wt, int64_t ldw, int64_t N, const float *bias,
+                                     const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act_out, void *out_f16,
+                                     int64_t ldo, float *stats, coma_stream_t stream) {
+    using namespace coma;
+    COMA_REQUIRE(x && Wt && out_f16, "null pointer");
+    COMA_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && N > 0, "bad sizes");
+    COMA_REQUIRE(H % CH_TH == 0 && W % CH_TW == 0, "halo conv: H must be a multiple of 16 and W of 8");
+    COMA_REQUIRE(C % 64 == 0 && N % 64 == 0, "halo conv: C and N must be multiples of 64");
+    COMA_REQUIRE(ldx % 8 == 0 && ldx >= C && ldw % 8 == 0 && ldw >= 9 * C && ldo % 8 == 0 && ldo >= N, "bad leading dimensions");
+    COMA_REQUIRE(((uintptr_t)x | (uintptr_t)Wt | (uintptr_t)out_f16 | (uintptr_t)residual | (uintptr_t)bias | (uintptr_t)bias_rows |
+                  (uintptr_t)scale | (uintptr_t)shift | (uintptr_t)stats) % 16 == 0, "pointers must be 16-byte aligned");
+    COMA_REQUIRE((scale == nullptr) == (shift == nullptr), "scale and shift come together");
+    COMA_REQUIRE(act_in >= 0 && act_in <= 1 && act_out >= 0 && act_out <= 1, "act must be 0 or 1");
+    COMA_REQUIRE(!bias_rows || bias_rows_ld % 4 == 0, "bias_rows_ld must be a multiple of 4");
+    const int bn = N % 256 == 0 ? 256 : (N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64));
+    HaloArgs a;
+    a.B = (int)B; a.H = (int)H; a.W = (int)W; a.C = (int)C; a.N = (int)N;
+    a.cblocks = (int)(C / 64);
+    a.tiles_x = (int)(W / CH_TW);
+    a.per_img = a.tiles_x * (int)(H / CH_TH);
+    a.n_tiles = (int)(N / bn);
+    const long long total = (long long)B * a.per_img * a.n_tiles;
+    COMA_REQUIRE(total < (1LL << 31), "too many output tiles");
+    a.total = (int)total;
+    a.scale = scale; a.shift = shift; a.act_in = act_in;
+    a.bias = bias; a.bias_rows = bias_rows; a.bias_rows_ld = bias_rows_ld > 0 ? bias_rows_ld : N;
+    a.residual = (const __half *)residual; a.ldo = ldo; a.act_out = act_out; a.stats = stats;
+    CUtensorMap tx, tw, to;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)(W * ldx) * 2, (cuuint64_t)(H * W * ldx) * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)CH_HW, (cuuint32_t)CH_HH, 1};
+        if (int e = halo_map(&tx, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "halo input")) return e;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)(9 * C), (cuuint64_t)N, 1, 1};
+        cuuint64_t str[3] = {(cuuint64_t)ldw * 2, (cuuint64_t)ldw * 2, (cuuint64_t)ldw * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)bn, 1, 1};
+        if (int e = halo_map(&tw, Wt, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "halo weights")) return e;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)(W * ldo) * 2, (cuuint64_t)(H * W * ldo) * 2};
+        cuuint32_t box[4] = {32, (cuuint32_t)CH_TW, 4, 1};
+        if (int e = halo_map(&to, out_f16, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, "halo output")) return e;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 256: return launch_halo<256>(tx, tw, to, a, st);
+        case 160: return launch_halo<160>(tx, tw, to, a, st);
+        case 128: return launch_halo<128>(tx, tw, to, a, st);
+        default: return launch_halo<64>(tx, tw, to, a, st);
+    }
+}

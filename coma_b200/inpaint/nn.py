@@ -4,6 +4,7 @@ Activations are NHWC fp16: an `Act` wraps a 2-D tensor [B*H*W, C] (row stride ma
 torch is used for allocation and views only; every arithmetic op is a coma_b200 kernel.
 """
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -103,6 +104,7 @@ def gemm_batched(A, lda, a_s1, a_s2, W, ldw, w_s1, w_s2, out, ldo, o_s1, o_s2, M
 
 
 SMALL_N_CONV = True     # conv_out layers (Cout <= 4) on the direct fused kernel C1 (A/B switch for tests and tuning)
+HALO_CONV = os.environ.get("COMA_NO_HALO_CONV") is None   # norm -> SiLU -> conv on the fused halo-tile kernel C2 (A/B switch)
 _GN_COUNTERS = {}
 FUSED_GN_STATS = True   # convolutions leave GroupNorm partial sums for their consumer (A/B switch for tests and tuning)
 
@@ -176,6 +178,26 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
             call("coma_conv3x3_small_n_f16", x.t.data_ptr(), x.B, x.H, x.W, x.C, x.ld, _ptr(scale), _ptr(shift), act if gn is not None else 0,
                  w.data_ptr(), w.stride(0), w.shape[0], _ptr(bias), out.t.data_ptr() if out_dtype == F32 else None,
                  out.t.data_ptr() if out_dtype == F16 else None, out.t.stride(0), _stream())
+        return out
+    if (HALO_CONV and gn is not None and stride == 1 and pad == 1 and not up and out_dtype == F16 and x.H % 16 == 0 and x.W % 8 == 0
+            and x.C % 64 == 0 and w.shape[0] % 64 == 0 and x.H * x.W >= 16384):
+        # C2: norm -> SiLU -> conv in one kernel (halo tiles, the affine + activation applied in shared memory): no normalised tensor in
+        # HBM. Used where it beats affine_act + implicit GEMM: the VAE's >= 128^2-pixel levels (tools/conv_halo_bench.py: 1.02-1.25x per
+        # layer; VAE decode 10.81 -> 10.35 ms, encode 5.30 -> 4.99 ms). At the UNet's 64^2 / 32^2 levels the tensors are L2-resident
+        # and the separate pass is cheap: measured neutral (10.03 vs 10.09 ms), left on the implicit-GEMM path.
+        N = w.shape[0]
+        out = new_act(x.B, Ho, Wo, N, x.t.device, F16)
+        if residual is not None:
+            assert residual.dtype == F16 and residual.stride(0) == out.t.stride(0)
+        want = stats and FUSED_GN_STATS and (Ho * Wo) % 32 == 0
+        st = torch.empty((x.B * Ho * Wo // 32, N, 2), dtype=F32, device=x.t.device) if want else None
+        with torch.cuda.device(x.t.device):
+            call("coma_conv3x3_halo_f16", x.t.data_ptr(), x.B, x.H, x.W, x.C, x.ld, _ptr(gn[0]), _ptr(gn[1]), act, w.data_ptr(), w.stride(0), N,
+                 _ptr(bias), None if bias_rows is None else bias_rows.data_ptr(), 0 if bias_rows is None else bias_rows.stride(0),
+                 None if residual is None else residual.data_ptr(), 0, out.t.data_ptr(), out.t.stride(0), None if st is None else st.data_ptr(),
+                 _stream())
+        if st is not None:
+            out.stats = st
         return out
     strided_ok = stride == 2 and not up and gn is None and Ho * Wo >= 128   # element-strided TMA tiles
     if IMPLICIT_CONV and ((stride == 1 and pad == 1) or strided_ok) and x.C % 64 == 0 and _tiles_128(Ho, Wo):

@@ -398,3 +398,47 @@ def test_conv3x3_small_n_fused(dev, B, H, W, C, Cout, gn, out32):
     finally:
         nn.SMALL_N_CONV = True
     _close(_nchw(out.t[:, :Cout], B, H, W), _nchw(old.t[:, :Cout], B, H, W), 2e-3)
+
+
+@pytest.mark.parametrize("B,H,W,C,N,fused,rows,res,act_out", [
+    (2, 32, 32, 64, 64, True, False, False, 0), (1, 64, 64, 128, 128, True, False, True, 0), (2, 32, 16, 320, 320, True, True, True, 0),
+    (1, 16, 8, 64, 256, False, False, False, 1), (3, 48, 24, 192, 640, True, True, False, 0), (1, 128, 128, 128, 128, True, False, False, 0)])
+def test_conv3x3_halo_fused(dev, B, H, W, C, N, fused, rows, res, act_out):
+    """C2 (`coma_conv3x3_halo_f16`): GroupNorm affine + SiLU + 3x3 conv from halo tiles (+ bias, per-sample bias rows, residual, output
+    SiLU, GroupNorm partial sums of the output) against fp32 torch on the same fp16 operands; the activated input is rounded to fp16 in
+    shared memory exactly like the tensor the unfused path stores. Shapes cover 1-5 channel blocks, every tile width (64 / 128 / 160 /
+    256), images of one tile and of many, several images per launch."""
+    from coma_b200._lib import _stream, call
+    g = torch.Generator(device=dev).manual_seed(C + H + N)
+    x = torch.randn((B, H, W, C), device=dev, generator=g).half()
+    w = (torch.randn((N, C, 3, 3), device=dev, generator=g) * (9 * C) ** -0.5).half()
+    bias = torch.randn(N, device=dev, generator=g) * 0.1
+    scale = (1.0 + 0.2 * torch.randn((B, C), device=dev, generator=g)).contiguous() if fused else None
+    shift = (0.3 * torch.randn((B, C), device=dev, generator=g)).contiguous() if fused else None
+    brows = (torch.randn((B, N), device=dev, generator=g) * 0.2).contiguous() if rows else None
+    resid = torch.randn((B * H * W, N), device=dev, generator=g).half() if res else None
+    wt = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = torch.zeros((B * H * W, N), dtype=torch.float16, device=dev)
+    stats = torch.zeros((B * H * W // 32, N, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("coma_conv3x3_halo_f16", x.data_ptr(), B, H, W, C, C, None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
+             1, wt.data_ptr(), 9 * C, N, bias.data_ptr(), None if brows is None else brows.data_ptr(), N, None if resid is None else resid.data_ptr(), act_out,
+             out.data_ptr(), N, stats.data_ptr(), _stream())
+    z = x.float()
+    if fused:
+        z = torch.nn.functional.silu(z * scale[:, None, None, :] + shift[:, None, None, :]).half().float()
+    ref = torch.nn.functional.conv2d(z.permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    if rows:
+        ref = ref + brows[:, None, None, :]
+    ref = ref.reshape(B * H * W, N)
+    if res:
+        ref = ref + resid.float()
+    if act_out:
+        ref = torch.nn.functional.silu(ref)
+    sc = ref.abs().max().item()
+    assert (out.float() - ref).abs().max().item() <= 2e-3 * sc, (out.float() - ref).abs().max().item() / sc
+    # GroupNorm partial sums: per (32-pixel block, channel) sum / sum of squares of the stored fp16 values; block order is the kernel's
+    # (tile, quarter) order, so compare what the consumer uses — the per-image totals
+    of = out.float().view(B, H * W, N)
+    tot = stats.view(B, H * W // 32, N, 2).sum(1)
+    assert torch.allclose(tot[..., 0], of.sum(1), rtol=1e-4, atol=1e-2 * sc) and torch.allclose(tot[..., 1], of.pow(2).sum(1), rtol=1e-4, atol=1e-2 * sc * sc)

@@ -8,11 +8,11 @@
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t a, uint32_t sbo = 1024) {
     uint64_t d = 0;
     d |= (uint64_t)((a & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(sbo >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -30,13 +30,13 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
 
 // ORDER 0: a-major (finish the 4-step chain of accumulator a, then the next a) ; 1: k-major (rotate over accumulators every instruction)
 template <int N, int NACC, bool TS, int ORDER>
-__global__ void __launch_bounds__(128, 1) k_umma(long long *out, int iters) {
+__global__ void __launch_bounds__(128, 1) k_umma(long long *out, int iters, int a_off, int a_sbo) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+    for (int i = threadIdx.x; i < 56 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128, 1) k_umma(long long *out, int iters) {
     const uint32_t tbase = slot;
     if (threadIdx.x == 32) {
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 16384;
+        const uint32_t sa = smem_u32(smem) + (uint32_t)a_off, sb = smem_u32(smem) + 24576;
         const uint32_t tA = tbase + 480;
         long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128, 1) k_umma(long long *out, int iters) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (TS) mma_ts(tbase + a * N, tA + k * 8, desc_sw128(sb + k * 32), idesc, (it | k) != 0);
-                        else mma_ss(tbase + a * N, desc_sw128(sa + k * 32), desc_sw128(sb + k * 32), idesc, (it | k) != 0);
+                        else mma_ss(tbase + a * N, desc_sw128(sa + k * 32, (uint32_t)a_sbo), desc_sw128(sb + k * 32), idesc, (it | k) != 0);
                     }
             } else {
 #pragma unroll
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128, 1) k_umma(long long *out, int iters) {
 #pragma unroll
                     for (int a = 0; a < NACC; ++a) {
                         if (TS) mma_ts(tbase + a * N, tA + k * 8, desc_sw128(sb + k * 32), idesc, (it | k) != 0);
-                        else mma_ss(tbase + a * N, desc_sw128(sa + k * 32), desc_sw128(sb + k * 32), idesc, (it | k) != 0);
+                        else mma_ss(tbase + a * N, desc_sw128(sa + k * 32, (uint32_t)a_sbo), desc_sw128(sb + k * 32), idesc, (it | k) != 0);
                     }
             }
         }
@@ -91,17 +91,18 @@ __global__ void __launch_bounds__(128, 1) k_umma(long long *out, int iters) {
 }
 
 template <int N, int NACC, bool TS, int ORDER>
-void run(long long *out) {
+void run(long long *out, int a_off = 0, int a_sbo = 1024) {
     const int iters = 256;
-    cudaFuncSetAttribute(k_umma<N, NACC, TS, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024);
-    k_umma<N, NACC, TS, ORDER><<<148, 128, 50 * 1024>>>(out, 8);
+    cudaFuncSetAttribute(k_umma<N, NACC, TS, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+    k_umma<N, NACC, TS, ORDER><<<148, 128, 60 * 1024>>>(out, 8, a_off, a_sbo);
     cudaDeviceSynchronize();
-    k_umma<N, NACC, TS, ORDER><<<148, 128, 50 * 1024>>>(out, iters);
+    k_umma<N, NACC, TS, ORDER><<<148, 128, 60 * 1024>>>(out, iters, a_off, a_sbo);
     cudaDeviceSynchronize();
     long long h[2];
     cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
     const double n = (double)iters * NACC * 4;
     cudaError_t e = cudaGetLastError();
+    if (a_off || a_sbo != 1024) printf("[A start +%d B, SBO %d B] ", a_off, a_sbo);
     printf("N=%3d accumulators=%d A=%s order=%s : issue %.1f clk/mma, complete %.1f clk/mma (floor %d) %s\n", N, NACC, TS ? "tmem" : "smem",
            ORDER ? "rotate" : "chain ", h[0] / n, h[1] / n, 128 * N / 256, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
@@ -127,5 +128,12 @@ int main() {
     run<128, 1, false, 0>(out);
     run<128, 2, false, 1>(out);
     run<256, 1, false, 0>(out);
+    // shifted / re-pitched A views (halo-tile convolution): does a start that is not 1024-byte aligned, or 8-row groups 1280 B apart, cost reads?
+    run<128, 1, false, 0>(out, 128, 1024);
+    run<128, 1, false, 0>(out, 0, 1280);
+    run<128, 1, false, 0>(out, 128 * 11, 1280);
+    run<128, 1, false, 0>(out, 128 * 22, 1280);
+    run<256, 1, false, 0>(out, 128 * 11, 1280);
+    run<64, 1, false, 0>(out, 128 * 11, 1280);
     return 0;
 }
