@@ -407,15 +407,19 @@ def occupancy_leg(args, dev, rank, world, barrier):
             if (c0 + j) in mine_set:
                 s["obj_verts"], s["obj_normals"] = obj
                 host.append(s)
-    occ.spatial_occupancy_grids.zero_()
-    occ.debug_obj_vert = occ.debug_obj_normal = None
-    barrier()
-    t0 = time.perf_counter()
-    for s in host:
-        occ.register_sample_to_cache(**s)
-    occ.aggregate_all_samples(exchange=world > 1)
-    f = occ.return_aggregated_spatial_grids().cpu().numpy()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = None
+    for _ in range(2):   # one untimed pass (pinned staging buffers, first-touch pages, NCCL channels of the exchange), then the timed one
+        occ.spatial_occupancy_grids.zero_()
+        occ.debug_obj_vert = occ.debug_obj_normal = None
+        occ.used, occ.used_count = {}, 0
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for s in host:
+            occ.register_sample_to_cache(**s)
+        occ.aggregate_all_samples(exchange=world > 1)
+        f = occ.return_aggregated_spatial_grids().cpu().numpy()
+        e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
