@@ -5,17 +5,18 @@
 // The implicit-GEMM kernel (gemm.cu, CONV) fetches the A operand of every (tap, 64-channel block) K-slab with its own TMA load — each
 // input pixel crosses L2 -> SMEM nine times — and needs the normalised + activated tensor materialised in HBM by a separate pass
 // (affine_act_kernel: 12-20 % of a VAE decode). Here:
-//   * an output tile is 16 rows x 8 columns of pixels; per 64-channel block ONE TMA load brings the 18 x 10 pixel halo
-//     (zero-filled outside the image = the convolution's padding), 23 KB instead of 9 x 16 KB;
+//   * an output tile is 16 rows x 8 columns of pixels; per 64-channel block its 18 x 10 pixel halo is staged ONCE in shared memory
+//     (23 KB instead of nine shifted 16 KB tiles): eight builder warps read it from global memory with coalesced 16-byte loads,
+//     apply act(x * scale[b, c] + shift[b, c]) in registers (fp16, the same roundings as the tensor the unfused path stores; pixels
+//     outside the image are the convolution's zero padding) and store it in the 128B-swizzled K-major layout, while the tensor core
+//     works on the previous blocks (4-deep ring);
 //   * the A operand of tap (ky, kx) is a SHIFTED VIEW of that halo tile: start address + (ky * 10 + kx) * 128 B, 8-row groups
 //     1280 B apart (SBO). The tensor core applies the 128B swizzle to absolute shared-memory address bits, so any 128-byte
-//     aligned start and any SBO address the tile TMA wrote (tools/ubench_umma_layout.cu: every shift, pitch 10 / 12 / 16: exact);
-//   * eight transform warps turn the raw halo into act(x * scale[b, c] + shift[b, c]) in place (fp16, the same roundings as the
-//     tensor the unfused path stores) while the tensor core works on the previous block; pixels outside the image stay zero;
+//     aligned start and any SBO address the tile correctly (tools/ubench_umma_layout.cu: every shift, pitch 10 / 12 / 16: exact);
 //   * weights stream through their own ring ([BN x 64] slabs, K order (ky, kx, cin) as in prep_conv3x3);
 //   * epilogue as in gemm.cu: TMEM -> registers -> bias / per-sample bias row (time embedding) / residual / SiLU -> 64B-swizzled
 //     32 x 32 panels -> TMA store (box 32 channels x 8 px x 4 rows), GroupNorm partial sums of the rounded output for the next norm.
-// Warps: 0 TMA producer, 1 MMA issuer (both converged, one elected lane), 2-5 epilogue, 6-13 transform.
+// Warps: 0 TMA producer (weights), 1 MMA issuer (both converged, one elected lane), 2-5 epilogue, 6-13 halo builders.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -40,6 +41,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {   // acquires what peer-CTA threads released with their remote arrive
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
@@ -101,7 +113,64 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ float exp2f_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }   // as affine_act_kernel (unet_ops.cu)
+// SiLU for the halo builders: ONE MUFU op per element (ex2) instead of two — the builders are MUFU-bound at BN = 128 (23040 ops per
+// 64-channel block against 2304 clk of MMAs). The reciprocal of 1 + e^-v runs on the FMA pipes: magic-constant seed (12 % off) + three
+// Newton steps (relative error < 1e-7, i.e. at least as accurate as MUFU.RCP's 1 ulp); v is clamped at -80 so that 1 + e^-v stays finite.
+__device__ __forceinline__ float silu_fma(float v) {
+    const float e = exp2f_approx(fmaxf(v, -80.0f) * -1.4426950408889634f);
+    const float y = 1.0f + e;
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(y));
+    r = r * fmaf(-y, r, 2.0f);
+    r = r * fmaf(-y, r, 2.0f);
+    r = r * fmaf(-y, r, 2.0f);
+    return v * r;
+}
+
+// ---- CTA pair (cta_group::2): the leader CTA (cluster rank 0) issues M256 x N x K16 instructions over BOTH CTAs' shared memory
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on the barrier at the same offset in the LEADER CTA of the pair (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_4d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z, int w) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y), "r"(z), "r"(w)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
 }  // namespace ch
 
 constexpr int CH_TW = 8, CH_TH = 16;                       // output tile: 16 rows x 8 columns = 128 pixels (TMEM lane = py * 8 + px)
@@ -109,19 +178,23 @@ constexpr int CH_HW = CH_TW + 2, CH_HH = CH_TH + 2;        // halo: 18 rows x 10
 constexpr int CH_HPIX = CH_HW * CH_HH;                     // 180 pixels x 128 B per 64-channel block
 constexpr int CH_HALO_BYTES = CH_HPIX * 128;               // 23040
 constexpr int CH_HALO_STRIDE = (CH_HALO_BYTES + 1023) / 1024 * 1024;
-constexpr int CH_NH = 3;                                   // halo ring: one block under the MMAs, one in the transform, one in flight
+constexpr int CH_NH = 4;                                   // halo ring: one block under the MMAs, one or two in the transform (a pair waits for the slower CTA), one in flight
 constexpr int CH_PANEL_BYTES = 32 * 32 * 2;
 __host__ __device__ constexpr int ch_epi_warps(int BN) { return 4; }   // K >= 576: the epilogue (TMEM read rate bound) hides behind the next tile's main loop even at BN = 256
 constexpr int CH_TWARPS = 8;                               // transform warps: two per scheduler hide each other's MUFU / LDS latencies
 __host__ __device__ constexpr int ch_threads(int BN) { return 64 + 32 * ch_epi_warps(BN) + 32 * CH_TWARPS; }
-__host__ __device__ constexpr int ch_b_stages(int BN) { return BN <= 128 ? 8 : (BN <= 160 ? 6 : 4); }   // 64-128 KB of weight slabs in flight (TMA latency ~2000 clk)
-__host__ __device__ constexpr size_t ch_smem(int BN) {
-    return (size_t)CH_NH * CH_HALO_STRIDE + (size_t)ch_b_stages(BN) * BN * 128 + (size_t)ch_epi_warps(BN) * 2 * CH_PANEL_BYTES + 256 + 1024;
+__host__ __device__ constexpr int ch_b_stages(int BN, bool pair) { return pair ? (BN <= 160 ? 8 : 6) : (BN <= 64 ? 8 : (BN <= 128 ? 6 : (BN <= 160 ? 5 : 3))); }   // 64-128 KB of weight slabs in flight (TMA latency ~2000 clk)
+__host__ __device__ constexpr int ch_b_rows(int BN, bool pair) { return pair ? BN / 2 : BN; }   // weight rows per CTA and slab: a pair splits the tile's N
+__host__ __device__ constexpr size_t ch_smem(int BN, bool pair) {
+    return (size_t)CH_NH * CH_HALO_STRIDE + (size_t)ch_b_stages(BN, pair) * ch_b_rows(BN, pair) * 128 + (size_t)ch_epi_warps(BN) * 2 * CH_PANEL_BYTES + 256 + 1024;
 }
 
 struct HaloArgs {
+    const void *x;                                    // [B, H, W, C] f16, pixel stride ldx
+    long long ldx;
     int B, H, W, C, N;
     int cblocks, tiles_x, per_img, n_tiles, total;   // total = m_tiles * n_tiles work items; id = mt * n_tiles + nt (N fastest)
+                                                     // PAIR: total = (m_tiles / 2) * n_tiles pair items; CTA `rank` of the pair owns pixel tile 2 * mp + rank
     const float *scale, *shift;                       // [B, C] or null: the input is used as stored
     int act_in;                                       // 1: SiLU after the affine
     const float *bias, *bias_rows;                    // [N]; [B, bias_rows_ld] per-sample rows (time embedding) or null
@@ -132,19 +205,27 @@ struct HaloArgs {
     float *stats;                                     // [B*H*W/32, N, 2] or null
 };
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one TPC) work on two pixel tiles of the same output-channel tile with ONE tcgen05.mma.cta_group::2 stream
+// (M = 256) issued by the leader: each CTA stages its own halo (A rows) but only HALF of every weight slab, and the tensor core reads
+// A 4 KB + B 2 KB per CTA and K step instead of 4 + 4 KB (BN = 128) — the single-CTA kernel runs 1.5-2.2x above the MMA floor on
+// shared-memory bandwidth. Cross-CTA protocol: weight slabs complete on the LEADER's b_full (cta_group::2 TMA,
+// expect_tx for both halves posted by the leader); halo_ready / tmem_empty of the leader count elected arrivals of both CTAs (remote
+// mbarrier.arrive); b_empty / halo_empty / tmem_full are released in both CTAs by multicast tcgen05.commit.
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(ch_threads(BN), 1)
-    conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
+    conv_halo_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
                      const HaloArgs a) {
     using namespace ch;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int EPI = ch_epi_warps(BN), PW = EPI / 4, NB = ch_b_stages(BN), B_BYTES = BN * 128;
+    constexpr int EPI = ch_epi_warps(BN), PW = EPI / 4, NB = ch_b_stages(BN, PAIR), B_ROWS = ch_b_rows(BN, PAIR), B_BYTES = B_ROWS * 128;
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     uint8_t *sH = smem;
     uint8_t *sB = sH + CH_NH * CH_HALO_STRIDE;
     uint8_t *sE = sB + NB * B_BYTES;
     uint64_t *bar = reinterpret_cast<uint64_t *>(sE + EPI * 2 * CH_PANEL_BYTES);
-    uint64_t *halo_full = bar, *halo_ready = halo_full + CH_NH, *halo_empty = halo_ready + CH_NH;
+    uint64_t *halo_ready = bar, *halo_empty = halo_ready + CH_NH;
     uint64_t *b_full = halo_empty + CH_NH, *b_empty = b_full + NB;
     uint64_t *tmem_full = b_empty + NB, *tmem_empty = tmem_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
@@ -152,12 +233,10 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
     constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
         for (int i = 0; i < CH_NH; ++i) {
-            mbar_init(halo_full + i, 1);
-            mbar_init(halo_ready + i, 32 * CH_TWARPS);
+            mbar_init(halo_ready + i, PAIR ? 2 * CH_TWARPS : 32 * CH_TWARPS);   // PAIR: one elected arrival per transform warp of both CTAs
             mbar_init(halo_empty + i, 1);
         }
         for (int i = 0; i < NB; ++i) {
@@ -166,24 +245,29 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tmem_full + i, 1);
-            mbar_init(tmem_empty + i, 32 * EPI);
+            mbar_init(tmem_empty + i, PAIR ? 2 * EPI : 32 * EPI);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers must exist before anything signals them
+    else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
 
-    // work item -> output-channel offset, image, tile origin
+    // work item -> output-channel offset, image, tile origin (PAIR: of THIS CTA's pixel tile of the pair item)
     auto coords = [&](int t, int &n0, int &img, int &x0, int &y0) {
-        const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+        const int nt = t % a.n_tiles, mt = PAIR ? 2 * (t / a.n_tiles) + (int)rank : t / a.n_tiles;
         n0 = nt * BN;
         img = mt / a.per_img;
         const int rem = mt - img * a.per_img;
@@ -193,35 +277,23 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
     };
 
     if (warp == 0) {
-        // ---- producer: halo blocks two ahead of the weight slabs of the block the tensor core is on
-        int hs = 0, bs = 0;
-        uint32_t hph = 0, bph = 0;
-        int ct = blockIdx.x, ccb = 0;   // cursor of the next halo block to issue
-        auto issue_halo = [&]() {
-            if (ct >= a.total) return;
-            int n0, img, x0, y0;
-            coords(ct, n0, img, x0, y0);
-            mbar_wait(halo_empty + hs, hph ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(halo_full + hs, CH_HALO_BYTES);
-                tma_load_4d(sH + hs * CH_HALO_STRIDE, &tmX, halo_full + hs, ccb * 64, x0 - 1, y0 - 1, img);
-            }
-            __syncwarp();
-            if (++hs == CH_NH) { hs = 0; hph ^= 1; }
-            if (++ccb == a.cblocks) { ccb = 0; ct += gridDim.x; }
-        };
-        issue_halo();
-        issue_halo();
-        for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+        // ---- producer: weight slabs only (the halo tiles are built by the last eight warps)
+        int bs = 0;
+        uint32_t bph = 0;
+        for (int t = item0; t < a.total; t += item_step) {
             int n0, img, x0, y0;
             coords(t, n0, img, x0, y0);
             for (int cb = 0; cb < a.cblocks; ++cb) {
-                issue_halo();
                 for (int tap = 0; tap < 9; ++tap) {
                     mbar_wait(b_empty + bs, bph ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(b_full + bs, B_BYTES);
-                        tma_load_4d(sB + bs * B_BYTES, &tmW, b_full + bs, (tap * a.cblocks + cb) * 64, n0, 0, 0);
+                        if (PAIR) {   // this CTA's half of the slab's rows; both halves complete on the leader's barrier
+                            if (rank == 0) mbar_expect_tx(b_full + bs, 2 * B_BYTES);
+                            tma_load_4d_pair(sB + bs * B_BYTES, &tmW, b_full + bs, (tap * a.cblocks + cb) * 64, n0 + (int)rank * B_ROWS, 0, 0);
+                        } else {
+                            mbar_expect_tx(b_full + bs, B_BYTES);
+                            tma_load_4d(sB + bs * B_BYTES, &tmW, b_full + bs, (tap * a.cblocks + cb) * 64, n0, 0, 0);
+                        }
                     }
                     __syncwarp();
                     if (++bs == NB) { bs = 0; bph ^= 1; }
@@ -230,18 +302,20 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
         }
         if (lane == 0) pdl_trigger();
     } else if (warp == 1) {
-        // ---- MMA issuer
-        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // ---- MMA issuer (PAIR: the leader CTA only; the peer's warp 1 has nothing to do)
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
         const uint64_t hdesc0 = umma_desc_sw128(smem_u32(sH), CH_HW * 128), bdesc0 = umma_desc_sw128(smem_u32(sB), 1024);
         int hs = 0, bs = 0, i = 0;
         uint32_t hph = 0, bph = 0;
-        for (int t = blockIdx.x; t < a.total; t += gridDim.x, ++i) {
+        for (int t = item0; t < a.total && rank == 0; t += item_step, ++i) {
             const int acc = i & 1;
-            mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);
+            if (PAIR) mbar_wait_cluster(tmem_empty + acc, ((i >> 1) & 1) ^ 1);
+            else mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
             for (int cb = 0; cb < a.cblocks; ++cb) {
-                mbar_wait(halo_ready + hs, hph);
+                if (PAIR) mbar_wait_cluster(halo_ready + hs, hph);
+                else mbar_wait(halo_ready + hs, hph);
                 const uint64_t hd = hdesc0 + (uint64_t)(hs * (CH_HALO_STRIDE >> 4));
                 for (int tap = 0; tap < 9; ++tap) {
                     mbar_wait(b_full + bs, bph);
@@ -250,12 +324,22 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                         const int ky = (tap * 11) >> 5, kx = tap - 3 * ky;
                         const uint64_t da = hd + (uint64_t)((ky * CH_HW + kx) * 8);      // (ky * 10 + kx) pixel rows of 128 B, in 16-byte units
                         const uint64_t db = bdesc0 + (uint64_t)(bs * (B_BYTES >> 4));
+                        if (PAIR) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
-                        umma_commit(b_empty + bs);
-                        if (tap == 8) {
-                            umma_commit(halo_empty + hs);
-                            if (cb == a.cblocks - 1) umma_commit(tmem_full + acc);
+                            for (int k = 0; k < 4; ++k) umma_f16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+                            umma_commit_pair(b_empty + bs);
+                            if (tap == 8) {
+                                umma_commit_pair(halo_empty + hs);
+                                if (cb == a.cblocks - 1) umma_commit_pair(tmem_full + acc);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+                            umma_commit(b_empty + bs);
+                            if (tap == 8) {
+                                umma_commit(halo_empty + hs);
+                                if (cb == a.cblocks - 1) umma_commit(tmem_full + acc);
+                            }
                         }
                     }
                     __syncwarp();
@@ -265,45 +349,68 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
             }
         }
     } else if (warp >= 2 + EPI) {
-        // ---- transform: raw halo -> act(x * scale + shift) in place; 16-byte chunk c8 of pixels prow, prow + 4 * CH_TWARPS, ...
+        // ---- halo builders: global -> registers -> act(x * scale + shift) -> swizzled shared memory. Thread (prow, c8) owns the 16-byte
+        // channel chunk c8 of halo pixels prow, prow + 32, ... (a warp reads 4 pixels x 128 B: coalesced). All of a block's loads are
+        // issued before the first is consumed. (First version: TMA load + in-place LDS / STS transform — ncu showed the builders stalled
+        // on those LDS behind the tensor core's own operand reads, and the MMA stream waiting for them: tensor pipe 49.6 % active.)
         const int tt = threadIdx.x - (2 + EPI) * 32, c8 = tt & 7, prow = tt >> 3;
+        constexpr int NPX = (CH_HPIX + 4 * CH_TWARPS - 1) / (4 * CH_TWARPS);   // pixels per thread and block (6)
         int hs = 0;
         uint32_t hph = 0;
-        for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+        const uint32_t ready0 = PAIR ? map_to_rank(smem_u32(halo_ready), 0) : 0u;   // the leader's halo_ready[0]
+        const __half *xg = reinterpret_cast<const __half *>(a.x);
+        for (int t = item0; t < a.total; t += item_step) {
             int n0, img, x0, y0;
             coords(t, n0, img, x0, y0);
             for (int cb = 0; cb < a.cblocks; ++cb) {
-                mbar_wait(halo_full + hs, hph);
+                uint4 raw[NPX];
+                bool ok[NPX];
+#pragma unroll
+                for (int i = 0; i < NPX; ++i) {
+                    const int pix = prow + i * 4 * CH_TWARPS;
+                    const int hy = pix / CH_HW, hx = pix - hy * CH_HW;
+                    const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                    ok[i] = pix < CH_HPIX && (unsigned)gy < (unsigned)a.H && (unsigned)gx < (unsigned)a.W;
+                    raw[i] = make_uint4(0u, 0u, 0u, 0u);   // outside the image: the convolution's zero padding (of the ACTIVATED tensor)
+                    if (ok[i]) raw[i] = __ldg(reinterpret_cast<const uint4 *>(xg + (((size_t)img * a.H + gy) * a.W + gx) * a.ldx + cb * 64 + c8 * 8));
+                }
+                float sc[8], sh[8];
                 if (a.scale) {
                     const size_t co = (size_t)img * a.C + cb * 64 + c8 * 8;
                     const float4 s0 = __ldg(reinterpret_cast<const float4 *>(a.scale + co)), s1 = __ldg(reinterpret_cast<const float4 *>(a.scale + co + 4));
                     const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.shift + co)), t1 = __ldg(reinterpret_cast<const float4 *>(a.shift + co + 4));
-                    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                    uint8_t *buf = sH + hs * CH_HALO_STRIDE;
-#pragma unroll 4
-                    for (int pix = prow; pix < CH_HPIX; pix += 4 * CH_TWARPS) {
-                        const int hy = pix / CH_HW, hx = pix - hy * CH_HW;
-                        const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
-                        if ((unsigned)gy >= (unsigned)a.H || (unsigned)gx >= (unsigned)a.W) continue;   // padding stays zero
-                        uint4 *p = reinterpret_cast<uint4 *>(buf + pix * 128 + ((c8 ^ (pix & 7)) << 4));
-                        uint4 raw = *p;
-                        __half2 *h = reinterpret_cast<__half2 *>(&raw);
+                    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                    sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+                }
+                mbar_wait(halo_empty + hs, hph ^ 1);   // the MMAs that read this buffer NH blocks ago have retired
+                uint8_t *buf = sH + hs * CH_HALO_STRIDE;
+#pragma unroll
+                for (int i = 0; i < NPX; ++i) {
+                    const int pix = prow + i * 4 * CH_TWARPS;
+                    if (pix >= CH_HPIX) continue;
+                    if (a.scale && ok[i]) {
+                        __half2 *h = reinterpret_cast<__half2 *>(&raw[i]);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float2 v = __half22float2(h[u]);
                             v.x = fmaf(v.x, sc[2 * u], sh[2 * u]);
                             v.y = fmaf(v.y, sc[2 * u + 1], sh[2 * u + 1]);
                             if (a.act_in == 1) {
-                                v.x = silu_f(v.x);
-                                v.y = silu_f(v.y);
+                                v.x = silu_fma(v.x);
+                                v.y = silu_fma(v.y);
                             }
                             h[u] = __floats2half2_rn(v.x, v.y);
                         }
-                        *p = raw;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                    *reinterpret_cast<uint4 *>(buf + pix * 128 + ((c8 ^ (pix & 7)) << 4)) = raw[i];
                 }
-                mbar_arrive(halo_ready + hs);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                if (PAIR) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(ready0 + (uint32_t)hs * 8);
+                } else {
+                    mbar_arrive(halo_ready + hs);
+                }
                 if (++hs == CH_NH) { hs = 0; hph ^= 1; }
             }
         }
@@ -316,7 +423,8 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
         const int py = q * 4 + (lane >> 3), px = lane & 7;
         uint32_t g = 0;
         int i = 0;
-        for (int t = blockIdx.x; t < a.total; t += gridDim.x, ++i) {
+        const uint32_t empty0 = PAIR ? map_to_rank(smem_u32(tmem_empty), 0) : 0u;   // the leader's tmem_empty[0]
+        for (int t = item0; t < a.total; t += item_step, ++i) {
             int n0, img, x0, y0;
             coords(t, n0, img, x0, y0);
             const int P = (min(BN, a.N - n0) + 31) >> 5;
@@ -404,20 +512,28 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                     q2.y += __shfl_down_sync(0xffffffffu, q2.y, 16);
                     const int col = nb + 2 * cp;
                     if (par == 0 && col < a.N) {
-                        const size_t blk = (size_t)(t / a.n_tiles) * 4 + q;
+                        const size_t blk = (size_t)(PAIR ? 2 * (t / a.n_tiles) + (int)rank : t / a.n_tiles) * 4 + q;
                         *reinterpret_cast<float4 *>(a.stats + (blk * a.N + col) * 2) = make_float4(s2.x, q2.x, s2.y, q2.y);
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tmem_empty + acc);
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(empty0 + (uint32_t)acc * 8);
+            } else {
+                mbar_arrive(tmem_empty + acc);
+            }
         }
         if (lane == 0) bulk_wait_read<0>();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (PAIR) {
+        cluster_sync_all();   // neither CTA may exit (or free tensor memory) while the pair's last instructions / remote arrivals are in flight
+        if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    } else {
+        __syncthreads();
+        if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -451,22 +567,43 @@ static int halo_map(CUtensorMap *m, const void *ptr, const cuuint64_t dims[4], c
     return 0;
 }
 
-template <int BN>
-static int launch_halo(const CUtensorMap &tx, const CUtensorMap &tw, const CUtensorMap &to, const HaloArgs &a, cudaStream_t st) {
-    constexpr size_t smem = ch_smem(BN);
+template <int BN, bool PAIR>
+static int launch_halo(const CUtensorMap &tw, const CUtensorMap &to, const HaloArgs &a, cudaStream_t st) {
+    constexpr size_t smem = ch_smem(BN, PAIR);
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
             return (int)e;
         }
         attr[dev] = true;
     }
-    const unsigned grid = (unsigned)(a.total < kNumSM ? a.total : kNumSM);
-    launch_pdl(conv_halo_kernel<BN>, dim3(grid), dim3(ch_threads(BN)), smem, st, tx, tw, to, a);
+    if (!PAIR) {
+        const unsigned grid = (unsigned)(a.total < kNumSM ? a.total : kNumSM);
+        launch_pdl(conv_halo_kernel<BN, PAIR>, dim3(grid), dim3(ch_threads(BN)), smem, st, tw, to, a);
+    } else {
+        // clusters of two CTAs (one TPC each); programmatic dependent launch as everywhere else
+        const unsigned pairs = (unsigned)(a.total < kNumSM / 2 ? a.total : kNumSM / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(ch_threads(BN));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        static const bool no_pdl = getenv("COMA_NO_PDL") != nullptr;
+        cfg.numAttrs = no_pdl ? 1 : 2;
+        cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, PAIR>, tw, to, a);
+    }
     return check_launch("conv_halo_kernel");
 }
 }  // namespace coma
@@ -493,28 +630,31 @@ extern "C" int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_
     COMA_REQUIRE(!bias_rows || bias_rows_ld % 4 == 0, "bias_rows_ld must be a multiple of 4");
     const int bn = N % 256 == 0 ? 256 : (N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64));
     HaloArgs a;
+    a.x = x; a.ldx = ldx;
     a.B = (int)B; a.H = (int)H; a.W = (int)W; a.C = (int)C; a.N = (int)N;
     a.cblocks = (int)(C / 64);
     a.tiles_x = (int)(W / CH_TW);
     a.per_img = a.tiles_x * (int)(H / CH_TH);
     a.n_tiles = (int)(N / bn);
-    const long long total = (long long)B * a.per_img * a.n_tiles;
+    const long long m_tiles = (long long)B * a.per_img;
+    // CTA pairs (cta_group::2; need an even number of pixel tiles) are built, parity-tested and OFF by default: measured on B200
+    // (tools/conv_halo_bench.py, profiles/r02_conv_halo_bench_pair.log) the pair kernel is 5-18 % faster than the single-CTA one WITHOUT
+    // the fused transform (512^2 x 128->128: 297 -> 284 us, 256->128: 643 -> 544 us, 256^2 x 256: 246 -> 228 us) but slower WITH it
+    // (322 -> 346 us, 661 -> 680 us; only 256^2 x 256->256 gains, 251 -> 236 us): the leader's MMA stream then waits for the slower of
+    // two transforms plus a remote mbarrier arrival per block. The VAE always runs fused, so COMA_HALO_PAIR=1 is opt-in.
+    static const bool pair_on = getenv("COMA_HALO_PAIR") && atoi(getenv("COMA_HALO_PAIR")) == 1;
+    const bool pair = pair_on && m_tiles % 2 == 0 && bn >= 64;
+    const long long total = (pair ? m_tiles / 2 : m_tiles) * a.n_tiles;
     COMA_REQUIRE(total < (1LL << 31), "too many output tiles");
     a.total = (int)total;
     a.scale = scale; a.shift = shift; a.act_in = act_in;
     a.bias = bias; a.bias_rows = bias_rows; a.bias_rows_ld = bias_rows_ld > 0 ? bias_rows_ld : N;
     a.residual = (const __half *)residual; a.ldo = ldo; a.act_out = act_out; a.stats = stats;
-    CUtensorMap tx, tw, to;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)(W * ldx) * 2, (cuuint64_t)(H * W * ldx) * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)CH_HW, (cuuint32_t)CH_HH, 1};
-        if (int e = halo_map(&tx, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "halo input")) return e;
-    }
+    CUtensorMap tw, to;
     {
         cuuint64_t dims[4] = {(cuuint64_t)(9 * C), (cuuint64_t)N, 1, 1};
         cuuint64_t str[3] = {(cuuint64_t)ldw * 2, (cuuint64_t)ldw * 2, (cuuint64_t)ldw * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)bn, 1, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)(pair ? bn / 2 : bn), 1, 1};
         if (int e = halo_map(&tw, Wt, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "halo weights")) return e;
     }
     {
@@ -524,10 +664,18 @@ extern "C" int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_
         if (int e = halo_map(&to, out_f16, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, "halo output")) return e;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (pair) {
+        switch (bn) {
+            case 256: return launch_halo<256, true>(tw, to, a, st);
+            case 160: return launch_halo<160, true>(tw, to, a, st);
+            case 128: return launch_halo<128, true>(tw, to, a, st);
+            default: return launch_halo<64, true>(tw, to, a, st);
+        }
+    }
     switch (bn) {
-        case 256: return launch_halo<256>(tx, tw, to, a, st);
-        case 160: return launch_halo<160>(tx, tw, to, a, st);
-        case 128: return launch_halo<128>(tx, tw, to, a, st);
-        default: return launch_halo<64>(tx, tw, to, a, st);
+        case 256: return launch_halo<256, false>(tw, to, a, st);
+        case 160: return launch_halo<160, false>(tw, to, a, st);
+        case 128: return launch_halo<128, false>(tw, to, a, st);
+        default: return launch_halo<64, false>(tw, to, a, st);
     }
 }

@@ -180,11 +180,10 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
                  out.t.data_ptr() if out_dtype == F16 else None, out.t.stride(0), _stream())
         return out
     if (HALO_CONV and gn is not None and stride == 1 and pad == 1 and not up and out_dtype == F16 and x.H % 16 == 0 and x.W % 8 == 0
-            and x.C % 64 == 0 and w.shape[0] % 64 == 0 and x.H * x.W >= 16384):
-        # C2: norm -> SiLU -> conv in one kernel (halo tiles, the affine + activation applied in shared memory): no normalised tensor in
-        # HBM. Used where it beats affine_act + implicit GEMM: the VAE's >= 128^2-pixel levels (tools/conv_halo_bench.py: 1.02-1.25x per
-        # layer; VAE decode 10.81 -> 10.35 ms, encode 5.30 -> 4.99 ms). At the UNet's 64^2 / 32^2 levels the tensors are L2-resident
-        # and the separate pass is cheap: measured neutral (10.03 vs 10.09 ms), left on the implicit-GEMM path.
+            and x.C % 64 == 0 and w.shape[0] % 64 == 0 and x.H * x.W >= 1024 and x.B * (x.H // 16) * (x.W // 8) >= 128):
+        # C2: norm -> SiLU -> conv in one kernel (halo tiles, the affine + activation applied while the tile is staged): no normalised
+        # tensor in HBM. Faster than affine_act + implicit GEMM on every level with >= 128 pixel tiles (tools/conv_halo_bench.py:
+        # 1.06-1.26x per layer); the 16^2 / 8^2 levels (a handful of tiles, split-K) stay on the implicit-GEMM path.
         N = w.shape[0]
         out = new_act(x.B, Ho, Wo, N, x.t.device, F16)
         if residual is not None:

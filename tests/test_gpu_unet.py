@@ -442,3 +442,16 @@ def test_conv3x3_halo_fused(dev, B, H, W, C, N, fused, rows, res, act_out):
     of = out.float().view(B, H * W, N)
     tot = stats.view(B, H * W // 32, N, 2).sum(1)
     assert torch.allclose(tot[..., 0], of.sum(1), rtol=1e-4, atol=1e-2 * sc) and torch.allclose(tot[..., 1], of.pow(2).sum(1), rtol=1e-4, atol=1e-2 * sc * sc)
+
+
+def test_conv3x3_halo_pair_mode(dev):
+    """The same C2 parity cases with COMA_HALO_PAIR=1: CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256) over both CTAs' shared memory
+    (the switch is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, COMA_HALO_PAIR="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_unet.py"), "-x", "-q", "-m", "gpu", "-k", "test_conv3x3_halo_fused"],
+                       env=env, cwd=os.path.dirname(here), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "6 passed" in r.stdout, r.stdout[-2000:]
