@@ -44,7 +44,7 @@ SIGNATURES = {
     "coma_conv3x3_f16_ws": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp, _i64, _vp],
     "coma_conv3x3_small_n_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp],
     "coma_conv3x3_halo_supported": [_i64, _i64, _i64, _i64, _i64],
-    "coma_conv3x3_halo_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _i64, _vp, _vp],
+    "coma_conv3x3_halo_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _int, _vp, _vp, _int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _i64, _vp, _vp],
     "coma_attention_fwd_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _vp],
     "coma_attention_fwd_ex_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _i64, _vp],
     "coma_attention_fwd_nt_f16": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _i64, _vp],

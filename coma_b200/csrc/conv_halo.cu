@@ -121,15 +121,17 @@ __device__ __forceinline__ float exp2f_approx(float x) {
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }   // as affine_act_kernel (unet_ops.cu)
 // SiLU for the halo builders: ONE MUFU op per element (ex2) instead of two — the builders are MUFU-bound at BN = 128 (23040 ops per
 // 64-channel block against 2304 clk of MMAs). The reciprocal of 1 + e^-v runs on the FMA pipes: magic-constant seed (12 % off) + three
-// Newton steps (relative error < 1e-7, i.e. at least as accurate as MUFU.RCP's 1 ulp); v is clamped at -80 so that 1 + e^-v stays finite.
-__device__ __forceinline__ float silu_fma(float v) {
-    const float e = exp2f_approx(fmaxf(v, -80.0f) * -1.4426950408889634f);
-    const float y = 1.0f + e;
-    float r = __int_as_float(0x7EF311C7 - __float_as_int(y));
-    r = r * fmaf(-y, r, 2.0f);
-    r = r * fmaf(-y, r, 2.0f);
-    r = r * fmaf(-y, r, 2.0f);
-    return v * r;
+// Newton steps (relative error < 4e-6 over [-90, 30]: 4e-5 of the fp16 results differ in the last bit from the exact value); v is clamped
+// at -80 so that 1 + e^-v stays finite.
+__device__ __forceinline__ float2 silu_fma2(float2 v) {   // two elements at a time in packed FP32x2 instructions (half the issue slots)
+    const float2 a = __fmul2_rn(make_float2(fmaxf(v.x, -80.0f), fmaxf(v.y, -80.0f)), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    const float2 y = __fadd2_rn(make_float2(exp2f_approx(a.x), exp2f_approx(a.y)), make_float2(1.0f, 1.0f));
+    const float2 ny = make_float2(-y.x, -y.y), two = make_float2(2.0f, 2.0f);
+    float2 r = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(y.x)), __int_as_float(0x7EF311C7 - __float_as_int(y.y)));
+    r = __fmul2_rn(r, __ffma2_rn(ny, r, two));
+    r = __fmul2_rn(r, __ffma2_rn(ny, r, two));
+    r = __fmul2_rn(r, __ffma2_rn(ny, r, two));
+    return __fmul2_rn(v, r);
 }
 
 // ---- CTA pair (cta_group::2): the leader CTA (cluster rank 0) issues M256 x N x K16 instructions over BOTH CTAs' shared memory
@@ -190,8 +192,9 @@ __host__ __device__ constexpr size_t ch_smem(int BN, bool pair) {
 }
 
 struct HaloArgs {
-    const void *x;                                    // [B, H, W, C] f16, pixel stride ldx
+    const void *x;                                    // [B, H, W, C] f16, pixel stride ldx; up: stored as [B, H/2, W/2, C], read as its nearest x2 upsampling
     long long ldx;
+    int up;
     int B, H, W, C, N;
     int cblocks, tiles_x, per_img, n_tiles, total;   // total = m_tiles * n_tiles work items; id = mt * n_tiles + nt (N fastest)
                                                      // PAIR: total = (m_tiles / 2) * n_tiles pair items; CTA `rank` of the pair owns pixel tile 2 * mp + rank
@@ -372,15 +375,18 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                     const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
                     ok[i] = pix < CH_HPIX && (unsigned)gy < (unsigned)a.H && (unsigned)gx < (unsigned)a.W;
                     raw[i] = make_uint4(0u, 0u, 0u, 0u);   // outside the image: the convolution's zero padding (of the ACTIVATED tensor)
-                    if (ok[i]) raw[i] = __ldg(reinterpret_cast<const uint4 *>(xg + (((size_t)img * a.H + gy) * a.W + gx) * a.ldx + cb * 64 + c8 * 8));
+                    if (ok[i]) {
+                        const size_t src = a.up ? ((size_t)img * (a.H >> 1) + (gy >> 1)) * (a.W >> 1) + (gx >> 1) : ((size_t)img * a.H + gy) * a.W + gx;
+                        raw[i] = __ldg(reinterpret_cast<const uint4 *>(xg + src * a.ldx + cb * 64 + c8 * 8));
+                    }
                 }
-                float sc[8], sh[8];
+                float2 sc[4], sh[4];
                 if (a.scale) {
                     const size_t co = (size_t)img * a.C + cb * 64 + c8 * 8;
                     const float4 s0 = __ldg(reinterpret_cast<const float4 *>(a.scale + co)), s1 = __ldg(reinterpret_cast<const float4 *>(a.scale + co + 4));
                     const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.shift + co)), t1 = __ldg(reinterpret_cast<const float4 *>(a.shift + co + 4));
-                    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-                    sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+                    sc[0] = make_float2(s0.x, s0.y); sc[1] = make_float2(s0.z, s0.w); sc[2] = make_float2(s1.x, s1.y); sc[3] = make_float2(s1.z, s1.w);
+                    sh[0] = make_float2(t0.x, t0.y); sh[1] = make_float2(t0.z, t0.w); sh[2] = make_float2(t1.x, t1.y); sh[3] = make_float2(t1.z, t1.w);
                 }
                 mbar_wait(halo_empty + hs, hph ^ 1);   // the MMAs that read this buffer NH blocks ago have retired
                 uint8_t *buf = sH + hs * CH_HALO_STRIDE;
@@ -392,13 +398,8 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                         __half2 *h = reinterpret_cast<__half2 *>(&raw[i]);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            float2 v = __half22float2(h[u]);
-                            v.x = fmaf(v.x, sc[2 * u], sh[2 * u]);
-                            v.y = fmaf(v.y, sc[2 * u + 1], sh[2 * u + 1]);
-                            if (a.act_in == 1) {
-                                v.x = silu_fma(v.x);
-                                v.y = silu_fma(v.y);
-                            }
+                            float2 v = __ffma2_rn(__half22float2(h[u]), sc[u], sh[u]);
+                            if (a.act_in == 1) v = silu_fma2(v);
                             h[u] = __floats2half2_rn(v.x, v.y);
                         }
                     }
@@ -613,7 +614,7 @@ extern "C" int coma_conv3x3_halo_supported(int64_t B, int64_t H, int64_t W, int6
             B * (H / coma::CH_TH) * (W / coma::CH_TW) >= 2 * coma::kNumSM) ? 1 : 0;
 }
 
-extern "C" int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const float *scale,
+extern "C" int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, int up, const float *scale,
                                      const float *shift, int act_in, const void *Wt, int64_t ldw, int64_t N, const float *bias,
                                      const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act_out, void *out_f16,
                                      int64_t ldo, float *stats, coma_stream_t stream) {
@@ -630,7 +631,7 @@ extern "C" int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_
     COMA_REQUIRE(!bias_rows || bias_rows_ld % 4 == 0, "bias_rows_ld must be a multiple of 4");
     const int bn = N % 256 == 0 ? 256 : (N % 160 == 0 ? 160 : (N % 128 == 0 ? 128 : 64));
     HaloArgs a;
-    a.x = x; a.ldx = ldx;
+    a.x = x; a.ldx = ldx; a.up = up ? 1 : 0;
     a.B = (int)B; a.H = (int)H; a.W = (int)W; a.C = (int)C; a.N = (int)N;
     a.cblocks = (int)(C / 64);
     a.tiles_x = (int)(W / CH_TW);

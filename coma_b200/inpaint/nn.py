@@ -179,10 +179,10 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
                  w.data_ptr(), w.stride(0), w.shape[0], _ptr(bias), out.t.data_ptr() if out_dtype == F32 else None,
                  out.t.data_ptr() if out_dtype == F16 else None, out.t.stride(0), _stream())
         return out
-    if (HALO_CONV and gn is not None and stride == 1 and pad == 1 and not up and out_dtype == F16 and x.H % 16 == 0 and x.W % 8 == 0
-            and x.C % 64 == 0 and w.shape[0] % 64 == 0 and x.H * x.W >= 1024 and x.B * (x.H // 16) * (x.W // 8) >= 128):
-        # C2: norm -> SiLU -> conv in one kernel (halo tiles, the affine + activation applied while the tile is staged): no normalised
-        # tensor in HBM. Faster than affine_act + implicit GEMM on every level with >= 128 pixel tiles (tools/conv_halo_bench.py:
+    if (HALO_CONV and (gn is not None or up) and stride == 1 and pad == 1 and out_dtype == F16 and Ho % 16 == 0 and Wo % 8 == 0
+            and x.C % 64 == 0 and w.shape[0] % 64 == 0 and Ho * Wo >= 1024 and x.B * (Ho // 16) * (Wo // 8) >= 128):
+        # C2: norm -> SiLU -> conv (and nearest x2 upsample -> conv) in one kernel (halo tiles, the affine + activation / the upsampling
+        # applied while the tile is staged): no normalised or upsampled tensor in HBM. Faster than affine_act + implicit GEMM on every level with >= 128 pixel tiles (tools/conv_halo_bench.py:
         # 1.06-1.26x per layer); the 16^2 / 8^2 levels (a handful of tiles, split-K) stay on the implicit-GEMM path.
         N = w.shape[0]
         out = new_act(x.B, Ho, Wo, N, x.t.device, F16)
@@ -191,7 +191,8 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
         want = stats and FUSED_GN_STATS and (Ho * Wo) % 32 == 0
         st = torch.empty((x.B * Ho * Wo // 32, N, 2), dtype=F32, device=x.t.device) if want else None
         with torch.cuda.device(x.t.device):
-            call("coma_conv3x3_halo_f16", x.t.data_ptr(), x.B, x.H, x.W, x.C, x.ld, _ptr(gn[0]), _ptr(gn[1]), act, w.data_ptr(), w.stride(0), N,
+            call("coma_conv3x3_halo_f16", x.t.data_ptr(), x.B, Ho, Wo, x.C, x.ld, int(up), None if gn is None else _ptr(gn[0]),
+                 None if gn is None else _ptr(gn[1]), act if gn is not None else 0, w.data_ptr(), w.stride(0), N,
                  _ptr(bias), None if bias_rows is None else bias_rows.data_ptr(), 0 if bias_rows is None else bias_rows.stride(0),
                  None if residual is None else residual.data_ptr(), 0, out.t.data_ptr(), out.t.stride(0), None if st is None else st.data_ptr(),
                  _stream())

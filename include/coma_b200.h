@@ -253,12 +253,13 @@ COMA_API int coma_conv3x3_small_n_f16(const void *x, int64_t B, int64_t H, int64
  * `norm -> SiLU -> conv` of diffusers' ResnetBlock2D (UNet utils/adaptive_mask_inpainting.py:1001, VAE :680 / :1086 / :1112) in one
  * tcgen05 kernel. Per 16 x 8 pixel output tile and 64-channel block ONE TMA load brings the 18 x 10 halo; the nine taps are shifted
  * views of it (no nine-fold L2 -> SMEM traffic); transform warps apply act_in(x * scale[b,c] + shift[b,c]) in shared memory, so the
- * normalised tensor is never written to HBM. x [B,H,W,C] NHWC f16 (row stride ldx); scale / shift [B,C] f32 or both NULL (input used
- * as stored); Wt [N, ldw >= 9C] f16, K order (ky,kx,c); bias [N]; bias_rows [B, bias_rows_ld] per-sample rows (time embedding) or
+ * normalised tensor is never written to HBM. x [B,H,W,C] NHWC f16 (row stride ldx) — with up != 0 x is stored as [B,H/2,W/2,C] and read
+ * as its nearest-neighbour x2 upsampling (diffusers Upsample2D: interpolate + conv, no 4x larger intermediate); scale / shift [B,C]
+ * f32 or both NULL (input used as stored); Wt [N, ldw >= 9C] f16, K order (ky,kx,c); bias [N]; bias_rows [B, bias_rows_ld] per-sample rows (time embedding) or
  * NULL; residual [B*H*W, ldo] f16 or NULL; out [B*H*W, ldo] f16; stats [B*H*W/32, N, 2] f32 or NULL (GroupNorm partial sums of the
  * output, as coma_conv3x3_strided_f16). Needs H % 16 == 0, W % 8 == 0, C % 64 == 0, N % 64 == 0 (coma_conv3x3_halo_supported). */
 COMA_API int coma_conv3x3_halo_supported(int64_t B, int64_t H, int64_t W, int64_t C, int64_t N);
-COMA_API int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, const float *scale,
+COMA_API int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, int up, const float *scale,
                                    const float *shift, int act_in, const void *Wt, int64_t ldw, int64_t N, const float *bias,
                                    const float *bias_rows, int64_t bias_rows_ld, const void *residual, int act_out, void *out_f16,
                                    int64_t ldo, float *stats, coma_stream_t stream);

@@ -421,7 +421,7 @@ def test_conv3x3_halo_fused(dev, B, H, W, C, N, fused, rows, res, act_out):
     out = torch.zeros((B * H * W, N), dtype=torch.float16, device=dev)
     stats = torch.zeros((B * H * W // 32, N, 2), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        call("coma_conv3x3_halo_f16", x.data_ptr(), B, H, W, C, C, None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
+        call("coma_conv3x3_halo_f16", x.data_ptr(), B, H, W, C, C, 0, None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
              1, wt.data_ptr(), 9 * C, N, bias.data_ptr(), None if brows is None else brows.data_ptr(), N, None if resid is None else resid.data_ptr(), act_out,
              out.data_ptr(), N, stats.data_ptr(), _stream())
     z = x.float()
@@ -455,3 +455,28 @@ def test_conv3x3_halo_pair_mode(dev):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_unet.py"), "-x", "-q", "-m", "gpu", "-k", "test_conv3x3_halo_fused"],
                        env=env, cwd=os.path.dirname(here), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "6 passed" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("B,H,W,C,N,fused", [(2, 32, 32, 128, 128, False), (1, 64, 48, 64, 256, True), (1, 128, 128, 256, 256, False)])
+def test_conv3x3_halo_upsample(dev, B, H, W, C, N, fused):
+    """C2 with the nearest x2 upsampling of diffusers' Upsample2D fused into the halo builders: x is stored at [H/2, W/2] and read as its
+    upsampling (optionally through the GroupNorm affine + SiLU); against F.interpolate(mode='nearest') + conv2d in fp32."""
+    from coma_b200._lib import _stream, call
+    g = torch.Generator(device=dev).manual_seed(C + H)
+    x = torch.randn((B, H // 2, W // 2, C), device=dev, generator=g).half()
+    w = (torch.randn((N, C, 3, 3), device=dev, generator=g) * (9 * C) ** -0.5).half()
+    bias = torch.randn(N, device=dev, generator=g) * 0.1
+    scale = (1.0 + 0.2 * torch.randn((B, C), device=dev, generator=g)).contiguous() if fused else None
+    shift = (0.3 * torch.randn((B, C), device=dev, generator=g)).contiguous() if fused else None
+    wt = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = torch.zeros((B * H * W, N), dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        call("coma_conv3x3_halo_f16", x.data_ptr(), B, H, W, C, C, 1, None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
+             1, wt.data_ptr(), 9 * C, N, bias.data_ptr(), None, 0, None, 0, out.data_ptr(), N, None, _stream())
+    z = x.float()
+    if fused:
+        z = F.silu(z * scale[:, None, None, :] + shift[:, None, None, :]).half().float()
+    z = F.interpolate(z.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(z, w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, N)
+    sc = ref.abs().max().item()
+    assert (out.float() - ref).abs().max().item() <= 2e-3 * sc, (out.float() - ref).abs().max().item() / sc

@@ -55,7 +55,7 @@ for B, H, C, N in SHAPES:
         call("coma_affine_act_f16", x.data_ptr(), B, H * H, C, C, scale.data_ptr(), shift.data_ptr(), 1, y.data_ptr(), C, _stream())
 
     def halo(fused):
-        call("coma_conv3x3_halo_f16", x.data_ptr(), B, H, H, C, C, scale.data_ptr() if fused else None, shift.data_ptr() if fused else None, 1, wt.data_ptr(),
+        call("coma_conv3x3_halo_f16", x.data_ptr(), B, H, H, C, C, 0, scale.data_ptr() if fused else None, shift.data_ptr() if fused else None, 1, wt.data_ptr(),
              9 * C, N, bias.data_ptr(), None, 0, None, 0, out.data_ptr(), N, stats.data_ptr(), _stream())
 
     t_conv = t_aff = t_plain = t_fused = 1e9

@@ -18,7 +18,7 @@ shift = torch.zeros((B, C), device=dev)
 out = torch.empty((B * H * H, N), dtype=torch.float16, device=dev)
 stats = torch.empty((B * H * H // 32, N, 2), dtype=torch.float32, device=dev)
 for _ in range(4):
-    call("coma_conv3x3_halo_f16", x.data_ptr(), B, H, H, C, C, scale.data_ptr(), shift.data_ptr(), 1, wt.data_ptr(), 9 * C, N, bias.data_ptr(), None, 0, None, 0,
+    call("coma_conv3x3_halo_f16", x.data_ptr(), B, H, H, C, C, 0, scale.data_ptr(), shift.data_ptr(), 1, wt.data_ptr(), 9 * C, N, bias.data_ptr(), None, 0, None, 0,
          out.data_ptr(), N, stats.data_ptr(), _stream())
 torch.cuda.synchronize()
 print("done")
