@@ -41,6 +41,7 @@ SIGNATURES = {
     "coma_conv3x3_strided_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp,
                                  _i64, _vp, _c.POINTER(_c.c_int), _vp],
     "coma_groupnorm_from_stats_f32": [_vp, _i64, _i64, _i64, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "coma_groupnorm_from_stats_rb_f32": [_vp, _i64, _i64, _i64, _i64, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "coma_conv3x3_f16_ws": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _i64, _vp, _i64, _vp],
     "coma_conv3x3_small_n_f16": [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp],
     "coma_conv3x3_halo_supported": [_i64, _i64, _i64, _i64, _i64],

@@ -188,7 +188,7 @@ __host__ __device__ constexpr int ch_threads(int BN) { return 64 + 32 * ch_epi_w
 __host__ __device__ constexpr int ch_b_stages(int BN, bool pair) { return pair ? (BN <= 160 ? 8 : 6) : (BN <= 64 ? 8 : (BN <= 128 ? 6 : (BN <= 160 ? 5 : 3))); }   // 64-128 KB of weight slabs in flight (TMA latency ~2000 clk)
 __host__ __device__ constexpr int ch_b_rows(int BN, bool pair) { return pair ? BN / 2 : BN; }   // weight rows per CTA and slab: a pair splits the tile's N
 __host__ __device__ constexpr size_t ch_smem(int BN, bool pair) {
-    return (size_t)CH_NH * CH_HALO_STRIDE + (size_t)ch_b_stages(BN, pair) * ch_b_rows(BN, pair) * 128 + (size_t)ch_epi_warps(BN) * 2 * CH_PANEL_BYTES + 256 + 1024;
+    return (size_t)CH_NH * CH_HALO_STRIDE + (size_t)ch_b_stages(BN, pair) * ch_b_rows(BN, pair) * 128 + (size_t)ch_epi_warps(BN) * 2 * CH_PANEL_BYTES + 2048 + 256 + 1024;
 }
 
 struct HaloArgs {
@@ -205,7 +205,7 @@ struct HaloArgs {
     const __half *residual;                           // [B*H*W, ldo] or null
     long long ldo;
     int act_out;
-    float *stats;                                     // [B*H*W/32, N, 2] or null
+    float *stats;                                     // [B*H*W/128, N, 2] (one row per 16 x 8 pixel tile) or null
 };
 
 // PAIR: two CTAs of a cluster (one TPC) work on two pixel tiles of the same output-channel tile with ONE tcgen05.mma.cta_group::2 stream
@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
     uint8_t *sH = smem;
     uint8_t *sB = sH + CH_NH * CH_HALO_STRIDE;
     uint8_t *sE = sB + NB * B_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sE + EPI * 2 * CH_PANEL_BYTES);
+    float4 *sRed = reinterpret_cast<float4 *>(sE + EPI * 2 * CH_PANEL_BYTES);   // [2][4 warps][16 lanes]: GroupNorm partial sums of a panel, per quarter
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sE + EPI * 2 * CH_PANEL_BYTES + 2048);
     uint64_t *halo_ready = bar, *halo_empty = halo_ready + CH_NH;
     uint64_t *b_full = halo_empty + CH_NH, *b_empty = b_full + NB;
     uint64_t *tmem_full = b_empty + NB, *tmem_empty = tmem_full + 2;
@@ -511,10 +512,20 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                     s2.y += __shfl_down_sync(0xffffffffu, s2.y, 16);
                     q2.x += __shfl_down_sync(0xffffffffu, q2.x, 16);
                     q2.y += __shfl_down_sync(0xffffffffu, q2.y, 16);
+                    // one (sum, sumsq) row per 128-pixel TILE: the four quarters meet in shared memory (double-buffered by panel parity,
+                    // one named barrier per panel) and warp 0 adds them in quarter order — 4x less for groupnorm_from_stats to read
+                    if (par == 0) sRed[(g & 1) * 64 + q * 16 + cp] = make_float4(s2.x, q2.x, s2.y, q2.y);
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
                     const int col = nb + 2 * cp;
-                    if (par == 0 && col < a.N) {
-                        const size_t blk = (size_t)(PAIR ? 2 * (t / a.n_tiles) + (int)rank : t / a.n_tiles) * 4 + q;
-                        *reinterpret_cast<float4 *>(a.stats + (blk * a.N + col) * 2) = make_float4(s2.x, q2.x, s2.y, q2.y);
+                    if (q == 0 && par == 0 && col < a.N) {
+                        float4 r = sRed[(g & 1) * 64 + cp];
+#pragma unroll
+                        for (int w = 1; w < 4; ++w) {
+                            const float4 o = sRed[(g & 1) * 64 + w * 16 + cp];
+                            r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+                        }
+                        const size_t blk = (size_t)(PAIR ? 2 * (t / a.n_tiles) + (int)rank : t / a.n_tiles);
+                        *reinterpret_cast<float4 *>(a.stats + (blk * a.N + col) * 2) = r;
                     }
                 }
             }

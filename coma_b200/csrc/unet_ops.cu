@@ -195,12 +195,12 @@ __global__ void __launch_bounds__(256)
 // grid (G, B), 256 threads. Thread t adds blocks t, t+256, ... of every channel of the group (fp64, fixed assignment), the 256
 // partials are combined in index order -> bit-reproducible; no pass over the activation tensor at all.
 __global__ void __launch_bounds__(256)
-    groupnorm_from_stats_kernel(const float *__restrict__ stats, int HW, int C, int G, float eps, const float *__restrict__ gamma,
+    groupnorm_from_stats_kernel(const float *__restrict__ stats, int HW, int rows_per_block, int C, int G, float eps, const float *__restrict__ gamma,
                                 const float *__restrict__ beta, float *__restrict__ mean, float *__restrict__ rstd,
                                 float *__restrict__ scale, float *__restrict__ shift) {
     pdl_trigger();
     pdl_wait();
-    const int g = blockIdx.x, b = blockIdx.y, cpg = C / G, nblk = HW / 32;
+    const int g = blockIdx.x, b = blockIdx.y, cpg = C / G, nblk = HW / rows_per_block;
     const float *base = stats + ((size_t)b * nblk * C + (size_t)g * cpg) * 2;
     double s = 0.0, q = 0.0;
     // four row blocks per iteration: their loads are independent (a one-row loop is pure L2 latency)
@@ -731,15 +731,21 @@ extern "C" int coma_groupnorm_affine_f16(const void *x, int64_t B, int64_t HW, i
     return check_launch("groupnorm_partial_kernel");
 }
 
+extern "C" int coma_groupnorm_from_stats_rb_f32(const float *stats, int64_t B, int64_t HW, int64_t rows_per_block, int64_t C, int G, float eps,
+                                                const float *gamma, const float *beta, float *mean, float *rstd, float *scale, float *shift,
+                                                coma_stream_t stream) {
+    COMA_REQUIRE(stats && scale && shift, "null pointer");
+    COMA_REQUIRE(B > 0 && HW > 0 && rows_per_block > 0 && HW % rows_per_block == 0 && C > 0 && G > 0 && C % G == 0 && B <= 65535 && G <= 65535, "bad sizes");
+    COMA_REQUIRE((uintptr_t)stats % 8 == 0, "stats must be 8-byte aligned");
+    launch_pdl(groupnorm_from_stats_kernel, dim3((unsigned)G, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, stats, (int)HW, (int)rows_per_block, (int)C,
+               G, eps, gamma, beta, mean, rstd, scale, shift);
+    return check_launch("groupnorm_from_stats_kernel");
+}
+
 extern "C" int coma_groupnorm_from_stats_f32(const float *stats, int64_t B, int64_t HW, int64_t C, int G, float eps, const float *gamma,
                                              const float *beta, float *mean, float *rstd, float *scale, float *shift,
                                              coma_stream_t stream) {
-    COMA_REQUIRE(stats && scale && shift, "null pointer");
-    COMA_REQUIRE(B > 0 && HW > 0 && HW % 32 == 0 && C > 0 && G > 0 && C % G == 0 && B <= 65535 && G <= 65535, "bad sizes");
-    COMA_REQUIRE((uintptr_t)stats % 8 == 0, "stats must be 8-byte aligned");
-    launch_pdl(groupnorm_from_stats_kernel, dim3((unsigned)G, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, stats, (int)HW, (int)C, G, eps,
-               gamma, beta, mean, rstd, scale, shift);
-    return check_launch("groupnorm_from_stats_kernel");
+    return coma_groupnorm_from_stats_rb_f32(stats, B, HW, 32, C, G, eps, gamma, beta, mean, rstd, scale, shift, stream);
 }
 
 extern "C" int coma_affine_act_f16(const void *x, int64_t B, int64_t HW, int64_t C, int64_t ldx, const float *scale,

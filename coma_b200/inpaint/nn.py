@@ -25,7 +25,8 @@ class Act:
     B: int
     H: int
     W: int
-    stats: torch.Tensor = None   # [B*H*W/32, C, 2] f32 partial (sum, sumsq) left by the producing conv's epilogue, or None
+    stats: torch.Tensor = None   # [B*H*W/stats_rows, C, 2] f32 partial (sum, sumsq) left by the producing conv's epilogue, or None
+    stats_rows: int = 32         # pixels per partial-sum row (32: implicit-GEMM conv, 128: halo-tile conv)
 
     @property
     def C(self):
@@ -117,7 +118,7 @@ def gn_affine(x: Act, gamma, beta, groups, eps):
         scale = torch.empty((x.B, x.C), dtype=F32, device=dev)
         shift = torch.empty((x.B, x.C), dtype=F32, device=dev)
         with torch.cuda.device(dev):
-            call("coma_groupnorm_from_stats_f32", x.stats.data_ptr(), x.B, x.H * x.W, x.C, groups, float(eps), _ptr(gamma), _ptr(beta),
+            call("coma_groupnorm_from_stats_rb_f32", x.stats.data_ptr(), x.B, x.H * x.W, x.stats_rows, x.C, groups, float(eps), _ptr(gamma), _ptr(beta),
                  None, None, scale.data_ptr(), shift.data_ptr(), _stream())
         return scale, shift
     ws = torch.empty(2 * groups * (4 * 148 + x.B), dtype=torch.float64, device=dev)
@@ -188,8 +189,8 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
         out = new_act(x.B, Ho, Wo, N, x.t.device, F16)
         if residual is not None:
             assert residual.dtype == F16 and residual.stride(0) == out.t.stride(0)
-        want = stats and FUSED_GN_STATS and (Ho * Wo) % 32 == 0
-        st = torch.empty((x.B * Ho * Wo // 32, N, 2), dtype=F32, device=x.t.device) if want else None
+        want = stats and FUSED_GN_STATS
+        st = torch.empty((x.B * Ho * Wo // 128, N, 2), dtype=F32, device=x.t.device) if want else None   # one row per 16 x 8 pixel tile
         with torch.cuda.device(x.t.device):
             call("coma_conv3x3_halo_f16", x.t.data_ptr(), x.B, Ho, Wo, x.C, x.ld, int(up), None if gn is None else _ptr(gn[0]),
                  None if gn is None else _ptr(gn[1]), act if gn is not None else 0, w.data_ptr(), w.stride(0), N,
@@ -197,7 +198,7 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
                  None if residual is None else residual.data_ptr(), 0, out.t.data_ptr(), out.t.stride(0), None if st is None else st.data_ptr(),
                  _stream())
         if st is not None:
-            out.stats = st
+            out.stats, out.stats_rows = st, 128
         return out
     strided_ok = stride == 2 and not up and gn is None and Ho * Wo >= 128   # element-strided TMA tiles
     if IMPLICIT_CONV and ((stride == 1 and pad == 1) or strided_ok) and x.C % 64 == 0 and _tiles_128(Ho, Wo):

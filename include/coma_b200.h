@@ -234,6 +234,10 @@ COMA_API int coma_conv3x3_strided_f16(const void *x, int64_t B, int64_t Hin, int
 COMA_API int coma_groupnorm_from_stats_f32(const float *stats, int64_t B, int64_t HW, int64_t C, int G, float eps, const float *gamma,
                                            const float *beta, float *mean, float *rstd, float *scale, float *shift,
                                            coma_stream_t stream);
+/* Same with partial sums per `rows_per_block` rows ([B*HW/rows_per_block, C, 2]): coma_conv3x3_halo_f16 leaves one row per 128-pixel tile. */
+COMA_API int coma_groupnorm_from_stats_rb_f32(const float *stats, int64_t B, int64_t HW, int64_t rows_per_block, int64_t C, int G, float eps,
+                                              const float *gamma, const float *beta, float *mean, float *rstd, float *scale, float *shift,
+                                              coma_stream_t stream);
 
 COMA_API int coma_gemm_f16_tn(const void *A, int64_t lda, const void *W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                               const float *bias, const void *residual, int act, void *out_f16, float *out_f32, int64_t ldo,
@@ -256,8 +260,8 @@ COMA_API int coma_conv3x3_small_n_f16(const void *x, int64_t B, int64_t H, int64
  * normalised tensor is never written to HBM. x [B,H,W,C] NHWC f16 (row stride ldx) — with up != 0 x is stored as [B,H/2,W/2,C] and read
  * as its nearest-neighbour x2 upsampling (diffusers Upsample2D: interpolate + conv, no 4x larger intermediate); scale / shift [B,C]
  * f32 or both NULL (input used as stored); Wt [N, ldw >= 9C] f16, K order (ky,kx,c); bias [N]; bias_rows [B, bias_rows_ld] per-sample rows (time embedding) or
- * NULL; residual [B*H*W, ldo] f16 or NULL; out [B*H*W, ldo] f16; stats [B*H*W/32, N, 2] f32 or NULL (GroupNorm partial sums of the
- * output, as coma_conv3x3_strided_f16). Needs H % 16 == 0, W % 8 == 0, C % 64 == 0, N % 64 == 0 (coma_conv3x3_halo_supported). */
+ * NULL; residual [B*H*W, ldo] f16 or NULL; out [B*H*W, ldo] f16; stats [B*H*W/128, N, 2] f32 or NULL (GroupNorm partial sums of the
+ * output, one row per 16 x 8 pixel tile: coma_groupnorm_from_stats_rb_f32 with rows_per_block = 128). Needs H % 16 == 0, W % 8 == 0, C % 64 == 0, N % 64 == 0 (coma_conv3x3_halo_supported). */
 COMA_API int coma_conv3x3_halo_supported(int64_t B, int64_t H, int64_t W, int64_t C, int64_t N);
 COMA_API int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ldx, int up, const float *scale,
                                    const float *shift, int act_in, const void *Wt, int64_t ldw, int64_t N, const float *bias,
