@@ -6,7 +6,7 @@
 // input pixel crosses L2 -> SMEM nine times — and needs the normalised + activated tensor materialised in HBM by a separate pass
 // (affine_act_kernel: 12-20 % of a VAE decode). Here:
 //   * an output tile is 16 rows x 8 columns of pixels; per 64-channel block its 18 x 10 pixel halo is staged ONCE in shared memory
-//     (23 KB instead of nine shifted 16 KB tiles): eight builder warps read it from global memory with coalesced 16-byte loads,
+//     (23 KB instead of nine shifted 16 KB tiles): twelve builder warps read it from global memory with coalesced 16-byte loads,
 //     apply act(x * scale[b, c] + shift[b, c]) in registers (fp16, the same roundings as the tensor the unfused path stores; pixels
 //     outside the image are the convolution's zero padding) and store it in the 128B-swizzled K-major layout, while the tensor core
 //     works on the previous blocks (4-deep ring);
@@ -16,7 +16,7 @@
 //   * weights stream through their own ring ([BN x 64] slabs, K order (ky, kx, cin) as in prep_conv3x3);
 //   * epilogue as in gemm.cu: TMEM -> registers -> bias / per-sample bias row (time embedding) / residual / SiLU -> 64B-swizzled
 //     32 x 32 panels -> TMA store (box 32 channels x 8 px x 4 rows), GroupNorm partial sums of the rounded output for the next norm.
-// Warps: 0 TMA producer (weights), 1 MMA issuer (both converged, one elected lane), 2-5 epilogue, 6-13 halo builders.
+// Warps: 0 TMA producer (weights), 1 MMA issuer (both converged, one elected lane), 2-5 epilogue, 6-17 halo builders.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -183,7 +183,7 @@ constexpr int CH_HALO_STRIDE = (CH_HALO_BYTES + 1023) / 1024 * 1024;
 constexpr int CH_NH = 4;                                   // halo ring: one block under the MMAs, one or two in the transform (a pair waits for the slower CTA), one in flight
 constexpr int CH_PANEL_BYTES = 32 * 32 * 2;
 __host__ __device__ constexpr int ch_epi_warps(int BN) { return 4; }   // K >= 576: the epilogue (TMEM read rate bound) hides behind the next tile's main loop even at BN = 256
-constexpr int CH_TWARPS = 8;                               // transform warps: two per scheduler hide each other's MUFU / LDS latencies
+constexpr int CH_TWARPS = 12;                              // halo builder warps: three per scheduler hide each other's load / MUFU latencies
 __host__ __device__ constexpr int ch_threads(int BN) { return 64 + 32 * ch_epi_warps(BN) + 32 * CH_TWARPS; }
 __host__ __device__ constexpr int ch_b_stages(int BN, bool pair) { return pair ? (BN <= 160 ? 8 : 6) : (BN <= 64 ? 8 : (BN <= 128 ? 6 : (BN <= 160 ? 5 : 3))); }   // 64-128 KB of weight slabs in flight (TMA latency ~2000 clk)
 __host__ __device__ constexpr int ch_b_rows(int BN, bool pair) { return pair ? BN / 2 : BN; }   // weight rows per CTA and slab: a pair splits the tile's N
@@ -649,13 +649,13 @@ extern "C" int coma_conv3x3_halo_f16(const void *x, int64_t B, int64_t H, int64_
     a.per_img = a.tiles_x * (int)(H / CH_TH);
     a.n_tiles = (int)(N / bn);
     const long long m_tiles = (long long)B * a.per_img;
-    // CTA pairs (cta_group::2; need an even number of pixel tiles) are built, parity-tested and OFF by default: measured on B200
-    // (tools/conv_halo_bench.py, profiles/r02_conv_halo_bench_pair.log) the pair kernel is 5-18 % faster than the single-CTA one WITHOUT
-    // the fused transform (512^2 x 128->128: 297 -> 284 us, 256->128: 643 -> 544 us, 256^2 x 256: 246 -> 228 us) but slower WITH it
-    // (322 -> 346 us, 661 -> 680 us; only 256^2 x 256->256 gains, 251 -> 236 us): the leader's MMA stream then waits for the slower of
-    // two transforms plus a remote mbarrier arrival per block. The VAE always runs fused, so COMA_HALO_PAIR=1 is opt-in.
-    static const bool pair_on = getenv("COMA_HALO_PAIR") && atoi(getenv("COMA_HALO_PAIR")) == 1;
-    const bool pair = pair_on && m_tiles % 2 == 0 && bn >= 64;
+    // CTA pairs (cta_group::2; need an even number of pixel tiles). Measured on B200 (tools/conv_halo_bench.py,
+    // profiles/r02_conv_halo_bench_pair.log): WITHOUT the fused transform the pair kernel beats the single-CTA one by 5-18 % everywhere;
+    // WITH it (every caller) it wins where a block's MMAs leave the builders time — 256-wide tiles: 256^2 x 512->256 419 -> 399 us,
+    // 128^2 x 512 210 -> 200 us, 256^2 x 256 221 -> 214 us — and loses at 128 / 160-wide tiles (512^2 x 256->128: 552 -> 609 us), where the
+    // leader's MMA stream waits for the slower of two builder groups. Default: pairs for 256-wide tiles; COMA_HALO_PAIR=0 / 1 forces.
+    static const int pair_env = getenv("COMA_HALO_PAIR") ? atoi(getenv("COMA_HALO_PAIR")) : -1;
+    const bool pair = (pair_env == 1 || (pair_env < 0 && bn == 256)) && m_tiles % 2 == 0;
     const long long total = (pair ? m_tiles / 2 : m_tiles) * a.n_tiles;
     COMA_REQUIRE(total < (1LL << 31), "too many output tiles");
     a.total = (int)total;
