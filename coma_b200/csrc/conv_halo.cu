@@ -113,6 +113,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// explicit shared-space accesses: the dynamic window's base is rounded up through an integer cast, so plain pointer dereferences
+// compile to GENERIC LD / ST (slower path, long-scoreboard latency) instead of LDS / STS
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float exp2f_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -390,7 +408,7 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                     sh[0] = make_float2(t0.x, t0.y); sh[1] = make_float2(t0.z, t0.w); sh[2] = make_float2(t1.x, t1.y); sh[3] = make_float2(t1.z, t1.w);
                 }
                 mbar_wait(halo_empty + hs, hph ^ 1);   // the MMAs that read this buffer NH blocks ago have retired
-                uint8_t *buf = sH + hs * CH_HALO_STRIDE;
+                const uint32_t buf = smem_u32(sH) + (uint32_t)(hs * CH_HALO_STRIDE);
 #pragma unroll
                 for (int i = 0; i < NPX; ++i) {
                     const int pix = prow + i * 4 * CH_TWARPS;
@@ -404,7 +422,7 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                             h[u] = __floats2half2_rn(v.x, v.y);
                         }
                     }
-                    *reinterpret_cast<uint4 *>(buf + pix * 128 + ((c8 ^ (pix & 7)) << 4)) = raw[i];
+                    sts128(buf + (uint32_t)(pix * 128 + ((c8 ^ (pix & 7)) << 4)), raw[i]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
                 if (PAIR) {
@@ -420,7 +438,7 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
         // ---- epilogue: warp owns TMEM lanes [32q, 32q + 32) = tile rows 4q .. 4q+3 (8 pixels each); panels of 32 output channels
         const int q = warp & 3, half = (warp - 2) >> 2;
         uint8_t *ebuf = sE + (warp - 2) * (2 * CH_PANEL_BYTES);
-        uint8_t *my_row = ebuf + lane * 64;
+        const uint32_t my_row = smem_u32(ebuf) + (uint32_t)lane * 64;
         const int sw = (lane >> 1) & 3;   // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
         const int py = q * 4 + (lane >> 3), px = lane & 7;
         uint32_t g = 0;
@@ -440,7 +458,7 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
 #pragma unroll 1
             for (int p = half; p < P; p += PW, ++g) {
                 const uint32_t buf = g & 1;
-                uint8_t *prow = my_row + buf * CH_PANEL_BYTES;
+                const uint32_t prow = my_row + buf * CH_PANEL_BYTES;
                 uint32_t v[32];
                 tmem_ld32(tmem_d + (uint32_t)(p * 32), v);
                 const int nb = n0 + p * 32;
@@ -486,7 +504,7 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                     __half2 *h = reinterpret_cast<__half2 *>(&w);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(f[c * 8 + 2 * u], f[c * 8 + 2 * u + 1]);
-                    *reinterpret_cast<uint4 *>(prow + ((c ^ sw) << 4)) = w;
+                    sts128(prow + (uint32_t)((c ^ sw) << 4), w);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -498,13 +516,13 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                     // GroupNorm partial sums of the ROUNDED fp16 panel (see gemm.cu): lane (cp, par) adds the 16 rows of parity par of
                     // column pair cp, parities combined in a fixed order; block id = (pixel tile, quarter) -> 32 pixels of one image
                     const int cp = lane & 15, par = lane >> 4;
-                    const uint8_t *pan = ebuf + buf * CH_PANEL_BYTES;
+                    const uint32_t pan = smem_u32(ebuf) + buf * CH_PANEL_BYTES;
                     float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int r16 = 0; r16 < 16; ++r16) {
                         const int r = 2 * r16 + par;
-                        const __half2 hv = *reinterpret_cast<const __half2 *>(pan + r * 64 + ((((cp >> 2) ^ ((r >> 1) & 3))) << 4) + (cp & 3) * 4);
-                        const float2 x = __half22float2(hv);
+                        const uint32_t hb = lds32(pan + (uint32_t)(r * 64 + ((((cp >> 2) ^ ((r >> 1) & 3))) << 4) + (cp & 3) * 4));
+                        const float2 x = __half22float2(*reinterpret_cast<const __half2 *>(&hb));
                         s2 = __fadd2_rn(s2, x);
                         q2 = __ffma2_rn(x, x, q2);
                     }
@@ -514,14 +532,15 @@ __global__ void __launch_bounds__(ch_threads(BN), 1)
                     q2.y += __shfl_down_sync(0xffffffffu, q2.y, 16);
                     // one (sum, sumsq) row per 128-pixel TILE: the four quarters meet in shared memory (double-buffered by panel parity,
                     // one named barrier per panel) and warp 0 adds them in quarter order — 4x less for groupnorm_from_stats to read
-                    if (par == 0) sRed[(g & 1) * 64 + q * 16 + cp] = make_float4(s2.x, q2.x, s2.y, q2.y);
+                    const uint32_t red = smem_u32(sRed) + (uint32_t)((g & 1) * 64) * 16;
+                    if (par == 0) sts128f(red + (uint32_t)(q * 16 + cp) * 16, make_float4(s2.x, q2.x, s2.y, q2.y));
                     asm volatile("bar.sync 2, 128;" ::: "memory");
                     const int col = nb + 2 * cp;
                     if (q == 0 && par == 0 && col < a.N) {
-                        float4 r = sRed[(g & 1) * 64 + cp];
+                        float4 r = lds128f(red + (uint32_t)cp * 16);
 #pragma unroll
                         for (int w = 1; w < 4; ++w) {
-                            const float4 o = sRed[(g & 1) * 64 + w * 16 + cp];
+                            const float4 o = lds128f(red + (uint32_t)(w * 16 + cp) * 16);
                             r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
                         }
                         const size_t blk = (size_t)(PAIR ? 2 * (t / a.n_tiles) + (int)rank : t / a.n_tiles);

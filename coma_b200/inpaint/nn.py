@@ -181,7 +181,7 @@ def conv3x3(x: Act, w, bias, stride=1, pad=1, up=False, gn=None, act=0, residual
                  out.t.data_ptr() if out_dtype == F16 else None, out.t.stride(0), _stream())
         return out
     if (HALO_CONV and (gn is not None or up) and stride == 1 and pad == 1 and out_dtype == F16 and Ho % 16 == 0 and Wo % 8 == 0
-            and x.C % 64 == 0 and w.shape[0] % 64 == 0 and Ho * Wo >= 1024 and x.B * (Ho // 16) * (Wo // 8) >= 128):
+            and x.C % 64 == 0 and w.shape[0] % 64 == 0 and Ho * Wo >= 1024 and x.B * (Ho // 16) * (Wo // 8) * max(1, w.shape[0] // 256) >= 128):
         # C2: norm -> SiLU -> conv (and nearest x2 upsample -> conv) in one kernel (halo tiles, the affine + activation / the upsampling
         # applied while the tile is staged): no normalised or upsampled tensor in HBM. Faster than affine_act + implicit GEMM on every level with >= 128 pixel tiles (tools/conv_halo_bench.py:
         # 1.06-1.26x per layer); the 16^2 / 8^2 levels (a handful of tiles, split-K) stay on the implicit-GEMM path.
