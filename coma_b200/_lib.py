@@ -24,6 +24,7 @@ SIGNATURES = {
     "coma_pair_accumulate_order_f32": [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _int, _vp, _vp, _vp],
     "coma_orient_accumulate_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _vp, _vp],
     "coma_orient_accumulate_cone_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _int, _int, _vp, _vp, _vp],
+    "coma_orient_accumulate_cone_ws_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _f64, _f64, _f32p, _f32p, _vp, _int, _int, _vp, _vp, _vp, _vp],
     "coma_orient_bin_patches": [_c.POINTER(_c.c_double), _i64, _c.POINTER(_c.c_int32)],
     "coma_canonicalize_f32": [_vp, _i64, _vp, _i64, _f32p, _f32p, _f32, _vp, _vp],
     "coma_canonicalize_order_f32": [_vp, _i64, _vp, _i64, _f32p, _f32p, _f32, _int, _vp, _vp],

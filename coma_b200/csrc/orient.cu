@@ -364,7 +364,9 @@ constexpr int K3C_PATCHES = 8;
 // second-largest stall and 80 registers (3 CTAs/SM). Rolled: ~12 KB of code, ~50 registers; the price is 7 conflict-free
 // shared-memory accesses per (patch, chunk) against ~900 instructions of work. Chunks are 64 samples (two per lane), which
 // halves the per-(patch, histogram) bookkeeping — ballots, compaction, loop set-up and remainder — per sample.
-template <int DEG, int MINB>
+// PRENORM: hn / on already hold normalize_ref() of the normals (normalize_vectors_kernel, once per launch) — the normalisation depends on
+// (sample, vertex) only, and recomputing it for every PAIR costs two IEEE square roots and six IEEE divisions per (pair, sample).
+template <int DEG, int MINB, bool PRENORM>
 __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
     orient_accumulate_cone_kernel(const float *__restrict__ hn, const float *__restrict__ on, int S, int H, int O,
                                   const double *__restrict__ grid, int N, const int *__restrict__ perm, ConeParams cp, float eps, int ord,
@@ -420,8 +422,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
             if (have[u]) {
                 const float *ph3 = hn + ((size_t)s * H + h) * 3;
                 const float *po3 = on + ((size_t)s * O + o) * 3;
-                const Vec3 a = normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps, ord);
-                const Vec3 b = normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps, ord);
+                const Vec3 a = PRENORM ? Vec3{ph3[0], ph3[1], ph3[2]} : normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps, ord);
+                const Vec3 b = PRENORM ? Vec3{po3[0], po3[1], po3[2]} : normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps, ord);
                 ch[u] = canonicalize_ref(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
                 co[u] = canonicalize_ref(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
             }
@@ -446,6 +448,16 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
             po[n] = sAcc[j][1][tid];
         }
     }
+}
+
+// out[i] = normalize_ref(in[i]) — utils/transformations.py:14-17 once per (sample, vertex), bit-identical to the in-kernel evaluation
+__global__ void normalize_vectors_kernel(const float *__restrict__ in, long long n, float eps, int ord, float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec3 v = normalize_ref(Vec3{in[3 * i], in[3 * i + 1], in[3 * i + 2]}, eps, ord);
+    out[3 * i + 0] = v.x;
+    out[3 * i + 1] = v.y;
+    out[3 * i + 2] = v.z;
 }
 
 __global__ void canonicalize_kernel(const float *__restrict__ a, int A, const float *__restrict__ b, int B, Vec3 p, Vec3 sp,
@@ -527,6 +539,14 @@ extern "C" int coma_orient_accumulate_cone_f32(const float *hn, const float *on,
                                                const double *grid, int64_t N, double sigma, double eps, const float *p_host,
                                                const float *sub_p_host, const int32_t *bin_perm, int drop_bits, int sum_order, float *PH,
                                                float *PO, coma_stream_t stream) {
+    return coma_orient_accumulate_cone_ws_f32(hn, on, S, H, O, grid, N, sigma, eps, p_host, sub_p_host, bin_perm, drop_bits, sum_order, PH, PO,
+                                              nullptr, stream);
+}
+
+extern "C" int coma_orient_accumulate_cone_ws_f32(const float *hn, const float *on, int64_t S, int64_t H, int64_t O,
+                                                  const double *grid, int64_t N, double sigma, double eps, const float *p_host,
+                                                  const float *sub_p_host, const int32_t *bin_perm, int drop_bits, int sum_order, float *PH,
+                                                  float *PO, float *workspace, coma_stream_t stream) {
     using namespace coma;
     COMA_REQUIRE(hn && on && grid && p_host && sub_p_host && PH && PO, "null pointer");
     COMA_REQUIRE(S >= 0 && H > 0 && O > 0 && N > 0, "bad sizes");
@@ -561,16 +581,29 @@ extern "C" int coma_orient_accumulate_cone_f32(const float *hn, const float *on,
     const long long pairs = (long long)H * O;
     const unsigned blocks = (unsigned)((pairs + K3_WARPS - 1) / K3_WARPS);
     static const int ctas = getenv("COMA_B200_K3C_CTAS") ? atoi(getenv("COMA_B200_K3C_CTAS")) : 4;   // A/B: CTAs per SM (read once; 4 = 64 registers, no spills)
-#define LAUNCH_CONE(DEG)                                                                                                          \
-    if (ctas == 4)                                                                                                                \
-        orient_accumulate_cone_kernel<DEG, 4><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
-                                                                                cp, epsf, ord, p, sp, PH, PO);                    \
-    else if (ctas == 6)                                                                                                           \
-        orient_accumulate_cone_kernel<DEG, 6><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
-                                                                                cp, epsf, ord, p, sp, PH, PO);                    \
-    else                                                                                                                          \
-        orient_accumulate_cone_kernel<DEG, 5><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
-                                                                                cp, epsf, ord, p, sp, PH, PO)
+    // workspace (>= 3 S (H + O) floats): the normals are normalised ONCE per (sample, vertex) instead of once per (pair, sample)
+    if (workspace) {
+        float *hn_n = workspace, *on_n = workspace + 3 * S * H;
+        const long long nh = (long long)S * H, no = (long long)S * O;
+        normalize_vectors_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(hn, nh, epsf, ord, hn_n);
+        normalize_vectors_kernel<<<(unsigned)((no + 255) / 256), 256, 0, st>>>(on, no, epsf, ord, on_n);
+        if (int e = check_launch("normalize_vectors_kernel")) return e;
+        hn = hn_n;
+        on = on_n;
+    }
+#define LAUNCH_CONE(DEG)                                                                                                                \
+    if (workspace)                                                                                                                      \
+        orient_accumulate_cone_kernel<DEG, 4, true><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+                                                                                      cp, epsf, ord, p, sp, PH, PO);                    \
+    else if (ctas == 4)                                                                                                                 \
+        orient_accumulate_cone_kernel<DEG, 4, false><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+                                                                                       cp, epsf, ord, p, sp, PH, PO);                   \
+    else if (ctas == 6)                                                                                                                 \
+        orient_accumulate_cone_kernel<DEG, 6, false><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+                                                                                       cp, epsf, ord, p, sp, PH, PO);                   \
+    else                                                                                                                                \
+        orient_accumulate_cone_kernel<DEG, 5, false><<<blocks, K3_WARPS * 32, 0, st>>>(hn, on, (int)S, (int)H, (int)O, grid, (int)N, bin_perm, \
+                                                                                       cp, epsf, ord, p, sp, PH, PO)
     switch (fit->deg) {
         case 3: LAUNCH_CONE(3); break;
         case 4: LAUNCH_CONE(4); break;

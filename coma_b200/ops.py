@@ -66,8 +66,20 @@ def orient_accumulate(hn, on, grid, sigma, eps, p, sub_p, PH, PO, bin_perm=None,
         if bin_perm is not None:
             _chk(bin_perm, torch.int32, "bin_perm")
             assert bin_perm.numel() == 32 * ((N + 31) // 32)
-        call("coma_orient_accumulate_cone_f32", _ptr(hn), _ptr(on), S, H, O, _ptr(grid), N, float(sigma), float(eps), _host3(p),
-             _host3(sub_p), _ptr(bin_perm), int(drop_bits), SUM_ORDERS[sum_order], _ptr(PH), _ptr(PO), _stream())
+        # scratch for the once-per-(sample, vertex) normalisation of the normals (cached per device; the cone kernel only)
+        ws = _orient_workspace(hn.device, 3 * S * (H + O)) if drop_bits else None
+        call("coma_orient_accumulate_cone_ws_f32", _ptr(hn), _ptr(on), S, H, O, _ptr(grid), N, float(sigma), float(eps), _host3(p),
+             _host3(sub_p), _ptr(bin_perm), int(drop_bits), SUM_ORDERS[sum_order], _ptr(PH), _ptr(PO), _ptr(ws), _stream())
+
+
+_ORIENT_WS = {}
+
+
+def _orient_workspace(device, n):
+    ws = _ORIENT_WS.get(device)
+    if ws is None or ws.numel() < n:
+        ws = _ORIENT_WS[device] = torch.empty(max(n, 1 << 20), dtype=torch.float32, device=device)
+    return ws
 
 
 def canonicalize(a, b, p, sub_p, eps, sum_order="cpu"):

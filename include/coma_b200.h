@@ -120,6 +120,12 @@ COMA_API int coma_orient_accumulate_cone_f32(const float *hn, const float *on, i
                                              int64_t N, double sigma, double eps, const float *p_host, const float *sub_p_host,
                                              const int32_t *bin_perm, int drop_bits, int sum_order, float *PH, float *PO,
                                              coma_stream_t stream);
+/* Same with a device workspace of >= 3*S*(H+O) floats (or NULL): the normals are normalised once per (sample, vertex) by a pre-pass into
+ * the workspace instead of once per (pair, sample) inside the kernel — bit-identical results (the same correctly rounded operations). */
+COMA_API int coma_orient_accumulate_cone_ws_f32(const float *hn, const float *on, int64_t S, int64_t H, int64_t O, const double *grid,
+                                                int64_t N, double sigma, double eps, const float *p_host, const float *sub_p_host,
+                                                const int32_t *bin_perm, int drop_bits, int sum_order, float *PH, float *PO,
+                                                float *workspace, coma_stream_t stream);
 /* HOST-only helper (no GPU work): groups the N <= 256 bin centres grid_host [N,3] f64 into ceil(N/32) patches of <= 32 compact
  * bins; perm_host [32 * ceil(N/32)] int32 receives the bin index of each (patch, lane) slot, -1 for empty slots. */
 COMA_API int coma_orient_bin_patches(const double *grid_host, int64_t N, int32_t *perm_host);

@@ -287,6 +287,38 @@ def test_orient_accumulate_cone_limited(dev, H, O, N, S, sigma, bits, order):
     assert not cone_applies or float((PH - dPH).abs().max()) > 0      # it really is a different evaluation
 
 
+@pytest.mark.parametrize("order", ["cpu", "cuda"])
+def test_orient_cone_prenormalised_workspace_bit_identical(dev, order):
+    """`coma_orient_accumulate_cone_ws_f32`: normalising the normals once per (sample, vertex) into a workspace (what `ops.orient_accumulate`
+    does) gives bit-identical grids to normalising them inside the kernel for every pair — the same correctly rounded operations.
+    Includes degenerate normals (zero vectors -> NaN directions must poison the same bins)."""
+    from coma_b200 import _lib, ops, synth
+    from coma_b200._lib import _host3, _ptr, _stream, call
+    from oracle import oracle
+    H, O, N, S, sigma = 37, 29, 250, 45, 0.25
+    samples = synth.make_samples(S, H, O, seed=3) + synth.make_adversarial_samples(H, O, 0.03, seed=4)
+    hn = np.stack([s["human_normals"] for s in samples]).astype(np.float32) * np.float32(1.7)   # not unit length: the normalisation matters
+    on = np.stack([s["obj_normals"] for s in samples]).astype(np.float32) * np.float32(0.3)
+    hn[1, 5] = 0.0
+    St = len(samples)
+    grid = oracle.fibonacci_sphere(N)
+    gt, perm = _t(grid, dev, torch.float64), ops.bin_patches(grid, dev)
+    hn_t, on_t = _t(hn, dev), _t(on, dev)
+    out = []
+    for use_ws in (False, True):
+        PH, PO = torch.zeros((H, O, N), device=dev), torch.zeros((H, O, N), device=dev)
+        ws = torch.empty(3 * St * (H + O), dtype=torch.float32, device=dev) if use_ws else None
+        with torch.cuda.device(dev):
+            call("coma_orient_accumulate_cone_ws_f32", _ptr(hn_t), _ptr(on_t), St, H, O, _ptr(gt), N, sigma, 1e-10, _host3([0, 0, 1]), _host3([0, 1, 0]),
+                 _ptr(perm), 32, ops.SUM_ORDERS[order], _ptr(PH), _ptr(PO), _ptr(ws), _stream())
+        assert _lib.last_kernel() == "orient_accumulate_cone_kernel"
+        out.append((PH, PO))
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+        assert torch.equal(torch.isnan(a), torch.isnan(b))
+    assert bool(torch.isnan(out[0][0][5]).any())
+
+
 # --------------------------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("name", ["occupancy_small", "occupancy_s30", "cuda_occupancy_small"])
 def test_occupancy_golden(dev, golden_dir, name):
