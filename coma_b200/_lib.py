@@ -14,6 +14,7 @@ _f32p = _c.POINTER(_c.c_float)
 
 # name -> argtypes, exactly the prototypes of include/coma_b200.h (device pointers travel as void*)
 SIGNATURES = {
+    "coma_layernorm_stats_f16": [_vp, _i64, _i64, _i64, _f32, _vp, _vp],
     "coma_host_stage_rows_f64_f32": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp],
     "coma_host_rows_equal_f64": [_vp, _i64, _vp, _i64, _vp],
     "coma_vertex_normals_f64": [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _f64, _vp, _vp],
@@ -77,7 +78,8 @@ class GemmArgs(ctypes.Structure):
                 ("out_f16", _vp), ("out_f32", _vp), ("ldo", _i64), ("o_s1", _i64), ("o_s2", _i64),
                 ("residual", _vp), ("bias", _vp), ("bias_rows", _vp), ("rows_per_bias", _i64), ("bias_rows_ld", _i64),
                 ("M", _i64), ("N", _i64), ("K", _i64), ("nb1", _i64), ("nb2", _i64),
-                ("alpha", _f32), ("act", _int), ("workspace", _vp), ("workspace_elems", _i64), ("geglu", _int)]
+                ("alpha", _f32), ("act", _int), ("workspace", _vp), ("workspace_elems", _i64), ("geglu", _int),
+                ("ln_row_stats", _vp), ("ln_c1", _vp), ("ln_partials_in", _vp), ("ln_eps", _f32), ("ln_partials_out", _vp)]
 
 _LIB = None
 

@@ -155,6 +155,12 @@ struct GemmEpilogue {
     int act;                 // 0 = identity, 1 = SiLU, 2 = quick-GELU x*sigmoid(1.702x)
     int nb1;                 // extent of batch dim 1 (blockIdx.z = b2 * nb1 + b1)
     int tma;                 // 1: fp16 output (and residual) move as 32x32 boxes through shared memory + TMA (tmO / tmR)
+    const float2 *ln_rows;   // or null: per-row (rstd, -rstd * mean) of a LayerNorm folded into W (W' = W * gamma): out = rstd * acc + (-rstd * mean) * ln_c1[n] + bias[n]
+    const float *ln_c1;      // [N] column sums of W' (with ln_rows / ln_part_in)
+    const float2 *ln_part_in;  // or null: instead of ln_rows, per-(row, 32-column block) (sum, sumsq) of the input row left by its PRODUCER's
+    int ln_parts;              //   epilogue (ln_part_out): [M, ln_parts] float2, ln_parts = K / 32; the row statistics are formed here
+    float ln_eps;
+    float2 *ln_part_out;     // or null: TMA form only — leave (sum, sumsq) of every 32-column panel of the rounded fp16 OUTPUT row: [M, N/32] float2
     float *stats;            // TMA form only, or null: [M/32, N, 2] per-(32-row block, column) sum / sum of squares of the fp16
                              // output, for the GroupNorm that consumes it (coma_groupnorm_from_stats_f32)
 };
@@ -402,6 +408,20 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
             const int P = (min(BN, N - n0) + PCOLS - 1) / PCOLS;
             const int brow_row = min(row0 + lane, M - 1) / ep.rows_per_bias;
             const float *brow = ep.bias_rows ? ep.bias_rows + (size_t)brow_row * ep.bias_rows_ld : nullptr;
+            float2 ln = ep.ln_rows ? __ldg(ep.ln_rows + min(row0 + lane, M - 1)) : make_float2(alpha, 0.0f);   // folded LayerNorm: row scale, row offset
+            if (ep.ln_part_in) {   // statistics of this thread's input row from its producer's per-panel sums, added in panel order
+                const float2 *pp = ep.ln_part_in + (size_t)min(row0 + lane, M - 1) * ep.ln_parts;
+                float sx = 0.f, sq = 0.f;
+                for (int i2 = 0; i2 < ep.ln_parts; ++i2) {
+                    const float2 v2 = __ldg(pp + i2);
+                    sx += v2.x;
+                    sq += v2.y;
+                }
+                const float inv_c = 1.0f / (float)(32 * ep.ln_parts);
+                const float mean = sx * inv_c, var = fmaxf(fmaf(-mean, mean, sq * inv_c), 0.0f);
+                const float rstd = rsqrtf(var + ep.ln_eps);
+                ln = make_float2(rstd, -rstd * mean);
+            }
             const int acc = i & 1;
             mbar_wait(tmem_full + acc, (i >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -425,12 +445,17 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                     for (int j = 0; j < 32; j += 4) {
                         const float4 bv = bias ? __ldg(reinterpret_cast<const float4 *>(bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         const float4 bg = bias ? __ldg(reinterpret_cast<const float4 *>(bias + nb + 32 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float bvs[4] = {bv.x, bv.y, bv.z, bv.w}, bgs[4] = {bg.x, bg.y, bg.z, bg.w};
+                        float bvs[4] = {bv.x, bv.y, bv.z, bv.w}, bgs[4] = {bg.x, bg.y, bg.z, bg.w};
+                        if (ep.ln_c1) {   // folded LayerNorm: + (-rstd * mean) * column sum of W'
+                            const float4 cv = __ldg(reinterpret_cast<const float4 *>(ep.ln_c1 + nb + j)), cg2 = __ldg(reinterpret_cast<const float4 *>(ep.ln_c1 + nb + 32 + j));
+                            bvs[0] = fmaf(ln.y, cv.x, bvs[0]); bvs[1] = fmaf(ln.y, cv.y, bvs[1]); bvs[2] = fmaf(ln.y, cv.z, bvs[2]); bvs[3] = fmaf(ln.y, cv.w, bvs[3]);
+                            bgs[0] = fmaf(ln.y, cg2.x, bgs[0]); bgs[1] = fmaf(ln.y, cg2.y, bgs[1]); bgs[2] = fmaf(ln.y, cg2.z, bgs[2]); bgs[3] = fmaf(ln.y, cg2.w, bgs[3]);
+                        }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             // value and gate pass through fp16 like the unfused projection output did (same roundings)
-                            const float a = __half2float(__float2half_rn(fmaf(__uint_as_float(v[j + u]), alpha, bvs[u])));
-                            const float x = __half2float(__float2half_rn(fmaf(__uint_as_float(gt[j + u]), alpha, bgs[u])));
+                            const float a = __half2float(__float2half_rn(fmaf(__uint_as_float(v[j + u]), ln.x, bvs[u])));
+                            const float x = __half2float(__float2half_rn(fmaf(__uint_as_float(gt[j + u]), ln.x, bgs[u])));
                             f[j + u] = a * (0.5f * x * (1.0f + erff(x * 0.70710678118654752f)));
                         }
                     }
@@ -461,6 +486,13 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                         if (ok && brow) f[j] += __ldg(brow + nb + j);
                     }
                 }
+                if (ep.ln_c1) {   // folded LayerNorm: + (-rstd * mean) * column sum of W' (N % 32 == 0 is required with ln)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 c4 = __ldg(reinterpret_cast<const float4 *>(ep.ln_c1 + nb + j));
+                        f[j] = fmaf(ln.y, c4.x, f[j]); f[j + 1] = fmaf(ln.y, c4.y, f[j + 1]); f[j + 2] = fmaf(ln.y, c4.z, f[j + 2]); f[j + 3] = fmaf(ln.y, c4.w, f[j + 3]);
+                    }
+                }
                 if (has_res) {
                     mbar_wait(rb + buf, (g / NBUF) & 1);
 #pragma unroll
@@ -479,7 +511,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                     __syncwarp();
                 }
                 tmem_wait_ld(v);
-                const float2 alpha2 = make_float2(alpha, alpha);
+                const float2 alpha2 = make_float2(ln.x, ln.x);   // alpha, or the row's rstd when a LayerNorm is folded into W
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {  // packed FP32x2 FMAs
                     const float2 r = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), alpha2,
@@ -495,14 +527,24 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                     for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-1.702f * f[j]));
                 }
                 }  // !GEGLU
+                float2 ls = make_float2(0.f, 0.f), lq = make_float2(0.f, 0.f);   // LayerNorm partial sums of the ROUNDED row (ln_part_out)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint4 w;
                     __half2 *h = reinterpret_cast<__half2 *>(&w);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(f[c * 8 + 2 * u], f[c * 8 + 2 * u + 1]);
+                    for (int u = 0; u < 4; ++u) {
+                        h[u] = __floats2half2_rn(f[c * 8 + 2 * u], f[c * 8 + 2 * u + 1]);
+                        if (!GEGLU && ep.ln_part_out) {
+                            const float2 r2 = __half22float2(h[u]);
+                            ls = __fadd2_rn(ls, r2);
+                            lq = __ffma2_rn(r2, r2, lq);
+                        }
+                    }
                     *reinterpret_cast<uint4 *>(prow + ((c ^ sw) << 4)) = w;
                 }
+                if (!GEGLU && ep.ln_part_out && row0 + lane < M && nb + 32 <= N)
+                    ep.ln_part_out[(size_t)(row0 + lane) * (N >> 5) + (nb >> 5)] = make_float2(ls.x + ls.y, lq.x + lq.y);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) {
@@ -862,7 +904,7 @@ static bool split_eligible(const GemmEpilogue &ep, int64_t N, int64_t nbatch, co
 static GemmEpilogue split_epilogue(GemmEpilogue &ep, float *ws, int64_t N) {
     const GemmEpilogue fin = ep;
     ep.bias = nullptr; ep.bias_rows = nullptr; ep.residual = nullptr; ep.out16 = nullptr; ep.out32 = ws; ep.ldo = (int)N;
-    ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = 0; ep.tma = 0; ep.rows_per_bias = 1; ep.stats = nullptr;
+    ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = 0; ep.tma = 0; ep.rows_per_bias = 1; ep.stats = nullptr; ep.ln_rows = nullptr; ep.ln_c1 = nullptr; ep.ln_part_in = nullptr; ep.ln_part_out = nullptr; ep.ln_parts = 0; ep.ln_eps = 0.f;
     return fin;
 }
 
@@ -924,6 +966,21 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     ep.act = g->act;
     ep.nb1 = (int)nb1;
     ep.stats = nullptr;
+    ep.ln_rows = reinterpret_cast<const float2 *>(g->ln_row_stats);
+    ep.ln_c1 = g->ln_c1;
+    ep.ln_part_in = reinterpret_cast<const float2 *>(g->ln_partials_in);
+    ep.ln_parts = (int)(K / 32);
+    ep.ln_eps = g->ln_eps;
+    ep.ln_part_out = reinterpret_cast<float2 *>(g->ln_partials_out);
+    COMA_REQUIRE(!(g->ln_row_stats && g->ln_partials_in), "ln_row_stats and ln_partials_in are alternatives");
+    COMA_REQUIRE(!g->ln_partials_in || (K % 32 == 0 && (uintptr_t)g->ln_partials_in % 8 == 0 && g->ln_eps > 0.f), "ln_partials_in: needs K % 32 == 0 and ln_eps > 0");
+    COMA_REQUIRE(!g->ln_partials_out || (N % 32 == 0 && !g->geglu && nb1 * nb2 == 1 && g->out_f16 && !g->out_f32 && (uintptr_t)g->ln_partials_out % 8 == 0),
+                 "ln_partials_out: needs N % 32 == 0, fp16 output, no batching / GEGLU");
+    COMA_REQUIRE(!(g->ln_row_stats || g->ln_partials_in) == !g->ln_c1, "ln_row_stats / ln_partials_in and ln_c1 come together");
+    if (ep.ln_part_in) ep.ln_rows = nullptr;
+    COMA_REQUIRE(!(g->ln_row_stats || g->ln_partials_in) || (N % 32 == 0 && g->alpha == 1.0f && nb1 * nb2 == 1 && g->out_f16 && !g->out_f32 && (uintptr_t)g->ln_row_stats % 8 == 0 &&
+                                                              (uintptr_t)g->ln_c1 % 16 == 0),
+                 "folded LayerNorm: needs N % 32 == 0, alpha = 1, no batching, fp16 output, aligned vectors");
     if (g->geglu) {
         // fused GEGLU: W / bias rows interleaved in blocks of 32 (value, gate); output [M, N/2] fp16
         COMA_REQUIRE(N % 256 == 0 && g->out_f16 && !g->out_f32 && !g->residual && !g->bias_rows && g->act == 0 && nb1 * nb2 == 1,
@@ -936,7 +993,7 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
         COMA_REQUIRE(ep.tma == 1, "geglu: output not eligible for the TMA epilogue");
         return launch_gemm<256, false, true>(ta, tb, to, tr, (int)M, (int)N, (int)K, ep, 1, (cudaStream_t)stream, 1, 0);
     }
-    const bool can_split = split_eligible(ep, N, nb1 * nb2, g->workspace);
+    const bool can_split = split_eligible(ep, N, nb1 * nb2, g->workspace) && !ep.ln_c1 && !ep.ln_part_out;   // the finishing pass does not know the folded LayerNorm
     const GemmPlan plan = plan_gemm((M + G_BM - 1) / G_BM, N, K, nb1 * nb2, M, can_split, g->workspace_elems);
     const int bn = plan.bn;
     CUtensorMap ta, tb, to, tr;
@@ -945,6 +1002,7 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     GemmEpilogue fin = ep;
     if (plan.ksplit > 1) fin = split_epilogue(ep, g->workspace, N);
     if (int e = setup_epilogue_maps(ep, &to, &tr, M, N, nb1, nb2)) return e;
+    COMA_REQUIRE(!(ep.ln_c1 || ep.ln_part_out) || ep.tma == 1, "folded LayerNorm: output not eligible for the TMA epilogue");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
     COMA_DISPATCH_BN(rc, bn, false, ta, tb, to, tr, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st, plan.ksplit, (long long)(M * N))
@@ -1022,6 +1080,12 @@ extern "C" int coma_conv3x3_strided_f16(const void *x, int64_t B, int64_t Hin, i
     ep.out16 = (__half *)out_f16; ep.out32 = out_f32; ep.ldo = (int)ldo; ep.o_s1 = 0; ep.o_s2 = 0; ep.alpha = 1.0f; ep.act = act;
     ep.nb1 = 1;
     ep.stats = nullptr;
+    ep.ln_rows = nullptr;
+    ep.ln_c1 = nullptr;
+    ep.ln_part_in = nullptr;
+    ep.ln_part_out = nullptr;
+    ep.ln_parts = 0;
+    ep.ln_eps = 0.f;
     // split-K needs every slab row < M to be written: tiles never straddle M except with an odd image count at TB > 1
     const bool can_split = split_eligible(ep, N, 1, workspace) && (TB == 1 || B % TB == 0);
     const GemmPlan plan = plan_gemm(m_tiles, N, K, 1, M, can_split, workspace_elems);

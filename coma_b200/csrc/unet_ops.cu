@@ -489,6 +489,51 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// LayerNorm statistics only: out[row] = (rstd, -rstd * mean) — what the GEMM epilogue needs to apply a LayerNorm that was folded into
+// its weights (gemm.cu, `ln_row_stats`): y = rstd * (x W'^T) - rstd * mean * c1 + c2. Same arithmetic as layernorm_vec_kernel (row held in
+// registers, centred variance), no output tensor.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+    layernorm_stats_kernel(const __half *__restrict__ x, long long M, int C, long long ldx, float eps, float2 *__restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nch = C / 8;
+    const __half *xr = x + row * ldx;
+    float v[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int ch = lane + 32 * j;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (ch < nch) raw = *reinterpret_cast<const uint4 *>(xr + ch * 8);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(h[t]);
+            v[j][2 * t] = f.x;
+            v[j][2 * t + 1] = f.y;
+            s += f.x + f.y;
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        if (lane + 32 * j < nch) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float d = v[j][t] - mean;
+                q = fmaf(d, d, q);
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (lane == 0) out[row] = make_float2(rstd, -rstd * mean);
+}
+
 // ---------------------------------------------------------------------------------------------- row softmax (in place)
 // Rows are read ONCE into registers, reduced with shuffles, and written once.
 //   L <= 1024 : one warp per row, up to 32 values per lane (cross-attention rows, L = 77, and the 16x16 / 32x32 levels)
@@ -825,6 +870,18 @@ extern "C" int coma_layernorm_f16(const void *x, int64_t M, int64_t C, int64_t l
     else
         launch_pdl(layernorm_kernel, grid, dim3(256), 0, st, (const __half *)x, M, (int)C, ldx, gamma, beta, eps, (__half *)y, ldy);
     return check_launch("layernorm_kernel");
+}
+
+extern "C" int coma_layernorm_stats_f16(const void *x, int64_t M, int64_t C, int64_t ldx, float eps, float *out, coma_stream_t stream) {
+    COMA_REQUIRE(x && out, "null pointer");
+    COMA_REQUIRE(M > 0 && C > 0 && ldx >= C && C % 8 == 0 && C <= 2048 && ldx % 8 == 0, "needs C % 8 == 0, C <= 2048, ldx % 8 == 0");
+    COMA_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)out % 8 == 0, "x must be 16-byte aligned, out 8-byte aligned");
+    const dim3 grid((unsigned)((M + 7) / 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 512) launch_pdl(layernorm_stats_kernel<2>, grid, dim3(256), 0, st, (const __half *)x, M, (int)C, ldx, eps, (float2 *)out);
+    else if (C <= 1024) launch_pdl(layernorm_stats_kernel<4>, grid, dim3(256), 0, st, (const __half *)x, M, (int)C, ldx, eps, (float2 *)out);
+    else launch_pdl(layernorm_stats_kernel<8>, grid, dim3(256), 0, st, (const __half *)x, M, (int)C, ldx, eps, (float2 *)out);
+    return check_launch("layernorm_stats_kernel");
 }
 
 extern "C" int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, coma_stream_t stream) {

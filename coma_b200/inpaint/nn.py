@@ -63,8 +63,29 @@ def splitk_workspace(device):
     return ws
 
 
-def gemm(a, w, bias=None, residual=None, act=0, out=None, out_dtype=F16, bias_rows=None, rows_per_bias=0, alpha=1.0, K=None):
-    """out[M,N] = act(alpha * a @ w[:, :K].T + bias + bias_rows[m // rows_per_bias] + residual). a [M,K] f16, w [N,>=K] f16."""
+def _set_ln(g, ln, M, N, K):
+    """ln = (stats, c1): stats [M, 2] f32 = layernorm_stats(a), or [M, K/32, 2] f32 = the per-panel sums the producer of `a` left (ln_out)."""
+    st, c1 = ln
+    assert st.dtype == F32 and st.is_contiguous() and c1.dtype == F32 and c1.numel() == N and st.shape[0] == M
+    if st.dim() == 3:
+        assert st.shape[1] * 32 == K and st.shape[2] == 2
+        g.ln_partials_in, g.ln_eps = st.data_ptr(), 1e-5
+    else:
+        assert st.shape == (M, 2)
+        g.ln_row_stats = st.data_ptr()
+    g.ln_c1 = c1.data_ptr()
+
+
+def ln_partials(M, N, device):
+    """Buffer for gemm(..., ln_out=): (sum, sumsq) of every 32-column panel of every output row."""
+    assert N % 32 == 0
+    return torch.empty((M, N // 32, 2), dtype=F32, device=device)
+
+
+def gemm(a, w, bias=None, residual=None, act=0, out=None, out_dtype=F16, bias_rows=None, rows_per_bias=0, alpha=1.0, K=None, ln=None, ln_out=None):
+    """out[M,N] = act(alpha * a @ w[:, :K].T + bias + bias_rows[m // rows_per_bias] + residual). a [M,K] f16, w [N,>=K] f16.
+    ln = (stats, c1): a LayerNorm of `a` folded into w / bias (fold_layernorm; stats: see _set_ln). ln_out = ln_partials(M, N) buffer: the
+    epilogue leaves the LayerNorm partial sums of the OUTPUT rows for the next folded projection (no statistics kernel at all)."""
     M = a.shape[0]
     K = a.shape[1] if K is None else K
     N = w.shape[0]
@@ -84,6 +105,11 @@ def gemm(a, w, bias=None, residual=None, act=0, out=None, out_dtype=F16, bias_ro
         assert bias_rows.dtype == F32 and bias_rows.stride(1) == 1 and bias_rows.shape[1] == N and rows_per_bias > 0
         g.bias_rows, g.rows_per_bias, g.bias_rows_ld = bias_rows.data_ptr(), rows_per_bias, bias_rows.stride(0)
     g.alpha, g.act = alpha, act
+    if ln is not None:
+        _set_ln(g, ln, M, N, K)
+    if ln_out is not None:
+        assert ln_out.shape == (M, N // 32, 2) and ln_out.dtype == F32 and ln_out.is_contiguous() and out.dtype == F16
+        g.ln_partials_out = ln_out.data_ptr()
     ws = splitk_workspace(a.device)
     g.workspace, g.workspace_elems = ws.data_ptr(), ws.numel()
     with torch.cuda.device(a.device):
@@ -247,6 +273,35 @@ def layernorm(x2d, gamma, beta, eps=1e-5):
     return y
 
 
+# LayerNorm folded into the projection that consumes it (gamma into the weights, beta into the bias, (rstd, -rstd * mean) applied per row in
+# the GEMM epilogue; statistics from layernorm_stats or from the producer GEMM's epilogue). Built, parity-tested — and OFF by default:
+# measured on the SD-1.5 UNet (B200, tools/unet_breakdown.py) the 48 LayerNorm launches (0.63 ms) disappear but the short-K projections are
+# epilogue-bound, and the extra epilogue work costs as much: 9.92 ms unfused, 9.79 ms with the statistics kernel, 9.98 ms with producer-side
+# statistics. COMA_FUSED_LN=1 turns it on.
+FUSED_LN = os.environ.get("COMA_FUSED_LN") == "1"
+
+
+def layernorm_stats(x2d, eps=1e-5):
+    """[M, 2] f32 = (rstd, -rstd * mean) per row: the per-row inputs of a LayerNorm folded into the consuming GEMM (no normalised tensor)."""
+    st = torch.empty((x2d.shape[0], 2), dtype=F32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        call("coma_layernorm_stats_f16", x2d.data_ptr(), x2d.shape[0], x2d.shape[1], x2d.stride(0), float(eps), st.data_ptr(), _stream())
+    return st
+
+
+def fold_layernorm(w, b, gamma, beta):
+    """LayerNorm(x) @ w.T + b  ==  rstd * (x @ w'.T) - rstd * mean * c1 + b'  with w' = w * gamma, c1 = row sums of w' (as stored: fp16),
+    b' = w @ beta + b. fp32 host tensors in -> (w' fp32 [N,K], b' fp32 [N]); c1 is taken from the prepared fp16 weight (ln_c1)."""
+    w, gamma, beta = w.float().reshape(w.shape[0], -1), gamma.float(), beta.float()
+    b2 = w @ beta + (b.float() if b is not None else 0.0)
+    return w * gamma[None, :], b2
+
+
+def ln_c1(w_prepared):
+    """Column-sum vector of a prepared (fp16, zero-padded) folded weight: c1[n] = sum_k w'[n, k] in fp32."""
+    return w_prepared.float().sum(1).contiguous()
+
+
 def prep_geglu(w, b, device):
     """Feed-forward projection [2F, C] (rows: F values, then F gates) -> rows interleaved in blocks of 32 (32 values, their 32
     gates, ...) so one 64-column accumulator group of the GEMM holds value and gate of the same features (fused GEGLU
@@ -259,8 +314,8 @@ def prep_geglu(w, b, device):
     return prep_linear(w[src], device), prep_vec(b[src], device)
 
 
-def gemm_geglu(a, w_il, b_il):
-    """out[M, F] = value * gelu(gate) of the interleaved projection (see prep_geglu), one kernel."""
+def gemm_geglu(a, w_il, b_il, ln=None):
+    """out[M, F] = value * gelu(gate) of the interleaved projection (see prep_geglu), one kernel. ln: as in gemm."""
     M, K = a.shape
     N = w_il.shape[0]
     out = torch.empty((M, N // 2), dtype=F16, device=a.device)
@@ -268,6 +323,8 @@ def gemm_geglu(a, w_il, b_il):
     g.A, g.lda, g.W, g.ldw = a.data_ptr(), a.stride(0), w_il.data_ptr(), w_il.stride(0)
     g.M, g.N, g.K, g.nb1, g.nb2 = M, N, K, 1, 1
     g.out_f16, g.ldo, g.bias, g.alpha, g.geglu = out.data_ptr(), out.stride(0), _ptr(b_il), 1.0, 1
+    if ln is not None:
+        _set_ln(g, ln, M, N, K)
     with torch.cuda.device(a.device):
         call("coma_gemm_f16_ex", ctypes.addressof(g), _stream())
     return out
@@ -313,10 +370,12 @@ def project_kv(xkv, B, L, wkv, heads):
     return kv[:, :C], vt
 
 
-def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual, wqkv=None, wkv=None, kv=None):
+def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual, wqkv=None, wkv=None, kv=None, ln=None, ln_out=None):
     """softmax(Q K^T / sqrt(d)) V followed by the output projection (+bias +residual). xq [B*S, C], xkv [B*L, Ckv] f16.
     wqkv ([3C, C], self-attention) / wkv ([2C, Ckv]) are the row-concatenated projection weights: one GEMM instead of three /
-    two; kv = (k, vt) supplies precomputed keys / transposed values (see project_kv)."""
+    two; kv = (k, vt) supplies precomputed keys / transposed values (see project_kv). ln = (row_stats, c1, bias'): xq is the
+    UN-normalised input and the LayerNorm is folded into wqkv (self-attention) / wq (fold_layernorm); ln_out: see gemm (output projection)."""
+    lnk = dict(bias=ln[2], ln=(ln[0], ln[1])) if ln is not None else {}
     dev = xq.device
     C = wo.shape[1] if wq is None else wq.shape[0]
     d = C // heads
@@ -327,10 +386,10 @@ def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual, wqkv=None, 
         in_place_v = not (L <= 128 and d <= 64)
         v = vt = None
         if kv is not None:
-            q = gemm(xq, wq)
+            q = gemm(xq, wq, **lnk)
             k, vt = kv
         elif wqkv is not None:
-            qkv = gemm(xq, wqkv)
+            qkv = gemm(xq, wqkv, **lnk)
             q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
         else:
             q = gemm(xq, wq)
@@ -352,7 +411,7 @@ def attention(xq, xkv, B, S, L, wq, wk, wv, wo, bo, heads, residual, wqkv=None, 
                     call("coma_transpose_heads_f16", v.data_ptr(), B, L, heads, d, v.stride(0), vt.data_ptr(), Lp, _stream())
                 call("coma_attention_fwd_f16", q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, heads, S, L, d, q.stride(0), k.stride(0), Lp,
                      float(d ** -0.5), o.data_ptr(), o.stride(0), _stream())
-        return gemm(o, wo, bo, residual)
+        return gemm(o, wo, bo, residual, ln_out=ln_out)
     if wq is None:
         wq, wk, wv = wqkv[:C], wqkv[C:2 * C], wqkv[2 * C:]
     elif wk is None:

@@ -53,6 +53,26 @@ class UNet:
             self.p[a + ".to_kv.weight"] = torch.cat([self.p.pop(a + ".to_k.weight"), self.p.pop(a + ".to_v.weight")], 0).contiguous()
             self.cross_layers.append(a)
 
+        # LayerNorm folded into the projection that consumes it (norm1 -> q|k|v, norm2 -> cross-attention q, norm3 -> feed-forward): the
+        # weights absorb gamma, the bias absorbs beta, and the GEMM epilogue applies the per-row (rstd, -rstd * mean) — no normalised
+        # tensor between LayerNorm and projection (48 passes per forward). Built from the fp32 checkpoint values.
+        self.ln_fold = {}
+        for k in [k for k in sd if k.endswith(".transformer_blocks.0.norm1.weight") and nn.FUSED_LN]:   # opt-in (see nn.FUSED_LN): no second copy of the weights otherwise
+            t = k[: -len(".norm1.weight")]
+            f32 = lambda name: sd[name].float()
+            w1 = torch.cat([f32(t + ".attn1.to_q.weight"), f32(t + ".attn1.to_k.weight"), f32(t + ".attn1.to_v.weight")], 0)
+            for tag, w, b, nrm in (("attn1", w1, None, "norm1"), ("attn2", f32(t + ".attn2.to_q.weight"), None, "norm2"),
+                                   ("ff", f32(t + ".ff.net.0.proj.weight"), f32(t + ".ff.net.0.proj.bias"), "norm3")):
+                wf, bf = nn.fold_layernorm(w, b, f32(f"{t}.{nrm}.weight"), f32(f"{t}.{nrm}.bias"))
+                if tag == "ff":
+                    fused = nn.prep_geglu(wf, bf, self.dev)
+                    if fused is None:
+                        continue
+                    wp, bp = fused
+                else:
+                    wp, bp = nn.prep_linear(wf, self.dev), nn.prep_vec(bf, self.dev)
+                self.ln_fold[f"{t}.{tag}"] = (wp, nn.ln_c1(wp), bp)
+
     # ------------------------------------------------------------------------------------------------
     def _resnet(self, x: Act, name, tproj):
         p, G = self.p, self.cfg["groups"]
@@ -77,20 +97,40 @@ class UNet:
         p, G, heads = self.p, self.cfg["groups"], self.cfg["heads"]
         B, S = x.B, x.H * x.W
         s, sh = nn.gn_affine(x, p[name + ".norm.weight"], p[name + ".norm.bias"], G, 1e-6)
-        h = nn.gemm(nn.affine_act(x, s, sh, 0).t, p[name + ".proj_in.weight"], p[name + ".proj_in.bias"])
         t = name + ".transformer_blocks.0"
-        n1 = nn.layernorm(h, p[t + ".norm1.weight"], p[t + ".norm1.bias"])
-        h = nn.attention(n1, n1, B, S, S, None, None, None, p[t + ".attn1.to_out.0.weight"], p[t + ".attn1.to_out.0.bias"], heads, h,
-                         wqkv=p[t + ".attn1.to_qkv.weight"])
-        n2 = nn.layernorm(h, p[t + ".norm2.weight"], p[t + ".norm2.bias"])
-        h = nn.attention(n2, ctx, B, S, L, p[t + ".attn2.to_q.weight"], None, None, p[t + ".attn2.to_out.0.weight"],
-                         p[t + ".attn2.to_out.0.bias"], heads, h, wkv=p[t + ".attn2.to_kv.weight"],
-                         kv=None if ctx_kv is None else ctx_kv[t + ".attn2"])
-        n3 = nn.layernorm(h, p[t + ".norm3.weight"], p[t + ".norm3.bias"])
-        if t + ".ff.geglu" in p:     # projection + GEGLU in one kernel (interleaved weight rows)
-            ff = nn.gemm_geglu(n3, *p[t + ".ff.geglu"])
+        fold = self.ln_fold if nn.FUSED_LN else {}
+        C, M = x.C, x.B * S
+        # LayerNorm statistics without a statistics kernel: every GEMM that writes the residual stream leaves per-panel (sum, sumsq) of its
+        # rounded output rows (ln_out), the folded projection that follows forms (rstd, -rstd * mean) from them in its epilogue
+        part = (lambda key: nn.ln_partials(M, C, x.t.device) if key in fold and C % 32 == 0 else None)
+        p1, p2, p3 = part(t + ".attn1"), part(t + ".attn2") if ctx_kv is not None else None, part(t + ".ff")
+        h = nn.gemm(nn.affine_act(x, s, sh, 0).t, p[name + ".proj_in.weight"], p[name + ".proj_in.bias"], ln_out=p1)
+        if p1 is not None:           # norm1 folded into the q|k|v projection
+            w, c1, b = fold[t + ".attn1"]
+            h = nn.attention(h, h, B, S, S, None, None, None, p[t + ".attn1.to_out.0.weight"], p[t + ".attn1.to_out.0.bias"], heads, h,
+                             wqkv=w, ln=(p1, c1, b), ln_out=p2)
         else:
-            ff = nn.geglu(nn.gemm(n3, p[t + ".ff.net.0.proj.weight"], p[t + ".ff.net.0.proj.bias"]))
+            n1 = nn.layernorm(h, p[t + ".norm1.weight"], p[t + ".norm1.bias"])
+            h = nn.attention(n1, n1, B, S, S, None, None, None, p[t + ".attn1.to_out.0.weight"], p[t + ".attn1.to_out.0.bias"], heads, h,
+                             wqkv=p[t + ".attn1.to_qkv.weight"], ln_out=p2)
+        if p2 is not None:
+            w, c1, b = fold[t + ".attn2"]
+            h = nn.attention(h, ctx, B, S, L, w, None, None, p[t + ".attn2.to_out.0.weight"], p[t + ".attn2.to_out.0.bias"], heads, h,
+                             wkv=p[t + ".attn2.to_kv.weight"], kv=ctx_kv[t + ".attn2"], ln=(p2, c1, b), ln_out=p3)
+        else:
+            n2 = nn.layernorm(h, p[t + ".norm2.weight"], p[t + ".norm2.bias"])
+            h = nn.attention(n2, ctx, B, S, L, p[t + ".attn2.to_q.weight"], None, None, p[t + ".attn2.to_out.0.weight"],
+                             p[t + ".attn2.to_out.0.bias"], heads, h, wkv=p[t + ".attn2.to_kv.weight"],
+                             kv=None if ctx_kv is None else ctx_kv[t + ".attn2"], ln_out=p3)
+        if p3 is not None:           # norm3 folded into the GEGLU projection
+            w, c1, b = fold[t + ".ff"]
+            ff = nn.gemm_geglu(h, w, b, ln=(p3, c1))
+        else:
+            n3 = nn.layernorm(h, p[t + ".norm3.weight"], p[t + ".norm3.bias"])
+            if t + ".ff.geglu" in p:     # projection + GEGLU in one kernel (interleaved weight rows)
+                ff = nn.gemm_geglu(n3, *p[t + ".ff.geglu"])
+            else:
+                ff = nn.geglu(nn.gemm(n3, p[t + ".ff.net.0.proj.weight"], p[t + ".ff.net.0.proj.bias"]))
         h = nn.gemm(ff, p[t + ".ff.net.2.weight"], p[t + ".ff.net.2.bias"], residual=h)
         out = nn.gemm(h, p[name + ".proj_out.weight"], p[name + ".proj_out.bias"], residual=x.t)
         return Act(out, x.B, x.H, x.W)

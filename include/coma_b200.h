@@ -205,6 +205,17 @@ typedef struct coma_gemm_args {
                                                 * too few output tiles for 148 SMs; NULL = never split */
     int geglu; /* 1: W / bias rows are interleaved in blocks of 32 (32 value rows, their 32 gate rows, ...) and the epilogue writes
                 * out[M, N/2] = value * gelu(gate) (diffusers GEGLU fused into its projection); needs N % 256 == 0 */
+    /* LayerNorm folded into the projection that consumes it (diffusers BasicTransformerBlock: norm1 -> to_q/k/v, norm2 -> to_q, norm3 ->
+     * ff): A is the UN-normalised input, W = W0 * gamma (column-wise), bias = W0 beta + b0, ln_c1[n] = sum_k W[n,k], ln_row_stats[m] =
+     * (rstd_m, -rstd_m * mean_m) from coma_layernorm_stats_f16; the epilogue computes rstd * acc - rstd * mean * c1 + bias. Both NULL: off. */
+    const float *ln_row_stats;
+    const float *ln_c1;
+    /* ... or without any statistics kernel: the GEMM that PRODUCES the LayerNorm's input leaves, per row and 32-column panel of its rounded
+     * fp16 output, (sum, sumsq) in ln_partials_out [M, N/32] float2; the consumer passes that buffer as ln_partials_in (+ ln_c1, ln_eps;
+     * K % 32 == 0) and forms (rstd, -rstd * mean) of its rows in the epilogue, adding the K/32 partials in panel order. */
+    const float *ln_partials_in;
+    float ln_eps;
+    float *ln_partials_out;
 } coma_gemm_args;
 COMA_API int coma_gemm_f16_ex(const coma_gemm_args *args, coma_stream_t stream);
 /* Host-only: the output-tile width (64 / 128 / 160 / 256) and split-K factor the scheduler picks for an M x N x K problem with
@@ -322,6 +333,9 @@ COMA_API int coma_im2col3x3_f16(const void *x, int64_t B, int64_t H, int64_t W, 
                                 coma_stream_t stream);
 COMA_API int coma_layernorm_f16(const void *x, int64_t M, int64_t C, int64_t ldx, const float *gamma, const float *beta, float eps,
                                 void *y, int64_t ldy, coma_stream_t stream);
+/* LayerNorm statistics only: out[m] = (rstd_m, -rstd_m * mean_m) as float2 — the per-row inputs of a LayerNorm folded into the consuming
+ * GEMM (coma_gemm_args.ln_row_stats). C % 8 == 0, C <= 2048. */
+COMA_API int coma_layernorm_stats_f16(const void *x, int64_t M, int64_t C, int64_t ldx, float eps, float *out, coma_stream_t stream);
 /* In-place softmax over the first L columns of each of R rows (row stride ld); columns [L, ld) are set to 0. */
 COMA_API int coma_softmax_rows_f16(void *s, int64_t R, int64_t L, int64_t ld, coma_stream_t stream);
 /* Same with a CAUSAL mask: the R rows form [S x L] matrices and row q of each only attends to columns <= q (the text-encoder

@@ -480,3 +480,52 @@ def test_conv3x3_halo_upsample(dev, B, H, W, C, N, fused):
     ref = F.conv2d(z, w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, N)
     sc = ref.abs().max().item()
     assert (out.float() - ref).abs().max().item() <= 2e-3 * sc, (out.float() - ref).abs().max().item() / sc
+
+
+@pytest.mark.parametrize("M,C,N,geglu", [(4096, 320, 960, False), (1000, 640, 640, False), (256, 1280, 1280, False), (4096, 320, 2560, True), (520, 1280, 10240, True)])
+def test_layernorm_folded_into_gemm(dev, M, C, N, geglu):
+    """LayerNorm folded into the projection that consumes it (`coma_layernorm_stats_f16` + `coma_gemm_args.ln_row_stats / ln_c1`, weights
+    from `nn.fold_layernorm`): against fp32 torch LayerNorm -> Linear (-> GEGLU) on the same fp16 input, and against the unfused kernels.
+    The input has a non-zero mean and per-row scale so that the rank-one correction term matters."""
+    from coma_b200.inpaint import nn
+    g = torch.Generator(device=dev).manual_seed(M + N)
+    x = (torch.randn((M, C), device=dev, generator=g) * (0.5 + torch.rand((M, 1), device=dev, generator=g)) + 0.7).half()
+    w = torch.randn((N, C), device=dev, generator=g) * C ** -0.5
+    b = torch.randn(N, device=dev, generator=g) * 0.1
+    gamma = 1.0 + 0.2 * torch.randn(C, device=dev, generator=g)
+    beta = 0.1 * torch.randn(C, device=dev, generator=g)
+    wf, bf = nn.fold_layernorm(w.cpu(), b.cpu(), gamma.cpu(), beta.cpu())
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
+    st = nn.layernorm_stats(x)
+    mean, var = x.float().mean(1), x.float().var(1, unbiased=False)
+    assert torch.allclose(st[:, 0], (var + 1e-5).rsqrt(), rtol=1e-5) and torch.allclose(st[:, 1], -mean * (var + 1e-5).rsqrt(), rtol=1e-4, atol=1e-5)
+    xn = nn.layernorm(x, gamma.contiguous(), beta.contiguous())
+    if geglu:
+        wp, bp = nn.prep_geglu(wf, bf, dev)
+        out = nn.gemm_geglu(x, wp, bp, ln=(st, nn.ln_c1(wp)))
+        val, gate = ref[:, : N // 2], ref[:, N // 2:]
+        ref = val * F.gelu(gate)
+        unfused = nn.gemm_geglu(xn, *nn.prep_geglu(w.cpu(), b.cpu(), dev))
+    else:
+        wp, bp = nn.prep_linear(wf, dev), nn.prep_vec(bf, dev)
+        out = nn.gemm(x, wp, bp, ln=(st, nn.ln_c1(wp)))
+        unfused = nn.gemm(xn, nn.prep_linear(w.cpu(), dev), nn.prep_vec(b.cpu(), dev))
+    sc = ref.abs().max().item()
+    e_f, e_u = (out.float() - ref).abs().max().item() / sc, (unfused.float() - ref).abs().max().item() / sc
+    assert e_f <= 3e-3 and e_f <= 2.0 * e_u + 1e-3, (e_f, e_u)      # as accurate as normalising to fp16 first
+    rms = lambda a: ((a.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rms(out) <= 1.5 * rms(unfused) + 1e-4, (rms(out), rms(unfused))
+    # statistics from the PRODUCER's epilogue instead of the statistics kernel: x2 = x @ w0.T + b0 + x (a residual-stream update) leaves
+    # per-panel (sum, sumsq) of its rounded rows; the folded projection forms (rstd, -rstd * mean) from them
+    w0 = nn.prep_linear((torch.randn((C, C), generator=torch.Generator().manual_seed(C)) * C ** -0.5 * 0.5), dev)
+    b0 = nn.prep_vec(torch.full((C,), 0.3), dev)
+    part = nn.ln_partials(M, C, dev)
+    x2 = nn.gemm(x, w0, b0, residual=x, ln_out=part)
+    assert torch.allclose(part[..., 0].sum(1), x2.float().sum(1), rtol=1e-5, atol=1e-3) and torch.allclose(part[..., 1].sum(1), x2.float().pow(2).sum(1), rtol=1e-5)
+    ref2 = F.layer_norm(x2.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
+    if geglu:
+        out2 = nn.gemm_geglu(x2, wp, bp, ln=(part, nn.ln_c1(wp)))
+        ref2 = ref2[:, : N // 2] * F.gelu(ref2[:, N // 2:])
+    else:
+        out2 = nn.gemm(x2, wp, bp, ln=(part, nn.ln_c1(wp)))
+    assert (out2.float() - ref2).abs().max().item() <= 3e-3 * ref2.abs().max().item()
