@@ -51,6 +51,27 @@ def _require_cuda(t, what):
                            f"(tensor is on '{t.device}')")
 
 
+class _RowGetter:
+    """Stager getter for one of the four per-sample arrays: `fill_many` converts a whole chunk (fp64 -> fp32, the rounding of
+    utils/misc.py:47-54) with one multi-threaded call of the library's host helper when every array is a plain float64 [*, 3] array,
+    and falls back to the per-sample numpy copy otherwise (other dtypes, non-contiguous views)."""
+
+    def __init__(self, samples, key, rows):
+        self.samples, self.key, self.rows = samples, key, rows
+
+    def __call__(self, i):
+        return self.samples[i][self.key][self.rows]
+
+    def fill_many(self, view, s0, n):
+        from .staging import stage_rows_f64
+        arrs = [self.samples[s0 + j][self.key] for j in range(n)]
+        row0 = self.rows.start or 0
+        ok = all(isinstance(a, np.ndarray) for a in arrs) and stage_rows_f64(arrs, view[:n], row0=row0) is not None
+        if not ok:
+            for j in range(n):
+                np.copyto(view[j], np.asarray(arrs[j])[self.rows], casting="same_kind")
+
+
 class ComA:
     # Which device's arithmetic of the reference the bit-exact contact count follows: torch's CUDA reduction adds the squared
     # distance as (x2+z2)+y2, its CPU reduction as (x2+y2)+z2 (include/coma_b200.h). The reference's production runs are
@@ -156,8 +177,8 @@ class ComA:
             # K2 / K3 of the previous one run; a K3 launch re-reads the grids, which costs ~3 % at 128 samples per launch
             chunk = min(chunk, 128, (len(samples) + 31) // 32 * 32)
         stager = BatchStager(dict(hv=Hs, hn=Hs, ov=O, on=O), chunk, self.significant_contact_count.device)
-        getters = dict(hv=lambda i: samples[i]["human_verts"][rows], hn=lambda i: samples[i]["human_normals"][rows],
-                       ov=lambda i: samples[i]["obj_verts"], on=lambda i: samples[i]["obj_normals"])
+        getters = dict(hv=_RowGetter(samples, "human_verts", rows), hn=_RowGetter(samples, "human_normals", rows),
+                       ov=_RowGetter(samples, "obj_verts", slice(None)), on=_RowGetter(samples, "obj_normals", slice(None)))
         total = 0
         if exchange:
             for n, b in exchanged_batches(stager, getters, len(samples), group):

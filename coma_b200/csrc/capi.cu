@@ -1,6 +1,9 @@
 // Library-level entry points: version, thread-local error string, launch counter.
+#include <algorithm>
 #include <atomic>
 #include <stdarg.h>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -31,20 +34,36 @@ int coma_host_stage_rows_f64_f32(const double *const *src, const double *const *
         return COMA_E_BADARG;
     }
     int64_t mism = -1;
-    for (int64_t i = 0; i < n; ++i) {
-        const double *s = src[i] + row0 * 3;
-        float *d = dst + i * rows * 3;
-        if (sub) {
-            const double o0 = sub[i][0], o1 = sub[i][1], o2 = sub[i][2];
-            if (equal_to && mism < 0 && !(o0 == equal_to[0] && o1 == equal_to[1] && o2 == equal_to[2])) mism = i;
-            for (int64_t r = 0; r < rows; ++r) {
-                d[3 * r + 0] = (float)(s[3 * r + 0] - o0);
-                d[3 * r + 1] = (float)(s[3 * r + 1] - o1);
-                d[3 * r + 2] = (float)(s[3 * r + 2] - o2);
+    if (sub && equal_to)
+        for (int64_t i = 0; i < n && mism < 0; ++i)
+            if (!(sub[i][0] == equal_to[0] && sub[i][1] == equal_to[1] && sub[i][2] == equal_to[2])) mism = i;
+    auto work = [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) {
+            const double *s = src[i] + row0 * 3;
+            float *d = dst + i * rows * 3;
+            if (sub) {
+                const double o0 = sub[i][0], o1 = sub[i][1], o2 = sub[i][2];
+                for (int64_t r = 0; r < rows; ++r) {
+                    d[3 * r + 0] = (float)(s[3 * r + 0] - o0);
+                    d[3 * r + 1] = (float)(s[3 * r + 1] - o1);
+                    d[3 * r + 2] = (float)(s[3 * r + 2] - o2);
+                }
+            } else {
+                for (int64_t e = 0; e < rows * 3; ++e) d[e] = (float)s[e];
             }
-        } else {
-            for (int64_t e = 0; e < rows * 3; ++e) d[e] = (float)s[e];
         }
+    };
+    // samples are independent: a few host threads for big chunks (the first chunk of a job is not hidden behind any kernel)
+    const int64_t bytes = n * rows * 3 * 8;
+    int nt = (int)std::min<int64_t>(8, std::min<int64_t>(n, bytes >> 20));   // >= 1 MiB of input per thread
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw > 0 && nt > (int)hw) nt = (int)hw;
+    if (nt <= 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+        for (auto &x : th) x.join();
     }
     if (first_mismatch) *first_mismatch = mism;
     return 0;
