@@ -113,6 +113,57 @@ __device__ __forceinline__ bool elect_one() {   // one lane of the (converged) w
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster (one TPC) own two adjacent 128-row tiles of the same N tile; the leader (cluster
+// rank 0) issues M256 x BN x K16 instructions that read each CTA's own A slab and its HALF of the W slab, so an SM's operand stream
+// (L2 -> shared memory, and the tensor core's shared-memory reads) per flop drops by a third at BN = 256. Same protocol as conv_halo.cu.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local, uint32_t rank) {   // shared::cluster address of a shared::cta address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {   // acquires what peer-CTA threads released with their remote arrive
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA load whose completion is signalled on the barrier at the same offset in the LEADER CTA of the pair (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_4d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z, int w) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y), "r"(z), "r"(w)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -214,8 +265,9 @@ struct TileSched {
 // rows, then their 32 gate rows: prep_geglu in nn.py), so accumulator columns [64p, 64p+32) / [64p+32, 64p+64) of a tile are
 // value / gate of the same 32 features and the epilogue writes value * gelu(gate) — half as many output columns, no
 // [M, 8C] intermediate and no separate GEGLU pass (diffusers GEGLU inside BasicTransformerBlock.ff).
-template <int BN, bool CONV, int STAGES, bool GEGLU = false>
-__global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
+// PAIR: launched as clusters of two CTAs; ts.total counts PAIR items (two adjacent M tiles x one N tile), ts.m_tiles pairs of M tiles.
+template <int BN, bool CONV, int STAGES, bool GEGLU = false, bool PAIR = false>
+__global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 1))
     gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, int M, int N, int K,
                        const GemmEpilogue ep, const ConvGeom cg, const TileSched ts) {
@@ -224,7 +276,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-    constexpr int A_BYTES = G_BM * G_BK * 2, B_BYTES = BN * G_BK * 2;
+    constexpr int A_BYTES = G_BM * G_BK * 2, B_BYTES = (PAIR ? BN / 2 : BN) * G_BK * 2;   // PAIR: this CTA's half of the W slab's rows
     constexpr int NBUF = gemm_epi_bufs(BN);
     constexpr int EPI_WARPS = gemm_epi_warps(BN);
     constexpr int PW = EPI_WARPS / 4;       // epilogue warps per TMEM lane quarter = panel stride of one warp
@@ -239,6 +291,8 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (K + G_BK - 1) / G_BK;
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const int t0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);  // power of two >= 2*BN
 
     if (warp == 0 && lane == 0) {
@@ -254,18 +308,23 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tmem_full + i, 1);
-            mbar_init(tmem_empty + i, 32 * EPI_WARPS);
+            mbar_init(tmem_empty + i, PAIR ? 2 * EPI_WARPS : 32 * EPI_WARPS);   // PAIR: one elected arrival per epilogue warp of both CTAs
         }
         for (int i = 0; i < EPI_WARPS * NBUF; ++i) mbar_init(res_full + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers must exist before anything signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     // PDL: everything above overlapped the previous kernel's tail; its results are visible after pdl_wait(). The trigger for
@@ -273,13 +332,14 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
     // shares its SMs for its whole duration with dependent CTAs parked in griddepcontrol.wait, and those cost issue slots
     // (measured: VAE decode 12.0 -> 14.8 ms with light-weight kernels behind every conv).
     pdl_wait();
+    const uint32_t empty0 = PAIR ? map_to_rank(smem_u32(tmem_empty), 0) : 0u;   // the leader's tmem_empty[0]
 
     // tile id -> coordinates
     auto decode = [&](int t, int &m0, int &n0, int &b1, int &b2, int &cx0, int &cy0, int &cb0) {
         t /= ts.ksplit;
         const int nt = t % ts.n_tiles;
         const int r = t / ts.n_tiles;
-        const int mt = r % ts.m_tiles, z = r / ts.m_tiles;
+        const int mt = PAIR ? 2 * (r % ts.m_tiles) + (int)rank : r % ts.m_tiles, z = r / ts.m_tiles;
         n0 = nt * BN;
         m0 = mt * G_BM;
         b1 = z % ep.nb1;
@@ -305,7 +365,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
     if (warp == 0) {
         int s = 0;
         uint32_t ph = 0;
-        for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+        for (int t = t0; t < ts.total; t += tstep) {
             int m0, n0, b1, b2, cx0, cy0, cb0;
             decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
             const int kb0 = (t % ts.ksplit) * ts.kb_per, kb1 = min(num_k, kb0 + ts.kb_per);
@@ -317,6 +377,17 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(empty + s, ph ^ 1);
                 if (elect_one()) {
+                    if (PAIR) {   // both CTAs' slabs complete on the LEADER's barrier (cta_group::2 loads)
+                        if (rank == 0) mbar_expect_tx(full + s, 2 * (A_BYTES + B_BYTES));
+                        if (CONV) {
+                            const int ty = (tap * 11) >> 5;
+                            tma_load_4d_pair(sA + s * A_BYTES, &tmA, full + s, cb * G_BK, cx0 * cg.stride + (tap - 3 * ty) - cg.pad,
+                                             cy0 * cg.stride + ty - cg.pad, cb0);
+                        } else {
+                            tma_load_4d_pair(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
+                        }
+                        tma_load_4d_pair(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0 + (int)rank * (BN / 2), b1, b2);
+                    } else {
                     mbar_expect_tx(full + s, A_BYTES + B_BYTES);
                     if (CONV) {
                         const int ty = (tap * 11) >> 5;   // tap / 3 for tap in [0, 9)
@@ -326,6 +397,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                         tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
                     }
                     tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0, b1, b2);
+                    }
                 }
                 __syncwarp();
                 if (CONV && ++cb == cg.cblocks) {
@@ -341,13 +413,14 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
         if (lane == 0) pdl_trigger();  // all of this CTA's operands are on their way: dependents may start launching
     } else if (warp == 1) {
         // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N>>3, M>>4
-        constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
+        constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * G_BM : G_BM) >> 4) << 24);
         const uint64_t da0 = umma_desc_sw128(smem_u32(sA)), db0 = umma_desc_sw128(smem_u32(sB));
         int s = 0, i = 0;
         uint32_t ph = 0;
-        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+        for (int t = t0; t < ts.total && rank == 0; t += tstep, ++i) {   // PAIR: the leader CTA issues for both
             const int acc = i & 1;
-            mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+            if (PAIR) mbar_wait_cluster(tmem_empty + acc, ((i >> 1) & 1) ^ 1);
+            else mbar_wait(tmem_empty + acc, ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
             const int kb0 = (t % ts.ksplit) * ts.kb_per, kb1 = min(num_k, kb0 + ts.kb_per);
@@ -356,11 +429,18 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint64_t da = da0 + (uint64_t)(s * (A_BYTES >> 4)), db = db0 + (uint64_t)(s * (B_BYTES >> 4));
+                    if (PAIR) {
+#pragma unroll
+                        for (int k = 0; k < G_BK / 16; ++k) umma_f16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                        umma_commit_pair(empty + s);   // multicast: frees the slab in both CTAs
+                        if (kb + 1 == kb1) umma_commit_pair(tmem_full + acc);
+                    } else {
 #pragma unroll
                     for (int k = 0; k < G_BK / 16; ++k)  // advance 32 B (16 fp16) inside the 128 B swizzle atom: +2 in 16-B units
                         umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
                     umma_commit(empty + s);  // frees the slab once the MMAs that read it have retired
                     if (kb + 1 == kb1) umma_commit(tmem_full + acc);
+                    }
                 }
                 __syncwarp();
                 if (++s == STAGES) {
@@ -386,7 +466,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
         uint8_t *my_row = ebuf + lane * 64;
         const int sw = (lane >> 1) & 3;  // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
         // load cursor (lane 0 only): walks the same (tile, panel) stream as the consumer loop, NBUF-1 panels ahead
-        int lt = blockIdx.x, lp = 0, lP = 0, lrow0 = 0, ln0 = 0, lb1 = 0, lb2 = 0;
+        int lt = t0, lp = 0, lP = 0, lrow0 = 0, ln0 = 0, lb1 = 0, lb2 = 0;
         uint32_t lg = 0;
         auto cursor_tile = [&]() {  // position the cursor on this warp's first panel of tile lt (skipping tiles without one)
             while (lt < ts.total) {
@@ -396,7 +476,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 ln0 = n0; lb1 = b1; lb2 = b2; lp = half;
                 lP = (min(BN, N - n0) + 31) >> 5;
                 if (lp < lP) break;
-                lt += gridDim.x;
+                lt += tstep;
             }
         };
         auto cursor_issue = [&]() {  // issue the residual load of the cursor's panel, then advance
@@ -407,7 +487,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
             ++lg;
             lp += PW;
             if (lp >= lP) {
-                lt += gridDim.x;
+                lt += tstep;
                 cursor_tile();
             }
         };
@@ -418,7 +498,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
         }
         uint32_t g = 0;
         int i = 0;
-        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+        for (int t = t0; t < ts.total; t += tstep, ++i) {
             int m0, n0, b1, b2, cx0, cy0, cb0;
             decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
             const int row0 = (CONV ? ((cb0 * cg.H + cy0) * cg.W + cx0) : m0) + q * 32;
@@ -602,7 +682,12 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tmem_empty + acc);
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(empty0 + (uint32_t)acc * 8);
+            } else {
+                mbar_arrive(tmem_empty + acc);
+            }
         }
         if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last stores' reads
     } else {
@@ -610,7 +695,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
         const int act = ep.act, ldo = ep.ldo;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         int i = 0;
-        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+        for (int t = t0; t < ts.total; t += tstep, ++i) {
             int m0, n0, b1, b2, cx0, cy0, cb0;
             decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
             const size_t obase = (size_t)b1 * ep.o_s1 + (size_t)b2 * ep.o_s2 + (size_t)(t % ts.ksplit) * ts.split_stride;
@@ -693,13 +778,21 @@ __global__ void __launch_bounds__(gemm_threads(BN), (BN <= 128 ? 2 : 1))
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tmem_empty + acc);  // 128 arrivals hand the accumulator back to the MMA warp
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(empty0 + (uint32_t)acc * 8);
+            } else {
+                mbar_arrive(tmem_empty + acc);  // 128 arrivals hand the accumulator back to the MMA warp
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (PAIR) {
+        cluster_sync_all();   // neither CTA may exit (or free tensor memory) while the pair's last instructions / remote arrivals are in flight
+        if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    } else {
+        __syncthreads();
+        if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -782,17 +875,22 @@ static int setup_epilogue_maps(GemmEpilogue &ep, CUtensorMap *to, CUtensorMap *t
     return 0;
 }
 
-template <int BN, bool CONV, bool GEGLU = false>
+template <int BN, bool CONV, bool GEGLU = false, bool PAIR = false>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr, int M, int N, int K,
                        const GemmEpilogue &ep, int nbatch, cudaStream_t st, int ksplit, long long split_stride,
                        const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
-    constexpr int STAGES = BN <= 128 ? 3 : (BN == 160 ? 5 : 4);  // short-K problems are TMA-latency bound: as many slabs in flight as shared memory allows
-    constexpr size_t smem = (size_t)STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + gemm_epi_warps(BN) * gemm_epi_bufs(BN) * E_PANEL_BYTES + 256;
+    // short-K problems are TMA-latency bound: as many slabs in flight as shared memory allows (PAIR: half a W slab per CTA)
+    constexpr int STAGES = PAIR ? (BN == 256 ? 6 : 7) : (BN <= 128 ? 3 : (BN == 160 ? 5 : 4));
+    // operand ring + epilogue panels + mbarriers (full / empty per stage, 2 + 2 accumulator barriers, one per residual panel) + the TMEM slot
+    constexpr size_t bars = (size_t)(2 * STAGES + 4 + gemm_epi_warps(BN) * gemm_epi_bufs(BN)) * 8 + 16;
+    constexpr size_t smem = (size_t)STAGES * (G_BM * G_BK * 2 + (PAIR ? BN / 2 : BN) * G_BK * 2) + gemm_epi_warps(BN) * gemm_epi_bufs(BN) * E_PANEL_BYTES +
+                            (bars > 256 ? 512 : 256);
+    static_assert(bars <= 512 && smem <= 232448, "shared-memory budget");
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
             return (int)e;
@@ -802,6 +900,13 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
     TileSched ts;
     ts.n_tiles = (N + BN - 1) / BN;
     ts.m_tiles = CONV ? m_tiles_conv : (M + G_BM - 1) / G_BM;
+    if (PAIR) {
+        if (ts.m_tiles % 2) {
+            set_error("gemm: CTA pairs need an even number of M tiles");
+            return COMA_E_BADARG;
+        }
+        ts.m_tiles /= 2;   // pairs of adjacent M tiles
+    }
     const int num_k = (K + G_BK - 1) / G_BK;
     ts.kb_per = (num_k + ksplit - 1) / ksplit;
     ts.ksplit = (num_k + ts.kb_per - 1) / ts.kb_per;  // every slice owns at least one K-slab
@@ -812,10 +917,42 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
         return COMA_E_BADARG;
     }
     ts.total = (int)total;
-    const int slots = kNumSM * (BN <= 128 ? 2 : 1);
-    const unsigned grid = (unsigned)(ts.total < slots ? ts.total : slots);
-    launch_pdl(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU>, dim3(grid), dim3(gemm_threads(BN)), smem, st, ta, tb, to, tr, M, N, K, ep, cg, ts);
+    if (!PAIR) {
+        const int slots = kNumSM * (BN <= 128 ? 2 : 1);
+        const unsigned grid = (unsigned)(ts.total < slots ? ts.total : slots);
+        launch_pdl(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR>, dim3(grid), dim3(gemm_threads(BN)), smem, st, ta, tb, to, tr, M, N, K, ep, cg, ts);
+    } else {
+        // clusters of two CTAs (one TPC each); programmatic dependent launch as everywhere else
+        const unsigned pairs = (unsigned)(ts.total < kNumSM / 2 ? ts.total : kNumSM / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(gemm_threads(BN));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        static const bool no_pdl = getenv("COMA_NO_PDL") != nullptr;
+        cfg.numAttrs = no_pdl ? 1 : 2;
+        cudaLaunchKernelEx(&cfg, gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR>, ta, tb, to, tr, M, N, K, ep, cg, ts);
+    }
     return check_launch("gemm_f16_tn_kernel");
+}
+
+// CTA pairs: 160- / 256-wide tiles with an even number of M tiles, a deep K and no K split. Measured on B200 (tools/gemm_bench.py,
+// interleaved A/B, forced on against forced off): 8192^3 894 -> 786 us (1230 -> 1399 TFLOP/s); K >= 1280 plain GEMMs at N = 320 / 640 /
+// 1280 / 10240 +10..13 %; K = 960 +3 %; K = 640 -1..6 %, K = 320 -10..12 % (a short main loop is epilogue-paced, and the pair's MMA
+// stream waits for the slower of two epilogues); split-K items (M = 512 convs) -17 %. COMA_GEMM_PAIR=0 / 1 forces (1: whenever the
+// tile shape allows).
+static bool gemm_use_pair(int bn, int64_t m_tiles, int64_t K, int ksplit) {
+    static const int env = getenv("COMA_GEMM_PAIR") ? atoi(getenv("COMA_GEMM_PAIR")) : -1;
+    if (env == 0 || (bn != 256 && bn != 160) || m_tiles % 2) return false;
+    return env == 1 || (K >= 16 * G_BK && ksplit == 1);
 }
 
 // ---- tile width and split-K factor from a small cost model (microseconds, calibrated on B200 with tools/gemm_bench.py) --
@@ -937,8 +1074,14 @@ static int launch_split_finish(const GemmEpilogue &fin, const float *ws, int ksp
     switch (bn) {                                                      \
         case 64: rc = launch_gemm<64, CONVF>(__VA_ARGS__); break;      \
         case 128: rc = launch_gemm<128, CONVF>(__VA_ARGS__); break;    \
-        case 160: rc = launch_gemm<160, CONVF>(__VA_ARGS__); break;    \
-        default: rc = launch_gemm<256, CONVF>(__VA_ARGS__); break;     \
+        case 160:                                                      \
+            if (pair) rc = launch_gemm<160, CONVF, false, true>(__VA_ARGS__); \
+            else rc = launch_gemm<160, CONVF>(__VA_ARGS__);            \
+            break;                                                     \
+        default:                                                       \
+            if (pair) rc = launch_gemm<256, CONVF, false, true>(__VA_ARGS__); \
+            else rc = launch_gemm<256, CONVF>(__VA_ARGS__);            \
+            break;                                                     \
     }
 
 }  // namespace coma
@@ -1006,17 +1149,20 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
         COMA_REQUIRE(g->ldo >= N / 2 && g->ldo % 8 == 0 && (uintptr_t)g->bias % 16 == 0, "geglu: bad output stride or bias alignment");
         CUtensorMap ta, tb, to, tr;
         if (int e = make_map(&ta, g->A, M, K, g->lda, G_BM, 1, 0, 1, 0)) return e;
-        if (int e = make_map(&tb, g->W, N, K, g->ldw, 256, 1, 0, 1, 0)) return e;
+        const bool pair = gemm_use_pair(256, (M + G_BM - 1) / G_BM, K, 1);
+        if (int e = make_map(&tb, g->W, N, K, g->ldw, pair ? 128 : 256, 1, 0, 1, 0)) return e;
         if (int e = setup_epilogue_maps(ep, &to, &tr, M, N / 2, 1, 1)) return e;
         COMA_REQUIRE(ep.tma == 1, "geglu: output not eligible for the TMA epilogue");
+        if (pair) return launch_gemm<256, false, true, true>(ta, tb, to, tr, (int)M, (int)N, (int)K, ep, 1, (cudaStream_t)stream, 1, 0);
         return launch_gemm<256, false, true>(ta, tb, to, tr, (int)M, (int)N, (int)K, ep, 1, (cudaStream_t)stream, 1, 0);
     }
     const bool can_split = split_eligible(ep, N, nb1 * nb2, g->workspace) && !ep.ln_c1 && !ep.ln_part_out;   // the finishing pass does not know the folded LayerNorm
     const GemmPlan plan = plan_gemm((M + G_BM - 1) / G_BM, N, K, nb1 * nb2, M, can_split, g->workspace_elems);
     const int bn = plan.bn;
+    const bool pair = gemm_use_pair(bn, (M + G_BM - 1) / G_BM, K, plan.ksplit);
     CUtensorMap ta, tb, to, tr;
     if (int e = make_map(&ta, g->A, M, K, g->lda, G_BM, nb1, g->a_s1, nb2, g->a_s2)) return e;
-    if (int e = make_map(&tb, g->W, N, K, g->ldw, bn, nb1, g->w_s1, nb2, g->w_s2)) return e;
+    if (int e = make_map(&tb, g->W, N, K, g->ldw, pair ? bn / 2 : bn, nb1, g->w_s1, nb2, g->w_s2)) return e;
     GemmEpilogue fin = ep;
     if (plan.ksplit > 1) fin = split_epilogue(ep, g->workspace, N);
     if (int e = setup_epilogue_maps(ep, &to, &tr, M, N, nb1, nb2)) return e;
@@ -1108,10 +1254,11 @@ extern "C" int coma_conv3x3_strided_f16(const void *x, int64_t B, int64_t Hin, i
     const bool can_split = split_eligible(ep, N, 1, workspace) && (TB == 1 || B % TB == 0);
     const GemmPlan plan = plan_gemm(m_tiles, N, K, 1, M, can_split, workspace_elems);
     const int bn = plan.bn;
+    const bool pair = gemm_use_pair(bn, m_tiles, K, plan.ksplit);
     CUtensorMap ta, tb, to, tr;
     COMA_REQUIRE(stride == 1 || TB == 1, "strided implicit conv: the output must have at least 128 pixels per image");
     if (int e = make_conv_map(&ta, x, B, Hin, Win, C, ldx, TW, TH, TB, stride)) return e;
-    if (int e = make_map(&tb, Wt, N, K, ldw, bn, 1, 0, 1, 0)) return e;
+    if (int e = make_map(&tb, Wt, N, K, ldw, pair ? bn / 2 : bn, 1, 0, 1, 0)) return e;
     GemmEpilogue fin = ep;
     if (plan.ksplit > 1) fin = split_epilogue(ep, workspace, N);
     if (int e = setup_epilogue_maps(ep, &to, &tr, M, N, 1, 1)) return e;

@@ -138,3 +138,43 @@ def test_gemm_geglu_fused(dev, M, C):
     torch.testing.assert_close(out.float(), ref, rtol=2e-3, atol=2e-3)
     unfused = nn.geglu(nn.gemm(x, nn.prep_linear(w, dev), b))
     torch.testing.assert_close(out.float(), unfused.float(), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,K,res", [(4096, 2560, 1280, True), (2048 + 256, 1280, 4096, False), (4096, 1024, 1024, True)])
+def test_gemm_cta_pair_default_policy(dev, M, N, K, res):
+    """160- / 256-wide tiles with an even number of M tiles and K >= 1024 run as CTA pairs (tcgen05.mma.cta_group::2, M = 256: each CTA stages
+    its own A slab and half of the W slab, the leader issues for both): same epilogue contract as the single-CTA kernel."""
+    from coma_b200._lib import call
+    from coma_b200.inpaint import nn
+    import ctypes
+    bn, ks = ctypes.c_int(0), ctypes.c_int(0)
+    call("coma_gemm_plan", M, N, K, 0, 0, ctypes.byref(bn), ctypes.byref(ks))
+    assert bn.value in (160, 256) and ks.value == 1 and ((M + 127) // 128) % 2 == 0
+    g = torch.Generator(device=dev).manual_seed(M + K)
+    a = (torch.randn((M, K), device=dev, generator=g) * 0.5).half()
+    w = (torch.randn((N, K), device=dev, generator=g) * K ** -0.5).half()
+    bias = torch.randn(N, device=dev, generator=g)
+    r = torch.randn((M, N), device=dev, generator=g).half() if res else None
+    ref = a.float() @ w.float().t() + bias
+    if res:
+        ref = ref + r.float()
+    out32 = nn.gemm(a, w, bias, r, out_dtype=torch.float32)
+    assert (out32 - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    out16 = torch.full((M + 2, N), 7.0, dtype=torch.float16, device=dev)
+    nn.gemm(a, w, bias, r, out=out16[:M])
+    torch.testing.assert_close(out16[:M].float(), ref, rtol=2e-3, atol=2e-3)
+    assert (out16[M:] == 7.0).all()
+
+
+def test_gemm_cta_pair_forced(dev):
+    """Every GEMM / implicit-conv parity case whose tile shape allows it, with COMA_GEMM_PAIR=1 (pairs regardless of K: short main loops,
+    split-K slabs, GEGLU, residual / statistics epilogues, strided and multi-image conv tiles). The switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, COMA_GEMM_PAIR="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_gemm.py"), os.path.join(here, "test_gpu_unet.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "(test_gemm and not cta_pair) or conv3x3_f16_out_tma or stride2 or from_conv_epilogue_stats or layernorm_folded"],
+                       env=env, cwd=os.path.dirname(here), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
