@@ -235,7 +235,13 @@ struct GemmEpilogue {
 };
 
 constexpr int E_PANEL_BYTES = 32 * 32 * 2;  // one epilogue panel: 32 rows x 32 fp16 columns, 64-byte rows, 64B-swizzled
-__host__ __device__ constexpr int gemm_epi_bufs(int BN) { return 2; }
+#ifndef COMA_GEMM_EPI_BUFS_160
+#define COMA_GEMM_EPI_BUFS_160 2
+#endif
+// staging panels per epilogue warp: the residual panel is prefetched NBUF - 1 panels ahead and NBUF - 1 stores may be in flight
+__host__ __device__ constexpr int gemm_epi_bufs(int BN) { return BN == 160 ? COMA_GEMM_EPI_BUFS_160 : 2; }
+// weight-stationary form: A ring depth next to WS resident W slabs
+__host__ __device__ constexpr int gemm_ws_stages(int BN, int WS) { return BN == 160 ? (gemm_epi_bufs(160) > 2 ? 3 : 4) : (BN == 192 ? 4 : 3); }
 
 // Implicit-GEMM 3x3 convolution (stride 1, pad 1) on an NHWC tensor: the A operand of K-slab (tap, channel block) is the
 // 128-pixel output tile shifted by (ky-1, kx-1), fetched by ONE 4-D TMA load whose out-of-image coordinates are
@@ -266,8 +272,12 @@ struct TileSched {
 // value / gate of the same 32 features and the epilogue writes value * gelu(gate) — half as many output columns, no
 // [M, 8C] intermediate and no separate GEGLU pass (diffusers GEGLU inside BasicTransformerBlock.ff).
 // PAIR: launched as clusters of two CTAs; ts.total counts PAIR items (two adjacent M tiles x one N tile), ts.m_tiles pairs of M tiles.
-template <int BN, bool CONV, int STAGES, bool GEGLU = false, bool PAIR = false>
-__global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 1))
+// WS > 0 ("weight-stationary", plain / GEGLU GEMMs with K <= 64 * WS): a CTA keeps ONE N tile for its whole life — its W tile (BN x K, all
+// WS slabs) is loaded into shared memory once and only A slabs stream through the ring. Short-K projections are bound by the L2 -> SM
+// operand stream (K = 320, BN = 160: 180 KB per tile, of which 100 KB is the same W tile again); CTA c owns N tile c % n_tiles and walks
+// the M tiles c / n_tiles, + gridDim / n_tiles, ... (ts.total = M tiles).
+template <int BN, bool CONV, int STAGES, bool GEGLU = false, bool PAIR = false, int WS = 0>
+__global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR && !WS) ? 2 : 1))
     gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, int M, int N, int K,
                        const GemmEpilogue ep, const ConvGeom cg, const TileSched ts) {
@@ -280,19 +290,22 @@ __global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 
     constexpr int NBUF = gemm_epi_bufs(BN);
     constexpr int EPI_WARPS = gemm_epi_warps(BN);
     constexpr int PW = EPI_WARPS / 4;       // epilogue warps per TMEM lane quarter = panel stride of one warp
+    constexpr int B_SLOTS = WS ? WS : STAGES;
     uint8_t *sA = smem, *sB = smem + STAGES * A_BYTES;
-    uint8_t *sE = sB + STAGES * B_BYTES;    // epilogue staging: EPI_WARPS warps x NBUF panels
+    uint8_t *sE = sB + B_SLOTS * B_BYTES;    // epilogue staging: EPI_WARPS warps x NBUF panels
     uint64_t *full = reinterpret_cast<uint64_t *>(sE + EPI_WARPS * NBUF * E_PANEL_BYTES);
     uint64_t *empty = full + STAGES;
     uint64_t *tmem_full = empty + STAGES;   // [2]
     uint64_t *tmem_empty = tmem_full + 2;   // [2]
     uint64_t *res_full = tmem_empty + 2;    // [EPI_WARPS][NBUF]: residual panel landed
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_full + EPI_WARPS * NBUF);
+    uint64_t *w_full = res_full + EPI_WARPS * NBUF;   // WS: the resident W tile has landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (K + G_BK - 1) / G_BK;
     const uint32_t rank = PAIR ? cluster_rank() : 0u;
-    const int t0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int t0 = WS ? (int)blockIdx.x / ts.n_tiles : (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
+    const int tstep = WS ? (int)gridDim.x / ts.n_tiles : (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x);
     constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);  // power of two >= 2*BN
 
     if (warp == 0 && lane == 0) {
@@ -311,6 +324,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 
             mbar_init(tmem_empty + i, PAIR ? 2 * EPI_WARPS : 32 * EPI_WARPS);   // PAIR: one elected arrival per epilogue warp of both CTAs
         }
         for (int i = 0; i < EPI_WARPS * NBUF; ++i) mbar_init(res_full + i, 1);
+        mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -337,8 +351,8 @@ __global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 
     // tile id -> coordinates
     auto decode = [&](int t, int &m0, int &n0, int &b1, int &b2, int &cx0, int &cy0, int &cb0) {
         t /= ts.ksplit;
-        const int nt = t % ts.n_tiles;
-        const int r = t / ts.n_tiles;
+        const int nt = WS ? (int)blockIdx.x % ts.n_tiles : t % ts.n_tiles;
+        const int r = WS ? t : t / ts.n_tiles;
         const int mt = PAIR ? 2 * (r % ts.m_tiles) + (int)rank : r % ts.m_tiles, z = r / ts.m_tiles;
         n0 = nt * BN;
         m0 = mt * G_BM;
@@ -365,6 +379,11 @@ __global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 
     if (warp == 0) {
         int s = 0;
         uint32_t ph = 0;
+        if (WS && t0 < ts.total && elect_one()) {   // the W tile of this CTA's N tile: once
+            mbar_expect_tx(w_full, (uint32_t)num_k * B_BYTES);
+            for (int kb = 0; kb < num_k; ++kb) tma_load_4d(sB + kb * B_BYTES, &tmB, w_full, kb * G_BK, ((int)blockIdx.x % ts.n_tiles) * BN, 0, 0);
+        }
+        __syncwarp();
         for (int t = t0; t < ts.total; t += tstep) {
             int m0, n0, b1, b2, cx0, cy0, cb0;
             decode(t, m0, n0, b1, b2, cx0, cy0, cb0);
@@ -387,6 +406,9 @@ __global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 
                             tma_load_4d_pair(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
                         }
                         tma_load_4d_pair(sB + s * B_BYTES, &tmB, full + s, kb * G_BK, n0 + (int)rank * (BN / 2), b1, b2);
+                    } else if (WS) {
+                        mbar_expect_tx(full + s, A_BYTES);
+                        tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * G_BK, m0, b1, b2);
                     } else {
                     mbar_expect_tx(full + s, A_BYTES + B_BYTES);
                     if (CONV) {
@@ -417,6 +439,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 
         const uint64_t da0 = umma_desc_sw128(smem_u32(sA)), db0 = umma_desc_sw128(smem_u32(sB));
         int s = 0, i = 0;
         uint32_t ph = 0;
+        if (WS && t0 < ts.total) mbar_wait(w_full, 0);
         for (int t = t0; t < ts.total && rank == 0; t += tstep, ++i) {   // PAIR: the leader CTA issues for both
             const int acc = i & 1;
             if (PAIR) mbar_wait_cluster(tmem_empty + acc, ((i >> 1) & 1) ^ 1);
@@ -428,7 +451,7 @@ __global__ void __launch_bounds__(gemm_threads(BN), ((BN <= 128 && !PAIR) ? 2 : 
                 mbar_wait(full + s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
-                    const uint64_t da = da0 + (uint64_t)(s * (A_BYTES >> 4)), db = db0 + (uint64_t)(s * (B_BYTES >> 4));
+                    const uint64_t da = da0 + (uint64_t)(s * (A_BYTES >> 4)), db = db0 + (uint64_t)((WS ? kb : s) * (B_BYTES >> 4));
                     if (PAIR) {
 #pragma unroll
                         for (int k = 0; k < G_BK / 16; ++k) umma_f16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
@@ -875,22 +898,22 @@ static int setup_epilogue_maps(GemmEpilogue &ep, CUtensorMap *to, CUtensorMap *t
     return 0;
 }
 
-template <int BN, bool CONV, bool GEGLU = false, bool PAIR = false>
+template <int BN, bool CONV, bool GEGLU = false, bool PAIR = false, int WS = 0>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &to, const CUtensorMap &tr, int M, int N, int K,
                        const GemmEpilogue &ep, int nbatch, cudaStream_t st, int ksplit, long long split_stride,
                        const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
     // short-K problems are TMA-latency bound: as many slabs in flight as shared memory allows (PAIR: half a W slab per CTA)
-    constexpr int STAGES = PAIR ? (BN == 256 ? 6 : 7) : (BN <= 128 ? 3 : (BN == 160 ? 5 : 4));
-    // operand ring + epilogue panels + mbarriers (full / empty per stage, 2 + 2 accumulator barriers, one per residual panel) + the TMEM slot
-    constexpr size_t bars = (size_t)(2 * STAGES + 4 + gemm_epi_warps(BN) * gemm_epi_bufs(BN)) * 8 + 16;
-    constexpr size_t smem = (size_t)STAGES * (G_BM * G_BK * 2 + (PAIR ? BN / 2 : BN) * G_BK * 2) + gemm_epi_warps(BN) * gemm_epi_bufs(BN) * E_PANEL_BYTES +
-                            (bars > 256 ? 512 : 256);
+    constexpr int STAGES = WS ? gemm_ws_stages(BN, WS) : (PAIR ? (BN == 256 ? 6 : (gemm_epi_bufs(160) > 2 ? 6 : 7)) : (BN <= 128 ? 3 : (BN == 160 ? (gemm_epi_bufs(160) > 2 ? 4 : 5) : 4)));
+    // operand ring + epilogue panels + mbarriers (full / empty per stage, 2 + 2 accumulator barriers, one per residual panel, w_full) + the TMEM slot
+    constexpr size_t bars = (size_t)(2 * STAGES + 5 + gemm_epi_warps(BN) * gemm_epi_bufs(BN)) * 8 + 16;
+    constexpr size_t smem = (size_t)STAGES * G_BM * G_BK * 2 + (size_t)(WS ? WS : STAGES) * ((PAIR ? BN / 2 : BN) * G_BK * 2) +
+                            gemm_epi_warps(BN) * gemm_epi_bufs(BN) * E_PANEL_BYTES + (bars > 256 ? 512 : 256);
     static_assert(bars <= 512 && smem <= 232448, "shared-memory budget");
     static bool attr[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
             return (int)e;
@@ -917,10 +940,20 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
         return COMA_E_BADARG;
     }
     ts.total = (int)total;
-    if (!PAIR) {
+    if (WS) {
+        // one N tile per CTA: gridDim = n_tiles x (CTAs per N tile); the kernel walks ts.total = M tiles per N tile
+        if (nbatch != 1 || ts.ksplit != 1 || num_k > WS || ts.n_tiles > kNumSM) {
+            set_error("gemm: weight-stationary form needs one batch, no K split, K <= %d and at most %d N tiles", 64 * WS, kNumSM);
+            return COMA_E_BADARG;
+        }
+        int per = kNumSM / ts.n_tiles;
+        if (per > ts.m_tiles) per = ts.m_tiles;
+        ts.total = ts.m_tiles;
+        launch_pdl(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR, WS>, dim3((unsigned)(per * ts.n_tiles)), dim3(gemm_threads(BN)), smem, st, ta, tb, to, tr, M, N, K, ep, cg, ts);
+    } else if (!PAIR) {
         const int slots = kNumSM * (BN <= 128 ? 2 : 1);
         const unsigned grid = (unsigned)(ts.total < slots ? ts.total : slots);
-        launch_pdl(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR>, dim3(grid), dim3(gemm_threads(BN)), smem, st, ta, tb, to, tr, M, N, K, ep, cg, ts);
+        launch_pdl(gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR, WS>, dim3(grid), dim3(gemm_threads(BN)), smem, st, ta, tb, to, tr, M, N, K, ep, cg, ts);
     } else {
         // clusters of two CTAs (one TPC each); programmatic dependent launch as everywhere else
         const unsigned pairs = (unsigned)(ts.total < kNumSM / 2 ? ts.total : kNumSM / 2);
@@ -939,7 +972,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
         cfg.attrs = at;
         static const bool no_pdl = getenv("COMA_NO_PDL") != nullptr;
         cfg.numAttrs = no_pdl ? 1 : 2;
-        cudaLaunchKernelEx(&cfg, gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR>, ta, tb, to, tr, M, N, K, ep, cg, ts);
+        cudaLaunchKernelEx(&cfg, gemm_f16_tn_kernel<BN, CONV, STAGES, GEGLU, PAIR, WS>, ta, tb, to, tr, M, N, K, ep, cg, ts);
     }
     return check_launch("gemm_f16_tn_kernel");
 }
@@ -953,6 +986,16 @@ static bool gemm_use_pair(int bn, int64_t m_tiles, int64_t K, int ksplit) {
     static const int env = getenv("COMA_GEMM_PAIR") ? atoi(getenv("COMA_GEMM_PAIR")) : -1;
     if (env == 0 || (bn != 256 && bn != 160) || m_tiles % 2) return false;
     return env == 1 || (K >= 16 * G_BK && ksplit == 1);
+}
+
+// Weight-stationary form: plain GEMMs with K <= 320, at least two 160-wide... see the kernel comment. COMA_GEMM_WS=0 disables.
+static bool gemm_use_ws(int64_t M, int64_t N, int64_t K, int64_t nbatch) {
+    static const int env = getenv("COMA_GEMM_WS") ? atoi(getenv("COMA_GEMM_WS")) : -1;
+    if (env == 0 || nbatch != 1 || K > 5 * G_BK || N < 160 || (N % 160 != 0 && N % 160 < 96)) return false;
+    const int64_t n_tiles = (N + 159) / 160, m_tiles = (M + G_BM - 1) / G_BM;
+    if (n_tiles > kNumSM) return false;
+    const int64_t per = kNumSM / n_tiles;
+    return m_tiles >= 2 * per;   // every CTA amortises its W tile over at least two M tiles
 }
 
 // ---- tile width and split-K factor from a small cost model (microseconds, calibrated on B200 with tools/gemm_bench.py) --
@@ -1158,17 +1201,19 @@ extern "C" int coma_gemm_f16_ex(const coma_gemm_args *g, coma_stream_t stream) {
     }
     const bool can_split = split_eligible(ep, N, nb1 * nb2, g->workspace) && !ep.ln_c1 && !ep.ln_part_out;   // the finishing pass does not know the folded LayerNorm
     const GemmPlan plan = plan_gemm((M + G_BM - 1) / G_BM, N, K, nb1 * nb2, M, can_split, g->workspace_elems);
-    const int bn = plan.bn;
-    const bool pair = gemm_use_pair(bn, (M + G_BM - 1) / G_BM, K, plan.ksplit);
+    const bool ws = gemm_use_ws(M, N, K, nb1 * nb2);
+    const int bn = ws ? 160 : plan.bn;
+    const bool pair = !ws && gemm_use_pair(bn, (M + G_BM - 1) / G_BM, K, plan.ksplit);
     CUtensorMap ta, tb, to, tr;
     if (int e = make_map(&ta, g->A, M, K, g->lda, G_BM, nb1, g->a_s1, nb2, g->a_s2)) return e;
     if (int e = make_map(&tb, g->W, N, K, g->ldw, pair ? bn / 2 : bn, nb1, g->w_s1, nb2, g->w_s2)) return e;
     GemmEpilogue fin = ep;
-    if (plan.ksplit > 1) fin = split_epilogue(ep, g->workspace, N);
+    if (plan.ksplit > 1 && !ws) fin = split_epilogue(ep, g->workspace, N);
     if (int e = setup_epilogue_maps(ep, &to, &tr, M, N, nb1, nb2)) return e;
     COMA_REQUIRE(!(ep.ln_c1 || ep.ln_part_out) || ep.tma == 1, "folded LayerNorm: output not eligible for the TMA epilogue");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
+    if (ws) return launch_gemm<160, false, false, false, 5>(ta, tb, to, tr, (int)M, (int)N, (int)K, ep, 1, st, 1, (long long)(M * N));
     COMA_DISPATCH_BN(rc, bn, false, ta, tb, to, tr, (int)M, (int)N, (int)K, ep, (int)(nb1 * nb2), st, plan.ksplit, (long long)(M * N))
     if (rc == 0 && plan.ksplit > 1) rc = launch_split_finish(fin, g->workspace, plan.ksplit, M, N, st);
     return rc;
