@@ -36,7 +36,10 @@ constexpr int G_BM = 128, G_BK = 64;
 #ifndef COMA_GEMM_WIDE_EPI_WARPS
 #define COMA_GEMM_WIDE_EPI_WARPS 8
 #endif
-__host__ __device__ constexpr int gemm_epi_warps(int BN) { return BN <= 128 ? 4 : COMA_GEMM_WIDE_EPI_WARPS; }
+#ifndef COMA_GEMM_EPI_WARPS_160
+#define COMA_GEMM_EPI_WARPS_160 12
+#endif
+__host__ __device__ constexpr int gemm_epi_warps(int BN) { return BN <= 128 ? 4 : (BN == 160 ? COMA_GEMM_EPI_WARPS_160 : COMA_GEMM_WIDE_EPI_WARPS); }
 __host__ __device__ constexpr int gemm_threads(int BN) { return 64 + 32 * gemm_epi_warps(BN); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -903,7 +906,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const CUten
                        const GemmEpilogue &ep, int nbatch, cudaStream_t st, int ksplit, long long split_stride,
                        const ConvGeom &cg = ConvGeom{}, int m_tiles_conv = 0) {
     // short-K problems are TMA-latency bound: as many slabs in flight as shared memory allows (PAIR: half a W slab per CTA)
-    constexpr int STAGES = WS ? gemm_ws_stages(BN, WS) : (PAIR ? (BN == 256 ? 6 : (gemm_epi_bufs(160) > 2 ? 6 : 7)) : (BN <= 128 ? 3 : (BN == 160 ? (gemm_epi_bufs(160) > 2 ? 4 : 5) : 4)));
+    constexpr int STAGES = WS ? gemm_ws_stages(BN, WS) : (PAIR ? (BN == 256 ? 6 : ((gemm_epi_bufs(160) > 2 || gemm_epi_warps(160) > 8) ? 6 : 7)) : (BN <= 128 ? 3 : (BN == 160 ? ((gemm_epi_bufs(160) > 2 || gemm_epi_warps(160) > 8) ? 4 : 5) : 4)));
     // operand ring + epilogue panels + mbarriers (full / empty per stage, 2 + 2 accumulator barriers, one per residual panel, w_full) + the TMEM slot
     constexpr size_t bars = (size_t)(2 * STAGES + 5 + gemm_epi_warps(BN) * gemm_epi_bufs(BN)) * 8 + 16;
     constexpr size_t smem = (size_t)STAGES * G_BM * G_BK * 2 + (size_t)(WS ? WS : STAGES) * ((PAIR ? BN / 2 : BN) * G_BK * 2) +

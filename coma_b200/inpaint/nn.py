@@ -56,7 +56,7 @@ def splitk_workspace(device):
     """Per-device fp32 scratch for the deterministic split-K schedule (deep-K problems with too few tiles for 148 SMs).
     Allocated once, outside any CUDA-graph capture (the eager warm-up of `Graphed` runs first); launches on one stream
     serialise on it."""
-    key = torch.device(device).index
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)   # concurrent streams must not share slabs
     ws = _SPLITK_WS.get(key)
     if ws is None:
         ws = _SPLITK_WS[key] = torch.empty(SPLITK_WS_ELEMS, dtype=F32, device=device)
@@ -148,9 +148,10 @@ def gn_affine(x: Act, gamma, beta, groups, eps):
                  None, None, scale.data_ptr(), shift.data_ptr(), _stream())
         return scale, shift
     ws = torch.empty(2 * groups * (4 * 148 + x.B), dtype=torch.float64, device=dev)
-    cnt = _GN_COUNTERS.get(dev.index)
+    ckey = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    cnt = _GN_COUNTERS.get(ckey)
     if cnt is None or cnt.numel() < x.B:   # ticket counters: zero once, every launch leaves them zero
-        cnt = _GN_COUNTERS[dev.index] = torch.zeros(max(1024, x.B), dtype=torch.int32, device=dev)
+        cnt = _GN_COUNTERS[ckey] = torch.zeros(max(1024, x.B), dtype=torch.int32, device=dev)
     scale = torch.empty((x.B, x.C), dtype=F32, device=dev)
     shift = torch.empty((x.B, x.C), dtype=F32, device=dev)
     with torch.cuda.device(dev):
