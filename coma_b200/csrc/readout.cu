@@ -181,24 +181,43 @@ __global__ void __launch_bounds__(256)
 }
 
 // K5c pass 1: per-vertex sums of the occupancy grid (one CTA per vertex)
-__global__ void __launch_bounds__(256) occupancy_rowsum_kernel(const float *__restrict__ grids, long long V, float *__restrict__ sums) {
-    const float *row = grids + (size_t)blockIdx.x * V;
+__global__ void __launch_bounds__(256) occupancy_rowsum_kernel(const float *__restrict__ grids, long long V, float *__restrict__ sums,
+                                                                unsigned *__restrict__ flags_t, int HW, unsigned *__restrict__ dense) {
+    // flags_t (optional, 16-byte path only): [granule][HW] bit matrix, bit h of word (g, h / 32) = "granule g (32 consecutive float4 =
+    // 512 B) of row h holds a non-zero bit pattern"; dense: bit h = "row h must be rewritten in full" (its sum is not a positive
+    // finite number: 0 -> every voxel becomes NaN, negative -> -0.0). Pass 2 then touches only the flagged granules.
+    const int h = blockIdx.x;
+    const float *row = grids + (size_t)h * V;
     float s = 0.f;
     if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(grids) & 15) == 0) {  // 16-byte loads, four in flight per thread
         const float4 *r4 = reinterpret_cast<const float4 *>(row);
         const long long V4 = V >> 2;
+        const int lane = threadIdx.x & 31;
+        const unsigned hbit = 1u << (h & 31);
+        unsigned *fl = flags_t ? flags_t + (h >> 5) : nullptr;
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        long long i = threadIdx.x;
-        for (; i + 3 * 256 < V4; i += 4 * 256) {
+        long long ib = threadIdx.x - lane;  // the warp's first float4 of this step (warp-uniform): one granule per load
+        for (; ib + 3 * 256 + 32 <= V4; ib += 4 * 256) {
             float4 a[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) a[u] = __ldcs(r4 + i + u * 256);
+            for (int u = 0; u < 4; ++u) a[u] = __ldcs(r4 + ib + u * 256 + lane);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) s4[u] += (a[u].x + a[u].y) + (a[u].z + a[u].w);
+            for (int u = 0; u < 4; ++u) {
+                s4[u] += (a[u].x + a[u].y) + (a[u].z + a[u].w);
+                if (fl) {
+                    const unsigned nz = (__float_as_uint(a[u].x) | __float_as_uint(a[u].y)) | (__float_as_uint(a[u].z) | __float_as_uint(a[u].w));
+                    if (__any_sync(0xffffffffu, nz != 0u) && lane == 0) atomicOr(fl + (size_t)((ib + u * 256) >> 5) * HW, hbit);
+                }
+            }
         }
-        for (; i < V4; i += 256) {
-            const float4 a = __ldcs(r4 + i);
+        for (; ib < V4; ib += 256) {  // tail: the last granule of a row may be partial
+            const bool in = ib + lane < V4;
+            const float4 a = in ? __ldcs(r4 + ib + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
             s4[0] += (a.x + a.y) + (a.z + a.w);
+            if (fl) {
+                const unsigned nz = (__float_as_uint(a.x) | __float_as_uint(a.y)) | (__float_as_uint(a.z) | __float_as_uint(a.w));
+                if (__any_sync(0xffffffffu, nz != 0u) && lane == 0) atomicOr(fl + (size_t)(ib >> 5) * HW, hbit);
+            }
         }
         s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     } else
@@ -210,7 +229,8 @@ __global__ void __launch_bounds__(256) occupancy_rowsum_kernel(const float *__re
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += part[w];
-        sums[blockIdx.x] = t;
+        sums[h] = t;
+        if (dense && !(t > 0.f && t < INFINITY)) atomicOr(dense + (h >> 5), 1u << (h & 31));
     }
 }
 
@@ -273,6 +293,61 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (m[k] != 0) atomicMax(f + k, m[k]);
+}
+
+// K5c pass 2, sparse form (16-byte path): a vertex's hits cluster where the vertex moves, so most 512-byte granules of its row are
+// untouched zeros, and 0 / sum = +0 rewrites what is already there and adds nothing to the max.  A warp owns granule g for a slab of
+// rows and visits only the rows whose bit is set in pass 1's flag matrix (or in `dense`): read, normalise, write, fold into the
+// max — bit-identical grids and field, HBM traffic = one full read (pass 1) + the occupied granules instead of two reads + a write.
+constexpr int K5C_WARPS = 8;
+__global__ void __launch_bounds__(K5C_WARPS * 32)
+    occupancy_norm_max_sparse_kernel(float *__restrict__ grids, int H, long long V, const float *__restrict__ sums,
+                                     const uint8_t *__restrict__ sel, const unsigned *__restrict__ flags_t, int HW,
+                                     const unsigned *__restrict__ dense, long long G, float *__restrict__ field) {
+    const int lane = threadIdx.x & 31;
+    const long long g = (long long)blockIdx.x * K5C_WARPS + (threadIdx.x >> 5);
+    if (g >= G) return;  // warp-uniform
+    const long long V4 = V >> 2, v4 = g * 32 + lane;
+    const bool in = v4 < V4;
+    const int per = (HW + gridDim.y - 1) / gridDim.y;
+    const int w_lo = blockIdx.y * per, w_hi = min(HW, w_lo + per);
+    float4 *g4 = reinterpret_cast<float4 *>(grids);
+    const unsigned *fl = flags_t + (size_t)g * HW;
+    int m[4] = {0, 0, 0, 0};
+    auto fold = [&](float4 &a, float sm, bool use) {
+        a.x = __fdiv_rn(a.x, sm); a.y = __fdiv_rn(a.y, sm); a.z = __fdiv_rn(a.z, sm); a.w = __fdiv_rn(a.w, sm);
+        if (use) {
+            m[0] = max(m[0], __float_as_int(a.x) & 0x7fffffff); m[1] = max(m[1], __float_as_int(a.y) & 0x7fffffff);
+            m[2] = max(m[2], __float_as_int(a.z) & 0x7fffffff); m[3] = max(m[3], __float_as_int(a.w) & 0x7fffffff);
+        }
+    };
+    for (int hw = w_lo; hw < w_hi; ++hw) {
+        unsigned w = fl[hw] | dense[hw];  // warp-uniform
+        while (w) {
+            int hs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // up to four rows in flight
+                hs[u] = w ? hw * 32 + (__ffs(w) - 1) : -1;
+                w &= w - 1;   // 0 stays 0
+            }
+            float4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (hs[u] >= 0 && hs[u] < H && in) a[u] = __ldcs(g4 + (size_t)hs[u] * V4 + v4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (hs[u] >= 0 && hs[u] < H && in) {
+                    fold(a[u], sums[hs[u]], !sel || sel[hs[u]]);
+                    __stcs(g4 + (size_t)hs[u] * V4 + v4, a[u]);
+                }
+        }
+    }
+    if (in) {
+        int *f = reinterpret_cast<int *>(field) + 4 * v4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (m[k] != 0) atomicMax(f + k, m[k]);
+    }
 }
 
 __global__ void mark_selected_kernel(const long long *__restrict__ idx, long long n, int H, uint8_t *__restrict__ sel) {
@@ -352,18 +427,30 @@ extern "C" int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, co
     COMA_REQUIRE(H > 0 && V > 0 && H < (int64_t)1 << 24, "bad sizes");
     COMA_REQUIRE(!sel_idx || nsel >= 0, "bad selection");
     cudaStream_t st = (cudaStream_t)stream;
-    // scratch: H row sums (+ H selection flags) — stream-ordered allocation, freed on the same stream
-    float *sums = nullptr;
-    uint8_t *sel = nullptr;
-    cudaError_t e = cudaMallocAsync(&sums, sizeof(float) * H + (size_t)H, st);
+    static const char *const force = getenv("COMA_B200_K5C");  // A/B runs only ("dense" = round 1's two-read pass 2), read once per process
+    const bool vec = (V & 3) == 0 && (reinterpret_cast<uintptr_t>(grids) & 15) == 0 && (reinterpret_cast<uintptr_t>(field) & 15) == 0;
+    const bool sparse = vec && !(force && force[0] == 'd');
+    // scratch: H row sums, H selection flags, and for the sparse form the [granules][HW] flag matrix + HW dense-row words —
+    // stream-ordered allocation, freed on the same stream
+    const int64_t HW = (H + 31) / 32, G = (V / 4 + 31) / 32;
+    const size_t off_sel = sizeof(float) * (size_t)H;
+    const size_t off_flags = (off_sel + (size_t)H + 15) / 16 * 16;
+    const size_t flag_bytes = sparse ? sizeof(unsigned) * (size_t)HW * (size_t)(G + 1) : 0;
+    char *scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, off_flags + flag_bytes, st);
     if (e != cudaSuccess) {
         set_error("coma_occupancy_readout_f32: scratch allocation failed: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    occupancy_rowsum_kernel<<<(unsigned)H, 256, 0, st>>>(grids, V, sums);
+    float *sums = reinterpret_cast<float *>(scratch);
+    uint8_t *sel = nullptr;
+    unsigned *dense = sparse ? reinterpret_cast<unsigned *>(scratch + off_flags) : nullptr;   // [HW]
+    unsigned *flags_t = sparse ? dense + HW : nullptr;                                         // [G][HW]
+    if (sparse) cudaMemsetAsync(dense, 0, flag_bytes, st);
+    occupancy_rowsum_kernel<<<(unsigned)H, 256, 0, st>>>(grids, V, sums, flags_t, (int)HW, dense);
     int rc = check_launch("occupancy_rowsum_kernel");
     if (!rc && sel_idx) {
-        sel = reinterpret_cast<uint8_t *>(sums + H);
+        sel = reinterpret_cast<uint8_t *>(scratch + off_sel);
         cudaMemsetAsync(sel, 0, (size_t)H, st);
         if (nsel > 0) {
             mark_selected_kernel<<<(unsigned)((nsel + 255) / 256), 256, 0, st>>>((const long long *)sel_idx, nsel, (int)H, sel);
@@ -371,17 +458,24 @@ extern "C" int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, co
         }
     }
     if (!rc) {
-        const bool vec = (V & 3) == 0 && (reinterpret_cast<uintptr_t>(grids) & 15) == 0 && (reinterpret_cast<uintptr_t>(field) & 15) == 0;
-        const long long vb = ((vec ? V / 4 : V) + 255) / 256;
-        long long hsplit = (8LL * kNumSM + vb - 1) / vb;
-        hsplit = hsplit < 1 ? 1 : (hsplit > H ? H : (hsplit > 65535 ? 65535 : hsplit));
         cudaMemsetAsync(field, 0, sizeof(float) * (size_t)V, st);
-        if (vec)
-            occupancy_norm_max4_kernel<<<dim3((unsigned)vb, (unsigned)hsplit), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
-        else
-            occupancy_norm_max_kernel<<<dim3((unsigned)vb, (unsigned)hsplit), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
+        if (sparse) {
+            const long long gb = (G + K5C_WARPS - 1) / K5C_WARPS;
+            long long hsplit = (64LL * kNumSM + gb - 1) / gb;   // >= 64 CTAs per SM in total: only the occupied granules carry work
+            hsplit = hsplit < 1 ? 1 : (hsplit > HW ? HW : (hsplit > 65535 ? 65535 : hsplit));
+            occupancy_norm_max_sparse_kernel<<<dim3((unsigned)gb, (unsigned)hsplit), K5C_WARPS * 32, 0, st>>>(
+                grids, (int)H, V, sums, sel, flags_t, (int)HW, dense, G, field);
+        } else {
+            const long long vb = ((vec ? V / 4 : V) + 255) / 256;
+            long long hsplit = (8LL * kNumSM + vb - 1) / vb;
+            hsplit = hsplit < 1 ? 1 : (hsplit > H ? H : (hsplit > 65535 ? 65535 : hsplit));
+            if (vec)
+                occupancy_norm_max4_kernel<<<dim3((unsigned)vb, (unsigned)hsplit), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
+            else
+                occupancy_norm_max_kernel<<<dim3((unsigned)vb, (unsigned)hsplit), 256, 0, st>>>(grids, (int)H, V, sums, sel, field);
+        }
         rc = check_launch("occupancy_norm_max_kernel");
     }
-    cudaFreeAsync(sums, st);
+    cudaFreeAsync(scratch, st);
     return rc;
 }

@@ -365,6 +365,83 @@ def test_occupancy_oracle(dev, H, Sg, S, tol):
     np.testing.assert_allclose(grids.cpu().numpy(), ref_norm, rtol=1e-6, equal_nan=True)   # normalised in place
 
 
+@pytest.mark.parametrize("Sg,tol", [(30, 3.0), (128, 3.0), (64, 0.6), (16, 7.5)])
+def test_occupancy_box_boundary(dev, Sg, tol):
+    """K4 derives a TIGHT candidate box from a linear index estimate (ceil / floor with 1/64 voxel of margin): vertices planted
+    within a few fp32 ulps of `centre +- thr` on one, two and three axes, on voxel centres and on voxel faces, must produce the
+    dense oracle's counts exactly (a box that is one voxel short loses exactly these hits). tol 7.5 makes the (j, k) plane of a
+    task larger than one 64-column pass; tol 0.6 makes most boxes a single voxel."""
+    from coma_b200 import ops
+    from oracle import oracle
+    centers, voxel = oracle.voxel_centers(Sg)
+    thr = voxel * tol
+    rng = np.random.default_rng(Sg)
+    pts = []
+    for _ in range(40):
+        i, j, k = rng.integers(0, Sg, 3)
+        c = np.array([centers[0][i], centers[1][j], centers[2][k]])
+        for axes in ((0,), (1,), (2,), (0, 1), (1, 2), (0, 1, 2)):
+            p = c.copy()
+            for a in axes:
+                p[a] += rng.choice([-1.0, 1.0]) * thr
+            pts.append(p)
+        pts.append(c)
+        pts.append(c + voxel / 2)
+    pts = np.asarray(pts)
+    H = len(pts)
+    hv = np.stack([pts, pts], 0)
+    # second sample: the same positions moved by -2 … +2 fp32 ulps per coordinate
+    f32 = hv[1].astype(np.float32)
+    for _ in range(2):
+        f32 = np.where(rng.random(f32.shape) < 0.5, np.nextafter(f32, np.float32(9)), np.nextafter(f32, np.float32(-9)))
+    hv[1] = f32.astype(np.float64)
+    ov = np.zeros((2, 2, 3))
+    ref = oracle.occupancy_accumulate(hv, ov, Sg, tol)
+    grids = torch.zeros((H, Sg, Sg, Sg), device=dev)
+    ops.occupancy_accumulate(_t(hv.astype(np.float32), dev), _t(centers, dev, torch.float64), thr, grids)
+    np.testing.assert_array_equal(grids.cpu().numpy(), ref)
+    assert ref.sum() > 0
+
+
+@pytest.mark.parametrize("H,Sg", [(70, 30), (33, 64), (5, 20)])
+def test_occupancy_readout_sparse_granules(dev, H, Sg):
+    """K5c's second pass visits only the 512-byte granules pass 1 flagged as occupied. Sparse grids with hits in the LAST (partial)
+    granule of a row, never-hit rows (0/0 -> NaN everywhere), a row whose sum is negative (0/neg = -0.0: rewritten in full), rows
+    beyond a multiple of 32, a selection — against the oracle's dense read-out; then a SECOND read-out of the already normalised
+    grids (the reference re-normalises on every call; NaN rows have a NaN sum)."""
+    from coma_b200 import ops
+    from oracle import oracle
+    rng = np.random.default_rng(H + Sg)
+    V = Sg ** 3
+    g = np.zeros((H, V), np.float32)
+    for h in range(H):
+        if h % 7 == 3:
+            continue                                   # never hit
+        n = int(rng.integers(1, 400))
+        at = rng.integers(0, V, n)
+        g[h, at] = rng.integers(1, 50, n).astype(np.float32)
+        if h % 5 == 0:
+            g[h, V - 1 - (h % 3)] = 7.0                # last granule of the row
+    g[1, :] = 0.0
+    g[1, 11] = -3.0                                    # negative row sum
+    g = g.reshape(H, Sg, Sg, Sg)
+    sel_idx = [0, 1, 2, H - 1]                         # none of the never-hit rows: the selected field carries values, not NaN
+    for _ in range(2):
+        ref_field, ref_norm = oracle.occupancy_field(g)
+        sub = ref_norm[sel_idx]
+        ref_sel = np.where(np.isnan(sub).any(0), np.nan, sub.max(0))
+        f_sel = ops.occupancy_readout(_t(g, dev), torch.tensor(sel_idx, device=dev)).cpu().numpy()
+        np.testing.assert_allclose(f_sel, ref_sel, rtol=1e-6, equal_nan=True)
+        grids = _t(g, dev)
+        field = ops.occupancy_readout(grids, None).cpu().numpy()
+        out = grids.cpu().numpy()
+        np.testing.assert_allclose(field, ref_field, rtol=1e-6, equal_nan=True)
+        np.testing.assert_allclose(out, ref_norm, rtol=1e-6, equal_nan=True)
+        ok = ~np.isnan(ref_norm)
+        assert np.array_equal(np.signbit(out[ok]), np.signbit(ref_norm[ok]))      # -0.0 of the negative-sum row
+        g = out                                        # second pass: normalise the normalised grids again
+
+
 # --------------------------------------------------------------------------------------------- classes / read-outs
 @pytest.mark.parametrize("name", ["contact_small", "contact_sigma02", "cuda_contact_small", "cuda_contact_sigma02", "cuda_contact_boundary"])
 def test_coma_class_matches_reference_golden(dev, golden_dir, name, tmp_path):
