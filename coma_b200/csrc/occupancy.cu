@@ -11,7 +11,8 @@
 // compare and the RED — the reference's sum ((x+y)+z) needs nothing else once y and z are known.  The box is tight
 // (ceil / floor of the linear index estimate with 1/64 voxel of margin instead of a whole voxel of slack on both sides:
 // 8 x 8 instead of 10 x 10 columns at scale_tolerance 3), and the per-axis reciprocal spacing is computed once per CTA.
-// ~230 warp-instructions per task against ~1300 for round 1's candidate-per-lane loop (`occupancy_kernel_v1`, kept behind
+// Lanes 0..2 derive one axis range each; the RED is predicated (no branch around it).
+// ~300 warp-instructions per task against ~1300 for round 1's candidate-per-lane loop (`occupancy_kernel_v1`, kept behind
 // COMA_B200_OCC_PATH=v1 for A/B runs): the kernel moves from issue-bound towards the RED rate (1.29 clk per lane-RED per SM).
 //
 // Bit-exactness: d < thr is decided as  ((dx*dx + dy*dy) + dz*dz) < T  in fp64 with explicitly rounded ops, where T is
@@ -95,6 +96,19 @@ __device__ __forceinline__ void axis_range(double c0, double inv, int Sg, double
     n = max(ihi - ilo + 1, 0);
 }
 
+// c -> (c / nk, c % nk) for a small non-negative c: float reciprocal estimate, corrected by at most one (exact for every size)
+__device__ __forceinline__ void split_column(int c, int nk, float rnk, int &j, int &k) {
+    j = __float2int_rz(((float)c + 0.5f) * rnk);
+    k = c - j * nk;
+    if (k < 0) { j -= 1; k += nk; }
+    else if (k >= nk) { j += 1; k -= nk; }
+}
+
+// grids[cell] += 1.0f if `hit`: a predicated RED.E.ADD.F32 (no branch, no reconvergence point around the atomic)
+__device__ __forceinline__ void red_add_one_if(float *p, bool hit) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q red.global.add.f32 [%0], 0f3F800000;\n\t}" ::"l"(p), "r"((int)hit) : "memory");
+}
+
 __global__ void __launch_bounds__(K4_WARPS * 32)
     occupancy_kernel(const float *__restrict__ hvc, int S, int H, const double *__restrict__ centers, int Sg, double thr,
                      double T, float *__restrict__ grids, int split) {
@@ -116,22 +130,26 @@ __global__ void __launch_bounds__(K4_WARPS * 32)
 
     float *dst = grids + (size_t)h * V;
     const double *cx = sc, *cy = sc + Sg, *cz = sc + 2 * Sg;
-    const double cx0 = s_c0[0], cy0 = s_c0[1], cz0 = s_c0[2], ix = s_inv[0], iy = s_inv[1], iz = s_inv[2];
+    const int ax = lane < 3 ? lane : 0;  // lanes 0..2 derive the index range of one axis each (the others repeat axis 0)
+    const double c0_ax = s_c0[ax], inv_ax = s_inv[ax];
     for (int s = part * K4_WARPS + warp; s < S; s += split * K4_WARPS) {
         const float *vp = hvc + ((size_t)s * H + h) * 3;
         const double v0 = (double)vp[0], v1 = (double)vp[1], v2 = (double)vp[2];
-        int ilo, ni, jlo, nj, klo, nk;
-        axis_range(cx0, ix, Sg, v0, thr, ilo, ni);
-        axis_range(cy0, iy, Sg, v1, thr, jlo, nj);
-        axis_range(cz0, iz, Sg, v2, thr, klo, nk);
+        int lo_ax, n_ax;
+        axis_range(c0_ax, inv_ax, Sg, ax == 0 ? v0 : (ax == 1 ? v1 : v2), thr, lo_ax, n_ax);
+        const int ilo = __shfl_sync(0xffffffffu, lo_ax, 0), ni = __shfl_sync(0xffffffffu, n_ax, 0);
+        const int jlo = __shfl_sync(0xffffffffu, lo_ax, 1), nj = __shfl_sync(0xffffffffu, n_ax, 1);
+        const int klo = __shfl_sync(0xffffffffu, lo_ax, 2), nk = __shfl_sync(0xffffffffu, n_ax, 2);
         const int plane = nj * nk;
         if (ni <= 0 || plane <= 0) continue;  // warp-uniform
+        const float rnk = 1.0f / (float)nk;
         for (int cb = 0; cb < plane; cb += 64) {
             // two (j, k) columns per lane: consecutive lanes take consecutive k (contiguous cells)
             const int ca = cb + lane, cc = ca + 32;
             bool ok_a = ca < plane, ok_b = cc < plane;
-            const int ja = ok_a ? ca / nk : 0, jb = ok_b ? cc / nk : 0;
-            const int ka = ok_a ? ca - ja * nk : 0, kb = ok_b ? cc - jb * nk : 0;
+            int ja, ka, jb, kb;
+            split_column(ok_a ? ca : 0, nk, rnk, ja, ka);
+            split_column(ok_b ? cc : 0, nk, rnk, jb, kb);
             const double dya = __dsub_rn(cy[jlo + ja], v1), dza = __dsub_rn(cz[klo + ka], v2);
             const double dyb = __dsub_rn(cy[jlo + jb], v1), dzb = __dsub_rn(cz[klo + kb], v2);
             const double yya = __dmul_rn(dya, dya), zza = __dmul_rn(dza, dza);
@@ -144,8 +162,8 @@ __global__ void __launch_bounds__(K4_WARPS * 32)
             for (int ii = 0; ii < ni; ++ii, pa += plane_stride, pb += plane_stride) {
                 const double dx = __dsub_rn(cx[ilo + ii], v0), xx = __dmul_rn(dx, dx);
                 if (!(xx < T)) continue;  // warp-uniform: the whole plane is out of range
-                if (ok_a && __dadd_rn(__dadd_rn(xx, yya), zza) < T) atomicAdd(pa, 1.0f);  // (x+y)+z, RED.E.ADD.F32
-                if (ok_b && __dadd_rn(__dadd_rn(xx, yyb), zzb) < T) atomicAdd(pb, 1.0f);
+                red_add_one_if(pa, ok_a && __dadd_rn(__dadd_rn(xx, yya), zza) < T);  // (x+y)+z
+                red_add_one_if(pb, ok_b && __dadd_rn(__dadd_rn(xx, yyb), zzb) < T);
             }
         }
     }

@@ -437,6 +437,20 @@ extern "C" int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, co
     const size_t off_flags = (off_sel + (size_t)H + 15) / 16 * 16;
     const size_t flag_bytes = sparse ? sizeof(unsigned) * (size_t)HW * (size_t)(G + 1) : 0;
     char *scratch = nullptr;
+    {   // keep freed scratch cached in the device's default pool: with the default release threshold (0) every synchronisation hands
+        // the memory back to the driver and the next read-out pays for a fresh mapping inside its critical path
+        static bool pool_set[64] = {false};
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_set[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = 256ull << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_set[dev] = true;
+            cudaGetLastError();
+        }
+    }
     cudaError_t e = cudaMallocAsync(&scratch, off_flags + flag_bytes, st);
     if (e != cudaSuccess) {
         set_error("coma_occupancy_readout_f32: scratch allocation failed: %s", cudaGetErrorString(e));
@@ -461,8 +475,10 @@ extern "C" int coma_occupancy_readout_f32(float *grids, int64_t H, int64_t V, co
         cudaMemsetAsync(field, 0, sizeof(float) * (size_t)V, st);
         if (sparse) {
             const long long gb = (G + K5C_WARPS - 1) / K5C_WARPS;
-            long long hsplit = (64LL * kNumSM + gb - 1) / gb;   // >= 64 CTAs per SM in total: only the occupied granules carry work
-            hsplit = hsplit < 1 ? 1 : (hsplit > HW ? HW : (hsplit > 65535 ? 65535 : hsplit));
+            // one 32-row word per slab (blockIdx.y), slabs in launch order: every resident CTA then works on the same few rows, like
+            // the lock-step row loop of the dense kernel. Measured on B200 (128^3, 1310 rows, tools/occ_ab.py): with 9 words per slab the
+            // hot warps drift apart over the whole 11 GB (rows are 8 MB apart) and the pass takes 32 ms instead of < 1 ms.
+            const long long hsplit = HW > 65535 ? 65535 : HW;
             occupancy_norm_max_sparse_kernel<<<dim3((unsigned)gb, (unsigned)hsplit), K5C_WARPS * 32, 0, st>>>(
                 grids, (int)H, V, sums, sel, flags_t, (int)HW, dense, G, field);
         } else {

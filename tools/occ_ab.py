@@ -54,6 +54,7 @@ def one(rows, samples, sg, iters):
     return dict(rows=rows, samples=samples, sg=sg, k4_ms=k4m, k5c_ms=k5m, hits=hits, nonzero_fraction=nz,
                 vertex_samples_per_s=rows * samples / k4m * 1e3, hits_per_s=hits / k4m * 1e3,
                 k5c_dense_equiv_gbs=12.0 * rows * V / k5m / 1e6, k5c_two_read_gbs=8.0 * rows * V / k5m / 1e6, field_checksum=field_sum,
+                k4_all_ms=[round(x, 4) for x in k4], k5c_all_ms=[round(x, 4) for x in k5],
                 occ_path=os.environ.get("COMA_B200_OCC_PATH", "default"), k5c=os.environ.get("COMA_B200_K5C", "default"))
 
 
