@@ -166,7 +166,8 @@ class ComA_Occupancy:
         h0, h1 = self._human_slice
         rows = self.human_res if exchange else max(h1 - h0, 1)
         chunk = max(32, min(8192, (_STAGING_BYTES // (rows * 12)) // 32 * 32))
-        chunk = min(chunk, 256) if exchange else min(chunk, (len(samples) + 31) // 32 * 32)
+        # <= 1024 samples per chunk: the host fill of chunk i + 1 overlaps the H2D copy and the K4 launch of chunk i (two buffers in flight)
+        chunk = min(chunk, 256) if exchange else min(chunk, 1024, (len(samples) + 31) // 32 * 32)
         stager = BatchStager(dict(hvc=self.human_res if exchange else h1 - h0), chunk, self.spatial_occupancy_grids.device)
         outer = self
 

@@ -9,6 +9,17 @@ namespace coma {
 
 constexpr int K5_WARPS = 8;
 
+// x / d, correctly rounded. div.rn's operand range check (FCHK) sends a ZERO numerator down its ~60-instruction slow path, and the
+// occupancy grids K5c normalises are full of exact zeros (voxels a vertex never touched). When the
+// divisor is a positive, finite, normal number — `plain`, uniform over a row — 0 / d is the zero itself, sign included, so only the
+// non-zero numerators are divided; any other divisor (0 -> NaN, negative -> -0.0, NaN, inf) takes the generic division.
+__device__ __forceinline__ bool plain_divisor(float d) { return d >= 1.17549435e-38f && d < INFINITY; }
+__device__ __forceinline__ float div_rn_zero_fast(float x, float d, bool plain) {
+    if (!plain) return __fdiv_rn(x, d);
+    const float q = __fdiv_rn(x == 0.f ? 1.0f : x, d);
+    return x == 0.f ? x : q;
+}
+
 // K5a: P[q,:] /= (sum P[q,:] + eps) in place; cmap[q] = (sum_n P[q,n] w[n]) * nom[q]/denom[q]
 __global__ void __launch_bounds__(K5_WARPS * 32)
     normalize_contact_kernel(float *__restrict__ P, long long HO, int N, float eps, const float *__restrict__ w,
@@ -67,7 +78,7 @@ __global__ void __launch_bounds__(K5_WARPS * 32)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if (lane + 32 * j < N) {
-                    const float x = __fdiv_rn(v[r][j], d);
+                    const float x = __fdiv_rn(v[r][j], d);   // (the zero-fast form below costs this register-bound kernel 12 %: 5051 -> 4487 GB/s on dense data)
                     __stcs(row + lane + 32 * j, x);
                     acc = fmaf(x, wv[j], acc);
                 }
@@ -315,7 +326,9 @@ __global__ void __launch_bounds__(K5C_WARPS * 32)
     const unsigned *fl = flags_t + (size_t)g * HW;
     int m[4] = {0, 0, 0, 0};
     auto fold = [&](float4 &a, float sm, bool use) {
-        a.x = __fdiv_rn(a.x, sm); a.y = __fdiv_rn(a.y, sm); a.z = __fdiv_rn(a.z, sm); a.w = __fdiv_rn(a.w, sm);
+        const bool plain = plain_divisor(sm);   // warp-uniform (one row); ncu before: 237 instructions per 512-byte row visit, issue 74 %
+        a.x = div_rn_zero_fast(a.x, sm, plain); a.y = div_rn_zero_fast(a.y, sm, plain);
+        a.z = div_rn_zero_fast(a.z, sm, plain); a.w = div_rn_zero_fast(a.w, sm, plain);
         if (use) {
             m[0] = max(m[0], __float_as_int(a.x) & 0x7fffffff); m[1] = max(m[1], __float_as_int(a.y) & 0x7fffffff);
             m[2] = max(m[2], __float_as_int(a.z) & 0x7fffffff); m[3] = max(m[3], __float_as_int(a.w) & 0x7fffffff);
