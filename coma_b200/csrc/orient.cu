@@ -56,6 +56,7 @@ __device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp
     const float b_dot_p = dot_ref(b, p, ord), a_dot_b = dot_ref(a, b, ord), a_dot_p = dot_ref(a, p, ord), a_dot_sp = dot_ref(a, sp, ord);
     const float one_plus = __fadd_rn(1.0f, b_dot_p);
     const bool replace = one_plus < eps;  // :143
+    const bool pos_div = one_plus > 0.0f && one_plus < INFINITY;
     // rows of the reference's "cross product matrix" (:149-155): [b0,-b2,b1], [b2,0,-b0], [-b1,0,0]
     Vec3 bxp;
     bxp.x = __fadd_rn(__fadd_rn(__fmul_rn(b.x, p.x), __fmul_rn(-b.z, p.y)), __fmul_rn(b.y, p.z));
@@ -68,7 +69,12 @@ __device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float v = __fmul_rn(xv[k], a_dot_bxp);                 // :162
-        v = replace ? 0.0f : __fdiv_rn(v, one_plus);           // :163
+        // :163. With p = (0,0,1) the third component of bxp is an exact zero for EVERY pair, and div.rn's operand check (FCHK) sends a
+        // zero numerator down its ~60-instruction slow path — the whole warp, four times per chunk. +-0 / (positive finite) is the
+        // zero itself, so only non-zero numerators are divided (bit-identical; a NaN divisor still takes the generic division).
+        const bool zero_num = v == 0.0f && pos_div;
+        const float q = __fdiv_rn(zero_num ? 1.0f : v, one_plus);
+        v = replace ? 0.0f : (zero_num ? v : q);
         v = __fadd_rn(v, __fmul_rn(b_dot_p, av[k]));           // :164
         v = __fadd_rn(v, __fmul_rn(a_dot_b, pv[k]));           // :165
         v = __fsub_rn(v, __fmul_rn(a_dot_p, bv[k]));           // :166
