@@ -447,6 +447,63 @@ def occupancy_leg(args, dev, rank, world, barrier):
             "gpu_launches": int(launches), "n_gpus": world}
 
 
+def cfg1_leg(cpu_samples=4):
+    """BASELINE.json configs[0] IN FULL: 32 samples, SMPL-X downsampled to 1000 vertices x 180 object vertices x 250 bins, preset
+    qual:backpack_human_contact — the reference's own CPU-runnable case — end to end through the class API (register ->
+    aggregate_all_samples -> get_aggregated_contact, host fp64 in, host maps out): the drop-in class on the B200, the UNMODIFIED
+    reference with device="cuda" on the same B200 (all 32 samples) and on the host cores (`cpu_samples` of the 32: its loop is
+    strictly per sample). The two aggregated human maps are compared on the spot (1e-4, the north-star tolerance)."""
+    import torch
+    from coma_b200 import synth
+    from oracle import ref_loader
+    from utils.coma import ComA, get_aggregated_contact
+    Hc, Oc, Sc = 1000, 180, 32
+    kw = dict(human_res=Hc, obj_res=Oc, normal_res=N, spatial_res=0, proximity_settings=dict(spatial_grid_size=0.07, spatial_grid_thres=0.03),
+              normal_gaussian_sigma=0.25, eps=1e-10)
+    base = synth.make_samples(Sc, Hc, Oc, seed=1)
+
+    class _Fresh:   # every run gets its own copies of the host arrays (made outside the timed region)
+        def __getitem__(self, sl):
+            return [{k: v.copy() for k, v in x.items()} for x in base[sl]]
+    samples = _Fresh()
+
+    def run(cls, gac, device, smp):
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        c = cls(device=device, **kw)
+        for x in smp:
+            c.register_sample_to_cache(**x)
+        c.aggregate_all_samples()
+        m, idx = gac(c, "human", 0.03)   # 0.03 x 32 samples: every pair that was hit at least once counts as significant
+        m = np.asarray(m.cpu() if hasattr(m, "cpu") else m)
+        return time.perf_counter() - t0, m, idx
+
+    out = {"config": f"BASELINE configs[0] in full: {Sc} samples, H={Hc}, O={Oc}, N={N}, preset qual:backpack_human_contact; class API end to end",
+           "unit": "vertex-pairs/s"}
+    run(ComA, get_aggregated_contact, "cuda", samples[:2])                      # warm-up: allocator, pinned staging
+    dt, mine, mine_idx = min((run(ComA, get_aggregated_contact, "cuda", samples[:]) for _ in range(3)), key=lambda r: r[0])
+    out["value"] = Sc * Hc * Oc / dt
+    out["s"] = dt
+    if ref_loader.available():
+        ref = ref_loader.load()
+        try:
+            _quiet(run, ref.ComA, ref.get_aggregated_contact, "cuda", samples[:2])
+            dt_r, theirs, their_idx = _quiet(run, ref.ComA, ref.get_aggregated_contact, "cuda", samples[:])
+            out["reference_cuda"] = {"value": Sc * Hc * Oc / dt_r, "s": dt_r, "kind": "reference", "sample": f"all {Sc} samples, device='cuda'"}
+            out["agrees_with_reference_cuda"] = bool(np.array_equal(np.asarray(mine_idx), np.asarray(their_idx))
+                                                     and np.allclose(mine, theirs, rtol=1e-4, atol=1e-12))
+            torch.set_num_threads(host_cores())
+            dt_c, _, _ = _quiet(run, ref.ComA, ref.get_aggregated_contact, "cpu", samples[:cpu_samples])
+            out["reference_cpu"] = {"value": cpu_samples * Hc * Oc / dt_c, "s": dt_c, "cores": host_cores(), "kind": "reference",
+                                    "sample": f"{cpu_samples} of the {Sc} samples, device='cpu' (per-sample loop)"}
+        except Exception as ex:  # informative leg only
+            out["reference_error"] = repr(ex)[:200]
+        finally:
+            torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -672,6 +729,10 @@ def main():
             line["cpu_baseline"] = cpu_reference_rate()
             if not args.no_reference_cuda:
                 line["reference_cuda"] = reference_cuda_rate()
+                try:
+                    line["cfg1"] = cfg1_leg()
+                except Exception as ex:   # informative leg: never lose the headline line over it
+                    line["cfg1"] = {"error": repr(ex)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -84,3 +84,34 @@ def test_occupancy_reference_cpu_vs_cuda_vs_kernels(ref, H, O, Sg, S):
     assert r_cuda["spatial_occupancy_grids"].sum() > 0
     np.testing.assert_allclose(mc.return_aggregated_spatial_grids().cpu().numpy(), rc.return_aggregated_spatial_grids().cpu().numpy(),
                                rtol=1e-6, equal_nan=True)
+
+
+def test_baseline_cfg1_in_full_vs_reference_cuda(ref):
+    """BASELINE.json configs[0] at FULL size — 32 samples, 1000 human x 180 object vertices x 250 bins, preset
+    qual:backpack_human_contact (constants/coma/qual.py: 0.07 / 0.03 / 0.25 / 1e-10) — the unmodified reference with device="cuda"
+    against the drop-in class: counts bit-exact, fp32 accumulators and every read-out the scripts use at 1e-4."""
+    from coma_b200 import synth
+    from utils.coma import ComA, get_aggregated_contact, get_nonphysical_score
+    H, O, N, S = 1000, 180, 250, 32
+    samples = synth.make_samples(S, H, O, seed=1)
+    kw = dict(human_res=H, obj_res=O, normal_res=N, spatial_res=0, proximity_settings=dict(spatial_grid_size=0.07, spatial_grid_thres=0.03),
+              normal_gaussian_sigma=0.25, eps=1e-10)
+    rc = _run(ref.ComA, samples, device="cuda", **kw)
+    mc = _run(ComA, samples, device="cuda", **kw)
+    r, m = rc.export(), mc.export()
+    assert set(r.keys()) == set(m.keys())
+    np.testing.assert_array_equal(m["significant_contact_count"], r["significant_contact_count"])
+    np.testing.assert_array_equal(m["contact_dist_expectation_grid_denom"], r["contact_dist_expectation_grid_denom"])
+    np.testing.assert_allclose(m["contact_dist_expectation_grid_nom"], r["contact_dist_expectation_grid_nom"], rtol=1e-4)
+    for k in ("prob_grid_canon_human_wrt_obj", "prob_grid_canon_obj_wrt_human"):
+        tol = 1e-4 * np.abs(r[k]) + 1e-30 + S * 2.0 ** -31      # cone-limited K3: terms < 2^-32 are dropped (include/coma_b200.h)
+        assert (np.abs(m[k].astype(np.float64) - r[k]) <= tol).all(), k
+    assert r["significant_contact_count"].sum() > 0
+    for typ in ("human", "obj"):
+        a, ia = get_aggregated_contact(mc, typ, 0.03)      # ratio 0.03 x 32 samples: every pair hit at least once is significant
+        b, ib = ref.get_aggregated_contact(rc, typ, 0.03)
+        np.testing.assert_array_equal(ia, ib)
+        assert len(ib) > 0 and np.asarray(b).max() > 0
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-12)
+        # entropy read-out (src/coma/extract_coma.py:460: n_bin = 1e6): round-half flips move a score by ~1e-6 each
+        np.testing.assert_allclose(np.asarray(get_nonphysical_score(mc, typ)), np.asarray(ref.coma.get_nonphysical_score(rc, typ)), atol=2e-5)
