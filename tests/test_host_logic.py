@@ -256,6 +256,25 @@ def test_host_stage_rows_helper():
     assert rows_equal_f64([o.astype(np.float32) for o in ov], ov[0][0]) is None
 
 
+def test_host_stage_rows_addresses():
+    """The data pointers handed to the host helper come from the buffer protocol (`_addresses`): read-only arrays (no writable buffer
+    export), offset views, and a run of identical objects (one shared object mesh — looked up once) must all stage the right values."""
+    from coma_b200.staging import _addresses, rows_equal_f64, stage_rows_f64
+    rng = np.random.default_rng(11)
+    H, n = 64, 6
+    hv = [rng.normal(size=(H + 5, 3)) for _ in range(n)]
+    ro = hv[2]
+    ro.flags.writeable = False                                                            # e.g. arrays that came out of np.load(mmap_mode="r")
+    views = [h[5:] for h in hv]                                                           # contiguous views that do not start at the base pointer
+    assert _addresses(views) == [v.ctypes.data for v in views]
+    assert _addresses([hv[0], hv[0], hv[1], hv[0]]) == [hv[0].ctypes.data, hv[0].ctypes.data, hv[1].ctypes.data, hv[0].ctypes.data]
+    obj = rng.normal(size=(3, 3))
+    out = np.zeros((n, H, 3), np.float32)
+    assert stage_rows_f64(views, out, row0=0, sub=[obj] * n, equal_to=obj[0]) == -1
+    assert np.array_equal(out, np.stack([(v - obj[0][None]).astype(np.float32) for v in views]))
+    assert rows_equal_f64([obj[1:]] * 3 + [obj[1:].copy()], obj[1]) is True                # offset view of the shared object, then an equal copy
+
+
 def test_occupancy_chunk_staging_matches_numpy_path():
     """ComA_Occupancy._stage_chunk (one library call per chunk) writes exactly what the per-sample numpy path writes, and declines
     (-> numpy path, which asserts / np.allclose's like the reference) when the object moves or an input is not float64."""

@@ -56,15 +56,13 @@ def main():
         g, _, meta = load_voxelgrid(2.4, Sg)
         centers = torch.from_numpy(np.ascontiguousarray(np.stack([g[0, :, 0, 0], g[1, 0, :, 0], g[2, 0, 0, :]]))).to(dev)
         grids = torch.zeros((Hh, Sg, Sg, Sg), device=dev)
-        for path in (("smem", "global") if Sg == 30 else ("global",)):
-            os.environ["COMA_B200_OCC_PATH"] = path
-            grids.zero_()
-            ms = timeit(lambda: ops.occupancy_accumulate(hvc, centers, meta["voxel_size"] * 3.0, grids), iters=3, warm=1)
-            hits = grids.sum().item() / 4
-            out[f"k4_Sg{Sg}_{path}"] = dict(ms=ms, vertex_samples_per_s=S * Hh / ms * 1e3, hits_per_vs=hits / (S * Hh))
-        os.environ.pop("COMA_B200_OCC_PATH")
+        # (A/B against round 1's kernels: tools/occ_ab.py — the COMA_B200_OCC_PATH / COMA_B200_K5C switches are read once per process)
+        grids.zero_()
+        ms = timeit(lambda: ops.occupancy_accumulate(hvc, centers, meta["voxel_size"] * 3.0, grids), iters=3, warm=1)
+        hits = grids.sum().item() / 4
+        out[f"k4_Sg{Sg}"] = dict(ms=ms, vertex_samples_per_s=S * Hh / ms * 1e3, hits_per_vs=hits / (S * Hh))
         ms = timeit(lambda: ops.occupancy_readout(grids, None), iters=2, warm=1)
-        out[f"k5c_Sg{Sg}"] = dict(ms=ms, gbs=3 * 4 * Hh * Sg**3 / ms / 1e6)
+        out[f"k5c_Sg{Sg}"] = dict(ms=ms, dense_equivalent_gbs=3 * 4 * Hh * Sg**3 / ms / 1e6)   # (re-normalising already normalised grids)
         del grids
     Hs, Os = 4000, 1500
     P = torch.rand((Hs, Os, N), device=dev)
