@@ -107,6 +107,10 @@ def inpaint_human(pipeline, embed_fn, num_img_per_combination, supercategories, 
             continue
         todo.append(it)
     done = 0
+    # PNG encoding (zlib, ~20-40 ms per 512^2 image) runs on a few host threads behind the next batch's GPU work instead of between two
+    # pipeline calls (the reference saves inline, src/generation/inpaint.py:350-352). A file appears under its final name
+    # only when it is complete, so an interrupted run never leaves a truncated PNG for --skip_done to trust.
+    writer = _PngWriter()
     for batch in group_batches(todo, batch_size):
         it = batch[0]
         init_image = Image.open(it["asset_render_pth"]).convert("RGB")
@@ -118,9 +122,43 @@ def inpaint_human(pipeline, embed_fn, num_img_per_combination, supercategories, 
                        enforce_full_mask_ratio=it["enforce_full_mask_ratio"], human_detection_thres=it["human_detection_thres"],
                        batch_size=len(batch))
         for b, img in zip(batch, res.images):
-            img.save(b["result_save_pth"])
+            writer.submit(img, b["result_save_pth"])
             done += 1
+    writer.close()      # every file is on disk (or its error raised) before the caller sees the count
     return done
+
+
+class _PngWriter:
+    """Background PNG writer: `submit` returns at once, `close` waits for every file and re-raises the first failure."""
+
+    def __init__(self, workers=4, max_pending=64):
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="png")
+        self._pending, self._max_pending = [], max_pending
+
+    @staticmethod
+    def _write(img, path):
+        tmp = f"{path}.tmp{os.getpid()}"
+        try:
+            img.save(tmp, format="PNG")
+            os.replace(tmp, path)
+        except BaseException:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise
+
+    def submit(self, img, path):
+        self._pending.append(self._pool.submit(self._write, img, path))
+        if len(self._pending) >= self._max_pending:      # bound the images held in memory if the disk is slower than the GPU
+            self._pending.pop(0).result()
+
+    def close(self):
+        try:
+            for f in self._pending:
+                f.result()
+        finally:
+            self._pending = []
+            self._pool.shutdown(wait=True)
 
 
 def load_state_dict(path):

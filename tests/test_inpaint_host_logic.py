@@ -78,3 +78,46 @@ def test_work_list_paths_order_batches_and_rank_slices(tmp_path):
             assert idx[lo:hi] == idx[r * step:(r + 1) * step]                    # the reference's python slice, element for element
             seen += idx[lo:hi]
         assert seen == idx
+
+
+def test_inpaint_human_writes_pngs_in_the_background(tmp_path):
+    """`inpaint_human` with a stand-in pipeline (no GPU): every work item of the rank's slice ends up as a complete PNG at the reference's
+    path, written by the background writer; `--skip_done` skips them on a second run; a failing write surfaces as an exception and leaves no
+    truncated file behind."""
+    import torch
+    from PIL import Image
+    from types import SimpleNamespace
+    from coma_b200.cli import inpaint as cli
+    render, mask, seg, prm = _make_tree(str(tmp_path), n_views=2, n_masks=1)
+    defaults = dict(ddim_steps=50, cfg_scale=11.0, strength=0.98, enforce_full_mask_ratio=0.0, human_detection_thres=0.015)
+    calls = []
+
+    class FakePipeline:
+        dev = torch.device("cpu")
+
+        def __call__(self, generator, batch_size, **kw):
+            calls.append(batch_size)
+            imgs = [Image.fromarray(np.full((16, 16, 3), int(g.initial_seed()) % 251, np.uint8)) for g in generator]
+            return SimpleNamespace(images=imgs)
+
+    args = (3, ["behave"], ["backpack"], render, mask, seg, prm, str(tmp_path / "out"), "ugly", defaults)
+    n = cli.inpaint_human(FakePipeline(), lambda text: None, *args, skip_done=True, verbose=False, parallel_num=1, parallel_idx=0, batch_size=8)
+    assert n == 2 * 1 * 2 * 3 and calls == [3] * 4
+    items = cli.enumerate_work(*args)
+    for it in items:
+        img = np.asarray(Image.open(it["result_save_pth"]))
+        assert img.shape == (16, 16, 3) and (img == it["inpaint_id"] % 251).all()
+        assert not [f for f in os.listdir(it["result_save_dir"]) if ".tmp" in f]
+    assert cli.inpaint_human(FakePipeline(), lambda text: None, *args, skip_done=True, verbose=False, parallel_num=1, parallel_idx=0) == 0
+
+    class Broken:
+        def save(self, path, format=None):
+            with open(path, "wb") as fh:
+                fh.write(b"half a file")
+            raise OSError("disk full")
+    w = cli._PngWriter(workers=2)
+    target = str(tmp_path / "broken.png")
+    w.submit(Broken(), target)
+    with pytest.raises(OSError):
+        w.close()
+    assert not os.path.exists(target) and not [f for f in os.listdir(tmp_path) if f.startswith("broken.png")]
