@@ -185,7 +185,7 @@ extern "C" int coma_occupancy_accumulate(const float *hvc, int64_t S, int64_t H,
                                          double thr, float *grids, coma_stream_t stream) {
     using namespace coma;
     COMA_REQUIRE(hvc && centers && grids, "null pointer");
-    COMA_REQUIRE(S >= 0 && H > 0 && Sg > 0 && Sg <= 2048, "bad sizes");
+    COMA_REQUIRE(S >= 0 && H > 0 && Sg > 0 && Sg <= 2040, "bad sizes (Sg <= 2040: the per-axis centres live in 48 KB of shared memory)");
     if (S == 0) return 0;
     const double T = squared_threshold(thr);
     cudaStream_t st = (cudaStream_t)stream;

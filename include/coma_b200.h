@@ -142,7 +142,7 @@ COMA_API int coma_canonicalize_order_f32(const float *a, int64_t A, const float 
  * hvc [S,H,3] f32 = fp32(human_verts - obj_verts[0]) (the host-side subtraction of :287-288);
  * centers [3,Sg] f64 per-axis voxel centres (load_voxelgrid :160-171): strictly increasing and uniformly spaced to within 1/64 of
  * the spacing (the kernel derives its candidate box from a linear index estimate; load_voxelgrid's centres are uniform to < 4e-4);
- * thr = voxel_size*scale_tolerance; grids [H,Sg,Sg,Sg] f32 accumulated in place. Bit-exact (integer counts). */
+ * thr = voxel_size*scale_tolerance; grids [H,Sg,Sg,Sg] f32 accumulated in place, Sg <= 2040. Bit-exact (integer counts). */
 COMA_API int coma_occupancy_accumulate(const float *hvc, int64_t S, int64_t H, const double *centers, int64_t Sg, double thr,
                               float *grids, coma_stream_t stream);
 
