@@ -29,6 +29,9 @@ namespace coma {
 
 constexpr int K4_WARPS = 8;
 constexpr int K4_SPLIT = 16;  // CTAs per vertex
+#ifndef K4_MIN_CTAS
+#define K4_MIN_CTAS 5  // <= 51 registers: 40 resident warps per SM for an issue-bound kernel with ~3 stall cycles per instruction
+#endif
 
 // ---- round-1 kernel (A/B reference): one candidate per lane and step, one voxel of slack around the box ----------------
 __device__ __forceinline__ void axis_range_v1(const double *c, int Sg, double v, double thr, int &lo, int &n) {
@@ -109,7 +112,7 @@ __device__ __forceinline__ void red_add_one_if(float *p, bool hit) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q red.global.add.f32 [%0], 0f3F800000;\n\t}" ::"l"(p), "r"((int)hit) : "memory");
 }
 
-__global__ void __launch_bounds__(K4_WARPS * 32)
+__global__ void __launch_bounds__(K4_WARPS * 32, K4_MIN_CTAS)
     occupancy_kernel(const float *__restrict__ hvc, int S, int H, const double *__restrict__ centers, int Sg, double thr,
                      double T, float *__restrict__ grids, int split) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
