@@ -298,3 +298,35 @@ def test_occupancy_chunk_staging_matches_numpy_path():
     assert not occ._stage_chunk(moved, fast, all_rows=False)
     f32 = [dict(s, human_verts=s["human_verts"].astype(np.float32)) for s in samples]
     assert not occ._stage_chunk(f32, fast, all_rows=False)
+
+
+@pytest.mark.parametrize("Sg,tol", [(7, 1.2), (30, 3.0), (64, 2.5), (128, 3.0), (2040, 3.0), (2040, 0.6)])
+def test_occupancy_candidate_box_contains_every_hit(Sg, tol):
+    """K4 (coma_b200/csrc/occupancy.cu: axis_range) tests only the voxels of an index box derived from a LINEAR estimate of the centre
+    positions: [ceil(x_lo - 1/64), floor(x_hi + 1/64)], x = (v -+ thr - c[0]) * (Sg - 1) / (c[Sg-1] - c[0]). The reference's centres
+    are not exactly uniform (fp32 middle term, utils/coma_occupancy.py:171), so the claim "the box contains every voxel the reference
+    would count" is checked here against the exact per-axis hit set, for random vertices and for vertices planted at centre +- thr
+    (+- one fp64 ulp, then rounded to fp32 like the staged input), from the smallest grid to the largest the kernel accepts."""
+    from oracle import oracle
+    centers, voxel = oracle.voxel_centers(Sg)
+    c = np.asarray(centers[0], np.float64)
+    thr = voxel * tol
+    T = thr * thr                                       # smallest double whose sqrt is >= thr (squared_threshold in occupancy.cu)
+    while np.sqrt(T) >= thr:
+        T = np.nextafter(T, 0.0)
+    while np.sqrt(T) < thr:
+        T = np.nextafter(T, np.inf)
+    rng = np.random.default_rng(Sg)
+    pick = c if Sg <= 512 else c[rng.integers(0, Sg, 512)]
+    v = np.concatenate([rng.uniform(-1.4, 1.4, 4000), pick + thr, pick - thr, np.nextafter(pick + thr, 9.0),
+                        np.nextafter(pick - thr, -9.0), pick, pick + voxel / 2]).astype(np.float32).astype(np.float64)
+    inv = (Sg - 1) / (c[-1] - c[0])
+    lo = np.maximum(np.ceil((v - thr - c[0]) * inv - 1.0 / 64.0), 0).astype(np.int64)
+    hi = np.minimum(np.floor((v + thr - c[0]) * inv + 1.0 / 64.0), Sg - 1).astype(np.int64)
+    idx = np.arange(Sg)[None, :]
+    for a in range(0, len(v), 1024):
+        d = c[None, :] - v[a:a + 1024, None]
+        hit = (d * d) < T                               # necessary for a 3-D hit: the other two squares only add
+        inbox = (idx >= lo[a:a + 1024, None]) & (idx <= hi[a:a + 1024, None])
+        assert not (hit & ~inbox).any()
+    assert (hi - lo + 1).max() <= int(np.ceil(2 * tol)) + 2          # and it is tight: at most one spare voxel per side
