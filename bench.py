@@ -173,7 +173,7 @@ def cpu_reference_rate(target_seconds=12.0):
         probe = _quiet(_reference_contact_once, ref, "cpu", hs, 1)
         hs = int(min(512, max(16, hs * target_seconds / max(probe, 1e-3)))) // 8 * 8   # its [hs,O,N,3] fp64 temporary is 9 MB per row
         dt = _quiet(_reference_contact_once, ref, "cpu", hs, 1)
-        return dict(value=hs * O / dt, unit="vertex-pairs/s", cores=cores, kind="reference",
+        return dict(value=hs * O / dt, unit="vertex-pairs/s", cores=cores, kind="reference", step_ms=dt * 1e3,
                     sample=f"unmodified reference ComA(device='cpu'), 1 sample x {hs} of {H} human rows x {O} object verts x {N} bins "
                            f"(register + aggregate_all_samples), {dt:.1f} s, torch {torch.__version__} with {cores} intra-op threads")
     from coma_b200 import synth
@@ -190,7 +190,7 @@ def cpu_reference_rate(target_seconds=12.0):
         return time.perf_counter() - t0
     hs = int(min(H, max(64, 64 * target_seconds / max(run(64), 1e-3)))) // 8 * 8
     dt = run(hs)
-    return dict(value=hs * O / dt, unit="vertex-pairs/s", cores=cores, kind="port",
+    return dict(value=hs * O / dt, unit="vertex-pairs/s", cores=cores, kind="port", step_ms=dt * 1e3,
                 sample=f"1 sample x {hs} of {H} human rows x {O} object verts x {N} bins (K2+K3), {dt:.1f} s on {cores} OpenMP threads")
 
 
@@ -242,7 +242,7 @@ def run_reference(args, rank):
     best = rates[int(np.argsort([r["value"] for r in rates])[len(rates) // 2])]
     line = {
         "impl": "reference", "metric": "ComA vertex-pairs/s", "value": best["value"], "unit": "vertex-pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": best.get("step_ms"), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"coma_contact cfg4-shape H={H} O={O} N={N}, K2+K3 (reference CPU path, kind={best['kind']})"},
         "cpu_baseline": best,
