@@ -11,7 +11,7 @@
 // compare and the RED — the reference's sum ((x+y)+z) needs nothing else once y and z are known.  The box is tight
 // (ceil / floor of the linear index estimate with 1/64 voxel of margin instead of a whole voxel of slack on both sides:
 // 8 x 8 instead of 10 x 10 columns at scale_tolerance 3), and the per-axis reciprocal spacing is computed once per CTA.
-// Lanes 0..2 derive one axis range each; the RED is predicated (no branch around it).
+// Lanes 0..2 derive one axis range each.
 // ~300 warp-instructions per task against ~1300 for round 1's candidate-per-lane loop (`occupancy_kernel_v1`, kept behind
 // COMA_B200_OCC_PATH=v1 for A/B runs): the kernel moves from issue-bound towards the RED rate (1.29 clk per lane-RED per SM).
 //
@@ -99,7 +99,7 @@ __device__ __forceinline__ void axis_range(double c0, double inv, int Sg, double
     n = max(ihi - ilo + 1, 0);
 }
 
-// c -> (c / nk, c % nk) for a small non-negative c: float reciprocal estimate, corrected by at most one (exact for every size)
+// c -> (c / nk, c % nk) for 0 <= c < 2^24 (a plane has <= 2040^2 columns): float reciprocal estimate, corrected by at most one
 __device__ __forceinline__ void split_column(int c, int nk, float rnk, int &j, int &k) {
     j = __float2int_rz(((float)c + 0.5f) * rnk);
     k = c - j * nk;
@@ -107,7 +107,8 @@ __device__ __forceinline__ void split_column(int c, int nk, float rnk, int &j, i
     else if (k >= nk) { j += 1; k -= nk; }
 }
 
-// grids[cell] += 1.0f if `hit`: a predicated RED.E.ADD.F32 (no branch, no reconvergence point around the atomic)
+// grids[cell] += 1.0f if `hit`: RED.E.ADD.F32 with the constant as an immediate. (Written as a predicated `red`; ptxas still emits a
+// short forward branch around every RED — SASS checked — so the per-plane cost that is left is this control flow.)
 __device__ __forceinline__ void red_add_one_if(float *p, bool hit) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q red.global.add.f32 [%0], 0f3F800000;\n\t}" ::"l"(p), "r"((int)hit) : "memory");
 }
