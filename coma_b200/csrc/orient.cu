@@ -51,7 +51,26 @@ __device__ __forceinline__ float dot_ref(Vec3 a, Vec3 b, int ord = 0) {
     return sum3_ref(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), ord);
 }
 
+// Three quotients by ONE divisor with a shared reciprocal: r = rcp(d) refined by one Newton step, then per numerator q = x r,
+// q += fma(-q, d, x) r (Markstein's correction). With a faithful r the result is the correctly rounded x / d except for rare
+// 1-ulp cases — good for K3 (1e-4 contract), NOT for the bit-exact canonicalisation entry point. 12 instructions instead of three
+// div.rn sequences (~33, each with its own MUFU.RCP, FCHK range check and slow-path branch). NaN / zero divisors give NaN like
+// the IEEE division; an infinite divisor gives NaN instead of 0 (a non-finite normal: the pair is poisoned either way).
+#ifndef K3C_FAST_DIV
+#define K3C_FAST_DIV 1
+#endif
+__device__ __forceinline__ void div3_shared(float &x, float &y, float &z, float d) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(d));
+    r = fmaf(r, fmaf(-d, r, 1.0f), r);
+    float q = x * r; x = fmaf(fmaf(-q, d, x), r, q);
+    q = y * r;       y = fmaf(fmaf(-q, d, y), r, q);
+    q = z * r;       z = fmaf(fmaf(-q, d, z), r, q);
+}
+
 // canonicalize_a_wrt_b_to_p for one (a, b) pair; a, b, p, sp already normalised — utils/coma.py:135-170
+// FASTDIV (K3's cone kernel only): the two triples of divisions use div3_shared.
+template <bool FASTDIV = false>
 __device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp, float eps, int ord = 0) {
     const float b_dot_p = dot_ref(b, p, ord), a_dot_b = dot_ref(a, b, ord), a_dot_p = dot_ref(a, p, ord), a_dot_sp = dot_ref(a, sp, ord);
     const float one_plus = __fadd_rn(1.0f, b_dot_p);
@@ -66,15 +85,25 @@ __device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp
     const float av[3] = {a.x, a.y, a.z}, bv[3] = {b.x, b.y, b.z}, pv[3] = {p.x, p.y, p.z}, sv[3] = {sp.x, sp.y, sp.z};
     const float xv[3] = {bxp.x, bxp.y, bxp.z};
     float f[3];
+    if (FASTDIV) {
+        float v0 = __fmul_rn(xv[0], a_dot_bxp), v1 = __fmul_rn(xv[1], a_dot_bxp), v2 = __fmul_rn(xv[2], a_dot_bxp);   // :162
+        div3_shared(v0, v1, v2, one_plus);                                                                         // :163
+        f[0] = v0; f[1] = v1; f[2] = v2;
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float v = __fmul_rn(xv[k], a_dot_bxp);                 // :162
-        // :163. With p = (0,0,1) the third component of bxp is an exact zero for EVERY pair, and div.rn's operand check (FCHK) sends a
-        // zero numerator down its ~60-instruction slow path — the whole warp, four times per chunk. +-0 / (positive finite) is the
-        // zero itself, so only non-zero numerators are divided (bit-identical; a NaN divisor still takes the generic division).
-        const bool zero_num = v == 0.0f && pos_div;
-        const float q = __fdiv_rn(zero_num ? 1.0f : v, one_plus);
-        v = replace ? 0.0f : (zero_num ? v : q);
+        float v;
+        if (FASTDIV) {
+            v = replace ? 0.0f : f[k];
+        } else {
+            v = __fmul_rn(xv[k], a_dot_bxp);                   // :162
+            // :163. With p = (0,0,1) the third component of bxp is an exact zero for EVERY pair, and div.rn's operand check (FCHK) sends a
+            // zero numerator down its ~60-instruction slow path — the whole warp, four times per chunk. +-0 / (positive finite) is the
+            // zero itself, so only non-zero numerators are divided (bit-identical; a NaN divisor still takes the generic division).
+            const bool zero_num = v == 0.0f && pos_div;
+            const float q = __fdiv_rn(zero_num ? 1.0f : v, one_plus);
+            v = replace ? 0.0f : (zero_num ? v : q);
+        }
         v = __fadd_rn(v, __fmul_rn(b_dot_p, av[k]));           // :164
         v = __fadd_rn(v, __fmul_rn(a_dot_b, pv[k]));           // :165
         v = __fsub_rn(v, __fmul_rn(a_dot_p, bv[k]));           // :166
@@ -82,6 +111,10 @@ __device__ __forceinline__ Vec3 canonicalize_ref(Vec3 a, Vec3 b, Vec3 p, Vec3 sp
         f[k] = v;
     }
     const float n = __fsqrt_rn(sum3_ref(__fmul_rn(f[0], f[0]), __fmul_rn(f[1], f[1]), __fmul_rn(f[2], f[2]), ord));
+    if (FASTDIV) {
+        div3_shared(f[0], f[1], f[2], n);                      // :170
+        return Vec3{f[0], f[1], f[2]};
+    }
     return Vec3{__fdiv_rn(f[0], n), __fdiv_rn(f[1], n), __fdiv_rn(f[2], n)};  // :170
 }
 
@@ -430,8 +463,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB)
                 const float *po3 = on + ((size_t)s * O + o) * 3;
                 const Vec3 a = PRENORM ? Vec3{ph3[0], ph3[1], ph3[2]} : normalize_ref(Vec3{ph3[0], ph3[1], ph3[2]}, eps, ord);
                 const Vec3 b = PRENORM ? Vec3{po3[0], po3[1], po3[2]} : normalize_ref(Vec3{po3[0], po3[1], po3[2]}, eps, ord);
-                ch[u] = canonicalize_ref(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
-                co[u] = canonicalize_ref(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
+                ch[u] = canonicalize_ref<K3C_FAST_DIV != 0>(a, b, p, sp, eps, ord);  // human normal w.r.t. object normal (:295-301)
+                co[u] = canonicalize_ref<K3C_FAST_DIV != 0>(b, a, p, sp, eps, ord);  // object normal w.r.t. human normal (:302-309)
             }
         }
 #pragma unroll 1
